@@ -1,0 +1,186 @@
+"""oracle/gen_golden.py -- TEST INFRASTRUCTURE.  Regenerates ``tests/golden/*.npz`` from the REAL reference.
+
+Run in the build container only (needs /root/reference):
+
+    python -m oracle.gen_golden            # writes tests/golden/*.npz
+
+Every output array below is produced by calling the reference's own, unmodified functions
+(``utils_match.hist_icp``, ``utils_hist.estimate_init_pose``, ``utils_icp.apply_icp``,
+``utils_icp_pytorch3d.iterative_closest_point``, ``utils_helper.nearest_neighbor_batch``,
+``utils_flow.flow_estimation_torch``) on torch CPU fp32 through ``oracle/ref_loader.py``; the inputs are
+stored next to them so the fixtures are self-contained on the GPU box.
+
+Fixtures
+    hist_test_vector.npz  inputs of hist_cuda/test.py:19-50 (torch.manual_seed(2022)) + histogram arg-max
+                          (analytic known answer (50,130,7)) and peak / total vote counts
+    c1_demo.npz           BASELINE config C1: demo.npz -> sklearn DBSCAN(eps .25, min 20) stand-in labels ->
+                          first 32 static pairs with both clouds <= 256 points, N=256, F=2.0 (demo.sh)
+    synth_hist.npz        24 ragged synthetic pairs, N=128, full hist_icp with F=3.333 (argparse default)
+    synth_icp20.npz       32 synthetic residual-only pairs, N=256: ICP only, 20 forced iterations
+                          (relative_rmse_thr=-1) and the reference stopping rule (1e-6, max 100)
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import ref_loader  # noqa: E402
+from icp_flow_b200 import synth  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def _args(**kw):
+    base = dict(thres_dist=0.1, translation_frame=3.333, chunk_size=50, max_points=256, min_cluster_size=20,
+                thres_box=0.1)
+    base.update(kw)
+    return types.SimpleNamespace(**base)
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _run_path(ref, args, src, dst):
+    """All reference outputs for one padded batch (torch CPU fp32)."""
+    src_t, dst_t = torch.from_numpy(src), torch.from_numpy(dst)
+    out = {}
+    T = ref.utils_match.hist_icp(args, src_t, dst_t)
+    out["T_hist_icp"] = _np(T)
+    # inner seams on the swapped copies, exactly as hist_icp builds them (utils_match.py:139-146)
+    n_s = (src_t[:, :, -1] > 0).sum(1)
+    n_d = (dst_t[:, :, -1] > 0).sum(1)
+    swap = n_s > n_d
+    a, c = src_t.clone(), dst_t.clone()
+    a[swap] = dst_t[swap]
+    c[swap] = src_t[swap]
+    init = ref.utils_hist.estimate_init_pose(args, a, c)
+    out["swapped"] = _np(swap)
+    out["init_pose"] = _np(init)
+    out["T_apply_icp"] = _np(ref.utils_icp.apply_icp(args, a, c, init))
+    moved = ref.utils_helper.transform_points_batch(a, init)
+    sol = ref.utils_icp_pytorch3d.iterative_closest_point(moved, c, thres=args.thres_dist, max_iterations=100,
+                                                          relative_rmse_thr=1e-6)
+    out["icp_R"], out["icp_T"], out["icp_rmse"] = _np(sol.RTs.R), _np(sol.RTs.T), _np(sol.rmse)
+    out["icp_iterations"] = np.int64(len(sol.t_history))
+    out["icp_converged"] = np.bool_(sol.converged)
+    idx, dist = ref.utils_helper.nearest_neighbor_batch(a, c)
+    out["nn_idx"], out["nn_dist"] = _np(idx), _np(dist)
+    return out
+
+
+def gen_hist_test_vector(ref):
+    torch.manual_seed(2022)
+    pts = torch.randn(3, 1000, 3)
+    flags = torch.randint(0, 2, size=(3, 1000, 1))
+    a = torch.cat([pts, flags], dim=-1)
+    b = a.clone()
+    b[:, :, 0] += 5.0
+    b[:, :, 1] += -3.0
+    b[:, :, 2] += -0.2
+    rng = (10.0, 10.0, 0.5)
+    thres = 0.1
+    lens = tuple(len(torch.arange(-r, r + thres, thres)) for r in rng)
+    from hist_cuda.hist import hist  # the stub == oracle leaf (the real kernel is CUDA-only)
+
+    h = hist(a, b, -rng[0], -rng[1], -rng[2], rng[0], rng[1], rng[2], *lens)
+    _, hh, ww, dd = h.shape
+    flat = h.reshape(3, -1).argmax(dim=1)
+    arg = torch.stack([flat // dd // ww % hh, flat // dd % ww, flat % dd], dim=1)
+    np.savez_compressed(os.path.join(GOLDEN, "hist_test_vector.npz"), X=_np(a), Y=_np(b),
+                        mins=np.array([-rng[0], -rng[1], -rng[2]], np.float32),
+                        maxs=np.array(rng, np.float32), lens=np.array(lens, np.int64),
+                        argmax=_np(arg), peak=_np(h.reshape(3, -1).max(dim=1)[0]), total=_np(h.sum(dim=(1, 2, 3))))
+    print("hist_test_vector: argmax", arg.tolist(), "peak", h.reshape(3, -1).max(dim=1)[0].tolist())
+
+
+def gen_c1_demo(ref):
+    from sklearn.cluster import DBSCAN
+
+    d = np.load(os.path.join(ref_loader.REFERENCE_ROOT, "demo.npz"))
+    pc_src = d["pc1"][d["pc1_flows_valid_idx"]].astype(np.float32)
+    pc_dst = d["pc2"][d["pc2_flows_valid_idx"]].astype(np.float32)
+    fused = np.concatenate([pc_dst, pc_src], axis=0)
+    labels = DBSCAN(eps=0.25, min_samples=20).fit_predict(fused[:, :3]).astype(np.int64)
+    lab_dst, lab_src = labels[: len(pc_dst)], labels[len(pc_dst):]
+    args = _args(translation_frame=2.0, max_points=256)
+    src_t, dst_t = torch.from_numpy(pc_src), torch.from_numpy(pc_dst)
+    ls_t, ld_t = torch.from_numpy(lab_src), torch.from_numpy(lab_dst)
+    uniq = torch.unique(torch.cat([ls_t, ld_t]))
+    uniq = uniq[uniq >= 0]
+    pairs = torch.stack([uniq, uniq], dim=1)
+    ok = ref.utils_check.sanity_check(args, src_t, dst_t, ls_t, ld_t, pairs).long()
+    chosen = []
+    for pr in ok:
+        if int((ls_t == pr[0]).sum()) <= 256 and int((ld_t == pr[1]).sum()) <= 256:
+            chosen.append(pr)
+        if len(chosen) == 32:
+            break
+    chosen = torch.stack(chosen)
+    src_b = torch.stack([ref.utils_helper.pad_segment(src_t[ls_t == pr[0], 0:3], 256) for pr in chosen])
+    dst_b = torch.stack([ref.utils_helper.pad_segment(dst_t[ld_t == pr[1], 0:3], 256) for pr in chosen])
+    out = _run_path(ref, args, _np(src_b), _np(dst_b))
+    # flow over the points of the chosen source clusters (utils_flow.py:57-69), identity ego pose
+    sel = torch.isin(ls_t, chosen[:, 0])
+    pts, lab = src_t[sel], ls_t[sel]
+    flow = ref.utils_flow.flow_estimation_torch(args, pts, None, lab, None, chosen.float(),
+                                                torch.from_numpy(out["T_hist_icp"]), torch.eye(4))
+    np.savez_compressed(os.path.join(GOLDEN, "c1_demo.npz"), src=_np(src_b), dst=_np(dst_b),
+                        thres_dist=np.float64(args.thres_dist), translation_frame=np.float64(args.translation_frame),
+                        chunk_size=np.int64(args.chunk_size), pair_labels=_np(chosen),
+                        flow_points=_np(pts), flow_labels=_np(lab), flow=_np(flow), **out)
+    print("c1_demo: pairs", len(chosen), "icp iterations", int(out["icp_iterations"]),
+          "nonzero init", int((np.abs(out["init_pose"][:, :3, 3]).sum(1) > 0).sum()))
+
+
+def gen_synth_hist(ref):
+    src, dst, meta = synth.make_pairs(24, 128, seed=77, ragged=True, residual_only=False, wrong_frac=0.1)
+    args = _args(translation_frame=3.333)
+    out = _run_path(ref, args, src, dst)
+    np.savez_compressed(os.path.join(GOLDEN, "synth_hist.npz"), src=src, dst=dst,
+                        thres_dist=np.float64(args.thres_dist), translation_frame=np.float64(args.translation_frame),
+                        chunk_size=np.int64(args.chunk_size), gt_translation=meta["translation"], gt_yaw=meta["yaw"],
+                        wrong=meta["wrong"], **out)
+    print("synth_hist: icp iterations", int(out["icp_iterations"]), "swapped", int(out["swapped"].sum()))
+
+
+def gen_synth_icp20(ref):
+    src, dst, meta = synth.make_pairs(32, 256, seed=1234, ragged=False, residual_only=True)
+    src_r, dst_r, _ = synth.make_pairs(16, 256, seed=4321, ragged=True, residual_only=True)
+    icp = ref.utils_icp_pytorch3d.iterative_closest_point
+    res = {}
+    for tag, (a, c) in {"full": (src, dst), "ragged": (src_r, dst_r)}.items():
+        a_t, c_t = torch.from_numpy(a), torch.from_numpy(c)
+        fixed = icp(a_t, c_t, thres=0.1, max_iterations=20, relative_rmse_thr=-1.0)
+        stop = icp(a_t, c_t, thres=0.1, max_iterations=100, relative_rmse_thr=1e-6)
+        res.update({
+            f"{tag}_src": a, f"{tag}_dst": c,
+            f"{tag}_fixed20_R": _np(fixed.RTs.R), f"{tag}_fixed20_T": _np(fixed.RTs.T),
+            f"{tag}_fixed20_rmse": _np(fixed.rmse), f"{tag}_fixed20_iterations": np.int64(len(fixed.t_history)),
+            f"{tag}_stop_R": _np(stop.RTs.R), f"{tag}_stop_T": _np(stop.RTs.T), f"{tag}_stop_rmse": _np(stop.rmse),
+            f"{tag}_stop_iterations": np.int64(len(stop.t_history)), f"{tag}_stop_converged": np.bool_(stop.converged),
+        })
+        print(f"synth_icp20[{tag}]: fixed its", len(fixed.t_history), "stop its", len(stop.t_history), stop.converged)
+    np.savez_compressed(os.path.join(GOLDEN, "synth_icp20.npz"), thres_dist=np.float64(0.1), **res)
+
+
+def main():
+    torch.set_num_threads(os.cpu_count() or 1)
+    os.makedirs(GOLDEN, exist_ok=True)
+    ref = ref_loader.load_reference()
+    gen_hist_test_vector(ref)
+    gen_synth_icp20(ref)
+    gen_synth_hist(ref)
+    gen_c1_demo(ref)
+
+
+if __name__ == "__main__":
+    main()
