@@ -1,0 +1,87 @@
+"""ctypes binding of libicpflow_b200.so (the C ABI declared in include/icpflow_b200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``python -m icp_flow_b200.build``; there is no CPU
+fallback -- if the shared object is missing or a call fails, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libicpflow_b200.so")
+
+# every symbol include/icpflow_b200.h declares (checked by tests/test_abi.py against the header text)
+EXPORTS = (
+    "icpf_version", "icpf_error_string", "icpf_default_params", "icpf_workspace_bytes",
+    "icpf_icp_f32", "icpf_nn_f32", "icpf_transform_points_f32", "icpf_host_kabsch", "icpf_profile_next_icp",
+)
+
+
+class IcpfParams(ctypes.Structure):
+    """Mirror of ``struct icpf_params``."""
+
+    _fields_ = [
+        ("thres_dist", ctypes.c_double),
+        ("max_iterations", ctypes.c_int32),
+        ("relative_rmse_thr", ctypes.c_float),
+        ("early_exit", ctypes.c_int32),
+        ("batch_stop", ctypes.c_int32),
+        ("nn_mode", ctypes.c_int32),
+        ("reserved", ctypes.c_int32 * 2),
+    ]
+
+
+class IcpfError(RuntimeError):
+    def __init__(self, code: int, where: str):
+        self.code = code
+        msg = lib().icpf_error_string(code).decode()
+        super().__init__(f"{where} failed: {msg} (code {code})")
+
+
+_LIB = None
+
+
+def lib() -> ctypes.CDLL:
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build the sm_100a extension first (python -c 'import __graft_entry__ as g; "
+            "g.build()' at the repo root). icp_flow_b200 has no CPU or PyTorch fallback."
+        )
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64p = ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p
+    L.icpf_version.restype = ctypes.c_int
+    L.icpf_version.argtypes = []
+    L.icpf_error_string.restype = ctypes.c_char_p
+    L.icpf_error_string.argtypes = [ctypes.c_int]
+    L.icpf_default_params.restype = None
+    L.icpf_default_params.argtypes = [ctypes.POINTER(IcpfParams)]
+    L.icpf_workspace_bytes.restype = ctypes.c_size_t
+    L.icpf_workspace_bytes.argtypes = [i32] * 5
+    L.icpf_icp_f32.restype = ctypes.c_int
+    L.icpf_icp_f32.argtypes = [vp, vp, vp, vp, i32, i32, ctypes.POINTER(IcpfParams), vp, vp, vp, vp, vp, vp, vp, vp,
+                               ctypes.c_size_t, vp]
+    L.icpf_nn_f32.restype = ctypes.c_int
+    L.icpf_nn_f32.argtypes = [vp, vp, i32, i32, i32, i32, i32, i64p, vp, vp]
+    L.icpf_transform_points_f32.restype = ctypes.c_int
+    L.icpf_transform_points_f32.argtypes = [vp, vp, i32, i32, vp, vp]
+    L.icpf_profile_next_icp.restype = None
+    L.icpf_profile_next_icp.argtypes = [vp, vp]
+    L.icpf_host_kabsch.restype = None
+    L.icpf_host_kabsch.argtypes = [vp, i32, vp]
+    _LIB = L
+    return L
+
+
+def check(code: int, where: str) -> None:
+    if code != 0:
+        raise IcpfError(code, where)
+
+
+def default_params() -> IcpfParams:
+    p = IcpfParams()
+    lib().icpf_default_params(ctypes.byref(p))
+    return p

@@ -1,0 +1,182 @@
+// icpf_icp.cu -- batched ICP loop: one CTA per (src, dst) cluster pair, tiles TMA-staged into shared memory once,
+// all iterations (NN search, gating, Kabsch sums, closed-form rotation, re-transform, rmse) run on-chip.
+//
+// Replaces utils_icp_pytorch3d.iterative_closest_point (/root/reference/utils_icp_pytorch3d.py:37-225) and its
+// batch-coupled stopping rule (:209) without any host synchronisation:
+//   kernel 1  every pair iterates to its bitwise fixed point (or max_iterations) and records, per iteration, whether
+//             its relative-rmse test passed (128-bit mask);
+//   kernel 2  AND-reduces the masks over the batch -> k* = first iteration at which the reference's `.all()` fires;
+//   kernel 3  re-runs (capped at k*+1 iterations) only the pairs that were still moving at k*.
+#include "icpf_internal.h"
+#include "icpf_pair.cuh"
+
+namespace icpf {
+
+struct IcpArgs {
+    const float* src;
+    const float* dst;
+    const float* init_R;   // [P,9] or NULL
+    const float* init_T;   // [P,3] or NULL
+    int P, N;
+    float tau2;
+    int max_it;
+    float rel_thr;
+    int early_exit;
+    float* out_R;
+    float* out_T;
+    float* out_rmse;
+    float* out_pose;       // [P,16] or NULL
+    int* iters;            // [P] (never NULL inside the library)
+    uint32_t* conv;        // [P,4]
+    const int* batch;      // rerun mode: batch[0] = k*+1 (iterations the reference executed); NULL in the first pass
+};
+
+__global__ void __launch_bounds__(kThreads) icp_pairs_kernel(IcpArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int p = blockIdx.x;
+    int max_it = a.max_it;
+    bool early_exit = a.early_exit != 0;
+    if (a.batch != nullptr) {
+        // second pass: only pairs that executed more iterations than the batch did need their state at k*
+        const int batch_iters = a.batch[0];
+        if (a.iters[p] <= batch_iters) return;
+        max_it = batch_iters;
+        early_exit = false;
+    }
+    const PairTiles tl = carve_pair_tiles(smem_raw, a.N);
+    if (threadIdx.x == 0) {
+        mbar_init(tl.bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    load_pair_tiles(tl, a.src + (size_t)p * a.N * 4, a.dst + (size_t)p * a.N * 4, a.N, 0);
+
+    // valid-row counts (knn `lengths`): number of rows with flag > 0  (utils_icp_pytorch3d.py:109-112)
+    float cnt[2] = {0.f, 0.f};
+    for (int q = threadIdx.x; q < a.N; q += kThreads) {
+        cnt[0] += (tl.src[q].w > 0.f) ? 1.f : 0.f;
+        cnt[1] += (tl.dst[q].w > 0.f) ? 1.f : 0.f;
+    }
+    block_allreduce_sum<2, kWarps>(cnt, tl.red + kRedC);
+    __syncthreads();   // kRedC is reused by the first iteration's rmse reduction only after two more barriers; keep it simple
+    const int n_s = (int)cnt[0], n_d = (int)cnt[1];
+
+    const IcpResult r = icp_iterations(tl, a.N, n_s, n_d, a.tau2, max_it, a.rel_thr, early_exit,
+                                       a.init_R ? a.init_R + (size_t)p * 9 : nullptr,
+                                       a.init_T ? a.init_T + (size_t)p * 3 : nullptr);
+
+    if (threadIdx.x < 9) a.out_R[(size_t)p * 9 + threadIdx.x] = r.r[threadIdx.x];
+    if (threadIdx.x < 3) a.out_T[(size_t)p * 3 + threadIdx.x] = r.t[threadIdx.x];
+    if (a.out_pose && threadIdx.x < 16) {
+        // column-convention 4x4 [[R^T, T],[0,1]]  (utils_icp.py:60-65)
+        const int row = threadIdx.x >> 2, col = threadIdx.x & 3;
+        float v;
+        if (row == 3) v = (col == 3) ? 1.f : 0.f;
+        else if (col == 3) v = r.t[row];
+        else v = r.r[col * 3 + row];
+        a.out_pose[(size_t)p * 16 + threadIdx.x] = v;
+    }
+    if (threadIdx.x == 0) {
+        if (a.out_rmse) a.out_rmse[p] = r.rmse;
+        a.iters[p] = r.iters;
+        if (a.batch == nullptr) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a.conv[(size_t)p * 4 + i] = r.conv[i];
+        }
+    }
+}
+
+// AND of the per-pair convergence masks -> first iteration k* where every pair passes (utils_icp_pytorch3d.py:209).
+// batch[0] = iterations the reference loop would have executed, batch[1] = converged flag.
+__global__ void __launch_bounds__(256) icp_resolve_batch_kernel(const uint32_t* conv, int P, int max_it, int batch_stop,
+                                                                int* batch) {
+    __shared__ uint32_t s_and[4];
+    if (threadIdx.x < 4) s_and[threadIdx.x] = 0xffffffffu;
+    __syncthreads();
+    uint32_t m[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) m[i] &= conv[(size_t)p * 4 + i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        for (int o = 16; o > 0; o >>= 1) m[i] &= __shfl_xor_sync(FULL_MASK, m[i], o);
+        if ((threadIdx.x & 31) == 0) atomicAnd(&s_and[i], m[i]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int kstar = -1;
+        if (batch_stop) {
+            for (int i = 0; i < 4 && kstar < 0; ++i) {
+                if (s_and[i]) kstar = i * 32 + (__ffs(s_and[i]) - 1);
+            }
+        }
+        if (kstar >= 0 && kstar < max_it) {
+            batch[0] = kstar + 1;
+            batch[1] = 1;
+        } else {
+            batch[0] = max_it;
+            batch[1] = 0;
+        }
+    }
+}
+
+static thread_local cudaEvent_t t_prof_start = nullptr, t_prof_stop = nullptr;
+
+void set_profile_events(cudaEvent_t start, cudaEvent_t stop) {
+    t_prof_start = start;
+    t_prof_stop = stop;
+}
+
+int launch_icp(const float* src, const float* dst, const float* init_R, const float* init_T, int P, int N,
+               const icpf_params& prm, float* out_R, float* out_T,
+               float* out_rmse, float* out_pose, int* out_iters, uint32_t* out_conv, int* out_batch, void* workspace,
+               size_t workspace_bytes, cudaStream_t stream) {
+    if (P == 0) return ICPF_OK;
+    const size_t smem = pair_smem_bytes(N);
+    if (smem > 227 * 1024) return ICPF_E_UNSUPPORTED;
+    // workspace: iters [P] | conv [P,4] | batch [2]
+    const size_t need = icp_workspace_bytes(P);
+    if (workspace == nullptr || workspace_bytes < need) return ICPF_E_WORKSPACE;
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    int* iters = out_iters ? out_iters : reinterpret_cast<int*>(ws);
+    uint32_t* conv = out_conv ? out_conv : reinterpret_cast<uint32_t*>(ws + align_up((size_t)P * 4, 256));
+    int* batch = out_batch ? out_batch
+                           : reinterpret_cast<int*>(ws + align_up((size_t)P * 4, 256) + align_up((size_t)P * 16, 256));
+
+    cudaError_t err = cudaFuncSetAttribute(icp_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return (int)err;
+
+    IcpArgs a;
+    a.src = src; a.dst = dst; a.init_R = init_R; a.init_T = init_T; a.P = P; a.N = N;
+    const float tau = (float)prm.thres_dist;
+    a.tau2 = (float)(prm.thres_dist * prm.thres_dist);   // python: thres**2 in double, compared in fp32
+    (void)tau;
+    a.max_it = prm.max_iterations;
+    a.rel_thr = prm.relative_rmse_thr;
+    a.early_exit = prm.early_exit;
+    a.out_R = out_R; a.out_T = out_T; a.out_rmse = out_rmse; a.out_pose = out_pose;
+    a.iters = iters; a.conv = conv; a.batch = nullptr;
+    if (t_prof_start && t_prof_stop) cudaEventRecord(t_prof_start, stream);
+    icp_pairs_kernel<<<P, kThreads, smem, stream>>>(a);
+    err = cudaGetLastError();
+    if (t_prof_start && t_prof_stop) {
+        cudaEventRecord(t_prof_stop, stream);
+        t_prof_start = t_prof_stop = nullptr;
+    }
+    if (err != cudaSuccess) return (int)err;
+
+    icp_resolve_batch_kernel<<<1, 256, 0, stream>>>(conv, P, prm.max_iterations, prm.batch_stop, batch);
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return (int)err;
+
+    if (prm.batch_stop) {
+        a.batch = batch;
+        icp_pairs_kernel<<<P, kThreads, smem, stream>>>(a);
+        err = cudaGetLastError();
+        if (err != cudaSuccess) return (int)err;
+    }
+    return ICPF_OK;
+}
+
+}  // namespace icpf

@@ -1,0 +1,214 @@
+"""Host-side mirror of the reference's operator interface for the per-cluster-pair registration path.
+
+Same names, argument meaning and error behaviour as the reference callables they replace; every function hands
+raw device pointers to the C ABI (include/icpflow_b200.h) on torch's current CUDA stream.  PyTorch is used for
+device memory and streams only.
+
+    iterative_closest_point   /root/reference/utils_icp_pytorch3d.py:37-225
+    nearest_neighbor_batch    /root/reference/utils_helper.py:20-30
+    transform_points_batch    /root/reference/utils_helper.py:76-87
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, NamedTuple, Optional, Union
+
+import torch
+
+from . import _lib
+
+
+class SimilarityTransform(NamedTuple):
+    """utils_icp_pytorch3d.py:23-26"""
+    R: torch.Tensor
+    T: torch.Tensor
+    s: torch.Tensor
+
+
+class ICPSolution(NamedTuple):
+    """utils_icp_pytorch3d.py:29-34"""
+    converged: bool
+    rmse: Union[torch.Tensor, None]
+    Xt: torch.Tensor
+    RTs: SimilarityTransform
+    t_history: List[SimilarityTransform]
+
+
+class IcpBatchResult(NamedTuple):
+    """Raw outputs of one ``icpf_icp_f32`` call (device tensors, no host sync)."""
+    R: torch.Tensor           # [P,3,3] row-vector convention  X R + T
+    T: torch.Tensor           # [P,3]
+    rmse: torch.Tensor        # [P]
+    pose: torch.Tensor        # [P,4,4] column-convention [[R^T, T],[0,1]] (utils_icp.py:60-65)
+    iterations: torch.Tensor  # [P] int32 iterations each pair executed
+    conv_mask: torch.Tensor   # [P,4] int32 bit k <=> relative rmse <= thr at iteration k
+    batch: torch.Tensor       # [2] int32 {batch iterations of the reference loop, converged}
+
+
+def _stream_ptr() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _require_cuda_f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not torch.is_tensor(t):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: icp_flow_b200 has no CPU implementation")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32 (got {t.dtype})")
+    return t.contiguous()
+
+
+def make_params(thres: float = 0.1, max_iterations: int = 100, relative_rmse_thr: float = 1e-6,
+                early_exit: bool = True, batch_stop: bool = True, nn_mode: int = 0) -> _lib.IcpfParams:
+    p = _lib.default_params()
+    p.thres_dist = float(thres)
+    p.max_iterations = int(max_iterations)
+    p.relative_rmse_thr = float(relative_rmse_thr)
+    p.early_exit = int(bool(early_exit))
+    p.batch_stop = int(bool(batch_stop))
+    p.nn_mode = int(nn_mode)
+    return p
+
+
+def icp_batch(src: torch.Tensor, dst: torch.Tensor, params: _lib.IcpfParams,
+              init_R: Optional[torch.Tensor] = None, init_T: Optional[torch.Tensor] = None,
+              out: Optional[IcpBatchResult] = None, workspace: Optional[torch.Tensor] = None) -> IcpBatchResult:
+    """Stream-ordered batched ICP on padded ``[P,N,4]`` CUDA tensors; no host synchronisation."""
+    src = _require_cuda_f32(src, "src")
+    dst = _require_cuda_f32(dst, "dst")
+    if src.dim() != 3 or dst.dim() != 3 or src.shape[2] != 4 or dst.shape[2] != 4:
+        raise ValueError("src and dst must be [P, N, 4] (x, y, z, flag)")
+    if src.shape[0] != dst.shape[0]:
+        raise ValueError("Point sets X and Y have to have the same number of batches and data dimensions.")
+    if src.shape[1] != dst.shape[1]:
+        raise ValueError("src and dst must be padded to the same number of rows")
+    P, N, _ = src.shape
+    dev = src.device
+    if out is None:
+        out = IcpBatchResult(
+            R=torch.empty(P, 3, 3, device=dev, dtype=torch.float32),
+            T=torch.empty(P, 3, device=dev, dtype=torch.float32),
+            rmse=torch.empty(P, device=dev, dtype=torch.float32),
+            pose=torch.empty(P, 4, 4, device=dev, dtype=torch.float32),
+            iterations=torch.empty(P, device=dev, dtype=torch.int32),
+            conv_mask=torch.empty(P, 4, device=dev, dtype=torch.int32),
+            batch=torch.empty(2, device=dev, dtype=torch.int32),
+        )
+    L = _lib.lib()
+    need = L.icpf_workspace_bytes(P, N, 0, 0, 0)
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(max(need, 1), device=dev, dtype=torch.uint8)
+    if init_R is not None:
+        init_R = _require_cuda_f32(init_R, "init_R")
+        init_T = _require_cuda_f32(init_T, "init_T")
+    with torch.cuda.device(dev):
+        code = L.icpf_icp_f32(_ptr(src), _ptr(dst), _ptr(init_R), _ptr(init_T), P, N, ctypes.byref(params),
+                              _ptr(out.R), _ptr(out.T), _ptr(out.rmse), _ptr(out.pose), _ptr(out.iterations),
+                              _ptr(out.conv_mask),
+                              _ptr(out.batch), _ptr(workspace), workspace.numel(), _stream_ptr())
+    _lib.check(code, "icpf_icp_f32")
+    return out
+
+
+def iterative_closest_point(X, Y, init_transform: Optional[SimilarityTransform] = None, thres: float = 0.1,
+                            max_iterations: int = 100, relative_rmse_thr: float = 1e-6,
+                            estimate_scale: bool = False, allow_reflection: bool = False,
+                            verbose: bool = False) -> ICPSolution:
+    """Drop-in for ``utils_icp_pytorch3d.iterative_closest_point`` on padded ``[P,N,4]`` CUDA tensors.
+
+    The reference's batch-coupled stopping rule is reproduced on the device.  ``t_history`` has one entry per batch
+    iteration like the reference's, but only the last entry (the returned transform) is materialised; earlier
+    entries are ``None``.  ``estimate_scale`` / ``allow_reflection`` are not used anywhere on the reference path
+    (utils_icp.py:56-57 passes False) and raise ``NotImplementedError`` when set.
+    """
+    if estimate_scale or allow_reflection:
+        raise NotImplementedError("the ICP-Flow path calls ICP with estimate_scale=False, allow_reflection=False")
+    if not torch.is_tensor(X) or not torch.is_tensor(Y):
+        raise ValueError("The inputs X, Y should be padded [P,N,4] tensors.")
+    if (X.shape[2] != Y.shape[2]) or (X.shape[0] != Y.shape[0]):
+        raise ValueError("Point sets X and Y have to have the same number of batches and data dimensions.")
+    b = X.shape[0]
+    init_R = init_T = None
+    if init_transform is not None:
+        try:
+            R0, T0, s0 = init_transform
+            assert R0.shape == torch.Size((b, 3, 3)) and T0.shape == torch.Size((b, 3)) and s0.shape == torch.Size((b,))
+        except Exception:
+            raise ValueError(
+                "The initial transformation init_transform has to be a named tuple SimilarityTransform with "
+                "elements (R, T, s). R are dim x dim orthonormal matrices of shape (minibatch, dim, dim), T is a "
+                "batch of dim-dimensional translations of shape (minibatch, dim) and s is a batch of scalars of "
+                "shape (minibatch,).") from None
+        init_R = (s0[:, None, None] * R0).float()
+        init_T = T0.float()
+    params = make_params(thres, max_iterations, relative_rmse_thr, early_exit=True, batch_stop=True)
+    r = icp_batch(X, Y, params, init_R, init_T)
+    batch = r.batch.tolist()           # the one host sync of this wrapper (the reference syncs every iteration)
+    iterations, converged = int(batch[0]), bool(batch[1])
+    if verbose:
+        print(f"ICP has converged in {iterations} iterations." if converged
+              else f"ICP has not converged in {max_iterations} iterations.")
+    s = r.T.new_ones(b)
+    Xt = (X[:, :, 0:3, None] * r.R[:, None, :, :]).sum(dim=2) + r.T[:, None, :]
+    final = SimilarityTransform(r.R, r.T, s)
+    history: List[Optional[SimilarityTransform]] = [None] * (iterations - 1) + [final]
+    return ICPSolution(converged, r.rmse, Xt, final, history)
+
+
+def nearest_neighbor_batch(src: torch.Tensor, dst: torch.Tensor):
+    """Drop-in for ``utils_helper.nearest_neighbor_batch``: unbounded K=1 NN over ALL rows -> (idx int64, dist)."""
+    assert src.dim() == 3
+    assert dst.dim() == 3
+    assert len(src) == len(dst)
+    assert src.shape[2] >= 3
+    assert dst.shape[2] >= 3
+    b, num, _ = src.shape
+
+    def rows(t, name):
+        if not t.is_cuda:
+            raise RuntimeError(f"{name} must be a CUDA tensor: icp_flow_b200 has no CPU implementation")
+        t = t.float()
+        # accept [B,N,3] / [B,N,4] contiguous storage directly, anything else is compacted to xyz
+        if t.is_contiguous() and t.shape[2] in (3, 4):
+            return t, t.shape[2]
+        return t[:, :, 0:3].contiguous(), 3
+
+    s, ss = rows(src, "src")
+    d, ds = rows(dst, "dst")
+    idx = torch.empty(b, num, device=s.device, dtype=torch.int64)
+    dist = torch.empty(b, num, device=s.device, dtype=torch.float32)
+    with torch.cuda.device(s.device):
+        code = _lib.lib().icpf_nn_f32(_ptr(s), _ptr(d), b, num, d.shape[1], ss, ds, _ptr(idx), _ptr(dist), _stream_ptr())
+    _lib.check(code, "icpf_nn_f32")
+    return idx.view(b, num), dist.view(b, num)
+
+
+def transform_points_batch(xyz: torch.Tensor, pose: torch.Tensor) -> torch.Tensor:
+    """Drop-in for ``utils_helper.transform_points_batch``: ``[x y z 1] @ pose^T`` keeping the flag column."""
+    assert xyz.dim() == 3
+    assert pose.dim() == 3
+    assert xyz.shape[2] == 4
+    assert pose.shape[1] == 4
+    assert pose.shape[2] == 4
+    assert len(xyz) == len(pose)
+    x = _require_cuda_f32(xyz, "xyz")
+    m = _require_cuda_f32(pose, "pose")
+    out = torch.empty_like(x)
+    b, n, _ = x.shape
+    with torch.cuda.device(x.device):
+        code = _lib.lib().icpf_transform_points_f32(_ptr(x), _ptr(m), b, n, _ptr(out), _stream_ptr())
+    _lib.check(code, "icpf_transform_points_f32")
+    return out
+
+
+def host_kabsch(H: torch.Tensor) -> torch.Tensor:
+    """CPU test hook: the kernels' closed-form Kabsch rotation for ``[n,3,3]`` cross-covariances (row convention)."""
+    h = H.detach().to(torch.float32).contiguous().cpu()
+    out = torch.empty_like(h)
+    _lib.lib().icpf_host_kabsch(ctypes.c_void_p(h.data_ptr()), h.shape[0], ctypes.c_void_p(out.data_ptr()))
+    return out

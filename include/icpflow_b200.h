@@ -1,0 +1,104 @@
+/*
+ * icpflow_b200.h -- C ABI of the B200-native batched ICP registration engine (libicpflow_b200.so).
+ *
+ * Drop-in boundary for ICP-Flow's per-cluster-pair alignment path.  Plain pointers and sizes only: no torch /
+ * ATen / pybind11 types cross this boundary (the reference's native boundary is a pybind11+ATen extension,
+ * /root/reference/hist_cuda/cpp/hist.h:4-10, hist.cpp:25-27; everything else on the path is Python calling
+ * torch/pytorch3d ops).  All `*_f32` entry points
+ *   - take DEVICE pointers (fp32, contiguous, the reference's padded layout: [P, N, 4] rows (x, y, z, flag),
+ *     valid rows first with flag > 0, padded rows (1e8, 1e8, 1e8, 0) -- utils_helper.py:185-196),
+ *   - enqueue their work on `stream` (a cudaStream_t passed as void*) and return without synchronising,
+ *   - never allocate or free device memory (the caller provides outputs and, where stated, a workspace),
+ *   - return 0 on success, a negative ICPF_E_* code for argument errors, or a positive cudaError_t.
+ * The `icpf_session_*` entry points take HOST buffers and own their device staging buffers.
+ */
+#ifndef ICPFLOW_B200_H
+#define ICPFLOW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ICPF_OK 0
+#define ICPF_E_NULL (-1)        /* required pointer is NULL                         */
+#define ICPF_E_SHAPE (-2)       /* P/N/len out of the supported range               */
+#define ICPF_E_PARAM (-3)       /* invalid parameter value                          */
+#define ICPF_E_ALIGN (-4)       /* pointer not 16-byte aligned                      */
+#define ICPF_E_WORKSPACE (-5)   /* workspace too small                              */
+#define ICPF_E_UNSUPPORTED (-6) /* configuration not implemented on this build      */
+
+#define ICPF_MAX_ITERATIONS 128 /* convergence history is a 128-bit mask per pair   */
+
+/* The values of `args` and the hard-coded constants the reference path reads
+ * (main.py:45-132; utils_icp.py:54-55; utils_hist.py:21). */
+typedef struct icpf_params {
+    double thres_dist;        /* args.thres_dist (tau): ICP gate d^2 <= fp32(tau^2), histogram bin width       */
+    int32_t max_iterations;   /* utils_icp.py:54 -> 100                                                        */
+    float relative_rmse_thr;  /* utils_icp.py:55 -> 1e-6; negative disables the batch stop                     */
+    int32_t early_exit;       /* 1: a pair stops at its bitwise fixed point (result-identical, SURVEY finding 1);
+                                 0: every pair executes the full batch iteration count                         */
+    int32_t batch_stop;       /* 1: reproduce the reference's batch-coupled stop (utils_icp_pytorch3d.py:209):
+                                 results are the state at the first iteration where ALL pairs satisfy the
+                                 relative-RMSE test; 0: each pair independent (max_iterations / fixed point)   */
+    int32_t nn_mode;          /* 0 auto, 1 brute force, 2 uniform grid (radius-bounded, result-identical)      */
+    int32_t reserved[2];
+} icpf_params;
+
+int icpf_version(void);
+const char* icpf_error_string(int code);
+
+/* Fill `p` with the reference defaults (tau 0.1, 100 iterations, thr 1e-6, early_exit 1, batch_stop 1). */
+void icpf_default_params(icpf_params* p);
+
+/* Bytes of device workspace needed by the calls below for P pairs of N padded rows and an lx*ly*lz histogram. */
+size_t icpf_workspace_bytes(int32_t P, int32_t N, int32_t lx, int32_t ly, int32_t lz);
+
+/*
+ * Batched ICP loop -- replaces utils_icp_pytorch3d.iterative_closest_point (utils_icp_pytorch3d.py:37-225) with
+ * init_transform=None, estimate_scale=False, allow_reflection=False, and the Kabsch solve it calls
+ * (corresponding_points_alignment, :233-382).  Row-vector convention of the reference:  X R + T ~ Y[NN].
+ *   src, dst   [P,N,4]            out_R [P,9] row-major   out_T [P,3]   out_rmse [P] (may be NULL)
+ *   init_R [P,9], init_T [P,3]    the reference's init_transform (both NULL = identity): used for the FIRST
+ *                                 correspondence search only, the transform is always re-estimated from `src`
+ *   out_pose   [P,16] the same transform packed as the reference's column-convention 4x4 [[R^T, T],[0,1]]
+ *              (utils_icp.py:60-65) (may be NULL)
+ *   out_iters  [P] int32 iterations this pair executed (may be NULL)
+ *   out_conv   [P,4] uint32 bit k set <=> relative rmse <= thr at iteration k (may be NULL)
+ *   out_batch  [2] int32: {batch iterations the reference would have executed, converged flag} (may be NULL)
+ *   workspace  icpf_workspace_bytes(P, N, 0, 0, 0)
+ */
+int icpf_icp_f32(const float* src, const float* dst, const float* init_R, const float* init_T, int32_t P, int32_t N,
+                 const icpf_params* params, float* out_R, float* out_T, float* out_rmse, float* out_pose,
+                 int32_t* out_iters, uint32_t* out_conv, int32_t* out_batch, void* workspace, size_t workspace_bytes,
+                 void* stream);
+
+/*
+ * Unbounded K=1 nearest neighbour over ALL rows -- replaces utils_helper.nearest_neighbor_batch
+ * (utils_helper.py:20-30; pytorch3d knn_points without lengths).  Rows are `stride` floats apart (3 or 4).
+ *   src [B,Ns,stride], dst [B,Nd,stride] -> out_idx [B,Ns] int64, out_dist [B,Ns] (sqrt of the min squared L2).
+ */
+int icpf_nn_f32(const float* src, const float* dst, int32_t B, int32_t Ns, int32_t Nd, int32_t src_stride,
+                int32_t dst_stride, int64_t* out_idx, float* out_dist, void* stream);
+
+/*
+ * Homogeneous transform that keeps the flag column -- replaces utils_helper.transform_points_batch
+ * (utils_helper.py:76-87).  xyz [B,N,4], pose [B,16] row-major 4x4 (column-vector convention) -> out [B,N,4].
+ */
+int icpf_transform_points_f32(const float* xyz, const float* pose, int32_t B, int32_t N, float* out, void* stream);
+
+/* Measurement hook (bench.py): when both handles are non-NULL the next icpf_icp_f32 call on this host thread records
+ * `start_event` / `stop_event` (cudaEvent_t) on its stream immediately around the launch of the dominant kernel
+ * (icp_pairs_kernel, first pass), then the hook clears itself.  No effect on results. */
+void icpf_profile_next_icp(void* start_event, void* stop_event);
+
+/* CPU-callable test hook: the closed-form 3x3 Kabsch rotation used inside the kernels, evaluated on the host
+ * for `n` row-major cross-covariance matrices H (n*9 floats) -> R (n*9 floats).  Not part of the data path. */
+void icpf_host_kabsch(const float* H, int32_t n, float* R);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICPFLOW_B200_H */

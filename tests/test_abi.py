@@ -1,0 +1,106 @@
+"""CPU: the C-ABI library loads, exports every symbol include/icpflow_b200.h declares, and its host-side logic
+(parameter defaults, argument validation, error strings, the Kabsch closed form) behaves -- no GPU compute calls."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from icp_flow_b200 import _lib, ops
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "icpflow_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(icpf_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    declared = _declared_symbols()
+    assert declared, "no declarations found in the header"
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/icpflow_b200.h but not exported"
+    assert sorted(_lib.EXPORTS) == declared
+    assert L.icpf_version() >= 100
+
+
+def test_default_params_match_reference_constants():
+    p = _lib.default_params()
+    # utils_icp.py:54-55 (100 iterations, 1e-6), main.py thres_dist default 0.1
+    assert p.thres_dist == pytest.approx(0.1)
+    assert p.max_iterations == 100
+    assert p.relative_rmse_thr == pytest.approx(1e-6)
+    assert p.early_exit == 1 and p.batch_stop == 1
+
+
+def test_argument_validation_without_gpu():
+    L = _lib.lib()
+    p = _lib.default_params()
+    null = ctypes.c_void_p(0)
+    fake = ctypes.c_void_p(4096)          # aligned, never dereferenced: validation fails first
+    odd = ctypes.c_void_p(4100)
+    call = lambda *a: L.icpf_icp_f32(*a)
+    assert call(null, null, null, null, 0, 8, ctypes.byref(p), null, null, null, null, null, null, null, null, 0, null) == 0
+    assert call(null, fake, null, null, 4, 8, ctypes.byref(p), fake, fake, null, null, null, null, null, null, 0, null) == -1
+    assert call(odd, fake, null, null, 4, 8, ctypes.byref(p), fake, fake, null, null, null, null, null, null, 0, null) == -4
+    assert call(fake, fake, null, null, -1, 8, ctypes.byref(p), fake, fake, null, null, null, null, null, null, 0, null) == -2
+    p.max_iterations = 1000
+    assert call(fake, fake, null, null, 4, 8, ctypes.byref(p), fake, fake, null, null, null, null, null, null, 0, null) == -3
+    p.max_iterations = 100
+    # workspace too small is detected before any launch
+    assert call(fake, fake, null, null, 4, 8, ctypes.byref(p), fake, fake, null, null, null, null, null, null, 0, null) == -5
+    assert L.icpf_workspace_bytes(1024, 512, 0, 0, 0) >= 1024 * 20
+    assert b"workspace" in L.icpf_error_string(-5)
+    assert L.icpf_nn_f32(fake, fake, 2, 8, 8, 2, 3, fake, fake, null) == -3
+
+
+def test_python_shim_refuses_cpu_tensors():
+    x = torch.zeros(2, 8, 4)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        ops.icp_batch(x, x, ops.make_params())
+    with pytest.raises(RuntimeError, match="no CPU"):
+        ops.nearest_neighbor_batch(x, x)
+    with pytest.raises(ValueError, match="same number of batches"):
+        ops.iterative_closest_point(torch.zeros(2, 8, 4), torch.zeros(3, 8, 4))
+
+
+def _kabsch_fp64(H):
+    U, S, Vt = np.linalg.svd(H.astype(np.float64))
+    E = np.tile(np.eye(3), (len(H), 1, 1))
+    E[:, 2, 2] = np.linalg.det(U @ Vt)
+    return U @ E @ Vt
+
+
+def test_kabsch_closed_form_matches_svd():
+    """utils_icp_pytorch3d.py:339-363: R = U diag(1,1,det(UV^T)) V^T -- generic, planar (rank 2) and reflected inputs."""
+    rng = np.random.default_rng(0)
+
+    def covs(n, planar, scale):
+        out = []
+        for _ in range(n):
+            X = rng.normal(size=(100, 3)) * np.array([2.0, 1.0, 0.0 if planar else 0.7])
+            a = rng.uniform(-0.2, 0.2)
+            c, s = np.cos(a), np.sin(a)
+            Y = X @ np.array([[c, -s, 0], [s, c, 0], [0, 0, 1.0]]) + rng.normal(size=X.shape) * 0.01
+            out.append((X - X.mean(0)).T @ (Y - Y.mean(0)) / 100 * scale)
+        return np.array(out, dtype=np.float32)
+
+    for planar in (False, True):
+        for scale in (1.0, 1e-6, 1e6):
+            H = covs(300, planar, scale)
+            R = ops.host_kabsch(torch.from_numpy(H)).numpy()
+            assert np.abs(R - _kabsch_fp64(H)).max() < 2e-6
+            assert np.abs(R @ R.transpose(0, 2, 1) - np.eye(3)).max() < 2e-6
+            assert np.linalg.det(R.astype(np.float64)).min() > 0.999
+    H = covs(300, False, 1.0)
+    H[:, :, 2] *= -1                                   # optimal orthogonal matrix would be a reflection
+    R = ops.host_kabsch(torch.from_numpy(H)).numpy()
+    assert np.abs(R - _kabsch_fp64(H)).max() < 2e-6
+    assert np.linalg.det(R.astype(np.float64)).min() > 0.999
+    # no inliers -> H = 0 -> identity (torch.svd of the zero matrix gives U = V = I)
+    assert np.array_equal(ops.host_kabsch(torch.zeros(1, 3, 3)).numpy()[0], np.eye(3, dtype=np.float32))

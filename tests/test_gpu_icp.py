@@ -1,0 +1,146 @@
+"""GPU parity: the CUDA ICP path (through the C ABI) against the CPU oracle and the committed reference goldens.
+
+Tolerances (BASELINE.json north_star: transforms within 1e-4 of the reference, fp32):
+  * moved points  max_i |(x_i R + T) - (x_i R_ref + T_ref)|_inf <= 1e-4 m over valid rows  (the flow difference)
+  * R entries within 1e-4; T entries reported (|T| grows with the distance of the cluster from the origin)
+"""
+import numpy as np
+import pytest
+import torch
+
+from icp_flow_b200 import ops, synth
+from oracle import icp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def _dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _moved_err(src, R, T, R_ref, T_ref):
+    pts = torch.from_numpy(src[:, :, :3]).double()
+    valid = torch.from_numpy(src[:, :, 3] > 0)
+    a = torch.bmm(pts, torch.as_tensor(R).double()) + torch.as_tensor(T).double()[:, None, :]
+    b = torch.bmm(pts, torch.as_tensor(R_ref).double()) + torch.as_tensor(T_ref).double()[:, None, :]
+    return ((a - b).abs().amax(dim=2) * valid).amax(dim=1).numpy()
+
+
+def _run(src, dst, **kw):
+    dev = _dev()
+    p = ops.make_params(**kw)
+    r = ops.icp_batch(torch.from_numpy(src).to(dev), torch.from_numpy(dst).to(dev), p)
+    torch.cuda.synchronize()
+    return r
+
+
+@pytest.mark.parametrize("tag", ["full", "ragged"])
+def test_fixed_20_iterations_vs_reference_golden(golden, tag):
+    """BASELINE config C2 call shape: max_iterations=20, relative_rmse_thr=-1 (no early stop)."""
+    g = golden("synth_icp20.npz")
+    src, dst = g[f"{tag}_src"], g[f"{tag}_dst"]
+    r = _run(src, dst, thres=0.1, max_iterations=20, relative_rmse_thr=-1.0, early_exit=False, batch_stop=True)
+    assert r.batch.tolist() == [20, 0]
+    assert (r.iterations.cpu().numpy() == 20).all()
+    err = _moved_err(src, r.R.cpu(), r.T.cpu(), g[f"{tag}_fixed20_R"], g[f"{tag}_fixed20_T"])
+    assert err.max() <= TOL, err
+    assert np.abs(r.R.cpu().numpy() - g[f"{tag}_fixed20_R"]).max() <= TOL
+    assert np.allclose(r.rmse.cpu().numpy(), g[f"{tag}_fixed20_rmse"], rtol=1e-3, atol=1e-6)
+
+
+@pytest.mark.parametrize("tag", ["full", "ragged"])
+def test_reference_stopping_rule_vs_golden(golden, tag):
+    g = golden("synth_icp20.npz")
+    src, dst = g[f"{tag}_src"], g[f"{tag}_dst"]
+    r = _run(src, dst, thres=0.1, max_iterations=100, relative_rmse_thr=1e-6, early_exit=True, batch_stop=True)
+    its, conv = r.batch.tolist()
+    assert conv == int(g[f"{tag}_stop_converged"])
+    # the batch stop iteration may move by one when a pair's relative rmse sits at the 1e-6 threshold
+    assert abs(its - int(g[f"{tag}_stop_iterations"])) <= 2
+    err = _moved_err(src, r.R.cpu(), r.T.cpu(), g[f"{tag}_stop_R"], g[f"{tag}_stop_T"])
+    assert err.max() <= TOL, err
+
+
+def test_early_exit_is_result_identical():
+    """SURVEY finding 1: stopping each pair at its bitwise fixed point does not change the result."""
+    src, dst, _ = synth.make_pairs(48, 192, seed=11, ragged=True, residual_only=True)
+    a = _run(src, dst, max_iterations=60, relative_rmse_thr=-1.0, early_exit=False, batch_stop=False)
+    b = _run(src, dst, max_iterations=60, relative_rmse_thr=-1.0, early_exit=True, batch_stop=False)
+    fixed = b.iterations.cpu().numpy() < 60
+    assert fixed.sum() > 0
+    assert torch.equal(a.R[torch.from_numpy(fixed)], b.R[torch.from_numpy(fixed)])
+    assert torch.equal(a.T[torch.from_numpy(fixed)], b.T[torch.from_numpy(fixed)])
+
+
+def test_oracle_parity_on_seeded_batch():
+    src, dst, _ = synth.make_pairs(40, 160, seed=21, ragged=True, residual_only=True, wrong_frac=0.15)
+    ref = O.icp_loop(torch.from_numpy(src), torch.from_numpy(dst), thres=0.1, max_iterations=100,
+                     relative_rmse_thr=1e-6)
+    r = _run(src, dst, max_iterations=100, relative_rmse_thr=1e-6)
+    err = _moved_err(src, r.R.cpu(), r.T.cpu(), ref.R, ref.T)
+    assert err.max() <= TOL, err
+
+
+def test_mirror_api_returns_reference_types():
+    dev = _dev()
+    src, dst, _ = synth.make_pairs(8, 64, seed=3, residual_only=True)
+    s, d = torch.from_numpy(src).to(dev), torch.from_numpy(dst).to(dev)
+    sol = ops.iterative_closest_point(s, d, thres=0.1, max_iterations=100, relative_rmse_thr=1e-6)
+    assert isinstance(sol.converged, bool) and sol.RTs.R.shape == (8, 3, 3) and sol.RTs.T.shape == (8, 3)
+    assert sol.Xt.shape == (8, 64, 3) and sol.rmse.shape == (8,) and len(sol.t_history) >= 1
+    assert torch.equal(sol.RTs.s, torch.ones(8, device=dev))
+    ref = O.icp_loop(torch.from_numpy(src), torch.from_numpy(dst))
+    assert abs(len(sol.t_history) - ref.iterations) <= 2
+    assert (sol.Xt.cpu() - (torch.bmm(torch.from_numpy(src[:, :, :3]), ref.R) + ref.T[:, None])).abs().max() <= TOL
+
+
+def test_degenerate_pairs():
+    """identity pair (rmse 0 -> NaN relative rmse in the reference), zero-inlier pair, tiny clusters."""
+    dev = _dev()
+    rng = np.random.default_rng(0)
+    N = 64
+    src = np.full((4, N, 4), 1e8, np.float32); src[..., 3] = 0
+    dst = src.copy()
+    pts = rng.uniform(-1, 1, size=(40, 3)).astype(np.float32) + np.array([20, -10, 1], np.float32)
+    src[0, :40, :3] = pts; src[0, :40, 3] = 1; dst[0, :40, :3] = pts; dst[0, :40, 3] = 1        # identical clouds
+    src[1, :40, :3] = pts; src[1, :40, 3] = 1; dst[1, :40, :3] = pts + 5; dst[1, :40, 3] = 1    # no inliers
+    src[2, :3, :3] = pts[:3]; src[2, :3, 3] = 1; dst[2, :3, :3] = pts[:3] + 0.01; dst[2, :3, 3] = 1  # 3 points
+    src[3, :40, :3] = pts; src[3, :40, 3] = 1; dst[3, :1, :3] = pts[:1]; dst[3, :1, 3] = 1       # single dst point
+    r = ops.icp_batch(torch.from_numpy(src).to(dev), torch.from_numpy(dst).to(dev),
+                      ops.make_params(max_iterations=100, relative_rmse_thr=1e-6, batch_stop=False))
+    R, T = r.R.cpu().numpy(), r.T.cpu().numpy()
+    assert np.isfinite(R).all() and np.isfinite(T).all()
+    eye = np.eye(3, dtype=np.float32)
+    assert np.abs(R[0] - eye).max() < 1e-5 and np.abs(T[0]).max() < 1e-3
+    assert np.array_equal(R[1], eye) and np.array_equal(T[1], np.zeros(3, np.float32))
+    assert r.iterations.cpu().numpy().max() < 100          # all reached a fixed point
+    ref = O.icp_loop(torch.from_numpy(src[:2]), torch.from_numpy(dst[:2]), max_iterations=30)
+    assert _moved_err(src[:2], R[:2], T[:2], ref.R, ref.T).max() <= TOL
+
+
+def test_nn_and_transform_seams(golden):
+    dev = _dev()
+    g = golden("c1_demo.npz")
+    src, dst = torch.from_numpy(g["src"]), torch.from_numpy(g["dst"])
+    swap = torch.from_numpy(g["swapped"])
+    a, c = src.clone(), dst.clone()
+    a[swap] = dst[swap]; c[swap] = src[swap]
+    idx, dist = ops.nearest_neighbor_batch(a.to(dev), c.to(dev))
+    assert np.array_equal(idx.cpu().numpy(), g["nn_idx"])            # index work: bit exact
+    assert np.array_equal(dist.cpu().numpy(), g["nn_dist"])          # same fp32 op order as the reference leaf
+    idx3, dist3 = ops.nearest_neighbor_batch(a[:, :, :3].to(dev), c[:, :, :3].to(dev))
+    assert torch.equal(idx3, idx) and torch.equal(dist3, dist)
+    pose = torch.from_numpy(g["init_pose"])
+    moved = ops.transform_points_batch(a.to(dev), pose.to(dev)).cpu()
+    assert torch.equal(moved, O.transform_points_batch(a, pose))     # translation-only poses: exact
+    torch.manual_seed(0)
+    q = torch.linalg.qr(torch.randn(len(a), 3, 3))[0]
+    pose2 = torch.eye(4).repeat(len(a), 1, 1); pose2[:, :3, :3] = q; pose2[:, :3, 3] = torch.randn(len(a), 3)
+    got = ops.transform_points_batch(a.to(dev), pose2.to(dev)).cpu()
+    want = O.transform_points_batch(a, pose2)
+    valid = a[:, :, 3] > 0
+    assert (got - want)[valid].abs().max() <= 2e-5
+    assert torch.equal(got[:, :, 3], a[:, :, 3])
