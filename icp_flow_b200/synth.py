@@ -29,12 +29,14 @@ def _shell_points(rng: np.random.Generator, extents: np.ndarray, n: int) -> np.n
 
 def make_pairs(num_pairs: int, max_points: int, seed: int = 1234, *, ragged: bool = False,
                residual_only: bool = False, wrong_frac: float = 0.05, noise: float = 0.01,
-               min_points: int | None = None):
+               min_points: int | None = None, keep_density: bool = True):
     """Return ``(src, dst, meta)`` with ``src, dst`` float32 ``[P, N, 4]`` and ``meta`` the ground-truth motion.
 
     residual_only: translation U[-0.05,0.05]^3 m (ICP started from identity has inliers; configs C2/C5);
     otherwise translation (U[-2,2], U[-2,2], U[-0.05,0.05]) m (needs the histogram init; config C3).
     ragged: valid counts n_s, n_d ~ U[N/4, N] independently, else all N rows valid.
+    keep_density: box extents are scaled by sqrt(min(N,512)/512) so that small test batches keep the surface density
+    of the N=512 benchmark clusters (~15 points/m^2; otherwise few points have a neighbour within thres_dist).
     """
     rng = np.random.default_rng(seed)
     P, N = int(num_pairs), int(max_points)
@@ -48,15 +50,16 @@ def make_pairs(num_pairs: int, max_points: int, seed: int = 1234, *, ragged: boo
     trans = np.zeros((P, 3))
     wrong = np.zeros(P, dtype=bool)
     lo = max(4, N // 4) if min_points is None else min_points
+    shrink = float(np.sqrt(min(N, 512) / 512.0)) if keep_density else 1.0
     for p in range(P):
-        extents = np.array([rng.uniform(1.5, 5.0), rng.uniform(0.8, 2.2), rng.uniform(0.8, 2.0)])
+        extents = np.array([rng.uniform(1.5, 5.0), rng.uniform(0.8, 2.2), rng.uniform(0.8, 2.0)]) * shrink
         centre = np.array([rng.uniform(-32, 32), rng.uniform(-32, 32), rng.uniform(0, 2)])
         n_s = int(rng.integers(lo, N + 1)) if ragged else N
         n_d = int(rng.integers(lo, N + 1)) if ragged else N
         a = _shell_points(rng, extents, n_s)
         is_wrong = rng.uniform() < wrong_frac
         if is_wrong:
-            extents_d = np.array([rng.uniform(1.5, 5.0), rng.uniform(0.8, 2.2), rng.uniform(0.8, 2.0)])
+            extents_d = np.array([rng.uniform(1.5, 5.0), rng.uniform(0.8, 2.2), rng.uniform(0.8, 2.0)]) * shrink
             b = _shell_points(rng, extents_d, n_d)
         else:
             b = _shell_points(rng, extents, n_d)

@@ -65,6 +65,10 @@ class IcpTrace(NamedTuple):
     conv_flags: torch.Tensor  # [iterations,P] bool: relative_rmse <= thr at that iteration
     R_hist: List[torch.Tensor]
     T_hist: List[torch.Tensor]
+    # conditioning diagnostics (not part of the reference; used by the parity tests to explain discrete flips)
+    min_gate_margin: Optional[torch.Tensor] = None   # [iterations,P] min over points of | |x - nn| - thres |  (m)
+    min_inliers: Optional[torch.Tensor] = None       # [P] min over iterations of the gated correspondence count
+    min_sigma_ratio: Optional[torch.Tensor] = None   # [P] min over iterations of sigma_2 / sigma_1 of the cross-covariance
 
 
 # ------------------------------------------------------------------------------------------ leaves
@@ -192,12 +196,12 @@ def kabsch_weighted(X: torch.Tensor, Y: torch.Tensor, w: torch.Tensor, eps: floa
     E[:, -1, -1] = torch.det(torch.bmm(U, V.transpose(2, 1)))
     R = torch.bmm(torch.bmm(U, E), V.transpose(2, 1))
     T = mu_y[:, 0, :] - torch.bmm(mu_x, R)[:, 0, :]
-    return R, T, H
+    return R, T, S
 
 
 # ---------------------------------------------------------------------------------------------- ICP
 def icp_loop(X: torch.Tensor, Y: torch.Tensor, thres: float = 0.1, max_iterations: int = 100,
-             relative_rmse_thr: float = 1e-6, keep_history: bool = False) -> IcpTrace:
+             relative_rmse_thr: float = 1e-6, keep_history: bool = False, diagnostics: bool = False) -> IcpTrace:
     """utils_icp_pytorch3d.py:100-225 with init_transform=None.
 
     Absolute transform re-estimated from the *initial* cloud every iteration; NN on the current cloud among
@@ -218,13 +222,22 @@ def icp_loop(X: torch.Tensor, Y: torch.Tensor, thres: float = 0.1, max_iteration
     rmse = None
     converged = False
     flags, Rh, Th = [], [], []
+    margin = []
+    inliers = torch.full((b,), 2 ** 31 - 1, dtype=torch.int64)
+    sig = torch.full((b,), float("inf"), dtype=torch.float64)
+    in_len = torch.arange(Xt.shape[1])[None, :] < len_x[:, None]
     it = -1
     for it in range(max_iterations):
         d2, idx = leaves.knn1(Xt, Yt, len_x, len_y)
         d2 = d2.to(Xt.dtype)
         nn_pts = torch.gather(Yt, 1, idx[:, :, None].expand(-1, -1, 3))
         m = torch.logical_and(valid_x0, d2 <= thres ** 2)
-        R, T, _ = kabsch_weighted(X0 * m[:, :, None], nn_pts * m[:, :, None], m)
+        R, T, S = kabsch_weighted(X0 * m[:, :, None], nn_pts * m[:, :, None], m)
+        if diagnostics:
+            gap = (d2.double().sqrt() - thres).abs().masked_fill(~(in_len & valid_x0), float("inf"))
+            margin.append(gap.amin(dim=1))
+            inliers = torch.minimum(inliers, m.sum(dim=1))
+            sig = torch.minimum(sig, (S[:, 1] / S[:, 0].clamp(min=1e-30)).double())
         Xt = torch.bmm(X0, R) + T[:, None, :]          # s == 1: ones * bmm is exact
         sq = ((Xt - nn_pts) ** 2).sum(2)
         rmse = ((sq[:, :, None] * m[..., None]).sum(dim=-2, keepdim=True)
@@ -240,7 +253,20 @@ def icp_loop(X: torch.Tensor, Y: torch.Tensor, thres: float = 0.1, max_iteration
             break
         prev = rmse
     return IcpTrace(R, T, rmse, it + 1, converged, torch.stack(flags) if flags else torch.zeros(0, b, dtype=torch.bool),
-                    Rh, Th)
+                    Rh, Th, torch.stack(margin) if diagnostics else None, inliers if diagnostics else None,
+                    sig if diagnostics else None)
+
+
+def unstable_pairs(trace: IcpTrace, margin_m: float = 3e-5, min_inliers: int = 6, sigma_ratio: float = 1e-3,
+                   last: int = 3):
+    """Pairs whose reference result is not numerically determined to 1e-4: during the last `last` iterations a
+    correspondence sat within `margin_m` of the gate (a differently-rounded but equally valid fp32 evaluation of
+    x R + T -- 1 ulp at 50 m is 4e-6 m -- flips it and moves the fixed point), or the Kabsch system was (nearly)
+    rank deficient (fewer than `min_inliers` correspondences / second singular value below `sigma_ratio` of the
+    first: the reference returns whatever LAPACK picks, SURVEY.md section 7 "3x3 SVD")."""
+    assert trace.min_gate_margin is not None, "run icp_loop(..., diagnostics=True)"
+    tail = trace.min_gate_margin[-last:].amin(dim=0)
+    return (tail < margin_m) | (trace.min_inliers < min_inliers) | (trace.min_sigma_ratio < sigma_ratio)
 
 
 def pack_rt(R: torch.Tensor, T: torch.Tensor) -> torch.Tensor:
