@@ -18,7 +18,8 @@ struct IcpArgs {
     const float* init_R;   // [P,9] or NULL
     const float* init_T;   // [P,3] or NULL
     int P, N;
-    float tau2;
+    float tau;             // fp32(thres)
+    float tau2;            // fp32(thres^2)
     int max_it;
     float rel_thr;
     int early_exit;
@@ -31,7 +32,8 @@ struct IcpArgs {
     const int* batch;      // rerun mode: batch[0] = k*+1 (iterations the reference executed); NULL in the first pass
 };
 
-__global__ void __launch_bounds__(kThreads) icp_pairs_kernel(IcpArgs a) {
+template <bool GRID>
+__global__ void __launch_bounds__(kThreads, 7) icp_pairs_kernel(IcpArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int p = blockIdx.x;
     int max_it = a.max_it;
@@ -43,7 +45,7 @@ __global__ void __launch_bounds__(kThreads) icp_pairs_kernel(IcpArgs a) {
         max_it = batch_iters;
         early_exit = false;
     }
-    const PairTiles tl = carve_pair_tiles(smem_raw, a.N);
+    const PairTiles tl = carve_pair_tiles<GRID>(smem_raw, a.N);
     if (threadIdx.x == 0) {
         mbar_init(tl.bar, 1);
         fence_barrier_init();
@@ -61,7 +63,9 @@ __global__ void __launch_bounds__(kThreads) icp_pairs_kernel(IcpArgs a) {
     __syncthreads();   // kRedC is reused by the first iteration's rmse reduction only after two more barriers; keep it simple
     const int n_s = (int)cnt[0], n_d = (int)cnt[1];
 
-    const IcpResult r = icp_iterations(tl, a.N, n_s, n_d, a.tau2, max_it, a.rel_thr, early_exit,
+    GridInfo g;
+    if (GRID && n_s > 0 && n_d > 0) g = build_grid(tl, n_d, a.tau);
+    const IcpResult r = icp_iterations<GRID>(tl, g, n_s, n_d, a.tau2, max_it, a.rel_thr, early_exit,
                                        a.init_R ? a.init_R + (size_t)p * 9 : nullptr,
                                        a.init_T ? a.init_T + (size_t)p * 3 : nullptr);
 
@@ -80,8 +84,10 @@ __global__ void __launch_bounds__(kThreads) icp_pairs_kernel(IcpArgs a) {
         if (a.out_rmse) a.out_rmse[p] = r.rmse;
         a.iters[p] = r.iters;
         if (a.batch == nullptr) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) a.conv[(size_t)p * 4 + i] = r.conv[i];
+            a.conv[(size_t)p * 4 + 0] = (uint32_t)r.conv_lo;
+            a.conv[(size_t)p * 4 + 1] = (uint32_t)(r.conv_lo >> 32);
+            a.conv[(size_t)p * 4 + 2] = (uint32_t)r.conv_hi;
+            a.conv[(size_t)p * 4 + 3] = (uint32_t)(r.conv_hi >> 32);
         }
     }
 }
@@ -133,8 +139,15 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
                float* out_rmse, float* out_pose, int* out_iters, uint32_t* out_conv, int* out_batch, void* workspace,
                size_t workspace_bytes, cudaStream_t stream) {
     if (P == 0) return ICPF_OK;
-    const size_t smem = pair_smem_bytes(N);
-    if (smem > 227 * 1024) return ICPF_E_UNSUPPORTED;
+    // nn_mode: 0 auto (grid whenever its tiles fit in shared memory), 1 brute force, 2 grid
+    const size_t kMaxSmem = 227 * 1024;
+    bool grid = prm.nn_mode != 1;
+    if (grid && pair_smem_bytes(N, true) > kMaxSmem) {
+        if (prm.nn_mode == 2) return ICPF_E_UNSUPPORTED;
+        grid = false;
+    }
+    const size_t smem = pair_smem_bytes(N, grid);
+    if (smem > kMaxSmem) return ICPF_E_UNSUPPORTED;
     // workspace: iters [P] | conv [P,4] | batch [2]
     const size_t need = icp_workspace_bytes(P);
     if (workspace == nullptr || workspace_bytes < need) return ICPF_E_WORKSPACE;
@@ -144,21 +157,21 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
     int* batch = out_batch ? out_batch
                            : reinterpret_cast<int*>(ws + align_up((size_t)P * 4, 256) + align_up((size_t)P * 16, 256));
 
-    cudaError_t err = cudaFuncSetAttribute(icp_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kernel = grid ? icp_pairs_kernel<true> : icp_pairs_kernel<false>;
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
 
     IcpArgs a;
     a.src = src; a.dst = dst; a.init_R = init_R; a.init_T = init_T; a.P = P; a.N = N;
-    const float tau = (float)prm.thres_dist;
+    a.tau = (float)prm.thres_dist;
     a.tau2 = (float)(prm.thres_dist * prm.thres_dist);   // python: thres**2 in double, compared in fp32
-    (void)tau;
     a.max_it = prm.max_iterations;
     a.rel_thr = prm.relative_rmse_thr;
     a.early_exit = prm.early_exit;
     a.out_R = out_R; a.out_T = out_T; a.out_rmse = out_rmse; a.out_pose = out_pose;
     a.iters = iters; a.conv = conv; a.batch = nullptr;
     if (t_prof_start && t_prof_stop) cudaEventRecord(t_prof_start, stream);
-    icp_pairs_kernel<<<P, kThreads, smem, stream>>>(a);
+    kernel<<<P, kThreads, smem, stream>>>(a);
     err = cudaGetLastError();
     if (t_prof_start && t_prof_stop) {
         cudaEventRecord(t_prof_stop, stream);
@@ -172,7 +185,7 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
 
     if (prm.batch_stop) {
         a.batch = batch;
-        icp_pairs_kernel<<<P, kThreads, smem, stream>>>(a);
+        kernel<<<P, kThreads, smem, stream>>>(a);
         err = cudaGetLastError();
         if (err != cudaSuccess) return (int)err;
     }

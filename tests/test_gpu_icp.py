@@ -188,3 +188,41 @@ def test_nn_and_transform_seams(golden):
     valid = a[:, :, 3] > 0
     assert (got - want)[valid].abs().max() <= 2e-5
     assert torch.equal(got[:, :, 3], a[:, :, 3])
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_grid_search_is_bitwise_identical_to_brute_force(ragged):
+    """SURVEY finding 2: a radius-bounded NN inside the ICP loop is result-identical to brute force.  Both modes rank
+    candidates by (squared distance, original row index), so every output must agree bit for bit."""
+    src, dst, _ = synth.make_pairs(64, 512 if not ragged else 384, seed=31, ragged=ragged, residual_only=True,
+                                   wrong_frac=0.1)
+    # duplicate a few dst rows so that exact distance ties occur
+    dst[:, 7, :3] = dst[:, 3, :3]
+    for kw in (dict(max_iterations=20, relative_rmse_thr=-1.0, early_exit=False),
+               dict(max_iterations=100, relative_rmse_thr=1e-6, early_exit=True)):
+        a = _run(src, dst, nn_mode=1, **kw)
+        b = _run(src, dst, nn_mode=2, **kw)
+        assert torch.equal(a.R, b.R) and torch.equal(a.T, b.T) and torch.equal(a.rmse, b.rmse)
+        assert torch.equal(a.iterations, b.iterations) and torch.equal(a.conv_mask, b.conv_mask)
+        assert torch.equal(a.batch, b.batch) and torch.equal(a.pose, b.pose)
+
+
+def test_grid_handles_large_and_flat_clusters():
+    """Grid cell size adapts when the bbox would need more than kGridMaxCells cells (long wall, planar patch)."""
+    rng = np.random.default_rng(5)
+    N = 512
+    src = np.zeros((3, N, 4), np.float32); src[..., 3] = 1
+    wall = np.stack([rng.uniform(0, 30, N), rng.uniform(0, 0.05, N), rng.uniform(0, 4, N)], 1)      # 30 m wall
+    flat = np.stack([rng.uniform(0, 6, N), rng.uniform(0, 6, N), np.zeros(N)], 1)                   # exactly planar
+    line = np.stack([rng.uniform(0, 8, N), np.zeros(N), np.zeros(N)], 1)                            # collinear
+    for k, pts in enumerate((wall, flat, line)):
+        src[k, :, :3] = pts + np.array([40.0, -25.0, 1.0])
+    dst = src.copy()
+    dst[:, :, 0] += 0.03; dst[:, :, 1] -= 0.02
+    dst[:, :, :3] += rng.normal(0, 0.002, size=dst[:, :, :3].shape).astype(np.float32)
+    a = _run(src, dst, nn_mode=1, max_iterations=30, relative_rmse_thr=-1.0, early_exit=False, batch_stop=False)
+    b = _run(src, dst, nn_mode=2, max_iterations=30, relative_rmse_thr=-1.0, early_exit=False, batch_stop=False)
+    assert torch.equal(a.R, b.R) and torch.equal(a.T, b.T) and torch.equal(a.rmse, b.rmse)
+    T = b.T.cpu().numpy()
+    moved = src[:2, :, :3] @ b.R.cpu().numpy()[:2] + T[:2, None]
+    assert np.abs(moved - dst[:2, :, :3]).max() < 0.02
