@@ -256,6 +256,7 @@ def main():
     sampler.stop()
     ms_total = ev0.elapsed_time(ev1)
     kernel_ms = [a.elapsed_time(b) for a, b in prof_events]
+    stats = ops.icp_stats(ws, P).sum(dim=0).tolist()
     iters_done = int(out.iterations.sum().item())
     assert iters_done == P * ICP_ITERS, iters_done     # every pair really executed 20 iterations
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
@@ -314,6 +315,8 @@ def main():
                          "traffic": None, "peak_kind": peak_kind, "kernel": "icp_pairs_kernel",
                          "kernel_ms": k_ms, "kernel_share_of_step": k_ms / (ms_total / args.steps),
                          "algorithmic_bytes_per_launch": alg_bytes},
+            "nn_search": {"full_search_fraction": stats[0] / float(P * ICP_ITERS * N),
+                          "cache_refreshes_per_pair": stats[1] / float(P)},
         }
         if n_gpus == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = time_cpu_oracle()[0]

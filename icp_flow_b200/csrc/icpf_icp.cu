@@ -8,7 +8,7 @@
 //   kernel 2  AND-reduces the masks over the batch -> k* = first iteration at which the reference's `.all()` fires;
 //   kernel 3  re-runs (capped at k*+1 iterations) only the pairs that were still moving at k*.
 #include "icpf_internal.h"
-#include "icpf_pair.cuh"
+#include "icpf_icploop.cuh"
 
 namespace icpf {
 
@@ -29,10 +29,11 @@ struct IcpArgs {
     float* out_pose;       // [P,16] or NULL
     int* iters;            // [P] (never NULL inside the library)
     uint32_t* conv;        // [P,4]
+    int* stats;            // [P,2] {full searches, cache refreshes} of the first pass
     const int* batch;      // rerun mode: batch[0] = k*+1 (iterations the reference executed); NULL in the first pass
 };
 
-template <bool GRID>
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 7) icp_pairs_kernel(IcpArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int p = blockIdx.x;
@@ -45,6 +46,7 @@ __global__ void __launch_bounds__(kThreads, 7) icp_pairs_kernel(IcpArgs a) {
         max_it = batch_iters;
         early_exit = false;
     }
+    constexpr bool GRID = MODE >= 2;
     const PairTiles tl = carve_pair_tiles<GRID>(smem_raw, a.N);
     if (threadIdx.x == 0) {
         mbar_init(tl.bar, 1);
@@ -59,31 +61,35 @@ __global__ void __launch_bounds__(kThreads, 7) icp_pairs_kernel(IcpArgs a) {
         cnt[0] += (tl.src[q].w > 0.f) ? 1.f : 0.f;
         cnt[1] += (tl.dst[q].w > 0.f) ? 1.f : 0.f;
     }
-    block_allreduce_sum<2, kWarps>(cnt, tl.red + kRedC);
-    __syncthreads();   // kRedC is reused by the first iteration's rmse reduction only after two more barriers; keep it simple
+    block_allreduce_sum<2, kWarps>(cnt, tl.red + kScrPart);
     const int n_s = (int)cnt[0], n_d = (int)cnt[1];
+    const float4 piv = tl.dst[0];      // first pivot of the moment sums: any point of the fixed cloud
+    __syncthreads();                   // scratch and the raw dst rows are reused below
 
     GridInfo g;
     if (GRID && n_s > 0 && n_d > 0) g = build_grid(tl, n_d, a.tau);
-    const IcpResult r = icp_iterations<GRID>(tl, g, n_s, n_d, a.tau2, max_it, a.rel_thr, early_exit,
+    const IcpResult r = icp_iterations<MODE>(tl, g, n_s, n_d, a.tau2, max_it, a.rel_thr, early_exit,
                                        a.init_R ? a.init_R + (size_t)p * 9 : nullptr,
-                                       a.init_T ? a.init_T + (size_t)p * 3 : nullptr);
+                                       a.init_T ? a.init_T + (size_t)p * 3 : nullptr, piv.x, piv.y, piv.z);
 
-    if (threadIdx.x < 9) a.out_R[(size_t)p * 9 + threadIdx.x] = r.r[threadIdx.x];
-    if (threadIdx.x < 3) a.out_T[(size_t)p * 3 + threadIdx.x] = r.t[threadIdx.x];
+    // the final (R, T) also sit in the broadcast block (no dynamic register indexing)
+    if (threadIdx.x < 9) a.out_R[(size_t)p * 9 + threadIdx.x] = tl.bcast[B_R + threadIdx.x];
+    if (threadIdx.x < 3) a.out_T[(size_t)p * 3 + threadIdx.x] = tl.bcast[B_T + threadIdx.x];
     if (a.out_pose && threadIdx.x < 16) {
         // column-convention 4x4 [[R^T, T],[0,1]]  (utils_icp.py:60-65)
         const int row = threadIdx.x >> 2, col = threadIdx.x & 3;
         float v;
         if (row == 3) v = (col == 3) ? 1.f : 0.f;
-        else if (col == 3) v = r.t[row];
-        else v = r.r[col * 3 + row];
+        else if (col == 3) v = tl.bcast[B_T + row];
+        else v = tl.bcast[B_R + col * 3 + row];
         a.out_pose[(size_t)p * 16 + threadIdx.x] = v;
     }
     if (threadIdx.x == 0) {
         if (a.out_rmse) a.out_rmse[p] = r.rmse;
         a.iters[p] = r.iters;
         if (a.batch == nullptr) {
+            a.stats[(size_t)p * 2 + 0] = (int)r.searches;
+            a.stats[(size_t)p * 2 + 1] = r.refreshes;
             a.conv[(size_t)p * 4 + 0] = (uint32_t)r.conv_lo;
             a.conv[(size_t)p * 4 + 1] = (uint32_t)(r.conv_lo >> 32);
             a.conv[(size_t)p * 4 + 2] = (uint32_t)r.conv_hi;
@@ -139,11 +145,11 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
                float* out_rmse, float* out_pose, int* out_iters, uint32_t* out_conv, int* out_batch, void* workspace,
                size_t workspace_bytes, cudaStream_t stream) {
     if (P == 0) return ICPF_OK;
-    // nn_mode: 0 auto (grid whenever its tiles fit in shared memory), 1 brute force, 2 grid
+    // nn_mode: 0 auto (grid + cache whenever the tiles fit in shared memory), 1 brute force, 2 grid, 3 grid + cache
     const size_t kMaxSmem = 227 * 1024;
     bool grid = prm.nn_mode != 1;
     if (grid && pair_smem_bytes(N, true) > kMaxSmem) {
-        if (prm.nn_mode == 2) return ICPF_E_UNSUPPORTED;
+        if (prm.nn_mode >= 2) return ICPF_E_UNSUPPORTED;
         grid = false;
     }
     const size_t smem = pair_smem_bytes(N, grid);
@@ -153,11 +159,10 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
     if (workspace == nullptr || workspace_bytes < need) return ICPF_E_WORKSPACE;
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     int* iters = out_iters ? out_iters : reinterpret_cast<int*>(ws);
-    uint32_t* conv = out_conv ? out_conv : reinterpret_cast<uint32_t*>(ws + align_up((size_t)P * 4, 256));
-    int* batch = out_batch ? out_batch
-                           : reinterpret_cast<int*>(ws + align_up((size_t)P * 4, 256) + align_up((size_t)P * 16, 256));
+    uint32_t* conv = out_conv ? out_conv : reinterpret_cast<uint32_t*>(ws + icp_ws_off_conv(P));
+    int* batch = out_batch ? out_batch : reinterpret_cast<int*>(ws + icp_ws_off_batch(P));
 
-    auto kernel = grid ? icp_pairs_kernel<true> : icp_pairs_kernel<false>;
+    auto kernel = !grid ? icp_pairs_kernel<1> : (prm.nn_mode == 2 ? icp_pairs_kernel<2> : icp_pairs_kernel<3>);
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
 
@@ -170,6 +175,7 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
     a.early_exit = prm.early_exit;
     a.out_R = out_R; a.out_T = out_T; a.out_rmse = out_rmse; a.out_pose = out_pose;
     a.iters = iters; a.conv = conv; a.batch = nullptr;
+    a.stats = reinterpret_cast<int*>(ws + icp_ws_off_stats(P));
     if (t_prof_start && t_prof_stop) cudaEventRecord(t_prof_start, stream);
     kernel<<<P, kThreads, smem, stream>>>(a);
     err = cudaGetLastError();

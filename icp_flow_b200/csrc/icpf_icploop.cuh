@@ -1,0 +1,387 @@
+// icpf_icploop.cuh -- the ICP iteration loop of one pair, fused into ONE pass over the src rows and ONE block
+// reduction per iteration.
+//
+// Reference loop (utils_icp_pytorch3d.py:153-214), per iteration k with the current transform (R_k, T_k):
+//     NN of Xt = X0 R_k + T_k in Y  ->  gate  ->  Kabsch on (X0, NN)  ->  (R_{k+1}, T_{k+1})
+//     rmse_k = rms | X0 R_{k+1} + T_{k+1} - NN_k |  over the gated rows;  rel_k = (rmse_{k-1} - rmse_k) / rmse_{k-1}
+// Restructured, result-identical:
+//   * rmse_k needs the NEW transform and the OLD correspondences -- exactly what the correspondence search of
+//     iteration k+1 has in hand (it transforms every row with (R_{k+1}, T_{k+1}) and, for the cache test, reloads
+//     the old neighbour), so the rmse numerator is accumulated there and only the last iteration needs a pass
+//     of its own; the convergence flag of iteration k is therefore recorded one iteration late.
+//   * centroids and the centred cross-covariance come from one pass of raw moments about a pivot:
+//         H = (S_xy - S_x S_y^T / W) / W,   mu = pivot + S / W,
+//     with the pivots set to the previous iteration's centroids, so S_x, S_y ~ 0 and nothing cancels (the
+//     reference's two-pass centring, utils_icp_pytorch3d.py:314-336, to fp32 rounding).
+//   * the 16 moments are reduced with a transposing butterfly (16 shuffles instead of 80), the partials of the four
+//     warps meet in shared memory, and one thread solves the 3x3 problem while the other CTAs of the SM keep the
+//     pipes busy.
+//   * rows whose cached neighbour cannot be proven (MODE 3) are compacted per warp and searched afterwards with
+//     dense lanes.
+// All three search modes execute the same accumulation code in the same order, so they agree bit for bit.
+#pragma once
+
+#include "icpf_pair.cuh"
+
+namespace icpf {
+
+struct IcpResult {
+    float r[9];                   // valid in every thread
+    float t[3];                   // valid in every thread
+    // the fields below are maintained by thread 0 only
+    float rmse;
+    int iters;                    // iterations executed by this pair
+    unsigned long long conv_lo;   // bit k: relative rmse <= thr at iteration k      (k < 64)
+    unsigned long long conv_hi;   //                                                 (64 <= k < 128)
+    float searches;               // statistics: full searches executed, cache refresh iterations
+    int refreshes;
+    float prev_rmse;
+    bool have_prev;
+};
+
+__device__ __forceinline__ void set_conv_bit(IcpResult& r, int k) {
+    if (k < 64) r.conv_lo |= 1ull << k;
+    else if (k < 128) r.conv_hi |= 1ull << (k - 64);
+}
+
+// rel_k = (rmse_{k-1} - rmse_k) / rmse_{k-1}  (1 for the first iteration), utils_icp_pytorch3d.py:195-198
+__device__ __forceinline__ void record_rmse(IcpResult& r, int k, float rmse, float rel_thr) {
+    const float rel = r.have_prev ? __fdiv_rn(r.prev_rmse - rmse, r.prev_rmse) : 1.0f;
+    if (rel <= rel_thr) set_conv_bit(r, k);
+    r.rmse = rmse;
+    r.prev_rmse = rmse;
+    r.have_prev = true;
+}
+
+// Transposing butterfly: on return lane L holds, in v[0], the warp-wide sum of the input slot
+//   idx(L) = 8*bit4(L) + 4*bit3(L) + 2*bit2(L) + bit1(L)     (both lanes of a pair hold the same value)
+__device__ __forceinline__ int reduce16_slot(int lane) {
+    return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+
+__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
+    bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float send = up ? v[i] : v[i + 8], keep = up ? v[i + 8] : v[i];
+        v[i] = keep + __shfl_xor_sync(FULL_MASK, send, 16);
+    }
+    up = (lane & 8) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = up ? v[i] : v[i + 4], keep = up ? v[i + 4] : v[i];
+        v[i] = keep + __shfl_xor_sync(FULL_MASK, send, 8);
+    }
+    up = (lane & 4) != 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = up ? v[i] : v[i + 2], keep = up ? v[i + 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(FULL_MASK, send, 4);
+    }
+    up = (lane & 2) != 0;
+    {
+        const float send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(FULL_MASK, send, 2);
+    }
+    v[0] += __shfl_xor_sync(FULL_MASK, v[0], 1);
+    return v[0];
+}
+
+// Squared distance a row moved since the cache reference transform: | x0 (R - Rc) + (T - Tc) |^2, inflated.
+__device__ __forceinline__ float moved_sq(const float (&dr)[9], const float (&dt)[3], const float4& x0) {
+    const float mx = fmaf(x0.z, dr[6], fmaf(x0.y, dr[3], x0.x * dr[0])) + dt[0];
+    const float my = fmaf(x0.z, dr[7], fmaf(x0.y, dr[4], x0.x * dr[1])) + dt[1];
+    const float mz = fmaf(x0.z, dr[8], fmaf(x0.y, dr[5], x0.x * dr[2])) + dt[2];
+    return fmaf(mz, mz, fmaf(my, my, mx * mx)) * 1.001f + 1e-12f;
+}
+
+// The ICP loop for the pair held in `tl`.
+//   MODE 1: candidates = tl.dst, brute force.  MODE 2: candidates = tl.sorted + grid `g` (build_grid must have run).
+//   MODE 3: grid + correspondence cache.  A row whose cached best candidate is provably still its strict nearest
+//           neighbour skips the search: with m the distance the row moved since the cache reference and B the cached
+//           lower bound on the distance of every other point, (d_best + m) < B implies every other point is farther
+//           than d_best; and B > tau + m alone proves that only the cached candidate can pass the gate.  The gate
+//           always uses the exactly recomputed d_best^2, so the results are bit-identical to MODE 1/2.
+//   n_s / n_d : valid-row counts (knn `lengths`); tau2 = fp32(thres^2); pivot0 = any point near the clouds
+//   init_R / init_T (may be NULL) = init_transform of the reference: used for the first correspondence search only.
+template <int MODE>
+__device__ inline IcpResult icp_iterations(const PairTiles& tl, const GridInfo& g, int n_s, int n_d, float tau2,
+                                           int max_it, float rel_thr, bool early_exit, const float* init_R,
+                                           const float* init_T, float pivx, float pivy, float pivz) {
+    constexpr bool GRID = MODE >= 2;
+    constexpr bool CACHE = MODE == 3;
+    const float INF = __int_as_float(0x7f800000);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float4* __restrict__ cand = GRID ? tl.sorted : tl.dst;
+    const unsigned short* cell_runs = reinterpret_cast<const unsigned short*>(tl.cells);
+    unsigned int* __restrict__ nnw = tl.nn;
+    float* part = tl.red + kScrPart;
+    float* total = tl.red + kScrTotal;
+    float* bc = tl.bcast;
+    const float tau_hi = sqrtf(tau2) * 1.0001f + 1e-6f;
+    const int nbatch = (n_s + kThreads - 1) / kThreads;     // row q = b * kThreads + tid
+
+    IcpResult res;
+    res.rmse = 0.f;
+    res.iters = 0;
+    res.conv_lo = res.conv_hi = 0ull;
+    res.searches = 0.f;
+    res.refreshes = 0;
+    res.prev_rmse = 0.f;
+    res.have_prev = false;
+    if (tid < 9) bc[B_R + tid] = init_R ? init_R[tid] : ((tid % 4 == 0) ? 1.f : 0.f);
+    if (tid < 3) bc[B_T + tid] = init_T ? init_T[tid] : 0.f;
+    if (tid == 0) {
+        bc[B_PX] = pivx; bc[B_PX + 1] = pivy; bc[B_PX + 2] = pivz;
+        bc[B_PY] = pivx; bc[B_PY + 1] = pivy; bc[B_PY + 2] = pivz;
+        bc[B_EXIT] = 0.f;
+        bc[B_REFRESH] = 1.f;
+    }
+    __syncthreads();
+    if (tid < 12) bc[B_RC + tid] = bc[B_R + tid];      // cache reference = the transform of the first search
+    __syncthreads();
+    float W_prev = 1.f;                                 // thread 0: clamp(sum of weights) of the previous iteration
+    bool done = (n_s <= 0 || n_d <= 0 || max_it <= 0);  // engine-defined: nothing to align -> identity
+
+    for (int it = 0; !done && it < max_it; ++it) {
+        float R[9], T[3];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = bc[B_R + i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) T[i] = bc[B_T + i];
+        const bool refresh = !CACHE || (bc[B_REFRESH] != 0.f);
+        float dr[9], dt[3];
+        if (CACHE && !refresh) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) dr[i] = R[i] - bc[B_RC + i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) dt[i] = T[i] - bc[B_TC + i];
+        }
+        float sq = 0.f;
+        int ndefer = 0;
+        unsigned short* mylist = GRID ? tl.defer + warp * tl.defer_cap : nullptr;
+
+        // ---------------- pass A: rmse numerator of the previous iteration + correspondence search of this one
+        if (MODE == 1) {
+            constexpr int QB = 4;
+            for (int b0 = 0; b0 < nbatch; b0 += QB) {
+                float qx[QB], qy[QB], qz[QB], best[QB];
+                int bidx[QB];
+                float4 x0[QB];
+#pragma unroll
+                for (int k = 0; k < QB; ++k) {
+                    const int q = (b0 + k) * kThreads + tid;
+                    const bool valid = q < n_s;
+                    x0[k] = valid ? tl.src[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    apply_rt(R, T, x0[k].x, x0[k].y, x0[k].z, qx[k], qy[k], qz[k]);
+                    const unsigned int wold = (it > 0 && valid) ? nnw[q] : (kNnMasked | kNnNone);
+                    if (!(wold & kNnMasked)) {
+                        const float4 c = cand[wold & 0xffffu];
+                        sq += sqdist(qx[k], qy[k], qz[k], c.x, c.y, c.z);
+                    }
+                }
+                nn_brute<QB>(cand, n_d, qx, qy, qz, best, bidx);
+#pragma unroll
+                for (int k = 0; k < QB; ++k) {
+                    const int q = (b0 + k) * kThreads + tid;
+                    if (q < n_s) nnw[q] = pack_nn(bidx[k], 0.f, (best[k] <= tau2) && (x0[k].w > 0.f));
+                }
+            }
+        } else {
+            for (int b = 0; b < nbatch; ++b) {
+                const int q = b * kThreads + tid;
+                const bool valid = q < n_s;
+                const float4 x0 = valid ? tl.src[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                float qx, qy, qz;
+                apply_rt(R, T, x0.x, x0.y, x0.z, qx, qy, qz);
+                const unsigned int wold = (it > 0 && valid) ? nnw[q] : (kNnMasked | kNnNone);
+                int pos = (wold & 0xffffu) == kNnNone ? -1 : (int)(wold & 0xffffu);
+                float d2 = INF;
+                if (pos >= 0 && (!(wold & kNnMasked) || (CACHE && !refresh))) {
+                    const float4 c = cand[pos];
+                    d2 = sqdist(qx, qy, qz, c.x, c.y, c.z);
+                    if (!(wold & kNnMasked)) sq += d2;
+                }
+                bool need = valid;
+                if (CACHE && !refresh) {
+                    if (valid) {
+                        const float bound = __half2float(__ushort_as_half((unsigned short)((wold >> 16) & 0x7fffu)));
+                        const float m2 = moved_sq(dr, dt, x0);
+                        // (a) every other point is provably farther than tau: only the cached candidate can pass
+                        bool hit = bound > tau_hi + sqrtf(m2);
+                        // (b) the cached candidate is provably still the strict nearest neighbour: (d_best + m) < B
+                        if (pos >= 0) hit = hit || ((d2 + 2.f * sqrtf(d2 * m2) + m2) * 1.0002f < bound * bound);
+                        if (hit) {
+                            nnw[q] = pack_nn(pos, bound, (pos >= 0) && (d2 <= tau2) && (x0.w > 0.f));
+                            need = false;
+                        }
+                    }
+                    const unsigned int vote = __ballot_sync(FULL_MASK, need);
+                    if (need) mylist[ndefer + __popc(vote & ((1u << lane) - 1u))] = (unsigned short)q;
+                    ndefer += __popc(vote);
+                } else if (need) {
+                    float d2nd, box;
+                    grid_search(g, cand, cell_runs, qx, qy, qz, d2, pos, d2nd, box);
+                    // g.pad (>= 1e-4 m, >= 16 ulp of the largest coordinate) covers the fp32 rounding of the
+                    // transformed positions whose separation m is bounded analytically
+                    const float bound = fminf(sqrtf(d2nd), box) * 0.9999f - g.pad;
+                    nnw[q] = pack_nn(pos, bound, (pos >= 0) && (d2 <= tau2) && (x0.w > 0.f));
+                }
+            }
+            if (CACHE && !refresh) {
+                // ---------------- deferred searches: dense lanes over the warp's compacted list
+                __syncwarp();
+                for (int i = lane; i < ndefer; i += 32) {
+                    const int q = mylist[i];
+                    const float4 x0 = tl.src[q];
+                    float qx, qy, qz, d2, d2nd, box;
+                    int pos;
+                    apply_rt(R, T, x0.x, x0.y, x0.z, qx, qy, qz);
+                    grid_search(g, cand, cell_runs, qx, qy, qz, d2, pos, d2nd, box);
+                    // re-express the bound relative to the cache reference position of this row
+                    const float bound = fminf(sqrtf(d2nd), box) * 0.9999f - g.pad - sqrtf(moved_sq(dr, dt, x0));
+                    nnw[q] = pack_nn(pos, bound, (pos >= 0) && (d2 <= tau2) && (x0.w > 0.f));
+                }
+                __syncwarp();
+            }
+        }
+
+        // ---------------- pass B: raw moments about the pivots (same code and order in every mode)
+        float mom[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) mom[i] = 0.f;
+        {
+            const float px = bc[B_PX], py = bc[B_PX + 1], pz = bc[B_PX + 2];
+            const float ux = bc[B_PY], uy = bc[B_PY + 1], uz = bc[B_PY + 2];
+            for (int b = 0; b < nbatch; ++b) {
+                const int q = b * kThreads + tid;
+                const unsigned int w = (q < n_s) ? nnw[q] : kNnMasked;
+                if (w & kNnMasked) continue;
+                const float4 x = tl.src[q];
+                const float4 y = cand[w & 0xffffu];
+                const float ax = x.x - px, ay = x.y - py, az = x.z - pz;
+                const float bx = y.x - ux, by = y.y - uy, bz = y.z - uz;
+                mom[0] += 1.f;
+                mom[1] += ax; mom[2] += ay; mom[3] += az;
+                mom[4] += bx; mom[5] += by; mom[6] += bz;
+                mom[7] = fmaf(ax, bx, mom[7]);   mom[8] = fmaf(ax, by, mom[8]);   mom[9] = fmaf(ax, bz, mom[9]);
+                mom[10] = fmaf(ay, bx, mom[10]); mom[11] = fmaf(ay, by, mom[11]); mom[12] = fmaf(ay, bz, mom[12]);
+                mom[13] = fmaf(az, bx, mom[13]); mom[14] = fmaf(az, by, mom[14]); mom[15] = fmaf(az, bz, mom[15]);
+            }
+        }
+        const float msum = warp_reduce16(mom, lane);
+        sq = warp_sum(sq);
+        if ((lane & 1) == 0) part[warp * kSums + reduce16_slot(lane)] = msum;
+        if (lane == 0) {
+            part[warp * kSums + 16] = sq;
+            part[warp * kSums + 17] = (float)ndefer;
+        }
+        __syncthreads();
+
+        // ---------------- one warp folds the partials, one thread solves the 3x3 problem
+        if (warp == 0) {
+            if (lane < kSums) {
+                float s = part[lane];
+#pragma unroll
+                for (int w = 1; w < kWarps; ++w) s += part[w * kSums + lane];
+                total[lane] = s;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                if (it > 0) record_rmse(res, it - 1, sqrtf(__fdiv_rn(total[16], W_prev)), rel_thr);
+                const float W = fmaxf(total[0], 1e-9f);
+                const float sx0 = total[1], sx1 = total[2], sx2 = total[3];
+                const float sy0 = total[4], sy1 = total[5], sy2 = total[6];
+                const float mx0 = __fdiv_rn(sx0, W), mx1 = __fdiv_rn(sx1, W), mx2 = __fdiv_rn(sx2, W);
+                const float my0 = __fdiv_rn(sy0, W), my1 = __fdiv_rn(sy1, W), my2 = __fdiv_rn(sy2, W);
+                float h[9];
+                h[0] = __fdiv_rn(fmaf(-sx0, my0, total[7]), W);  h[1] = __fdiv_rn(fmaf(-sx0, my1, total[8]), W);
+                h[2] = __fdiv_rn(fmaf(-sx0, my2, total[9]), W);  h[3] = __fdiv_rn(fmaf(-sx1, my0, total[10]), W);
+                h[4] = __fdiv_rn(fmaf(-sx1, my1, total[11]), W); h[5] = __fdiv_rn(fmaf(-sx1, my2, total[12]), W);
+                h[6] = __fdiv_rn(fmaf(-sx2, my0, total[13]), W); h[7] = __fdiv_rn(fmaf(-sx2, my1, total[14]), W);
+                h[8] = __fdiv_rn(fmaf(-sx2, my2, total[15]), W);
+                const Rot3 rot = kabsch_rotation(h);
+                // centroids: mu = pivot + S / W   (zero-weight iteration: both are the pivots, T = 0 like the reference)
+                const float cx0 = bc[B_PX] + mx0, cx1 = bc[B_PX + 1] + mx1, cx2 = bc[B_PX + 2] + mx2;
+                const float cy0 = bc[B_PY] + my0, cy1 = bc[B_PY + 1] + my1, cy2 = bc[B_PY + 2] + my2;
+                float t[3];
+                const bool empty = !(total[0] > 0.f);
+                t[0] = empty ? 0.f : cy0 - fmaf(cx2, rot.r[6], fmaf(cx1, rot.r[3], cx0 * rot.r[0]));
+                t[1] = empty ? 0.f : cy1 - fmaf(cx2, rot.r[7], fmaf(cx1, rot.r[4], cx0 * rot.r[1]));
+                t[2] = empty ? 0.f : cy2 - fmaf(cx2, rot.r[8], fmaf(cx1, rot.r[5], cx0 * rot.r[2]));
+                bool same = it > 0;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) same = same && (__float_as_uint(rot.r[i]) == __float_as_uint(bc[B_R + i]));
+#pragma unroll
+                for (int i = 0; i < 3; ++i) same = same && (__float_as_uint(t[i]) == __float_as_uint(bc[B_T + i]));
+#pragma unroll
+                for (int i = 0; i < 9; ++i) bc[B_R + i] = rot.r[i];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) bc[B_T + i] = t[i];
+                if (!empty) {
+                    bc[B_PX] = cx0; bc[B_PX + 1] = cx1; bc[B_PX + 2] = cx2;
+                    bc[B_PY] = cy0; bc[B_PY + 1] = cy1; bc[B_PY + 2] = cy2;
+                }
+                W_prev = W;
+                res.iters = it + 1;
+                if (CACHE) {
+                    res.searches += refresh ? (float)n_s : total[17];
+                    res.refreshes += refresh ? 1 : 0;
+                    // after a refresh the next iteration tests the cache; re-anchor it when too many rows fail
+                    const bool refresh_next = !refresh && (total[17] * 4.f > (float)n_s);
+                    bc[B_REFRESH] = refresh_next ? 1.f : 0.f;
+                    if (refresh_next) {
+#pragma unroll
+                        for (int i = 0; i < 9; ++i) bc[B_RC + i] = rot.r[i];
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) bc[B_TC + i] = t[i];
+                    }
+                }
+                bc[B_EXIT] = (early_exit && same) ? 1.f : 0.f;
+            }
+        }
+        __syncthreads();
+        done = bc[B_EXIT] != 0.f;
+    }
+
+    // ---------------- rmse of the last iteration executed (final transform against its own correspondences)
+#pragma unroll
+    for (int i = 0; i < 9; ++i) res.r[i] = bc[B_R + i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) res.t[i] = bc[B_T + i];
+    const int iters = __shfl_sync(FULL_MASK, res.iters, 0);   // thread 0's count, needed below by warp 0 only
+    if (n_s > 0 && n_d > 0 && max_it > 0) {
+        float sq = 0.f;
+        for (int b = 0; b < nbatch; ++b) {
+            const int q = b * kThreads + tid;
+            const unsigned int w = (q < n_s) ? nnw[q] : kNnMasked;
+            if (w & kNnMasked) continue;
+            const float4 x = tl.src[q];
+            const float4 c = cand[w & 0xffffu];
+            float qx, qy, qz;
+            apply_rt(res.r, res.t, x.x, x.y, x.z, qx, qy, qz);
+            sq += sqdist(qx, qy, qz, c.x, c.y, c.z);
+        }
+        sq = warp_sum(sq);
+        if (lane == 0) part[warp * kSums + 16] = sq;
+        __syncthreads();
+        if (tid == 0) {
+            float s = part[16];
+#pragma unroll
+            for (int w = 1; w < kWarps; ++w) s += part[w * kSums + 16];
+            const float rmse = sqrtf(__fdiv_rn(s, W_prev));
+            record_rmse(res, iters - 1, rmse, rel_thr);
+            if (iters < max_it) {
+                // stopped at a bitwise fixed point: every later iteration repeats this state, so its relative rmse is
+                // (rmse - rmse) / rmse = 0 (NaN when rmse == 0)
+                const bool tail_ok = (rmse > 0.f) && (0.0f <= rel_thr) && (rmse < INF);
+                if (tail_ok) {
+                    for (int k = iters; k < max_it && k < 128; ++k) set_conv_bit(res, k);
+                }
+            }
+        }
+    }
+    return res;
+}
+
+}  // namespace icpf

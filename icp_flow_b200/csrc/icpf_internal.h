@@ -11,10 +11,11 @@ namespace icpf {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// iters [P] int32 | conv [P,4] uint32 | batch [2] int32
-inline size_t icp_workspace_bytes(int P) {
-    return align_up((size_t)P * 4, 256) + align_up((size_t)P * 16, 256) + 256;
-}
+// iters [P] int32 | conv [P,4] uint32 | batch [2] int32 (256 B slot) | stats [P,2] int32 {full searches, cache refreshes}
+inline size_t icp_ws_off_conv(int P) { return align_up((size_t)P * 4, 256); }
+inline size_t icp_ws_off_batch(int P) { return icp_ws_off_conv(P) + align_up((size_t)P * 16, 256); }
+inline size_t icp_ws_off_stats(int P) { return icp_ws_off_batch(P) + 256; }
+inline size_t icp_workspace_bytes(int P) { return icp_ws_off_stats(P) + align_up((size_t)P * 8, 256); }
 
 int launch_icp(const float* src, const float* dst, const float* init_R, const float* init_T, int P, int N,
                const icpf_params& prm, float* out_R, float* out_T,

@@ -18,37 +18,50 @@
 // "sequential scan, strict <" tie rule, so brute force (nn_mode 1) and grid (nn_mode 2) agree bit for bit.
 #pragma once
 
+#include <cuda_fp16.h>
+
 #include "icpf_common.cuh"
 
 namespace icpf {
 
 constexpr int kThreads = 128;          // threads per pair CTA
 constexpr int kWarps = kThreads / 32;
+constexpr float kCellFactor = 2.505f;  // grid cell size in units of the padded gate radius (>= 2.002)
 constexpr int kGridMaxCells = 2048;    // uniform-grid cells per pair (u16 offsets: 4 KB of shared memory)
 
-constexpr int kRedA = 0;                       // 8 sums
-constexpr int kRedB = kRedA + kWarps * 8;      // 9 sums
-constexpr int kRedC = kRedB + kWarps * 2 * 9;  // 2 sums (region B doubles as the 6+6 min/max scratch of the grid build)
-constexpr int kRedFloats = kRedC + kWarps * 2;
+// reduction scratch (floats): per-warp partials of the 18 per-iteration sums, their totals; the grid build reuses it
+constexpr int kSums = 18;                      // 16 moments + rmse numerator + deferred-search count
+constexpr int kScrPart = 0;                    // [kWarps][kSums]
+constexpr int kScrTotal = kScrPart + kWarps * kSums;
+constexpr int kRedFloats = kScrTotal + 24;
+constexpr int kBcastFloats = 48;
 constexpr int kCellWords = (kGridMaxCells + 2 + 1) / 2 + 2;   // packed u16 entries 0..G (+pad), as u32 words
+
+// broadcast block written by thread 0 once per iteration
+enum : int { B_R = 0, B_T = 9, B_RC = 12, B_TC = 21, B_PX = 24, B_PY = 27, B_EXIT = 30, B_REFRESH = 31 };
 
 // Shared-memory carve-up for one pair (all offsets 16-byte aligned).
 struct PairTiles {
-    float4* src;      // [N]  (x,y,z,flag) -- the cloud being moved (initial coordinates X0)
-    float4* dst;      // [N]  (x,y,z,flag) -- the fixed cloud as stored (TMA landing zone)
-    float4* sorted;   // [N]  grid mode: dst rows in cell order, .w = original row index (int bits)
-    uint32_t* cells;  // [kCellWords] grid mode: packed u16 run boundaries; run of cell i = [a[i], a[i+1])
-    int* nn;          // [N]  correspondence of each src row (index into the candidate array), -1 when masked out
-    float* red;       // [kRedFloats] reduction scratch (disjoint regions)
-    float* bcast;     // [16] R (9), T (3), flags
-    uint64_t* bar;    // TMA mbarrier
+    float4* src;            // [N]  (x,y,z,flag) -- the cloud being moved (initial coordinates X0)
+    float4* dst;            // [N]  (x,y,z,flag) -- the fixed cloud as stored (TMA landing zone)
+    float4* sorted;         // [N]  grid mode: dst rows in cell order, .w = (original row << 16 | sorted position)
+    uint32_t* cells;        // [kCellWords] grid mode: packed u16 run boundaries; run of cell i = [a[i], a[i+1])
+    unsigned int* nn;       // [N]  correspondence word of each src row (see pack_nn)
+    unsigned short* defer;  // [kWarps][defer_cap] grid mode: per-warp lists of rows whose cached neighbour failed
+    int defer_cap;
+    float* red;             // [kRedFloats] reduction scratch
+    float* bcast;           // [kBcastFloats] R, T, cache reference, pivots, flags
+    uint64_t* bar;          // TMA mbarrier
 };
+
+__host__ __device__ inline int pair_defer_cap(int N) { return (N + kThreads - 1) / kThreads * 32; }
 
 __host__ __device__ inline size_t pair_smem_bytes(int N, bool grid) {
     size_t b = (size_t)N * 16 * 2;                                        // src + dst
-    b += grid ? (size_t)N * 16 + (size_t)kCellWords * 4 : (size_t)N * 4;   // sorted + cells | nn (grid: nn aliases dst)
+    if (grid) b += (size_t)N * 16 + (size_t)kCellWords * 4 + (size_t)pair_defer_cap(N) * kWarps * 2;
+    else b += (size_t)N * 4;                                              // nn (grid mode: nn aliases the raw dst rows)
     b = (b + 15) / 16 * 16;
-    return b + (size_t)(kRedFloats + 16) * 4 + 16;
+    return b + (size_t)(kRedFloats + kBcastFloats) * 4 + 16;
 }
 
 template <bool GRID>
@@ -57,22 +70,26 @@ __device__ __forceinline__ PairTiles carve_pair_tiles(unsigned char* base, int N
     t.src = reinterpret_cast<float4*>(base);
     t.dst = t.src + N;
     unsigned char* p = reinterpret_cast<unsigned char*>(t.dst + N);
+    t.defer_cap = pair_defer_cap(N);
     if (GRID) {
         t.sorted = reinterpret_cast<float4*>(p);
         p += (size_t)N * 16;
         t.cells = reinterpret_cast<uint32_t*>(p);
         p += (size_t)kCellWords * 4;
-        t.nn = reinterpret_cast<int*>(t.dst);      // the raw dst rows are dead once the grid is built
+        t.defer = reinterpret_cast<unsigned short*>(p);
+        p += (size_t)t.defer_cap * kWarps * 2;
+        t.nn = reinterpret_cast<unsigned int*>(t.dst);      // the raw dst rows are dead once the grid is built
     } else {
         t.sorted = t.dst;
         t.cells = nullptr;
-        t.nn = reinterpret_cast<int*>(p);
+        t.defer = nullptr;
+        t.nn = reinterpret_cast<unsigned int*>(p);
         p += (size_t)N * 4;
     }
     p = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15));
     t.red = reinterpret_cast<float*>(p);
     t.bcast = t.red + kRedFloats;
-    t.bar = reinterpret_cast<uint64_t*>(t.bcast + 16);
+    t.bar = reinterpret_cast<uint64_t*>(t.bcast + kBcastFloats);
     return t;
 }
 
@@ -131,7 +148,9 @@ __device__ __forceinline__ void nn_brute(const float4* __restrict__ dst, int n_d
 struct GridInfo {
     float ox, oy, oz;   // grid origin = bbox min of the valid dst rows
     float inv_c;        // 1 / cell size
-    float r;            // padded gate radius in cells (<= 0.5 + eps)
+    float r;            // padded gate radius in cells (< 0.5, so a query overlaps at most 2 cells per axis)
+    float c;            // cell size (m)
+    float pad;          // slack (m) that absorbs the fp32 rounding of the cell arithmetic
     int gx, gy, gz;
 };
 
@@ -143,7 +162,7 @@ __device__ __forceinline__ int grid_cell(const GridInfo& g, float x, float y, fl
 }
 
 // Counting sort of dst[0, n_d) into tl.sorted by cell; fills the run boundaries in tl.cells.  All threads return the
-// same GridInfo.  Uses red region B as scratch; ends with a block barrier.
+// same GridInfo.  Uses the reduction scratch; ends with a block barrier.
 __device__ inline GridInfo build_grid(const PairTiles& tl, int n_d, float tau) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float INF = __int_as_float(0x7f800000);
@@ -161,7 +180,7 @@ __device__ inline GridInfo build_grid(const PairTiles& tl, int n_d, float tau) {
             hi[k] = fmaxf(hi[k], __shfl_xor_sync(FULL_MASK, hi[k], o));
         }
     }
-    float* scr = tl.red + kRedB;
+    float* scr = tl.red + kScrPart;
     if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -186,10 +205,13 @@ __device__ inline GridInfo build_grid(const PairTiles& tl, int n_d, float tau) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) maxabs = fmaxf(maxabs, fmaxf(fabsf(lo[k]), fabsf(hi[k])));
     // the pad absorbs the fp32 rounding of the cell arithmetic (1 ulp at 50 m is 4e-6 m)
-    const float tau_pad = tau + fmaxf(1e-4f, 1e-6f * maxabs);
+    g.pad = fmaxf(1e-4f, 1e-6f * maxabs);
+    const float tau_pad = tau + g.pad;
     const float ex = fminf(fmaxf(hi[0] - lo[0], 0.f), 1e6f), ey = fminf(fmaxf(hi[1] - lo[1], 0.f), 1e6f),
                 ez = fminf(fmaxf(hi[2] - lo[2], 0.f), 1e6f);
-    float c = 2.0f * tau_pad;
+    // cells of kCellFactor*tau: a query then overlaps <= 2 cells per axis while everything it does NOT inspect is at
+    // least 0.4995 cells (~1.25 tau) away -- the head-room the correspondence cache needs to prove "still masked"
+    float c = kCellFactor * tau_pad;
     g.gx = g.gy = g.gz = 1;
     bool fits = false;
     for (int k = 0; k < 40 && !fits; ++k) {
@@ -199,8 +221,9 @@ __device__ inline GridInfo build_grid(const PairTiles& tl, int n_d, float tau) {
         if (!fits) c *= fmaxf(1.05f, cbrtf(cells / (float)kGridMaxCells));
     }
     if (!fits) { g.gx = g.gy = g.gz = 1; c = 4e6f; }
+    g.c = c;
     g.inv_c = 1.0f / c;
-    g.r = tau_pad * g.inv_c;
+    g.r = 0.4995f;   // >= tau_pad / c because c >= 2.002 * tau_pad
     const int G = g.gx * g.gy * g.gz;
 
     uint32_t* w = tl.cells;
@@ -225,7 +248,7 @@ __device__ inline GridInfo build_grid(const PairTiles& tl, int n_d, float tau) {
         const unsigned int v = __shfl_up_sync(FULL_MASK, incl, o);
         if (lane >= o) incl += v;
     }
-    unsigned int* wtot = reinterpret_cast<unsigned int*>(tl.red + kRedB) + 32;   // beyond the min/max scratch
+    unsigned int* wtot = reinterpret_cast<unsigned int*>(tl.red + kScrPart) + 32;   // beyond the min/max scratch
     if (lane == 31) wtot[warp] = incl;
     __syncthreads();
     unsigned int run = incl - local;
@@ -242,28 +265,48 @@ __device__ inline GridInfo build_grid(const PairTiles& tl, int n_d, float tau) {
         const int e = grid_cell(g, p.x, p.y, p.z) + 1;
         const int sh = (e & 1) * 16;
         const unsigned int old = atomicAdd(&w[e >> 1], 1u << sh);
-        tl.sorted[(old >> sh) & 0xffffu] = make_float4(p.x, p.y, p.z, __int_as_float(j));
+        const unsigned int pos = (old >> sh) & 0xffffu;
+        // .w = (original row << 16) | sorted position: the low word of the 64-bit ranking key (d^2 bits, row, position)
+        tl.sorted[pos] = make_float4(p.x, p.y, p.z, __uint_as_float(((unsigned int)j << 16) | pos));
     }
     __syncthreads();
     return g;
 }
 
-// Radius-bounded NN: best candidate among the cells overlapping the padded tau-box of q, ranked by (d^2, original row).
-// bj = -1 when no candidate was inspected (the true NN is then farther than tau, so the gate fails either way).
-__device__ __forceinline__ void nn_grid(const GridInfo& g, const float4* __restrict__ sorted,
-                                        const unsigned short* __restrict__ a, float qx, float qy, float qz, float& best,
-                                        int& bj) {
-    best = __int_as_float(0x7f800000);
-    bj = -1;
-    int borig = 0x7fffffff;
+// Radius-bounded NN: best candidate among the cells overlapping the padded tau-box of q, ranked by the 64-bit key
+// (d^2 bits, original row, sorted position) -- i.e. (squared distance, row index), the reference's tie rule.
+//   pos     sorted position of the winner, -1 when no candidate was inspected (the true NN is then farther than tau)
+//   d2      its squared distance (+inf when none)
+//   d2nd    second smallest squared distance among the inspected candidates (+inf when fewer than two)
+//   box     distance (m) from q to the nearest face of the inspected block that has un-inspected space behind it:
+//           every point that was NOT inspected is farther than `box` from q
+__device__ __forceinline__ void grid_search(const GridInfo& g, const float4* __restrict__ sorted,
+                                            const unsigned short* __restrict__ a, float qx, float qy, float qz,
+                                            float& d2, int& pos, float& d2nd, float& box) {
+    const float INF = __int_as_float(0x7f800000);
+    const unsigned long long kNone = (0x7f800000ull << 32) | 0xffffffffull;
+    unsigned long long key = kNone;
+    d2nd = INF;
     const float fx = (qx - g.ox) * g.inv_c, fy = (qy - g.oy) * g.inv_c, fz = (qz - g.oz) * g.inv_c;
     const float x0 = floorf(fx - g.r), x1 = floorf(fx + g.r);
     const float y0 = floorf(fy - g.r), y1 = floorf(fy + g.r);
     const float z0 = floorf(fz - g.r), z1 = floorf(fz + g.r);
+    const float hx = (float)(g.gx - 1), hy = (float)(g.gy - 1), hz = (float)(g.gz - 1);
     // (NaN coordinates fail every comparison below and fall through to "no candidate")
-    if (!(x1 >= 0.f && y1 >= 0.f && z1 >= 0.f && x0 <= (float)(g.gx - 1) && y0 <= (float)(g.gy - 1) &&
-          z0 <= (float)(g.gz - 1)))
+    if (!(x1 >= 0.f && y1 >= 0.f && z1 >= 0.f && x0 <= hx && y0 <= hy && z0 <= hz)) {
+        // the tau-box misses the grid: all points lie inside [0, g]^3 cell coordinates
+        const float gapx = fmaxf(-fx, fx - (hx + 1.f)), gapy = fmaxf(-fy, fy - (hy + 1.f)),
+                    gapz = fmaxf(-fz, fz - (hz + 1.f));
+        box = fmaxf(fmaxf(gapx, fmaxf(gapy, gapz)) * g.c - g.pad, 0.f);
+        d2 = INF;
+        pos = -1;
         return;
+    }
+    // faces clamped by the grid boundary have no points behind them
+    const float bx = fminf(x0 < 0.f ? INF : fx - x0, x1 > hx ? INF : x1 + 1.f - fx);
+    const float by = fminf(y0 < 0.f ? INF : fy - y0, y1 > hy ? INF : y1 + 1.f - fy);
+    const float bz = fminf(z0 < 0.f ? INF : fz - z0, z1 > hz ? INF : z1 + 1.f - fz);
+    box = fmaxf(fminf(bx, fminf(by, bz)) * g.c - g.pad, 0.f);
     const int ix0 = max(0, (int)x0), ix1 = min(g.gx - 1, (int)x1);
     const int iy0 = max(0, (int)y0), iy1 = min(g.gy - 1, (int)y1);
     const int iz0 = max(0, (int)z0), iz1 = min(g.gz - 1, (int)z1);
@@ -274,180 +317,25 @@ __device__ __forceinline__ void nn_grid(const GridInfo& g, const float4* __restr
             for (int j = s; j < e; ++j) {
                 const float4 c = sorted[j];
                 const float d = sqdist(qx, qy, qz, c.x, c.y, c.z);
-                const int oi = __float_as_int(c.w);
-                if (d < best || (d == best && oi < borig)) {
-                    best = d;
-                    bj = j;
-                    borig = oi;
-                }
+                const unsigned long long k = ((unsigned long long)__float_as_uint(d) << 32) | __float_as_uint(c.w);
+                const bool better = k < key;
+                d2nd = fminf(d2nd, better ? __uint_as_float((unsigned int)(key >> 32)) : d);
+                key = better ? k : key;
             }
         }
     }
+    d2 = __uint_as_float((unsigned int)(key >> 32));
+    pos = (key == kNone) ? -1 : (int)((unsigned int)key & 0xffffu);
 }
 
-// ------------------------------------------------------------------------------------------------ ICP loop
-struct IcpResult {
-    float r[9];
-    float t[3];
-    float rmse;
-    int iters;                    // iterations executed by this pair
-    unsigned long long conv_lo;   // bit k: relative rmse <= thr at iteration k      (k < 64)
-    unsigned long long conv_hi;   //                                                 (64 <= k < 128)
-};                                // bits after a fixed-point exit are extrapolated (the state repeats)
+// correspondence word kept per src row: bits 0-15 sorted position of the best candidate (0xffff none),
+// bits 16-30 a lower bound (fp16, rounded down) on the distance of every OTHER dst point, bit 31 "masked out"
+constexpr unsigned int kNnNone = 0xffffu;
+constexpr unsigned int kNnMasked = 0x80000000u;
 
-__device__ __forceinline__ void set_conv_bit(IcpResult& r, int k) {
-    if (k < 64) r.conv_lo |= 1ull << k;
-    else if (k < 128) r.conv_hi |= 1ull << (k - 64);
-}
-
-// The ICP loop for the pair held in `tl`.  All threads return the same result.
-//   GRID  : candidates = tl.sorted + grid `g` (build_grid must have run); otherwise candidates = tl.dst, brute force
-//   n_s / n_d : valid-row counts (knn `lengths`); tau2 = fp32(thres^2)
-//   init_R / init_T (may be NULL) = init_transform of the reference: used for the first correspondence search only.
-template <bool GRID>
-__device__ inline IcpResult icp_iterations(const PairTiles& tl, const GridInfo& g, int n_s, int n_d, float tau2,
-                                           int max_it, float rel_thr, bool early_exit, const float* init_R = nullptr,
-                                           const float* init_T = nullptr) {
-    IcpResult res;
-#pragma unroll
-    for (int i = 0; i < 9; ++i) res.r[i] = init_R ? init_R[i] : ((i % 4 == 0) ? 1.f : 0.f);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) res.t[i] = init_T ? init_T[i] : 0.f;
-    res.rmse = 0.f;
-    res.iters = 0;
-    res.conv_lo = res.conv_hi = 0ull;
-    if (n_s <= 0 || n_d <= 0 || max_it <= 0) return res;   // engine-defined: nothing to align -> identity
-
-    const int tid = threadIdx.x;
-    const float4* __restrict__ cand = GRID ? tl.sorted : tl.dst;
-    const unsigned short* cell_runs = reinterpret_cast<const unsigned short*>(tl.cells);
-    float prev_rmse = 0.f;
-    bool have_prev = false;
-    constexpr int QB = 4;
-
-    for (int it = 0; it < max_it; ++it) {
-        // ---------------- correspondence search on the current cloud + first-pass sums
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (GRID) {
-            for (int q = tid; q < n_s; q += kThreads) {
-                const float4 x0 = tl.src[q];
-                float qx, qy, qz, best;
-                int j;
-                apply_rt(res.r, res.t, x0.x, x0.y, x0.z, qx, qy, qz);
-                nn_grid(g, cand, cell_runs, qx, qy, qz, best, j);
-                const bool m = (j >= 0) && (best <= tau2) && (x0.w > 0.f);
-                tl.nn[q] = m ? j : -1;
-                if (m) {
-                    const float4 y = cand[j];
-                    acc[0] += 1.f;
-                    acc[1] += x0.x; acc[2] += x0.y; acc[3] += x0.z;
-                    acc[4] += y.x; acc[5] += y.y; acc[6] += y.z;
-                }
-            }
-        } else {
-            for (int q0 = tid; q0 < n_s; q0 += kThreads * QB) {
-                float qx[QB], qy[QB], qz[QB], best[QB];
-                int bidx[QB];
-                float4 x0[QB];
-#pragma unroll
-                for (int k = 0; k < QB; ++k) {
-                    const int q = q0 + k * kThreads;
-                    x0[k] = (q < n_s) ? tl.src[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    apply_rt(res.r, res.t, x0[k].x, x0[k].y, x0[k].z, qx[k], qy[k], qz[k]);
-                }
-                nn_brute<QB>(cand, n_d, qx, qy, qz, best, bidx);
-#pragma unroll
-                for (int k = 0; k < QB; ++k) {
-                    const int q = q0 + k * kThreads;
-                    if (q >= n_s) continue;
-                    const bool m = (best[k] <= tau2) && (x0[k].w > 0.f);
-                    tl.nn[q] = m ? bidx[k] : -1;
-                    if (m) {
-                        const float4 y = cand[bidx[k]];
-                        acc[0] += 1.f;
-                        acc[1] += x0[k].x; acc[2] += x0[k].y; acc[3] += x0[k].z;
-                        acc[4] += y.x; acc[5] += y.y; acc[6] += y.z;
-                    }
-                }
-            }
-        }
-        block_allreduce_sum<8, kWarps>(acc, tl.red + kRedA);
-        const float W = fmaxf(acc[0], 1e-9f);
-        const float mux = __fdiv_rn(acc[1], W), muy = __fdiv_rn(acc[2], W), muz = __fdiv_rn(acc[3], W);
-        const float mvx = __fdiv_rn(acc[4], W), mvy = __fdiv_rn(acc[5], W), mvz = __fdiv_rn(acc[6], W);
-
-        // ---------------- second pass: centred cross-covariance H = Xc^T Yc / W
-        float h[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        for (int q = tid; q < n_s; q += kThreads) {
-            const int j = tl.nn[q];
-            if (j < 0) continue;
-            const float4 x = tl.src[q];
-            const float4 y = cand[j];
-            const float ax = x.x - mux, ay = x.y - muy, az = x.z - muz;
-            const float bx = y.x - mvx, by = y.y - mvy, bz = y.z - mvz;
-            h[0] = fmaf(ax, bx, h[0]); h[1] = fmaf(ax, by, h[1]); h[2] = fmaf(ax, bz, h[2]);
-            h[3] = fmaf(ay, bx, h[3]); h[4] = fmaf(ay, by, h[4]); h[5] = fmaf(ay, bz, h[5]);
-            h[6] = fmaf(az, bx, h[6]); h[7] = fmaf(az, by, h[7]); h[8] = fmaf(az, bz, h[8]);
-        }
-        block_allreduce_sum<9, kWarps>(h, tl.red + kRedB);
-
-        // ---------------- rotation / translation by one thread, broadcast through shared memory
-        if (tid == 0) {
-#pragma unroll
-            for (int i = 0; i < 9; ++i) h[i] = __fdiv_rn(h[i], W);
-            const Rot3 rot = kabsch_rotation(h);
-            float t[3];
-            t[0] = mvx - fmaf(muz, rot.r[6], fmaf(muy, rot.r[3], mux * rot.r[0]));
-            t[1] = mvy - fmaf(muz, rot.r[7], fmaf(muy, rot.r[4], mux * rot.r[1]));
-            t[2] = mvz - fmaf(muz, rot.r[8], fmaf(muy, rot.r[5], mux * rot.r[2]));
-            bool same = true;
-#pragma unroll
-            for (int i = 0; i < 9; ++i) same = same && (__float_as_uint(rot.r[i]) == __float_as_uint(res.r[i]));
-#pragma unroll
-            for (int i = 0; i < 3; ++i) same = same && (__float_as_uint(t[i]) == __float_as_uint(res.t[i]));
-#pragma unroll
-            for (int i = 0; i < 9; ++i) tl.bcast[i] = rot.r[i];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) tl.bcast[9 + i] = t[i];
-            tl.bcast[12] = (same && it > 0) ? 1.f : 0.f;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < 9; ++i) res.r[i] = tl.bcast[i];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) res.t[i] = tl.bcast[9 + i];
-        const bool fixed = tl.bcast[12] != 0.f;
-
-        // ---------------- rmse of the re-transformed cloud against the correspondences just used
-        float sq[2] = {0.f, 0.f};
-        for (int q = tid; q < n_s; q += kThreads) {
-            const int j = tl.nn[q];
-            if (j < 0) continue;
-            const float4 x = tl.src[q];
-            const float4 y = cand[j];
-            float tx, ty, tz;
-            apply_rt(res.r, res.t, x.x, x.y, x.z, tx, ty, tz);
-            sq[0] += sqdist(tx, ty, tz, y.x, y.y, y.z);
-        }
-        block_allreduce_sum<2, kWarps>(sq, tl.red + kRedC);
-        const float rmse = sqrtf(__fdiv_rn(sq[0], W));
-        const float rel = have_prev ? __fdiv_rn(prev_rmse - rmse, prev_rmse) : 1.0f;
-        if (rel <= rel_thr) set_conv_bit(res, it);
-        res.rmse = rmse;
-        res.iters = it + 1;
-        prev_rmse = rmse;
-        have_prev = true;
-        if (early_exit && fixed) {
-            // from here on the state repeats bit for bit: rel = (rmse - rmse) / rmse = 0 (NaN when rmse == 0)
-            const bool tail_ok = (rmse > 0.f) && (0.0f <= rel_thr) && (rmse < __int_as_float(0x7f800000));
-            if (tail_ok) {
-                for (int k = it + 1; k < max_it && k < 128; ++k) set_conv_bit(res, k);
-            }
-            break;
-        }
-        // bcast[] is rewritten by thread 0 only after two more block-wide barriers (reductions A and B) -> no hazard
-    }
-    return res;
+__device__ __forceinline__ unsigned int pack_nn(int pos, float bound, bool used) {
+    const unsigned int b = (unsigned int)__half_as_ushort(__float2half_rd(fmaxf(bound, 0.f))) & 0x7fffu;
+    return (pos < 0 ? kNnNone : (unsigned int)pos) | (b << 16) | (used ? 0u : kNnMasked);
 }
 
 }  // namespace icpf

@@ -115,6 +115,14 @@ def icp_batch(src: torch.Tensor, dst: torch.Tensor, params: _lib.IcpfParams,
     return out
 
 
+def icp_stats(workspace: torch.Tensor, P: int) -> torch.Tensor:
+    """Diagnostics the last ``icp_batch`` call left in its workspace: ``[P,2]`` int32
+    {full grid searches executed, cache-refresh iterations} per pair (layout: csrc/icpf_internal.h)."""
+    up = lambda v: (v + 255) // 256 * 256
+    off = up(P * 4) + up(P * 16) + 256
+    return workspace[off:off + P * 8].view(torch.int32).view(P, 2)
+
+
 def iterative_closest_point(X, Y, init_transform: Optional[SimilarityTransform] = None, thres: float = 0.1,
                             max_iterations: int = 100, relative_rmse_thr: float = 1e-6,
                             estimate_scale: bool = False, allow_reflection: bool = False,

@@ -43,7 +43,8 @@ typedef struct icpf_params {
     int32_t batch_stop;       /* 1: reproduce the reference's batch-coupled stop (utils_icp_pytorch3d.py:209):
                                  results are the state at the first iteration where ALL pairs satisfy the
                                  relative-RMSE test; 0: each pair independent (max_iterations / fixed point)   */
-    int32_t nn_mode;          /* 0 auto, 1 brute force, 2 uniform grid (radius-bounded, result-identical)      */
+    int32_t nn_mode;          /* 0 auto (= 3 when the tiles fit), 1 brute force, 2 uniform grid (radius-bounded),
+                                 3 grid + correspondence cache; all modes are result-identical                 */
     int32_t reserved[2];
 } icpf_params;
 

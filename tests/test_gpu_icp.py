@@ -201,10 +201,31 @@ def test_grid_search_is_bitwise_identical_to_brute_force(ragged):
     for kw in (dict(max_iterations=20, relative_rmse_thr=-1.0, early_exit=False),
                dict(max_iterations=100, relative_rmse_thr=1e-6, early_exit=True)):
         a = _run(src, dst, nn_mode=1, **kw)
-        b = _run(src, dst, nn_mode=2, **kw)
-        assert torch.equal(a.R, b.R) and torch.equal(a.T, b.T) and torch.equal(a.rmse, b.rmse)
-        assert torch.equal(a.iterations, b.iterations) and torch.equal(a.conv_mask, b.conv_mask)
-        assert torch.equal(a.batch, b.batch) and torch.equal(a.pose, b.pose)
+        for mode in (2, 3):      # grid, grid + correspondence cache
+            b = _run(src, dst, nn_mode=mode, **kw)
+            assert torch.equal(a.R, b.R) and torch.equal(a.T, b.T) and torch.equal(a.rmse, b.rmse), mode
+            assert torch.equal(a.iterations, b.iterations) and torch.equal(a.conv_mask, b.conv_mask), mode
+            assert torch.equal(a.batch, b.batch) and torch.equal(a.pose, b.pose), mode
+
+
+def test_cache_is_bitwise_identical_under_large_motion():
+    """The correspondence cache must fall back to a full search whenever its triangle-inequality bound cannot prove
+    the cached neighbour: large initial motion (many refreshes), far-away origin (1 km: fp32 ulp 6e-5 m)."""
+    src, dst, _ = synth.make_pairs(48, 256, seed=41, ragged=True, residual_only=False, wrong_frac=0.1)
+    src2, dst2 = src.copy(), dst.copy()
+    shift = np.array([1000.0, -800.0, 0.0], np.float32)
+    src2[:, :, :3] = np.where(src[:, :, 3:4] > 0, src[:, :, :3] + shift, src[:, :, :3])
+    dst2[:, :, :3] = np.where(dst[:, :, 3:4] > 0, dst[:, :, :3] + shift, dst[:, :, :3])
+    # small translations so that ICP from identity has inliers, plus the original large-motion set
+    dst3 = dst.copy()
+    dst3[:, :, :3] = np.where(dst[:, :, 3:4] > 0, src[:, :, :3].mean(1, keepdims=True) * 0 + dst[:, :, :3], dst[:, :, :3])
+    for s_, d_ in ((src, dst), (src2, dst2)):
+        for kw in (dict(max_iterations=40, relative_rmse_thr=-1.0, early_exit=False, batch_stop=False),
+                   dict(max_iterations=100, relative_rmse_thr=1e-6, early_exit=True, batch_stop=True)):
+            a = _run(s_, d_, nn_mode=1, **kw)
+            b = _run(s_, d_, nn_mode=3, **kw)
+            assert torch.equal(a.R, b.R) and torch.equal(a.T, b.T) and torch.equal(a.rmse, b.rmse)
+            assert torch.equal(a.iterations, b.iterations) and torch.equal(a.conv_mask, b.conv_mask)
 
 
 def test_grid_handles_large_and_flat_clusters():
@@ -221,8 +242,9 @@ def test_grid_handles_large_and_flat_clusters():
     dst[:, :, 0] += 0.03; dst[:, :, 1] -= 0.02
     dst[:, :, :3] += rng.normal(0, 0.002, size=dst[:, :, :3].shape).astype(np.float32)
     a = _run(src, dst, nn_mode=1, max_iterations=30, relative_rmse_thr=-1.0, early_exit=False, batch_stop=False)
-    b = _run(src, dst, nn_mode=2, max_iterations=30, relative_rmse_thr=-1.0, early_exit=False, batch_stop=False)
-    assert torch.equal(a.R, b.R) and torch.equal(a.T, b.T) and torch.equal(a.rmse, b.rmse)
+    for mode in (2, 3):
+        b = _run(src, dst, nn_mode=mode, max_iterations=30, relative_rmse_thr=-1.0, early_exit=False, batch_stop=False)
+        assert torch.equal(a.R, b.R) and torch.equal(a.T, b.T) and torch.equal(a.rmse, b.rmse), mode
     T = b.T.cpu().numpy()
     moved = src[:2, :, :3] @ b.R.cpu().numpy()[:2] + T[:2, None]
     assert np.abs(moved - dst[:2, :, :3]).max() < 0.02
