@@ -26,7 +26,7 @@ namespace icpf {
 
 constexpr int kThreads = 128;          // threads per pair CTA
 constexpr int kWarps = kThreads / 32;
-constexpr float kCellFactor = 2.505f;  // grid cell size in units of the padded gate radius (>= 2.002)
+constexpr float kCellFactor = 2.002f;  // grid cell size in units of the padded gate radius (>= 2.002)
 constexpr int kGridMaxCells = 2048;    // uniform-grid cells per pair (u16 offsets: 4 KB of shared memory)
 
 // reduction scratch (floats): per-warp partials of the 18 per-iteration sums, their totals; the grid build reuses it
