@@ -1,0 +1,16 @@
+"""icp_flow_b200 -- B200-native batched ICP registration engine behind ICP-Flow's per-cluster-pair alignment path.
+
+Public surface = the reference's own callables for that path (same names / signatures), backed by hand-written sm_100a
+kernels reached through the C ABI in ``include/icpflow_b200.h`` (``libicpflow_b200.so``, built in-tree).  There is no
+CPU or PyTorch fallback: importing works anywhere (so the CPU test-suite can check the ABI), calling needs a GPU.
+"""
+from .ops import (ICPSolution, SimilarityTransform, IcpBatchResult, apply_icp, estimate_init_pose, hist, hist_icp,
+                  icp_batch, iterative_closest_point, make_params, nearest_neighbor_batch, pytorch3d_icp,
+                  transform_points_batch)
+from .install import install, uninstall
+
+__all__ = [
+    "ICPSolution", "SimilarityTransform", "IcpBatchResult", "apply_icp", "estimate_init_pose", "hist", "hist_icp",
+    "icp_batch", "iterative_closest_point", "make_params", "nearest_neighbor_batch", "pytorch3d_icp",
+    "transform_points_batch", "install", "uninstall",
+]

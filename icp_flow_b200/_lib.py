@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libicpflow_b200.so")
 EXPORTS = (
     "icpf_version", "icpf_error_string", "icpf_default_params", "icpf_workspace_bytes",
     "icpf_icp_f32", "icpf_nn_f32", "icpf_transform_points_f32", "icpf_host_kabsch", "icpf_profile_next_icp",
+    "icpf_hist_votes_f32", "icpf_hist_init_f32", "icpf_apply_icp_f32", "icpf_hist_icp_f32",
 )
 
 
@@ -29,6 +30,20 @@ class IcpfParams(ctypes.Structure):
         ("batch_stop", ctypes.c_int32),
         ("nn_mode", ctypes.c_int32),
         ("reserved", ctypes.c_int32 * 2),
+    ]
+
+
+class IcpfHistBins(ctypes.Structure):
+    """Mirror of ``struct icpf_hist_bins``."""
+
+    _fields_ = [
+        ("bins_x", ctypes.c_void_p),
+        ("bins_y", ctypes.c_void_p),
+        ("bins_z", ctypes.c_void_p),
+        ("len", ctypes.c_int32 * 3),
+        ("min", ctypes.c_float * 3),
+        ("max", ctypes.c_float * 3),
+        ("half_bin", ctypes.c_float),
     ]
 
 
@@ -68,6 +83,18 @@ def lib() -> ctypes.CDLL:
     L.icpf_nn_f32.argtypes = [vp, vp, i32, i32, i32, i32, i32, i64p, vp, vp]
     L.icpf_transform_points_f32.restype = ctypes.c_int
     L.icpf_transform_points_f32.argtypes = [vp, vp, i32, i32, vp, vp]
+    f3, i3 = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32)
+    L.icpf_hist_votes_f32.restype = ctypes.c_int
+    L.icpf_hist_votes_f32.argtypes = [vp, vp, i32, i32, i32, f3, f3, i3, vp, vp]
+    L.icpf_hist_init_f32.restype = ctypes.c_int
+    L.icpf_hist_init_f32.argtypes = [vp, vp, i32, i32, ctypes.POINTER(IcpfHistBins), i32, vp, vp, vp, vp, vp, vp,
+                                     ctypes.c_size_t, vp]
+    L.icpf_apply_icp_f32.restype = ctypes.c_int
+    L.icpf_apply_icp_f32.argtypes = [vp, vp, vp, i32, i32, ctypes.POINTER(IcpfParams), i32, vp, vp, vp, vp, vp,
+                                     ctypes.c_size_t, vp]
+    L.icpf_hist_icp_f32.restype = ctypes.c_int
+    L.icpf_hist_icp_f32.argtypes = [vp, vp, i32, i32, ctypes.POINTER(IcpfHistBins), ctypes.POINTER(IcpfParams), vp, vp,
+                                    vp, vp, ctypes.c_size_t, vp]
     L.icpf_profile_next_icp.restype = None
     L.icpf_profile_next_icp.argtypes = [vp, vp]
     L.icpf_host_kabsch.restype = None

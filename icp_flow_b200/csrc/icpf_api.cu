@@ -39,9 +39,8 @@ void icpf_default_params(icpf_params* p) {
 }
 
 size_t icpf_workspace_bytes(int32_t P, int32_t N, int32_t lx, int32_t ly, int32_t lz) {
-    (void)N; (void)lx; (void)ly; (void)lz;
-    if (P < 0) return 0;
-    return icp_workspace_bytes(P);
+    if (P < 0 || lx < 0 || ly < 0 || lz < 0) return 0;
+    return path_workspace_bytes(P, N, lx, ly, lz);
 }
 
 int icpf_icp_f32(const float* src, const float* dst, const float* init_R, const float* init_T, int32_t P, int32_t N,
@@ -56,7 +55,7 @@ int icpf_icp_f32(const float* src, const float* dst, const float* init_R, const 
     if (params->max_iterations < 1 || params->max_iterations > ICPF_MAX_ITERATIONS) return ICPF_E_PARAM;
     if (!(params->thres_dist > 0.0)) return ICPF_E_PARAM;
     if ((init_R == nullptr) != (init_T == nullptr)) return ICPF_E_NULL;
-    return launch_icp(src, dst, init_R, init_T, P, N, *params, out_R, out_T, out_rmse, out_pose, out_iters, out_conv, out_batch, workspace,
+    return launch_icp(src, dst, init_R, init_T, nullptr, 0, P, N, *params, out_R, out_T, out_rmse, out_pose, out_iters, out_conv, out_batch, workspace,
                       workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
@@ -75,6 +74,78 @@ int icpf_transform_points_f32(const float* xyz, const float* pose, int32_t B, in
     if (!xyz || !pose || !out) return ICPF_E_NULL;
     if (!aligned16(xyz) || !aligned16(out)) return ICPF_E_ALIGN;
     return launch_transform_points(xyz, pose, B, N, out, static_cast<cudaStream_t>(stream));
+}
+
+static int check_params(const icpf_params* params) {
+    if (!params) return ICPF_E_NULL;
+    if (params->max_iterations < 1 || params->max_iterations > ICPF_MAX_ITERATIONS) return ICPF_E_PARAM;
+    if (!(params->thres_dist > 0.0)) return ICPF_E_PARAM;
+    return ICPF_OK;
+}
+
+static int check_bins(const icpf_hist_bins* b) {
+    if (!b) return ICPF_E_NULL;
+    if (!b->bins_x || !b->bins_y || !b->bins_z) return ICPF_E_NULL;
+    for (int k = 0; k < 3; ++k) {
+        if (b->len[k] < 1 || b->len[k] > 4096) return ICPF_E_SHAPE;
+        if (!(b->max[k] > b->min[k])) return ICPF_E_PARAM;
+    }
+    return ICPF_OK;
+}
+
+int icpf_hist_votes_f32(const float* X, const float* Y, int32_t B, int32_t NX, int32_t NY, const float* min_xyz,
+                        const float* max_xyz, const int32_t* len_xyz, float* bins, void* stream) {
+    if (B < 0 || NX < 0 || NY < 0 || B > 65535) return ICPF_E_SHAPE;
+    if (!min_xyz || !max_xyz || !len_xyz) return ICPF_E_NULL;
+    for (int k = 0; k < 3; ++k) {
+        if (len_xyz[k] < 1 || len_xyz[k] > 4096) return ICPF_E_SHAPE;
+        if (!(max_xyz[k] > min_xyz[k])) return ICPF_E_PARAM;
+    }
+    if (B == 0) return ICPF_OK;
+    if (!X || !Y || !bins) return ICPF_E_NULL;
+    if (!aligned16(X) || !aligned16(Y)) return ICPF_E_ALIGN;
+    return launch_hist_votes(X, Y, B, NX, NY, min_xyz, max_xyz, len_xyz, bins, 0, static_cast<cudaStream_t>(stream));
+}
+
+int icpf_hist_init_f32(const float* src, const float* dst, int32_t P, int32_t N, const icpf_hist_bins* bins,
+                       int32_t auto_swap, float* out_pose, int32_t* out_cand, float* out_votes, float* out_scores,
+                       int32_t* out_which, void* workspace, size_t workspace_bytes, void* stream) {
+    const int rc = check_bins(bins);
+    if (rc != ICPF_OK) return rc;
+    if (P < 0 || N <= 0 || P > 65535 * 64) return ICPF_E_SHAPE;
+    if (P == 0) return ICPF_OK;
+    if (!src || !dst || !out_pose) return ICPF_E_NULL;
+    if (!aligned16(src) || !aligned16(dst)) return ICPF_E_ALIGN;
+    return launch_hist_init(src, dst, P, N, *bins, auto_swap, out_pose, out_cand, out_votes, out_scores, out_which,
+                            workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int icpf_apply_icp_f32(const float* src, const float* dst, const float* init_pose, int32_t P, int32_t N,
+                       const icpf_params* params, int32_t auto_swap, float* out_pose, float* out_err,
+                       int32_t* out_flags, int32_t* out_batch, void* workspace, size_t workspace_bytes, void* stream) {
+    const int rc = check_params(params);
+    if (rc != ICPF_OK) return rc;
+    if (P < 0 || N <= 0) return ICPF_E_SHAPE;
+    if (P == 0) return ICPF_OK;
+    if (!src || !dst || !init_pose || !out_pose) return ICPF_E_NULL;
+    if (!aligned16(src) || !aligned16(dst)) return ICPF_E_ALIGN;
+    return launch_apply_icp(src, dst, init_pose, P, N, *params, auto_swap, out_pose, out_err, out_flags, out_batch,
+                            workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int icpf_hist_icp_f32(const float* src, const float* dst, int32_t P, int32_t N, const icpf_hist_bins* bins,
+                      const icpf_params* params, float* out_pose, float* out_init, int32_t* out_batch,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_params(params);
+    if (rc != ICPF_OK) return rc;
+    rc = check_bins(bins);
+    if (rc != ICPF_OK) return rc;
+    if (P < 0 || N <= 0) return ICPF_E_SHAPE;
+    if (P == 0) return ICPF_OK;
+    if (!src || !dst || !out_pose) return ICPF_E_NULL;
+    if (!aligned16(src) || !aligned16(dst)) return ICPF_E_ALIGN;
+    return launch_hist_icp(src, dst, P, N, *bins, *params, out_pose, out_init, out_batch, workspace, workspace_bytes,
+                           static_cast<cudaStream_t>(stream));
 }
 
 void icpf_profile_next_icp(void* start_event, void* stop_event) {

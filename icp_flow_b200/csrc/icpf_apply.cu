@@ -1,0 +1,238 @@
+// icpf_apply.cu -- the wrapper around the ICP loop (utils_icp.apply_icp, utils_icp.py:20-48) and the orchestration of
+// the whole per-pair path (utils_match.hist_icp, utils_match.py:138-157) as stream-ordered launches:
+//
+//   hist_votes -> hist_peaks -> hist_score            (init pose, icpf_hist.cu; histogram chunked over pairs)
+//   icp_pairs (init pose applied on load) -> resolve batch stop -> re-run pass        (icpf_icp.cu)
+//   icp_finalize: compose ICP with the init pose, mean NN error before/after, roll back, undo the swap
+#include "icpf_internal.h"
+#include "icpf_pair.cuh"
+
+namespace icpf {
+
+struct FinalizeArgs {
+    const float* src;        // [P,N,4]
+    const float* dst;        // [P,N,4]
+    int N;
+    const float* init_pose;  // [P,16]
+    const float* icp_R;      // [P,9]  row-vector convention
+    const float* icp_T;      // [P,3]
+    int auto_swap;
+    float* out_pose;         // [P,16]
+    float* out_err;          // [P,2] {error_init, error_icp} (may be NULL)
+    int* out_flags;          // [P]   bit 0 rolled back, bit 1 swapped (may be NULL)
+};
+
+// mean over the valid rows of S of the unbounded NN distance of (pose * S_i) among D[0, n_d)   (utils_icp.py:28-33)
+__device__ inline float mean_nn_error(const float (&m)[12], const float4* S, int n_s, const float4* D, int n_d,
+                                      float* scratch) {
+    float sum[1] = {0.f};
+    constexpr int QB = 4;
+    for (int q0 = threadIdx.x; q0 < n_s; q0 += kThreads * QB) {
+        float qx[QB], qy[QB], qz[QB], best[QB];
+        int bidx[QB];
+#pragma unroll
+        for (int k = 0; k < QB; ++k) {
+            const int q = q0 + k * kThreads;
+            const float4 s = transform_row(m, q < n_s ? S[q] : make_float4(0.f, 0.f, 0.f, 0.f));
+            qx[k] = s.x; qy[k] = s.y; qz[k] = s.z;
+        }
+        nn_brute<QB>(D, n_d, qx, qy, qz, best, bidx);
+#pragma unroll
+        for (int k = 0; k < QB; ++k) {
+            const int q = q0 + k * kThreads;
+            if (q < n_s && S[q].w > 0.f) sum[0] += sqrtf(best[k]);
+        }
+    }
+    block_allreduce_sum<1, kWarps>(sum, scratch);
+    __syncthreads();
+    return sum[0];
+}
+
+__global__ void __launch_bounds__(kThreads) icp_finalize_kernel(FinalizeArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int p = blockIdx.x, tid = threadIdx.x;
+    PairTiles tl = carve_pair_tiles<false>(smem_raw, a.N);
+    if (tid == 0) {
+        mbar_init(tl.bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    load_pair_tiles(tl, a.src + (size_t)p * a.N * 4, a.dst + (size_t)p * a.N * 4, a.N, 0);
+    float cnt[2] = {0.f, 0.f};
+    for (int q = tid; q < a.N; q += kThreads) {
+        cnt[0] += (tl.src[q].w > 0.f) ? 1.f : 0.f;
+        cnt[1] += (tl.dst[q].w > 0.f) ? 1.f : 0.f;
+    }
+    block_allreduce_sum<2, kWarps>(cnt, tl.red + kScrPart);
+    __syncthreads();
+    int n_s = (int)cnt[0], n_d = (int)cnt[1];
+    const float4* S = tl.src;
+    const float4* D = tl.dst;
+    const bool swapped = a.auto_swap && n_s > n_d;
+    if (swapped) {
+        const float4* t = S; S = D; D = t;
+        const int n = n_s; n_s = n_d; n_d = n;
+    }
+    // M0 = init pose, Micp = [[R^T, T],[0,1]] (utils_icp.py:60-65), M = Micp * M0 (utils_icp.py:24)
+    float m0[16], mi[16], mm[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m0[i] = a.init_pose[(size_t)p * 16 + i];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) mi[4 * r + c] = a.icp_R[(size_t)p * 9 + c * 3 + r];
+        mi[4 * r + 3] = a.icp_T[(size_t)p * 3 + r];
+    }
+    mi[12] = mi[13] = mi[14] = 0.f;
+    mi[15] = 1.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            mm[4 * r + c] = fmaf(mi[4 * r + 3], m0[12 + c],
+                                 fmaf(mi[4 * r + 2], m0[8 + c], fmaf(mi[4 * r + 1], m0[4 + c], mi[4 * r] * m0[c])));
+    float a0[12], a1[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { a0[i] = m0[i]; a1[i] = mm[i]; }
+    const float e0 = __fdiv_rn(mean_nn_error(a0, S, n_s, D, n_d, tl.red + kScrPart), (float)n_s);
+    const float e1 = __fdiv_rn(mean_nn_error(a1, S, n_s, D, n_d, tl.red + kScrPart), (float)n_s);
+    if (tid == 0) {
+        const bool rolled = e1 >= e0;          // utils_icp.py:34-35 (NaN compares false: keep the ICP result)
+        float out[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) out[i] = rolled ? m0[i] : mm[i];
+        if (swapped) {
+            // torch.linalg.inv of the 4x4 (utils_match.py:152-154); the last row is (0,0,0,1) by construction, so
+            // the inverse is [[A^-1, -A^-1 b],[0,1]] with A^-1 = adj(A) / det(A)
+            const float A00 = out[0], A01 = out[1], A02 = out[2], A10 = out[4], A11 = out[5], A12 = out[6], A20 = out[8],
+                        A21 = out[9], A22 = out[10], b0 = out[3], b1 = out[7], b2 = out[11];
+            const float c00 = A11 * A22 - A12 * A21, c01 = A02 * A21 - A01 * A22, c02 = A01 * A12 - A02 * A11;
+            const float c10 = A12 * A20 - A10 * A22, c11 = A00 * A22 - A02 * A20, c12 = A02 * A10 - A00 * A12;
+            const float c20 = A10 * A21 - A11 * A20, c21 = A01 * A20 - A00 * A21, c22 = A00 * A11 - A01 * A10;
+            const float det = A00 * c00 + A01 * c10 + A02 * c20;
+            const float id = 1.0f / det;
+            const float i00 = c00 * id, i01 = c01 * id, i02 = c02 * id, i10 = c10 * id, i11 = c11 * id, i12 = c12 * id,
+                        i20 = c20 * id, i21 = c21 * id, i22 = c22 * id;
+            out[0] = i00; out[1] = i01; out[2] = i02; out[3] = -(i00 * b0 + i01 * b1 + i02 * b2);
+            out[4] = i10; out[5] = i11; out[6] = i12; out[7] = -(i10 * b0 + i11 * b1 + i12 * b2);
+            out[8] = i20; out[9] = i21; out[10] = i22; out[11] = -(i20 * b0 + i21 * b1 + i22 * b2);
+            out[12] = 0.f; out[13] = 0.f; out[14] = 0.f; out[15] = 1.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a.out_pose[(size_t)p * 16 + i] = out[i];
+        if (a.out_err) {
+            a.out_err[(size_t)p * 2] = e0;
+            a.out_err[(size_t)p * 2 + 1] = e1;
+        }
+        if (a.out_flags) a.out_flags[p] = (rolled ? 1 : 0) | (swapped ? 2 : 0);
+    }
+}
+
+int launch_icp_finalize(const float* src, const float* dst, int P, int N, const float* init_pose, const float* icp_R,
+                        const float* icp_T, int auto_swap, float* out_pose, float* out_err, int* out_flags,
+                        cudaStream_t stream) {
+    if (P == 0) return ICPF_OK;
+    const size_t smem = pair_smem_bytes(N, false);
+    if (smem > 227 * 1024) return ICPF_E_UNSUPPORTED;
+    cudaError_t err = cudaFuncSetAttribute(icp_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return (int)err;
+    FinalizeArgs a{src, dst, N, init_pose, icp_R, icp_T, auto_swap, out_pose, out_err, out_flags};
+    icp_finalize_kernel<<<P, kThreads, smem, stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ orchestration
+// workspace: [icp workspace][R P*9][T P*3][init pose P*16][cand idx P*5][votes P*5][histogram chunk]
+size_t path_workspace_bytes(int P, int N, int lx, int ly, int lz) {
+    (void)N;
+    size_t b = icp_workspace_bytes(P);
+    b += align_up((size_t)P * 9 * 4, 256) + align_up((size_t)P * 3 * 4, 256) + align_up((size_t)P * 16 * 4, 256);
+    b += 2 * align_up((size_t)P * 5 * 4, 256);
+    if (lx > 0 && ly > 0 && lz > 0) b += align_up((size_t)hist_chunk_pairs(P, lx, ly, lz) * lx * ly * lz * 4, 256);
+    return b;
+}
+
+int hist_chunk_pairs(int P, int lx, int ly, int lz) {
+    const size_t per = (size_t)lx * ly * lz * 4;
+    const size_t budget = (size_t)64 << 20;          // keep the live histograms L2-resident (126 MB L2)
+    size_t c = budget / (per ? per : 1);
+    if (c < 1) c = 1;
+    if (c > (size_t)P) c = (size_t)P;
+    return (int)(c > 0 ? c : 1);
+}
+
+struct PathWs {
+    unsigned char* icp;
+    float* R;
+    float* T;
+    float* init;
+    int* cand;
+    float* votes;
+    float* hist;
+};
+
+static PathWs carve_ws(void* workspace, int P) {
+    PathWs w;
+    unsigned char* p = static_cast<unsigned char*>(workspace);
+    w.icp = p; p += icp_workspace_bytes(P);
+    w.R = reinterpret_cast<float*>(p); p += align_up((size_t)P * 9 * 4, 256);
+    w.T = reinterpret_cast<float*>(p); p += align_up((size_t)P * 3 * 4, 256);
+    w.init = reinterpret_cast<float*>(p); p += align_up((size_t)P * 16 * 4, 256);
+    w.cand = reinterpret_cast<int*>(p); p += align_up((size_t)P * 5 * 4, 256);
+    w.votes = reinterpret_cast<float*>(p); p += align_up((size_t)P * 5 * 4, 256);
+    w.hist = reinterpret_cast<float*>(p);
+    return w;
+}
+
+int launch_hist_init(const float* src, const float* dst, int P, int N, const icpf_hist_bins& hb, int auto_swap,
+                     float* out_pose, int* out_cand, float* out_votes, float* out_scores, int* out_which,
+                     void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    if (P == 0) return ICPF_OK;
+    if (workspace == nullptr || workspace_bytes < path_workspace_bytes(P, N, hb.len[0], hb.len[1], hb.len[2]))
+        return ICPF_E_WORKSPACE;
+    PathWs w = carve_ws(workspace, P);
+    int* cand = out_cand ? out_cand : w.cand;
+    float* votes = out_votes ? out_votes : w.votes;
+    const int chunk = hist_chunk_pairs(P, hb.len[0], hb.len[1], hb.len[2]);
+    for (int lo = 0; lo < P; lo += chunk) {
+        const int n = (P - lo < chunk) ? (P - lo) : chunk;
+        // utils_hist.py:69: hist(dst, src, ...) -> votes dst_i - src_j
+        int rc = launch_hist_votes(dst + (size_t)lo * N * 4, src + (size_t)lo * N * 4, n, N, N, hb.min, hb.max, hb.len,
+                                   w.hist, auto_swap, stream);
+        if (rc != ICPF_OK) return rc;
+        rc = launch_hist_peaks(w.hist, n, hb.len[0], hb.len[1], hb.len[2], cand + (size_t)lo * 5,
+                               votes + (size_t)lo * 5, stream);
+        if (rc != ICPF_OK) return rc;
+    }
+    return launch_hist_score(src, dst, P, N, cand, hb.bins_x, hb.bins_y, hb.bins_z, hb.len[0], hb.len[1], hb.len[2],
+                             hb.half_bin, auto_swap, out_pose, out_scores, out_which, stream);
+}
+
+int launch_apply_icp(const float* src, const float* dst, const float* init_pose, int P, int N, const icpf_params& prm,
+                     int auto_swap, float* out_pose, float* out_err, int* out_flags, int* out_batch, void* workspace,
+                     size_t workspace_bytes, cudaStream_t stream) {
+    if (P == 0) return ICPF_OK;
+    if (workspace == nullptr || workspace_bytes < path_workspace_bytes(P, N, 0, 0, 0)) return ICPF_E_WORKSPACE;
+    PathWs w = carve_ws(workspace, P);
+    int rc = launch_icp(src, dst, nullptr, nullptr, init_pose, auto_swap, P, N, prm, w.R, w.T, nullptr, nullptr,
+                        nullptr, nullptr, out_batch, w.icp, icp_workspace_bytes(P), stream);
+    if (rc != ICPF_OK) return rc;
+    return launch_icp_finalize(src, dst, P, N, init_pose, w.R, w.T, auto_swap, out_pose, out_err, out_flags, stream);
+}
+
+int launch_hist_icp(const float* src, const float* dst, int P, int N, const icpf_hist_bins& hb, const icpf_params& prm,
+                    float* out_pose, float* out_init, int* out_batch, void* workspace, size_t workspace_bytes,
+                    cudaStream_t stream) {
+    if (P == 0) return ICPF_OK;
+    if (workspace == nullptr || workspace_bytes < path_workspace_bytes(P, N, hb.len[0], hb.len[1], hb.len[2]))
+        return ICPF_E_WORKSPACE;
+    PathWs w = carve_ws(workspace, P);
+    float* init = out_init ? out_init : w.init;
+    int rc = launch_hist_init(src, dst, P, N, hb, 1, init, nullptr, nullptr, nullptr, nullptr, workspace,
+                              workspace_bytes, stream);
+    if (rc != ICPF_OK) return rc;
+    return launch_apply_icp(src, dst, init, P, N, prm, 1, out_pose, nullptr, nullptr, out_batch, workspace,
+                            workspace_bytes, stream);
+}
+
+}  // namespace icpf

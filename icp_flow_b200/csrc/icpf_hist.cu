@@ -1,0 +1,370 @@
+// icpf_hist.cu -- histogram-vote translation initialisation (utils_hist.py:33-124) as three stream-ordered kernels:
+//
+//   hist_votes_kernel   all-pairs difference histogram, bit-compatible with the reference's only CUDA kernel
+//                       (hist_cuda/cpp/hist_cuda_core.cuh:35-62): one vote per (X_i, Y_j) with both flags > 0 whose
+//                       difference lies in the half-open range, bin = floor((v - min) / (max - min) * len) in fp32
+//   hist_peaks_kernel   3-D non-maximum suppression (11^3 window == all three z bins) + top-5 (utils_hist.py:21-29)
+//   hist_score_kernel   the 5 decoded translations + the zero translation, scored by the smaller of the two mean
+//                       unbounded NN distances, arg-min -> 4x4 translation pose (utils_hist.py:78-122)
+//
+// X rows are staged through shared memory (one coalesced pass over HBM); votes are fp32 atomic adds of 1.0 into an
+// L2-resident histogram (exact: counts stay far below 2^24), cheap rejects first (|dz| < tau discards most pairs).
+#include "icpf_internal.h"
+#include "icpf_pair.cuh"
+
+namespace icpf {
+
+// ------------------------------------------------------------------------------------------------ votes
+constexpr int kVoteThreads = 256;
+constexpr int kVoteTile = 1024;   // Y rows per shared-memory tile
+
+struct HistGeom {
+    float min_x, min_y, min_z, max_x, max_y, max_z;
+    int len_x, len_y, len_z;
+};
+
+// hist(X, Y): votes X_i - Y_j.  If `auto_swap`, the roles follow utils_match.py:139-146 / utils_hist.py:69, i.e. the
+// call is hist(dst_, src_) with (src_, dst_) = (src, dst) swapped whenever src has more valid rows than dst.
+__global__ void __launch_bounds__(kVoteThreads) hist_votes_kernel(const float4* __restrict__ X,
+                                                                  const float4* __restrict__ Y, int NX, int NY,
+                                                                  HistGeom gm, float* __restrict__ bins, int auto_swap) {
+    __shared__ float4 tile[kVoteTile];
+    __shared__ int s_cnt[2];
+    const int b = blockIdx.y;
+    const float4* xb = X + (size_t)b * NX;
+    const float4* yb = Y + (size_t)b * NY;
+    int nx = NX, ny = NY;
+    if (auto_swap) {
+        // here X = dst and Y = src of the caller: swap when n_valid(src) > n_valid(dst)
+        if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+        __syncthreads();
+        int cx = 0, cy = 0;
+        for (int i = threadIdx.x; i < NX; i += kVoteThreads) cx += xb[i].w > 0.f;
+        for (int i = threadIdx.x; i < NY; i += kVoteThreads) cy += yb[i].w > 0.f;
+        cx = __reduce_add_sync(FULL_MASK, cx);
+        cy = __reduce_add_sync(FULL_MASK, cy);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&s_cnt[0], cx);
+            atomicAdd(&s_cnt[1], cy);
+        }
+        __syncthreads();
+        if (s_cnt[1] > s_cnt[0]) {
+            const float4* t = xb; xb = yb; yb = t;
+            nx = NY; ny = NX;
+        }
+        __syncthreads();
+    }
+    float* hb = bins + (size_t)b * gm.len_x * gm.len_y * gm.len_z;
+    const float rx = __fsub_rn(gm.max_x, gm.min_x), ry = __fsub_rn(gm.max_y, gm.min_y),
+                rz = __fsub_rn(gm.max_z, gm.min_z);
+    const float flx = (float)gm.len_x, fly = (float)gm.len_y, flz = (float)gm.len_z;
+    const int i = blockIdx.x * kVoteThreads + threadIdx.x;
+    float4 xi = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < nx) xi = xb[i];
+    const bool live = (i < nx) && (xi.w > 0.f);
+    for (int base = 0; base < ny; base += kVoteTile) {
+        const int n = min(kVoteTile, ny - base);
+        __syncthreads();
+        for (int j = threadIdx.x; j < n; j += kVoteThreads) tile[j] = yb[base + j];
+        __syncthreads();
+        if (!live) continue;
+        for (int j = 0; j < n; ++j) {
+            const float4 yj = tile[j];
+            const float vz = __fsub_rn(xi.z, yj.z);
+            if (!(yj.w > 0.f) || !(vz >= gm.min_z && vz < gm.max_z)) continue;
+            const float vx = __fsub_rn(xi.x, yj.x), vy = __fsub_rn(xi.y, yj.y);
+            if (vx >= gm.min_x && vx < gm.max_x && vy >= gm.min_y && vy < gm.max_y) {
+                int px = __float2int_rd(__fmul_rn(__fdiv_rn(__fsub_rn(vx, gm.min_x), rx), flx));
+                int py = __float2int_rd(__fmul_rn(__fdiv_rn(__fsub_rn(vy, gm.min_y), ry), fly));
+                int pz = __float2int_rd(__fmul_rn(__fdiv_rn(__fsub_rn(vz, gm.min_z), rz), flz));
+                // (v - min) can round up to (max - min) for v one ulp below max; the reference would then write out
+                // of the pair's histogram -- clamp instead
+                px = min(px, gm.len_x - 1); py = min(py, gm.len_y - 1); pz = min(pz, gm.len_z - 1);
+                atomicAdd(hb + ((size_t)px * gm.len_y + py) * gm.len_z + pz, 1.0f);
+            }
+        }
+    }
+}
+
+int launch_hist_votes(const float* X, const float* Y, int B, int NX, int NY, const float* mins, const float* maxs,
+                      const int* lens, float* bins, int auto_swap, cudaStream_t stream) {
+    if (B == 0) return ICPF_OK;
+    HistGeom gm{mins[0], mins[1], mins[2], maxs[0], maxs[1], maxs[2], lens[0], lens[1], lens[2]};
+    const size_t bytes = (size_t)B * lens[0] * lens[1] * lens[2] * sizeof(float);
+    cudaError_t err = cudaMemsetAsync(bins, 0, bytes, stream);    // at::zeros of hist_cuda.cu:59
+    if (err != cudaSuccess) return (int)err;
+    const int nmax = auto_swap ? max(NX, NY) : NX;
+    dim3 grid((nmax + kVoteThreads - 1) / kVoteThreads, B);
+    hist_votes_kernel<<<grid, kVoteThreads, 0, stream>>>(reinterpret_cast<const float4*>(X),
+                                                         reinterpret_cast<const float4*>(Y), NX, NY, gm, bins,
+                                                         auto_swap);
+    return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ NMS + top-k
+constexpr int kPeakThreads = 256;
+constexpr int kTopK = 5;        // utils_hist.py:21
+constexpr int kNmsHalf = 5;     // kernel_size 11 -> +-5 bins; the z extent (3 bins) is always inside the window
+
+// key = (vote count bits, ~flat index): larger = more votes, ties -> lowest flat index (torch.topk's CPU order)
+__device__ __forceinline__ unsigned long long peak_key(float v, int idx) {
+    return ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(0x7fffffff - idx);
+}
+
+__global__ void __launch_bounds__(kPeakThreads) hist_peaks_kernel(const float* __restrict__ bins, int lx, int ly,
+                                                                  int lz, int* __restrict__ out_idx,
+                                                                  float* __restrict__ out_votes) {
+    extern __shared__ float sm[];
+    float* colmax = sm;                 // [lx*ly] max over z
+    float* rowmax = sm + lx * ly;       // [lx*ly] max over the y window
+    __shared__ unsigned long long s_best[kPeakThreads / 32];
+    __shared__ unsigned long long s_pick[kTopK];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float* hb = bins + (size_t)b * lx * ly * lz;
+    const int ncol = lx * ly;
+    for (int c = tid; c < ncol; c += kPeakThreads) {
+        float m = hb[(size_t)c * lz];
+        for (int z = 1; z < lz; ++z) m = fmaxf(m, hb[(size_t)c * lz + z]);
+        colmax[c] = m;
+    }
+    __syncthreads();
+    for (int c = tid; c < ncol; c += kPeakThreads) {
+        const int x = c / ly, y = c - x * ly;
+        float m = colmax[c];
+        for (int d = max(0, y - kNmsHalf); d <= min(ly - 1, y + kNmsHalf); ++d) m = fmaxf(m, colmax[x * ly + d]);
+        rowmax[c] = m;
+    }
+    __syncthreads();
+    // each thread keeps its own top-k of surviving positive bins (value desc, index asc)
+    unsigned long long top[kTopK];
+#pragma unroll
+    for (int k = 0; k < kTopK; ++k) top[k] = 0ull;
+    for (int c = tid; c < ncol; c += kPeakThreads) {
+        const int x = c / ly, y = c - x * ly;
+        float m = rowmax[c];
+        for (int d = max(0, x - kNmsHalf); d <= min(lx - 1, x + kNmsHalf); ++d) m = fmaxf(m, rowmax[d * ly + y]);
+        if (!(m > 0.f)) continue;
+        for (int z = 0; z < lz; ++z) {
+            const float v = hb[(size_t)c * lz + z];
+            if (v == m) {          // x == max_pool3d(x): plateaus all survive
+                unsigned long long key = peak_key(v, c * lz + z);
+#pragma unroll
+                for (int k = 0; k < kTopK; ++k) {
+                    if (key > top[k]) { const unsigned long long t = top[k]; top[k] = key; key = t; }
+                }
+            }
+        }
+    }
+    // k rounds of block arg-max over the heads of the per-thread lists
+    for (int round = 0; round < kTopK; ++round) {
+        unsigned long long best = top[0];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(FULL_MASK, best, o);
+            best = other > best ? other : best;
+        }
+        if ((tid & 31) == 0) s_best[tid >> 5] = best;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long m = s_best[0];
+            for (int w = 1; w < kPeakThreads / 32; ++w) m = s_best[w] > m ? s_best[w] : m;
+            s_pick[round] = m;
+        }
+        __syncthreads();
+        const unsigned long long win = s_pick[round];
+        if (win != 0ull && top[0] == win) {      // keys are unique (they embed the flat index): pop it
+#pragma unroll
+            for (int k = 0; k + 1 < kTopK; ++k) top[k] = top[k + 1];
+            top[kTopK - 1] = 0ull;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        // fewer than k positive peaks: torch.topk pads with zero-valued entries of x * mask; those are arbitrary
+        // zero-vote bins in the reference (implementation-defined order) -- take the lowest flat indices
+        int picked[kTopK];
+        int np = 0;
+        for (int k = 0; k < kTopK; ++k) {
+            if (s_pick[k] != 0ull) {
+                picked[np] = 0x7fffffff - (int)(unsigned int)(s_pick[k] & 0xffffffffu);
+                out_votes[(size_t)b * kTopK + np] = __uint_as_float((unsigned int)(s_pick[k] >> 32));
+                ++np;
+            }
+        }
+        int fill = 0;
+        const int npos = np;
+        while (np < kTopK) {
+            bool used = false;
+            for (int k = 0; k < npos; ++k) used = used || (picked[k] == fill);
+            if (!used) {
+                picked[np] = fill;
+                out_votes[(size_t)b * kTopK + np] = 0.f;
+                ++np;
+            }
+            ++fill;
+        }
+        for (int k = 0; k < kTopK; ++k) out_idx[(size_t)b * kTopK + k] = picked[k];
+    }
+}
+
+int launch_hist_peaks(const float* bins, int B, int lx, int ly, int lz, int* out_idx, float* out_votes,
+                      cudaStream_t stream) {
+    if (B == 0) return ICPF_OK;
+    const size_t smem = (size_t)lx * ly * 2 * sizeof(float);
+    if (smem > 200 * 1024) return ICPF_E_UNSUPPORTED;
+    cudaError_t err = cudaFuncSetAttribute(hist_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return (int)err;
+    hist_peaks_kernel<<<B, kPeakThreads, smem, stream>>>(bins, lx, ly, lz, out_idx, out_votes);
+    return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ candidate scoring
+constexpr int kCand = kTopK + 1;   // + the zero translation, last (utils_hist.py:83)
+
+struct ScoreArgs {
+    const float* src;        // [P,N,4]
+    const float* dst;        // [P,N,4]
+    int N;
+    const int* cand_idx;     // [P,5] flat histogram indices
+    const float* bins_x;     // [lx] bin starts (torch.arange of the reference, utils_hist.py:63-65)
+    const float* bins_y;     // [ly]
+    const float* bins_z;     // [lz]
+    int lx, ly, lz;
+    float half_bin;          // args.thres_dist // 2  (utils_hist.py:78; 0.0 for tau = 0.1)
+    int auto_swap;
+    float* out_pose;         // [P,16]
+    float* out_scores;       // [P,6] (may be NULL)
+    int* out_which;          // [P]   (may be NULL)
+};
+
+__global__ void __launch_bounds__(kThreads) hist_score_kernel(ScoreArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ float s_t[kCand][3];
+    __shared__ float s_sum[2][kCand];
+    __shared__ float s_part[kWarps][2][kCand];
+    const int p = blockIdx.x, tid = threadIdx.x;
+    PairTiles tl = carve_pair_tiles<false>(smem_raw, a.N);
+    if (tid == 0) {
+        mbar_init(tl.bar, 1);
+        fence_barrier_init();
+    }
+    if (tid < 2 * kCand) s_sum[tid / kCand][tid % kCand] = 0.f;
+    __syncthreads();
+    load_pair_tiles(tl, a.src + (size_t)p * a.N * 4, a.dst + (size_t)p * a.N * 4, a.N, 0);
+    float cnt[2] = {0.f, 0.f};
+    for (int q = tid; q < a.N; q += kThreads) {
+        cnt[0] += (tl.src[q].w > 0.f) ? 1.f : 0.f;
+        cnt[1] += (tl.dst[q].w > 0.f) ? 1.f : 0.f;
+    }
+    block_allreduce_sum<2, kWarps>(cnt, tl.red + kScrPart);
+    int n_s = (int)cnt[0], n_d = (int)cnt[1];
+    const float4* S = tl.src;
+    const float4* D = tl.dst;
+    if (a.auto_swap && n_s > n_d) {     // always register the smaller cloud onto the larger one (utils_match.py:139-146)
+        const float4* t = S; S = D; D = t;
+        const int n = n_s; n_s = n_d; n_d = n;
+    }
+    if (tid < kCand) {
+        float tx = 0.f, ty = 0.f, tz = 0.f;
+        if (tid < kTopK) {
+            // flat -> (i // d // w % h, i // d % w, i % d)  (utils_hist.py:78)
+            const int flat = a.cand_idx[(size_t)p * kTopK + tid];
+            const int iz = flat % a.lz, iy = (flat / a.lz) % a.ly, ix = (flat / a.lz / a.ly) % a.lx;
+            tx = __fadd_rn(a.bins_x[ix], a.half_bin);
+            ty = __fadd_rn(a.bins_y[iy], a.half_bin);
+            tz = __fadd_rn(a.bins_z[iz], a.half_bin);
+        }
+        s_t[tid][0] = tx; s_t[tid][1] = ty; s_t[tid][2] = tz;
+    }
+    __syncthreads();
+    float t[kCand][3];
+#pragma unroll
+    for (int k = 0; k < kCand; ++k) { t[k][0] = s_t[k][0]; t[k][1] = s_t[k][1]; t[k][2] = s_t[k][2]; }
+    const float INF = __int_as_float(0x7f800000);
+
+    // forward: NN of (src_i + t_k) among the dst rows; backward: NN of dst_i among the (src_j + t_k)
+    float fsum[kCand], bsum[kCand];
+#pragma unroll
+    for (int k = 0; k < kCand; ++k) fsum[k] = bsum[k] = 0.f;
+    for (int i = tid; i < n_s; i += kThreads) {
+        const float4 s = S[i];
+        float best[kCand], qx[kCand], qy[kCand], qz[kCand];
+#pragma unroll
+        for (int k = 0; k < kCand; ++k) {
+            best[k] = INF;
+            qx[k] = __fadd_rn(s.x, t[k][0]); qy[k] = __fadd_rn(s.y, t[k][1]); qz[k] = __fadd_rn(s.z, t[k][2]);
+        }
+        for (int j = 0; j < n_d; ++j) {
+            const float4 c = D[j];
+#pragma unroll
+            for (int k = 0; k < kCand; ++k) best[k] = fminf(best[k], sqdist(qx[k], qy[k], qz[k], c.x, c.y, c.z));
+        }
+#pragma unroll
+        for (int k = 0; k < kCand; ++k) fsum[k] += sqrtf(best[k]);
+    }
+    for (int i = tid; i < n_d; i += kThreads) {
+        const float4 d = D[i];
+        float best[kCand];
+#pragma unroll
+        for (int k = 0; k < kCand; ++k) best[k] = INF;
+        for (int j = 0; j < n_s; ++j) {
+            const float4 c = S[j];
+#pragma unroll
+            for (int k = 0; k < kCand; ++k) {
+                const float cx = __fadd_rn(c.x, t[k][0]), cy = __fadd_rn(c.y, t[k][1]), cz = __fadd_rn(c.z, t[k][2]);
+                best[k] = fminf(best[k], sqdist(d.x, d.y, d.z, cx, cy, cz));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kCand; ++k) bsum[k] += sqrtf(best[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < kCand; ++k) {
+        fsum[k] = warp_sum(fsum[k]);
+        bsum[k] = warp_sum(bsum[k]);
+    }
+    if ((tid & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < kCand; ++k) {
+            s_part[tid >> 5][0][k] = fsum[k];
+            s_part[tid >> 5][1][k] = bsum[k];
+        }
+    }
+    __syncthreads();
+    if (tid < 2 * kCand) {        // warps added in a fixed order: deterministic
+        float s = 0.f;
+        for (int w = 0; w < kWarps; ++w) s += s_part[w][tid / kCand][tid % kCand];
+        s_sum[tid / kCand][tid % kCand] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int which = 0;
+        float best = 0.f;
+        for (int k = 0; k < kCand; ++k) {
+            const float ef = __fdiv_rn(s_sum[0][k], (float)n_s), eb = __fdiv_rn(s_sum[1][k], (float)n_d);
+            const float e = fminf(ef, eb);        // torch.minimum
+            if (a.out_scores) a.out_scores[(size_t)p * kCand + k] = e;
+            if (k == 0 || e < best) { best = e; which = k; }      // errors.min(dim=-1): first minimum
+        }
+        if (a.out_which) a.out_which[p] = which;
+        float* o = a.out_pose + (size_t)p * 16;
+        for (int i = 0; i < 16; ++i) o[i] = (i % 5 == 0) ? 1.f : 0.f;
+        o[3] = s_t[which][0]; o[7] = s_t[which][1]; o[11] = s_t[which][2];
+    }
+}
+
+int launch_hist_score(const float* src, const float* dst, int P, int N, const int* cand_idx, const float* bins_x,
+                      const float* bins_y, const float* bins_z, int lx, int ly, int lz, float half_bin, int auto_swap,
+                      float* out_pose, float* out_scores, int* out_which, cudaStream_t stream) {
+    if (P == 0) return ICPF_OK;
+    const size_t smem = pair_smem_bytes(N, false);
+    if (smem > 227 * 1024) return ICPF_E_UNSUPPORTED;
+    cudaError_t err = cudaFuncSetAttribute(hist_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return (int)err;
+    ScoreArgs a{src, dst, N, cand_idx, bins_x, bins_y, bins_z, lx, ly, lz, half_bin, auto_swap, out_pose, out_scores,
+                out_which};
+    hist_score_kernel<<<P, kThreads, smem, stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace icpf

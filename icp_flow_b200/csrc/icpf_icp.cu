@@ -17,6 +17,8 @@ struct IcpArgs {
     const float* dst;
     const float* init_R;   // [P,9] or NULL
     const float* init_T;   // [P,3] or NULL
+    const float* init_pose;  // [P,16] or NULL: 4x4 applied to the moved cloud before ICP (utils_icp.py:21)
+    int auto_swap;           // 1: register the cloud with fewer valid rows onto the other (utils_match.py:139-146)
     int P, N;
     float tau;             // fp32(thres)
     float tau2;            // fp32(thres^2)
@@ -47,7 +49,7 @@ __global__ void __launch_bounds__(kThreads, 7) icp_pairs_kernel(IcpArgs a) {
         early_exit = false;
     }
     constexpr bool GRID = MODE >= 2;
-    const PairTiles tl = carve_pair_tiles<GRID>(smem_raw, a.N);
+    PairTiles tl = carve_pair_tiles<GRID>(smem_raw, a.N);
     if (threadIdx.x == 0) {
         mbar_init(tl.bar, 1);
         fence_barrier_init();
@@ -62,9 +64,25 @@ __global__ void __launch_bounds__(kThreads, 7) icp_pairs_kernel(IcpArgs a) {
         cnt[1] += (tl.dst[q].w > 0.f) ? 1.f : 0.f;
     }
     block_allreduce_sum<2, kWarps>(cnt, tl.red + kScrPart);
-    const int n_s = (int)cnt[0], n_d = (int)cnt[1];
+    int n_s = (int)cnt[0], n_d = (int)cnt[1];
+    if (a.auto_swap && n_s > n_d) {
+        float4* t = tl.src; tl.src = tl.dst; tl.dst = t;
+        const int n = n_s; n_s = n_d; n_d = n;
+        if (GRID) tl.nn = reinterpret_cast<unsigned int*>(tl.dst);
+        else tl.sorted = tl.dst;
+    }
     const float4 piv = tl.dst[0];      // first pivot of the moment sums: any point of the fixed cloud
     __syncthreads();                   // scratch and the raw dst rows are reused below
+    if (a.init_pose != nullptr) {
+        // src' = [x y z 1] pose^T with the flag carried through (utils_helper.py:76-87)
+        if (threadIdx.x < 12) tl.bcast[threadIdx.x] = a.init_pose[(size_t)p * 16 + threadIdx.x];
+        __syncthreads();
+        float m[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) m[i] = tl.bcast[i];
+        for (int q = threadIdx.x; q < n_s; q += kThreads) tl.src[q] = transform_row(m, tl.src[q]);
+        __syncthreads();
+    }
 
     GridInfo g;
     if (GRID && n_s > 0 && n_d > 0) g = build_grid(tl, n_d, a.tau);
@@ -140,8 +158,8 @@ void set_profile_events(cudaEvent_t start, cudaEvent_t stop) {
     t_prof_stop = stop;
 }
 
-int launch_icp(const float* src, const float* dst, const float* init_R, const float* init_T, int P, int N,
-               const icpf_params& prm, float* out_R, float* out_T,
+int launch_icp(const float* src, const float* dst, const float* init_R, const float* init_T, const float* init_pose,
+               int auto_swap, int P, int N, const icpf_params& prm, float* out_R, float* out_T,
                float* out_rmse, float* out_pose, int* out_iters, uint32_t* out_conv, int* out_batch, void* workspace,
                size_t workspace_bytes, cudaStream_t stream) {
     if (P == 0) return ICPF_OK;
@@ -168,6 +186,7 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
 
     IcpArgs a;
     a.src = src; a.dst = dst; a.init_R = init_R; a.init_T = init_T; a.P = P; a.N = N;
+    a.init_pose = init_pose; a.auto_swap = auto_swap;
     a.tau = (float)prm.thres_dist;
     a.tau2 = (float)(prm.thres_dist * prm.thres_dist);   // python: thres**2 in double, compared in fp32
     a.max_it = prm.max_iterations;

@@ -17,12 +17,35 @@ inline size_t icp_ws_off_batch(int P) { return icp_ws_off_conv(P) + align_up((si
 inline size_t icp_ws_off_stats(int P) { return icp_ws_off_batch(P) + 256; }
 inline size_t icp_workspace_bytes(int P) { return icp_ws_off_stats(P) + align_up((size_t)P * 8, 256); }
 
-int launch_icp(const float* src, const float* dst, const float* init_R, const float* init_T, int P, int N,
-               const icpf_params& prm, float* out_R, float* out_T,
+int launch_icp(const float* src, const float* dst, const float* init_R, const float* init_T, const float* init_pose,
+               int auto_swap, int P, int N, const icpf_params& prm, float* out_R, float* out_T,
                float* out_rmse, float* out_pose, int* out_iters, uint32_t* out_conv, int* out_batch, void* workspace,
                size_t workspace_bytes, cudaStream_t stream);
 
 void set_profile_events(cudaEvent_t start, cudaEvent_t stop);
+
+int hist_chunk_pairs(int P, int lx, int ly, int lz);
+size_t path_workspace_bytes(int P, int N, int lx, int ly, int lz);
+
+int launch_hist_votes(const float* X, const float* Y, int B, int NX, int NY, const float* mins, const float* maxs,
+                      const int* lens, float* bins, int auto_swap, cudaStream_t stream);
+int launch_hist_peaks(const float* bins, int B, int lx, int ly, int lz, int* out_idx, float* out_votes,
+                      cudaStream_t stream);
+int launch_hist_score(const float* src, const float* dst, int P, int N, const int* cand_idx, const float* bins_x,
+                      const float* bins_y, const float* bins_z, int lx, int ly, int lz, float half_bin, int auto_swap,
+                      float* out_pose, float* out_scores, int* out_which, cudaStream_t stream);
+int launch_icp_finalize(const float* src, const float* dst, int P, int N, const float* init_pose, const float* icp_R,
+                        const float* icp_T, int auto_swap, float* out_pose, float* out_err, int* out_flags,
+                        cudaStream_t stream);
+int launch_hist_init(const float* src, const float* dst, int P, int N, const icpf_hist_bins& hb, int auto_swap,
+                     float* out_pose, int* out_cand, float* out_votes, float* out_scores, int* out_which,
+                     void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int launch_apply_icp(const float* src, const float* dst, const float* init_pose, int P, int N, const icpf_params& prm,
+                     int auto_swap, float* out_pose, float* out_err, int* out_flags, int* out_batch, void* workspace,
+                     size_t workspace_bytes, cudaStream_t stream);
+int launch_hist_icp(const float* src, const float* dst, int P, int N, const icpf_hist_bins& hb, const icpf_params& prm,
+                    float* out_pose, float* out_init, int* out_batch, void* workspace, size_t workspace_bytes,
+                    cudaStream_t stream);
 
 int launch_nn(const float* src, const float* dst, int B, int Ns, int Nd, int src_stride, int dst_stride,
               int64_t* out_idx, float* out_dist, cudaStream_t stream);

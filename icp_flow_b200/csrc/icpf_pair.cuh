@@ -120,6 +120,17 @@ __device__ __forceinline__ void apply_rt(const float (&r)[9], const float (&t)[3
     oz = __fadd_rn(fmaf(z, r[8], fmaf(y, r[5], __fmul_rn(x, r[2]))), t[2]);
 }
 
+// [x y z 1] pose^T for the first three rows of a row-major 4x4 (m[0..11]); the flag column is carried through
+// (utils_helper.transform_points_batch, utils_helper.py:76-87)
+__device__ __forceinline__ float4 transform_row(const float (&m)[12], const float4& p) {
+    float4 o;
+    o.x = fmaf(1.0f, m[3], fmaf(p.z, m[2], fmaf(p.y, m[1], p.x * m[0])));
+    o.y = fmaf(1.0f, m[7], fmaf(p.z, m[6], fmaf(p.y, m[5], p.x * m[4])));
+    o.z = fmaf(1.0f, m[11], fmaf(p.z, m[10], fmaf(p.y, m[9], p.x * m[8])));
+    o.w = p.w;
+    return o;
+}
+
 // Brute-force NN of QB query points held in registers against dst[0, n_d): ties -> lowest index.
 template <int QB>
 __device__ __forceinline__ void nn_brute(const float4* __restrict__ dst, int n_d, const float (&qx)[QB],

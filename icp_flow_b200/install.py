@@ -1,0 +1,61 @@
+"""``install()`` swaps the reference's per-cluster-pair registration callables for the B200 engine.
+
+The reference pipeline (``utils_track.track`` -> ``utils_match.match_pcds`` -> ``match_pairs``) stays untouched;
+only the hot-path entry points are rebound, exactly at the seams SURVEY.md section 8b lists:
+
+    utils_match.hist_icp              <- icp_flow_b200.hist_icp            (sole caller: utils_match.py:92)
+    utils_hist.estimate_init_pose     <- icp_flow_b200.estimate_init_pose
+    utils_icp.apply_icp               <- icp_flow_b200.apply_icp
+    utils_icp.pytorch3d_icp           <- icp_flow_b200.pytorch3d_icp
+    utils_icp_pytorch3d.iterative_closest_point <- icp_flow_b200.iterative_closest_point
+    utils_helper.nearest_neighbor_batch / transform_points_batch (and the names re-imported by utils_match / utils_icp /
+    utils_hist) <- the engine's, used by match_eval on CUDA tensors
+
+``uninstall()`` restores the originals.  The reference modules must already be importable (``sys.path``).
+"""
+from __future__ import annotations
+
+import importlib
+import sys
+
+from . import ops
+
+_SAVED = {}
+
+_BINDINGS = (
+    ("utils_match", "hist_icp", ops.hist_icp),
+    ("utils_match", "estimate_init_pose", ops.estimate_init_pose),
+    ("utils_match", "apply_icp", ops.apply_icp),
+    ("utils_hist", "estimate_init_pose", ops.estimate_init_pose),
+    ("utils_icp", "apply_icp", ops.apply_icp),
+    ("utils_icp", "pytorch3d_icp", ops.pytorch3d_icp),
+    ("utils_icp", "iterative_closest_point", ops.iterative_closest_point),
+    ("utils_icp_pytorch3d", "iterative_closest_point", ops.iterative_closest_point),
+)
+
+_HELPERS = (
+    ("utils_helper", "nearest_neighbor_batch", ops.nearest_neighbor_batch),
+    ("utils_helper", "transform_points_batch", ops.transform_points_batch),
+    ("utils_match", "nearest_neighbor_batch", ops.nearest_neighbor_batch),
+    ("utils_match", "transform_points_batch", ops.transform_points_batch),
+)
+
+
+def install(patch_helpers: bool = False):
+    """Rebind the reference's hot-path callables.  ``patch_helpers`` also routes the NN / transform helpers that
+    ``match_eval`` calls (they require CUDA tensors)."""
+    todo = _BINDINGS + (_HELPERS if patch_helpers else ())
+    for mod_name, attr, fn in todo:
+        mod = sys.modules.get(mod_name) or importlib.import_module(mod_name)
+        if hasattr(mod, attr):
+            _SAVED.setdefault((mod_name, attr), getattr(mod, attr))
+            setattr(mod, attr, fn)
+    return sorted({m for m, _, _ in todo})
+
+
+def uninstall():
+    for (mod_name, attr), fn in list(_SAVED.items()):
+        mod = sys.modules.get(mod_name)
+        if mod is not None:
+            setattr(mod, attr, fn)
+        del _SAVED[(mod_name, attr)]

@@ -220,3 +220,163 @@ def host_kabsch(H: torch.Tensor) -> torch.Tensor:
     out = torch.empty_like(h)
     _lib.lib().icpf_host_kabsch(ctypes.c_void_p(h.data_ptr()), h.shape[0], ctypes.c_void_p(out.data_ptr()))
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Histogram initialisation, apply_icp and hist_icp: the remaining seams of the path (same signatures as the reference)
+# ----------------------------------------------------------------------------------------------------------------
+class _HistBins:
+    """Bin starts built exactly like utils_hist.py:60-65 (torch.arange in the default dtype) + the C struct."""
+
+    def __init__(self, thres_dist: float, translation_frame: float, device):
+        eps = 1e-8
+        f, tau = translation_frame, thres_dist
+        self.x = torch.arange(-f, f + tau - eps, tau, dtype=torch.float32).to(device)
+        self.y = torch.arange(-f, f + tau - eps, tau, dtype=torch.float32).to(device)
+        self.z = torch.arange(-tau, tau + tau - eps, tau, dtype=torch.float32).to(device)
+        lo = [float(self.x.min()), float(self.y.min()), float(self.z.min())]
+        hi = [float(self.x.max()), float(self.y.max()), float(self.z.max())]
+        self.lens = (len(self.x), len(self.y), len(self.z))
+        c = _lib.IcpfHistBins()
+        c.bins_x, c.bins_y, c.bins_z = self.x.data_ptr(), self.y.data_ptr(), self.z.data_ptr()
+        for k in range(3):
+            c.len[k] = self.lens[k]
+            c.min[k] = lo[k]
+            c.max[k] = hi[k]
+        c.half_bin = float(thres_dist // 2)        # utils_hist.py:78: python floor division
+        self.c = c
+
+
+_BINS_CACHE = {}
+
+
+def _hist_bins(thres_dist, translation_frame, device) -> _HistBins:
+    key = (float(thres_dist), float(translation_frame), str(device))
+    hb = _BINS_CACHE.get(key)
+    if hb is None:
+        if len(_BINS_CACHE) > 64:
+            _BINS_CACHE.clear()
+        hb = _BINS_CACHE[key] = _HistBins(float(thres_dist), float(translation_frame), device)
+    return hb
+
+
+def _workspace(P, N, lens, device):
+    need = _lib.lib().icpf_workspace_bytes(P, N, lens[0], lens[1], lens[2])
+    return torch.empty(max(int(need), 1), device=device, dtype=torch.uint8)
+
+
+def _check_pair_batch(src, dst):
+    src = _require_cuda_f32(src, "src")
+    dst = _require_cuda_f32(dst, "dst")
+    assert len(src) == len(dst)
+    if src.dim() != 3 or dst.dim() != 3 or src.shape[2] != 4 or dst.shape[2] != 4 or src.shape[1] != dst.shape[1]:
+        raise ValueError("src and dst must be [P, N, 4] (x, y, z, flag) padded to the same N")
+    return src, dst
+
+
+def hist(X, Y, min_x, min_y, min_z, max_x, max_y, max_z, len_x, len_y, len_z, mini_batch=8):
+    """Drop-in for ``hist_cuda.hist.hist`` (hist_cuda/hist.py:39-51): ``[B,len_x,len_y,len_z]`` fp32 vote counts of
+    ``X[b,i,:3] - Y[b,j,:3]`` over rows whose flags are both > 0.  ``mini_batch`` is accepted and ignored (the
+    reference needed it to keep its flat thread index inside an int)."""
+    if not X.is_contiguous() or not Y.is_contiguous():
+        raise RuntimeError("input tensor has to be contiguous")
+    if not X.is_cuda or not Y.is_cuda:
+        raise RuntimeError("input must be a CUDA tensor")
+    if X.size(0) != Y.size(0):
+        raise RuntimeError(f"batch_X ({X.size(0)}) != batch_Y ({Y.size(0)}).")
+    if X.size(2) != Y.size(2):
+        raise RuntimeError(f"dim_X ({X.size(2)}) != dim_Y ({Y.size(2)}).")
+    if X.size(2) != 4:
+        raise RuntimeError(f"dim ({X.size(2)}) != 4; 3 for (x, y, z); 1 for indicator,padded or not.")
+    X, Y = X.float(), Y.float()
+    B = X.size(0)
+    out = torch.empty(B, int(len_x), int(len_y), int(len_z), device=X.device, dtype=torch.float32)
+    mins = (ctypes.c_float * 3)(float(min_x), float(min_y), float(min_z))
+    maxs = (ctypes.c_float * 3)(float(max_x), float(max_y), float(max_z))
+    lens = (ctypes.c_int32 * 3)(int(len_x), int(len_y), int(len_z))
+    with torch.cuda.device(X.device):
+        code = _lib.lib().icpf_hist_votes_f32(_ptr(X), _ptr(Y), B, X.size(1), Y.size(1), mins, maxs, lens, _ptr(out),
+                                              _stream_ptr())
+    _lib.check(code, "icpf_hist_votes_f32")
+    return out
+
+
+def estimate_init_pose(args, src, dst, return_debug: bool = False, auto_swap: bool = False):
+    """Drop-in for ``utils_hist.estimate_init_pose(args, src, dst) -> [P,4,4]`` (reads ``args.thres_dist`` and
+    ``args.translation_frame``; ``args.chunk_size`` only bounded the reference's memory and is not needed)."""
+    src, dst = _check_pair_batch(src, dst)
+    P, N, _ = src.shape
+    dev = src.device
+    hb = _hist_bins(args.thres_dist, args.translation_frame, dev)
+    pose = torch.empty(P, 4, 4, device=dev, dtype=torch.float32)
+    dbg = None
+    if return_debug:
+        dbg = {"flat_idx": torch.empty(P, 5, device=dev, dtype=torch.int32),
+               "votes": torch.empty(P, 5, device=dev, dtype=torch.float32),
+               "scores": torch.empty(P, 6, device=dev, dtype=torch.float32),
+               "which": torch.empty(P, device=dev, dtype=torch.int32)}
+    ws = _workspace(P, N, hb.lens, dev)
+    with torch.cuda.device(dev):
+        code = _lib.lib().icpf_hist_init_f32(
+            _ptr(src), _ptr(dst), P, N, ctypes.byref(hb.c), int(auto_swap), _ptr(pose),
+            _ptr(dbg["flat_idx"]) if dbg else None, _ptr(dbg["votes"]) if dbg else None,
+            _ptr(dbg["scores"]) if dbg else None, _ptr(dbg["which"]) if dbg else None,
+            _ptr(ws), ws.numel(), _stream_ptr())
+    _lib.check(code, "icpf_hist_init_f32")
+    return (pose, dbg) if return_debug else pose
+
+
+def _path_params(args) -> _lib.IcpfParams:
+    # utils_icp.py:52-58: thres=args.thres_dist, max_iterations=100, relative_rmse_thr=1e-6
+    return make_params(thres=args.thres_dist, max_iterations=100, relative_rmse_thr=1e-6, early_exit=True,
+                       batch_stop=True)
+
+
+def apply_icp(args, src, dst, init_poses, return_debug: bool = False, auto_swap: bool = False):
+    """Drop-in for ``utils_icp.apply_icp(args, src, dst, init_poses) -> [P,4,4]``."""
+    src, dst = _check_pair_batch(src, dst)
+    init = _require_cuda_f32(init_poses, "init_poses")
+    P, N, _ = src.shape
+    dev = src.device
+    assert init.shape == (P, 4, 4)
+    out = torch.empty(P, 4, 4, device=dev, dtype=torch.float32)
+    err = torch.empty(P, 2, device=dev, dtype=torch.float32) if return_debug else None
+    flags = torch.empty(P, device=dev, dtype=torch.int32) if return_debug else None
+    batch = torch.empty(2, device=dev, dtype=torch.int32) if return_debug else None
+    ws = _workspace(P, N, (0, 0, 0), dev)
+    params = _path_params(args)
+    with torch.cuda.device(dev):
+        code = _lib.lib().icpf_apply_icp_f32(_ptr(src), _ptr(dst), _ptr(init), P, N, ctypes.byref(params),
+                                             int(auto_swap), _ptr(out), _ptr(err), _ptr(flags), _ptr(batch), _ptr(ws),
+                                             ws.numel(), _stream_ptr())
+    _lib.check(code, "icpf_apply_icp_f32")
+    if return_debug:
+        return out, {"errors": err, "flags": flags, "batch": batch}
+    return out
+
+
+def pytorch3d_icp(args, src, dst):
+    """Drop-in for ``utils_icp.pytorch3d_icp(args, src, dst) -> [P,4,4]`` (utils_icp.py:50-73)."""
+    src, dst = _check_pair_batch(src, dst)
+    return icp_batch(src, dst, _path_params(args)).pose
+
+
+def hist_icp(args, src, dst, return_debug: bool = False):
+    """Drop-in for ``utils_match.hist_icp(args, src, dst) -> [P,4,4]``: the whole per-cluster-pair path (swap so the
+    smaller cloud moves, histogram init, ICP with roll-back, un-swap) in one stream-ordered native call."""
+    src, dst = _check_pair_batch(src, dst)
+    P, N, _ = src.shape
+    dev = src.device
+    hb = _hist_bins(args.thres_dist, args.translation_frame, dev)
+    out = torch.empty(P, 4, 4, device=dev, dtype=torch.float32)
+    init = torch.empty(P, 4, 4, device=dev, dtype=torch.float32) if return_debug else None
+    batch = torch.empty(2, device=dev, dtype=torch.int32) if return_debug else None
+    ws = _workspace(P, N, hb.lens, dev)
+    params = _path_params(args)
+    with torch.cuda.device(dev):
+        code = _lib.lib().icpf_hist_icp_f32(_ptr(src), _ptr(dst), P, N, ctypes.byref(hb.c), ctypes.byref(params),
+                                            _ptr(out), _ptr(init), _ptr(batch), _ptr(ws), ws.numel(), _stream_ptr())
+    _lib.check(code, "icpf_hist_icp_f32")
+    if return_debug:
+        return out, {"init": init, "batch": batch}
+    return out

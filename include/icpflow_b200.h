@@ -48,6 +48,20 @@ typedef struct icpf_params {
     int32_t reserved[2];
 } icpf_params;
 
+/* Histogram geometry of the translation initialisation.  The reference builds the bin starts with torch.arange in
+ * the default dtype and passes bins.min() / bins.max() -- the LAST BIN START, not the upper edge -- to the vote
+ * kernel, then decodes the winning bins with bins[idx] (utils_hist.py:63-78); the shim therefore builds the three
+ * arrays with the same torch call and hands them over instead of recomputing edges in C. */
+typedef struct icpf_hist_bins {
+    const float* bins_x;      /* DEVICE [len[0]]  torch.arange(-F, F + tau - 1e-8, tau)                          */
+    const float* bins_y;      /* DEVICE [len[1]]                                                                 */
+    const float* bins_z;      /* DEVICE [len[2]]  torch.arange(-tau, 2 tau - 1e-8, tau)                          */
+    int32_t len[3];
+    float min[3];             /* bins.min()                                                                      */
+    float max[3];             /* bins.max()                                                                      */
+    float half_bin;           /* args.thres_dist // 2 (python floor division: 0.0 for tau = 0.1)                 */
+} icpf_hist_bins;
+
 int icpf_version(void);
 const char* icpf_error_string(int code);
 
@@ -89,6 +103,48 @@ int icpf_nn_f32(const float* src, const float* dst, int32_t B, int32_t Ns, int32
  * (utils_helper.py:76-87).  xyz [B,N,4], pose [B,16] row-major 4x4 (column-vector convention) -> out [B,N,4].
  */
 int icpf_transform_points_f32(const float* xyz, const float* pose, int32_t B, int32_t N, float* out, void* stream);
+
+/*
+ * All-pairs difference histogram -- bit-compatible replacement of HIST.hist (hist_cuda/cpp/hist.cpp:25-27,
+ * hist_cuda.cu:19-90, hist_cuda_core.cuh:23-64; python wrapper hist_cuda/hist.py:39-51).  Votes X_i - Y_j over rows
+ * whose flags are both > 0.  X [B,NX,4], Y [B,NY,4] -> bins [B,len_x,len_y,len_z] fp32 counts (zero-filled here).
+ * min/max/len are HOST arrays of 3.
+ */
+int icpf_hist_votes_f32(const float* X, const float* Y, int32_t B, int32_t NX, int32_t NY, const float* min_xyz,
+                        const float* max_xyz, const int32_t* len_xyz, float* bins, void* stream);
+
+/*
+ * Histogram-vote translation initialisation -- replaces utils_hist.estimate_init_pose (utils_hist.py:33-124): votes,
+ * 3-D NMS + top-5 (topk_nms, :21-29), candidate scoring by bidirectional mean NN distance, arg-min.
+ *   src, dst [P,N,4] -> out_pose [P,16] (identity rotation + best translation)
+ *   auto_swap 1: apply hist_icp's "smaller cloud is the moved one" rule per pair (utils_match.py:139-146)
+ *   optional diagnostics: out_cand [P,5] int32 flat bin indices, out_votes [P,5], out_scores [P,6], out_which [P] int32
+ *   workspace  icpf_workspace_bytes(P, N, len[0], len[1], len[2])
+ */
+int icpf_hist_init_f32(const float* src, const float* dst, int32_t P, int32_t N, const icpf_hist_bins* bins,
+                       int32_t auto_swap, float* out_pose, int32_t* out_cand, float* out_votes, float* out_scores,
+                       int32_t* out_which, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * ICP from an initial pose with roll-back -- replaces utils_icp.apply_icp / pytorch3d_icp (utils_icp.py:20-73):
+ * src' = init * src, ICP(src', dst), T = ICP o init, mean NN error before / after, T = init where it did not drop.
+ *   init_pose [P,16] -> out_pose [P,16]; out_err [P,2] {error_init, error_icp}, out_flags [P] int32 (bit 0 rolled
+ *   back, bit 1 swapped), out_batch [2] int32 (all optional).  With auto_swap = 1 the result of a swapped pair is
+ *   inverted like utils_match.py:152-154.   workspace  icpf_workspace_bytes(P, N, 0, 0, 0)
+ */
+int icpf_apply_icp_f32(const float* src, const float* dst, const float* init_pose, int32_t P, int32_t N,
+                       const icpf_params* params, int32_t auto_swap, float* out_pose, float* out_err,
+                       int32_t* out_flags, int32_t* out_batch, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * The whole per-cluster-pair path -- replaces utils_match.hist_icp (utils_match.py:138-157).
+ *   src, dst [P,N,4] -> out_pose [P,16] column-convention 4x4 transforms  p' = T[:3,:3] p + T[:3,3]
+ *   out_init [P,16] (may be NULL) the histogram initialisation in the swapped frame; out_batch [2] (may be NULL)
+ *   workspace  icpf_workspace_bytes(P, N, len[0], len[1], len[2])
+ */
+int icpf_hist_icp_f32(const float* src, const float* dst, int32_t P, int32_t N, const icpf_hist_bins* bins,
+                      const icpf_params* params, float* out_pose, float* out_init, int32_t* out_batch,
+                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* Measurement hook (bench.py): when both handles are non-NULL the next icpf_icp_f32 call on this host thread records
  * `start_event` / `stop_event` (cudaEvent_t) on its stream immediately around the launch of the dominant kernel

@@ -134,6 +134,19 @@ def topk_nms(x: torch.Tensor, k: int = 5, kernel_size: int = 11):
     return votes, idxs.long()
 
 
+def ambiguous_topk_rows(src: torch.Tensor, dst: torch.Tensor, p: PathParams) -> torch.Tensor:
+    """Pairs whose top-k peak SET is not determined by the reference: the k-th and (k+1)-th largest surviving vote
+    counts are equal, so which of the tied peaks ``torch.topk`` keeps is implementation-defined (CPU partial sort vs
+    CUDA radix select give different answers).  Diagnostics for the parity tests, not part of the reference."""
+    hist, _ = vote_histogram(src, dst, p)
+    b = hist.shape[0]
+    x5 = hist.unsqueeze(1)
+    pooled = torch.nn.functional.max_pool3d(x5, kernel_size=p.nms_kernel, stride=1, padding=(p.nms_kernel - 1) // 2)
+    kept = (x5 * (x5 == pooled).float()).view(b, -1)
+    top = torch.topk(kept, k=p.topk + 1, dim=1)[0]
+    return (top[:, p.topk] > 0) & (top[:, p.topk - 1] == top[:, p.topk])
+
+
 # ------------------------------------------------------------------------------------ histogram init
 def estimate_init_pose(src: torch.Tensor, dst: torch.Tensor, p: PathParams, return_debug: bool = False):
     """utils_hist.py:33-44 -- chunked driver around the per-chunk estimate."""
