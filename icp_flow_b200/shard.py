@@ -1,0 +1,54 @@
+"""Multi-GPU sharding of the per-cluster-pair path: pairs are independent units, so each rank registers a contiguous
+block of pairs and the 4x4 transforms (64 B per pair) are all-gathered -- the only collective of the path
+(SURVEY.md section 8e).  One process per GPU, ``torch.distributed`` (NCCL on GPUs; gloo works for the host logic)."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(num_pairs: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous block [lo, hi) of pairs owned by ``rank``; the first ``num_pairs % world_size`` ranks get one more."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError("invalid rank / world_size")
+    base, extra = divmod(int(num_pairs), world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def gather_transforms(local: torch.Tensor, num_pairs: int, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """All-gather the per-rank ``[p_local, 4, 4]`` transforms into ``[num_pairs, 4, 4]`` on every rank.
+
+    Shards may differ by one pair; every rank contributes a block padded to the largest shard (one fixed-size
+    ``all_gather_into_tensor`` over NVLink / NVSwitch, 64 B per pair) and the padding is dropped on arrival."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    lo, hi = shard_range(num_pairs, rank, world)
+    if local.shape[0] != hi - lo:
+        raise ValueError(f"rank {rank} owns pairs [{lo}, {hi}) but holds {local.shape[0]} transforms")
+    biggest = -(-int(num_pairs) // world)
+    send = local.reshape(hi - lo, 16)
+    if hi - lo < biggest:
+        send = torch.cat([send, send.new_zeros(biggest - (hi - lo), 16)], dim=0)
+    recv = send.new_empty(world * biggest, 16)
+    dist.all_gather_into_tensor(recv, send.contiguous(), group=group)
+    if num_pairs % world == 0:
+        return recv.view(num_pairs, 4, 4)
+    parts = []
+    for r in range(world):
+        rlo, rhi = shard_range(num_pairs, r, world)
+        parts.append(recv[r * biggest: r * biggest + (rhi - rlo)])
+    return torch.cat(parts, dim=0).view(num_pairs, 4, 4)
+
+
+def hist_icp_sharded(args, src: torch.Tensor, dst: torch.Tensor, group: Optional[dist.ProcessGroup] = None):
+    """``hist_icp`` over the pairs of ALL ranks: ``src`` / ``dst`` are this rank's shard (``shard_range``) of the
+    global padded batch; returns the transforms of every pair, ``[num_pairs, 4, 4]``, on every rank."""
+    from . import ops
+
+    counts = torch.tensor([src.shape[0]], device=src.device, dtype=torch.int64)
+    dist.all_reduce(counts, group=group)
+    local = ops.hist_icp(args, src, dst)
+    return gather_transforms(local, int(counts.item()), group)

@@ -1,0 +1,59 @@
+"""CPU, world_size 2 over gloo: the sharding / all-gather host logic of the multi-GPU path (no GPU compute)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from icp_flow_b200 import shard
+
+
+def test_shard_range_partitions_exactly():
+    for P in (0, 1, 7, 8, 1024, 32768 + 3):
+        for world in (1, 2, 3, 8):
+            spans = [shard.shard_range(P, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == P
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard.shard_range(8, 2, 2)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, num_pairs, ok):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = shard.shard_range(num_pairs, rank, world)
+        # transform of global pair i carries i in every entry
+        local = torch.arange(lo, hi, dtype=torch.float32)[:, None, None].expand(hi - lo, 4, 4).contiguous()
+        full = shard.gather_transforms(local, num_pairs)
+        want = torch.arange(num_pairs, dtype=torch.float32)[:, None, None].expand(num_pairs, 4, 4)
+        ok[rank] = int(full.shape == (num_pairs, 4, 4) and torch.equal(full, want))
+        with pytest.raises(ValueError):
+            shard.gather_transforms(local[:-1], num_pairs)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("num_pairs", [8, 11])
+def test_gather_transforms_world2_gloo(num_pairs):
+    world = 2
+    ctx = mp.get_context("spawn")
+    ok = ctx.Array("i", [0] * world)
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, num_pairs, ok)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert list(ok) == [1] * world
