@@ -380,3 +380,49 @@ def hist_icp(args, src, dst, return_debug: bool = False):
     if return_debug:
         return out, {"init": init, "batch": batch}
     return out
+
+
+class IcpHostPipeline:
+    """Host-buffer front end of the ICP stage: pinned host inputs -> H2D -> kernels -> D2H of the 4x4 transforms.
+
+    Steps are double-buffered: the H2D copy of step k+1 (copy stream) overlaps the kernels of step k (compute stream),
+    so a sequence of batches runs at max(PCIe, kernel) instead of their sum.  ``submit`` never blocks the host; call
+    ``synchronize`` (or wait on the returned event) before reading the output buffer.
+    """
+
+    def __init__(self, num_pairs: int, max_points: int, params: _lib.IcpfParams, device=None):
+        self.P, self.N, self.params = int(num_pairs), int(max_points), params
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        with torch.cuda.device(self.dev):
+            self.copy_stream = torch.cuda.Stream()
+            self.compute_stream = torch.cuda.Stream()
+            self.d_src = [torch.empty(self.P, self.N, 4, device=self.dev) for _ in range(2)]
+            self.d_dst = [torch.empty(self.P, self.N, 4, device=self.dev) for _ in range(2)]
+            self.copied = [torch.cuda.Event() for _ in range(2)]
+            self.consumed = [torch.cuda.Event() for _ in range(2)]
+            self.outs = [None, None]
+            self.ws = torch.empty(_lib.lib().icpf_workspace_bytes(self.P, self.N, 0, 0, 0), device=self.dev,
+                                  dtype=torch.uint8)
+        self.k = 0
+
+    def submit(self, host_src: torch.Tensor, host_dst: torch.Tensor, host_pose_out: torch.Tensor):
+        """host_src / host_dst: pinned ``[P,N,4]`` fp32; host_pose_out: pinned ``[P,4,4]`` fp32 (written async)."""
+        s = self.k & 1
+        with torch.cuda.device(self.dev):
+            with torch.cuda.stream(self.copy_stream):
+                if self.k >= 2:
+                    self.copy_stream.wait_event(self.consumed[s])       # the kernels of step k-2 released this slot
+                self.d_src[s].copy_(host_src, non_blocking=True)
+                self.d_dst[s].copy_(host_dst, non_blocking=True)
+                self.copied[s].record(self.copy_stream)
+            with torch.cuda.stream(self.compute_stream):
+                self.compute_stream.wait_event(self.copied[s])
+                self.outs[s] = icp_batch(self.d_src[s], self.d_dst[s], self.params, out=self.outs[s], workspace=self.ws)
+                self.consumed[s].record(self.compute_stream)
+                host_pose_out.copy_(self.outs[s].pose, non_blocking=True)
+        self.k += 1
+        return self.outs[s]
+
+    def synchronize(self):
+        self.copy_stream.synchronize()
+        self.compute_stream.synchronize()
