@@ -42,6 +42,17 @@ def algorithmic_bytes_per_pair_iter(n_s: int, n_d: int) -> int:
     return 16 * (n_s + n_d) + 64
 
 
+def load_ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "ncu_r1_metrics.json")
+    try:
+        with open(path) as f:
+            m = json.load(f)
+        return float(m["dram_bytes_read"]) + float(m["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -335,7 +346,7 @@ def main():
                     "steps": e2e_steps},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_kind": peak_kind, "kernel": "icp_pairs_kernel",
+                         "traffic": load_ncu_traffic(), "peak_kind": peak_kind, "kernel": "icp_pairs_kernel",
                          "kernel_ms": k_ms, "kernel_share_of_step": k_ms / (ms_total / args.steps),
                          "algorithmic_bytes_per_launch": alg_bytes},
             "nn_search": {"full_search_fraction": stats[0] / float(P * ICP_ITERS * N),
