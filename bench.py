@@ -191,6 +191,7 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nn-mode", type=int, default=0)
+    ap.add_argument("--cell-factor", type=int, default=0, help="tuning: grid cell size in 1/1000 of the gate radius")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
     if args.impl == "reference":
@@ -225,6 +226,7 @@ def main():
         dst_pool.append(torch.from_numpy(d).to(dev))
     params = ops.make_params(thres=THRES, max_iterations=ICP_ITERS, relative_rmse_thr=-1.0, early_exit=False,
                              batch_stop=True, nn_mode=args.nn_mode)
+    params.reserved[0] = args.cell_factor
     L = _lib.lib()
     ws = torch.empty(L.icpf_workspace_bytes(P, N, 0, 0, 0), device=dev, dtype=torch.uint8)
     out = None

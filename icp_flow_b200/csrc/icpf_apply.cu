@@ -23,7 +23,7 @@ struct FinalizeArgs {
 };
 
 // mean over the valid rows of S of the unbounded NN distance of (pose * S_i) among D[0, n_d)   (utils_icp.py:28-33)
-__device__ inline float mean_nn_error(const float (&m)[12], const float4* S, int n_s, const float4* D, int n_d,
+__device__ __forceinline__ float mean_nn_error(const float (&m)[12], const float4* S, int n_s, const float4* D, int n_d,
                                       float* scratch) {
     float sum[1] = {0.f};
     constexpr int QB = 4;
@@ -49,30 +49,29 @@ __device__ inline float mean_nn_error(const float (&m)[12], const float4* S, int
 }
 
 __global__ void __launch_bounds__(kThreads) icp_finalize_kernel(FinalizeArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int p = blockIdx.x, tid = threadIdx.x;
-    PairTiles tl = carve_pair_tiles<false>(smem_raw, a.N);
+    PairTiles tl = carve_pair_tiles<false>(a.N);
     if (tid == 0) {
-        mbar_init(tl.bar, 1);
+        mbar_init(tl.bar(), 1);
         fence_barrier_init();
     }
     __syncthreads();
     load_pair_tiles(tl, a.src + (size_t)p * a.N * 4, a.dst + (size_t)p * a.N * 4, a.N, 0);
     float cnt[2] = {0.f, 0.f};
     for (int q = tid; q < a.N; q += kThreads) {
-        cnt[0] += (tl.src[q].w > 0.f) ? 1.f : 0.f;
-        cnt[1] += (tl.dst[q].w > 0.f) ? 1.f : 0.f;
+        cnt[0] += (tl.src()[q].w > 0.f) ? 1.f : 0.f;
+        cnt[1] += (tl.dst()[q].w > 0.f) ? 1.f : 0.f;
     }
-    block_allreduce_sum<2, kWarps>(cnt, tl.red + kScrPart);
+    block_allreduce_sum<2, kWarps>(cnt, tl.red() + kScrPart);
     __syncthreads();
     int n_s = (int)cnt[0], n_d = (int)cnt[1];
-    const float4* S = tl.src;
-    const float4* D = tl.dst;
     const bool swapped = a.auto_swap && n_s > n_d;
     if (swapped) {
-        const float4* t = S; S = D; D = t;
+        tl.swap_clouds<false>();
         const int n = n_s; n_s = n_d; n_d = n;
     }
+    const float4* S = tl.src();
+    const float4* D = tl.dst();
     // M0 = init pose, Micp = [[R^T, T],[0,1]] (utils_icp.py:60-65), M = Micp * M0 (utils_icp.py:24)
     float m0[16], mi[16], mm[16];
 #pragma unroll
@@ -94,8 +93,8 @@ __global__ void __launch_bounds__(kThreads) icp_finalize_kernel(FinalizeArgs a) 
     float a0[12], a1[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) { a0[i] = m0[i]; a1[i] = mm[i]; }
-    const float e0 = __fdiv_rn(mean_nn_error(a0, S, n_s, D, n_d, tl.red + kScrPart), (float)n_s);
-    const float e1 = __fdiv_rn(mean_nn_error(a1, S, n_s, D, n_d, tl.red + kScrPart), (float)n_s);
+    const float e0 = __fdiv_rn(mean_nn_error(a0, S, n_s, D, n_d, tl.red() + kScrPart), (float)n_s);
+    const float e1 = __fdiv_rn(mean_nn_error(a1, S, n_s, D, n_d, tl.red() + kScrPart), (float)n_s);
     if (tid == 0) {
         const bool rolled = e1 >= e0;          // utils_icp.py:34-35 (NaN compares false: keep the ICP result)
         float out[16];

@@ -238,14 +238,13 @@ struct ScoreArgs {
 };
 
 __global__ void __launch_bounds__(kThreads) hist_score_kernel(ScoreArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ float s_t[kCand][3];
     __shared__ float s_sum[2][kCand];
     __shared__ float s_part[kWarps][2][kCand];
     const int p = blockIdx.x, tid = threadIdx.x;
-    PairTiles tl = carve_pair_tiles<false>(smem_raw, a.N);
+    PairTiles tl = carve_pair_tiles<false>(a.N);
     if (tid == 0) {
-        mbar_init(tl.bar, 1);
+        mbar_init(tl.bar(), 1);
         fence_barrier_init();
     }
     if (tid < 2 * kCand) s_sum[tid / kCand][tid % kCand] = 0.f;
@@ -253,17 +252,17 @@ __global__ void __launch_bounds__(kThreads) hist_score_kernel(ScoreArgs a) {
     load_pair_tiles(tl, a.src + (size_t)p * a.N * 4, a.dst + (size_t)p * a.N * 4, a.N, 0);
     float cnt[2] = {0.f, 0.f};
     for (int q = tid; q < a.N; q += kThreads) {
-        cnt[0] += (tl.src[q].w > 0.f) ? 1.f : 0.f;
-        cnt[1] += (tl.dst[q].w > 0.f) ? 1.f : 0.f;
+        cnt[0] += (tl.src()[q].w > 0.f) ? 1.f : 0.f;
+        cnt[1] += (tl.dst()[q].w > 0.f) ? 1.f : 0.f;
     }
-    block_allreduce_sum<2, kWarps>(cnt, tl.red + kScrPart);
+    block_allreduce_sum<2, kWarps>(cnt, tl.red() + kScrPart);
     int n_s = (int)cnt[0], n_d = (int)cnt[1];
-    const float4* S = tl.src;
-    const float4* D = tl.dst;
     if (a.auto_swap && n_s > n_d) {     // always register the smaller cloud onto the larger one (utils_match.py:139-146)
-        const float4* t = S; S = D; D = t;
+        tl.swap_clouds<false>();
         const int n = n_s; n_s = n_d; n_d = n;
     }
+    const float4* S = tl.src();
+    const float4* D = tl.dst();
     if (tid < kCand) {
         float tx = 0.f, ty = 0.f, tz = 0.f;
         if (tid < kTopK) {

@@ -22,6 +22,7 @@ struct IcpArgs {
     int P, N;
     float tau;             // fp32(thres)
     float tau2;            // fp32(thres^2)
+    float cell_factor;     // grid cell size in units of the padded gate radius
     int max_it;
     float rel_thr;
     int early_exit;
@@ -37,7 +38,6 @@ struct IcpArgs {
 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 7) icp_pairs_kernel(IcpArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int p = blockIdx.x;
     int max_it = a.max_it;
     bool early_exit = a.early_exit != 0;
@@ -49,9 +49,9 @@ __global__ void __launch_bounds__(kThreads, 7) icp_pairs_kernel(IcpArgs a) {
         early_exit = false;
     }
     constexpr bool GRID = MODE >= 2;
-    PairTiles tl = carve_pair_tiles<GRID>(smem_raw, a.N);
+    PairTiles tl = carve_pair_tiles<GRID>(a.N);
     if (threadIdx.x == 0) {
-        mbar_init(tl.bar, 1);
+        mbar_init(tl.bar(), 1);
         fence_barrier_init();
     }
     __syncthreads();
@@ -60,46 +60,44 @@ __global__ void __launch_bounds__(kThreads, 7) icp_pairs_kernel(IcpArgs a) {
     // valid-row counts (knn `lengths`): number of rows with flag > 0  (utils_icp_pytorch3d.py:109-112)
     float cnt[2] = {0.f, 0.f};
     for (int q = threadIdx.x; q < a.N; q += kThreads) {
-        cnt[0] += (tl.src[q].w > 0.f) ? 1.f : 0.f;
-        cnt[1] += (tl.dst[q].w > 0.f) ? 1.f : 0.f;
+        cnt[0] += (tl.src()[q].w > 0.f) ? 1.f : 0.f;
+        cnt[1] += (tl.dst()[q].w > 0.f) ? 1.f : 0.f;
     }
-    block_allreduce_sum<2, kWarps>(cnt, tl.red + kScrPart);
+    block_allreduce_sum<2, kWarps>(cnt, tl.red() + kScrPart);
     int n_s = (int)cnt[0], n_d = (int)cnt[1];
     if (a.auto_swap && n_s > n_d) {
-        float4* t = tl.src; tl.src = tl.dst; tl.dst = t;
+        tl.swap_clouds<GRID>();
         const int n = n_s; n_s = n_d; n_d = n;
-        if (GRID) tl.nn = reinterpret_cast<unsigned int*>(tl.dst);
-        else tl.sorted = tl.dst;
     }
-    const float4 piv = tl.dst[0];      // first pivot of the moment sums: any point of the fixed cloud
+    const float4 piv = tl.dst()[0];      // first pivot of the moment sums: any point of the fixed cloud
     __syncthreads();                   // scratch and the raw dst rows are reused below
     if (a.init_pose != nullptr) {
         // src' = [x y z 1] pose^T with the flag carried through (utils_helper.py:76-87)
-        if (threadIdx.x < 12) tl.bcast[threadIdx.x] = a.init_pose[(size_t)p * 16 + threadIdx.x];
+        if (threadIdx.x < 12) tl.bcast()[threadIdx.x] = a.init_pose[(size_t)p * 16 + threadIdx.x];
         __syncthreads();
         float m[12];
 #pragma unroll
-        for (int i = 0; i < 12; ++i) m[i] = tl.bcast[i];
-        for (int q = threadIdx.x; q < n_s; q += kThreads) tl.src[q] = transform_row(m, tl.src[q]);
+        for (int i = 0; i < 12; ++i) m[i] = tl.bcast()[i];
+        for (int q = threadIdx.x; q < n_s; q += kThreads) tl.src()[q] = transform_row(m, tl.src()[q]);
         __syncthreads();
     }
 
     GridInfo g;
-    if (GRID && n_s > 0 && n_d > 0) g = build_grid(tl, n_d, a.tau);
+    if (GRID && n_s > 0 && n_d > 0) g = build_grid(tl, n_d, a.tau, a.cell_factor);
     const IcpResult r = icp_iterations<MODE>(tl, g, n_s, n_d, a.tau2, max_it, a.rel_thr, early_exit,
                                        a.init_R ? a.init_R + (size_t)p * 9 : nullptr,
                                        a.init_T ? a.init_T + (size_t)p * 3 : nullptr, piv.x, piv.y, piv.z);
 
     // the final (R, T) also sit in the broadcast block (no dynamic register indexing)
-    if (threadIdx.x < 9) a.out_R[(size_t)p * 9 + threadIdx.x] = tl.bcast[B_R + threadIdx.x];
-    if (threadIdx.x < 3) a.out_T[(size_t)p * 3 + threadIdx.x] = tl.bcast[B_T + threadIdx.x];
+    if (threadIdx.x < 9) a.out_R[(size_t)p * 9 + threadIdx.x] = tl.bcast()[B_R + threadIdx.x];
+    if (threadIdx.x < 3) a.out_T[(size_t)p * 3 + threadIdx.x] = tl.bcast()[B_T + threadIdx.x];
     if (a.out_pose && threadIdx.x < 16) {
         // column-convention 4x4 [[R^T, T],[0,1]]  (utils_icp.py:60-65)
         const int row = threadIdx.x >> 2, col = threadIdx.x & 3;
         float v;
         if (row == 3) v = (col == 3) ? 1.f : 0.f;
-        else if (col == 3) v = tl.bcast[B_T + row];
-        else v = tl.bcast[B_R + col * 3 + row];
+        else if (col == 3) v = tl.bcast()[B_T + row];
+        else v = tl.bcast()[B_R + col * 3 + row];
         a.out_pose[(size_t)p * 16 + threadIdx.x] = v;
     }
     if (threadIdx.x == 0) {
@@ -189,6 +187,7 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
     a.init_pose = init_pose; a.auto_swap = auto_swap;
     a.tau = (float)prm.thres_dist;
     a.tau2 = (float)(prm.thres_dist * prm.thres_dist);   // python: thres**2 in double, compared in fp32
+    a.cell_factor = prm.reserved[0] > 0 ? (float)prm.reserved[0] * 1e-3f : kCellFactor;
     a.max_it = prm.max_iterations;
     a.rel_thr = prm.relative_rmse_thr;
     a.early_exit = prm.early_exit;

@@ -96,7 +96,7 @@ __device__ __forceinline__ float moved_sq(const float (&dr)[9], const float (&dt
 }
 
 // The ICP loop for the pair held in `tl`.
-//   MODE 1: candidates = tl.dst, brute force.  MODE 2: candidates = tl.sorted + grid `g` (build_grid must have run).
+//   MODE 1: candidates = tl.dst(), brute force.  MODE 2: candidates = tl.sorted() + grid `g` (build_grid must have run).
 //   MODE 3: grid + correspondence cache.  A row whose cached best candidate is provably still its strict nearest
 //           neighbour skips the search: with m the distance the row moved since the cache reference and B the cached
 //           lower bound on the distance of every other point, (d_best + m) < B implies every other point is farther
@@ -105,19 +105,19 @@ __device__ __forceinline__ float moved_sq(const float (&dr)[9], const float (&dt
 //   n_s / n_d : valid-row counts (knn `lengths`); tau2 = fp32(thres^2); pivot0 = any point near the clouds
 //   init_R / init_T (may be NULL) = init_transform of the reference: used for the first correspondence search only.
 template <int MODE>
-__device__ inline IcpResult icp_iterations(const PairTiles& tl, const GridInfo& g, int n_s, int n_d, float tau2,
+__device__ __forceinline__ IcpResult icp_iterations(const PairTiles& tl, const GridInfo& g, int n_s, int n_d, float tau2,
                                            int max_it, float rel_thr, bool early_exit, const float* init_R,
                                            const float* init_T, float pivx, float pivy, float pivz) {
     constexpr bool GRID = MODE >= 2;
     constexpr bool CACHE = MODE == 3;
     const float INF = __int_as_float(0x7f800000);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float4* __restrict__ cand = GRID ? tl.sorted : tl.dst;
-    const unsigned short* cell_runs = reinterpret_cast<const unsigned short*>(tl.cells);
-    unsigned int* __restrict__ nnw = tl.nn;
-    float* part = tl.red + kScrPart;
-    float* total = tl.red + kScrTotal;
-    float* bc = tl.bcast;
+    const float4* __restrict__ cand = GRID ? tl.sorted() : tl.dst();
+    const unsigned short* cell_runs = reinterpret_cast<const unsigned short*>(tl.cells());
+    unsigned int* __restrict__ nnw = tl.nn();
+    float* part = tl.red() + kScrPart;
+    float* total = tl.red() + kScrTotal;
+    float* bc = tl.bcast();
     const float tau_hi = sqrtf(tau2) * 1.0001f + 1e-6f;
     const int nbatch = (n_s + kThreads - 1) / kThreads;     // row q = b * kThreads + tid
 
@@ -159,7 +159,7 @@ __device__ inline IcpResult icp_iterations(const PairTiles& tl, const GridInfo& 
         }
         float sq = 0.f;
         int ndefer = 0;
-        unsigned short* mylist = GRID ? tl.defer + warp * tl.defer_cap : nullptr;
+        unsigned short* mylist = GRID ? tl.defer() + warp * tl.defer_cap : nullptr;
 
         // ---------------- pass A: rmse numerator of the previous iteration + correspondence search of this one
         if (MODE == 1) {
@@ -172,7 +172,7 @@ __device__ inline IcpResult icp_iterations(const PairTiles& tl, const GridInfo& 
                 for (int k = 0; k < QB; ++k) {
                     const int q = (b0 + k) * kThreads + tid;
                     const bool valid = q < n_s;
-                    x0[k] = valid ? tl.src[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    x0[k] = valid ? tl.src()[q] : make_float4(0.f, 0.f, 0.f, 0.f);
                     apply_rt(R, T, x0[k].x, x0[k].y, x0[k].z, qx[k], qy[k], qz[k]);
                     const unsigned int wold = (it > 0 && valid) ? nnw[q] : (kNnMasked | kNnNone);
                     if (!(wold & kNnMasked)) {
@@ -191,7 +191,7 @@ __device__ inline IcpResult icp_iterations(const PairTiles& tl, const GridInfo& 
             for (int b = 0; b < nbatch; ++b) {
                 const int q = b * kThreads + tid;
                 const bool valid = q < n_s;
-                const float4 x0 = valid ? tl.src[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 x0 = valid ? tl.src()[q] : make_float4(0.f, 0.f, 0.f, 0.f);
                 float qx, qy, qz;
                 apply_rt(R, T, x0.x, x0.y, x0.z, qx, qy, qz);
                 const unsigned int wold = (it > 0 && valid) ? nnw[q] : (kNnMasked | kNnNone);
@@ -233,7 +233,7 @@ __device__ inline IcpResult icp_iterations(const PairTiles& tl, const GridInfo& 
                 __syncwarp();
                 for (int i = lane; i < ndefer; i += 32) {
                     const int q = mylist[i];
-                    const float4 x0 = tl.src[q];
+                    const float4 x0 = tl.src()[q];
                     float qx, qy, qz, d2, d2nd, box;
                     int pos;
                     apply_rt(R, T, x0.x, x0.y, x0.z, qx, qy, qz);
@@ -257,7 +257,7 @@ __device__ inline IcpResult icp_iterations(const PairTiles& tl, const GridInfo& 
                 const int q = b * kThreads + tid;
                 const unsigned int w = (q < n_s) ? nnw[q] : kNnMasked;
                 if (w & kNnMasked) continue;
-                const float4 x = tl.src[q];
+                const float4 x = tl.src()[q];
                 const float4 y = cand[w & 0xffffu];
                 const float ax = x.x - px, ay = x.y - py, az = x.z - pz;
                 const float bx = y.x - ux, by = y.y - uy, bz = y.z - uz;
@@ -356,7 +356,7 @@ __device__ inline IcpResult icp_iterations(const PairTiles& tl, const GridInfo& 
             const int q = b * kThreads + tid;
             const unsigned int w = (q < n_s) ? nnw[q] : kNnMasked;
             if (w & kNnMasked) continue;
-            const float4 x = tl.src[q];
+            const float4 x = tl.src()[q];
             const float4 c = cand[w & 0xffffu];
             float qx, qy, qz;
             apply_rt(res.r, res.t, x.x, x.y, x.z, qx, qy, qz);

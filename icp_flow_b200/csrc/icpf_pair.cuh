@@ -40,56 +40,68 @@ constexpr int kCellWords = (kGridMaxCells + 2 + 1) / 2 + 2;   // packed u16 entr
 // broadcast block written by thread 0 once per iteration
 enum : int { B_R = 0, B_T = 9, B_RC = 12, B_TC = 21, B_PX = 24, B_PY = 27, B_EXIT = 30, B_REFRESH = 31 };
 
-// Shared-memory carve-up for one pair (all offsets 16-byte aligned).
+// Dynamic shared memory of every pair kernel.  Tiles are addressed as OFFSETS into this one array so that the
+// compiler always knows the address space (a run-time swap of two pointers degrades every access to a generic LD/ST).
+extern __shared__ __align__(128) float4 g_tile[];
+
+// Shared-memory carve-up for one pair (float4 / 16-byte units unless noted).
 struct PairTiles {
-    float4* src;            // [N]  (x,y,z,flag) -- the cloud being moved (initial coordinates X0)
-    float4* dst;            // [N]  (x,y,z,flag) -- the fixed cloud as stored (TMA landing zone)
-    float4* sorted;         // [N]  grid mode: dst rows in cell order, .w = (original row << 16 | sorted position)
-    uint32_t* cells;        // [kCellWords] grid mode: packed u16 run boundaries; run of cell i = [a[i], a[i+1])
-    unsigned int* nn;       // [N]  correspondence word of each src row (see pack_nn)
-    unsigned short* defer;  // [kWarps][defer_cap] grid mode: per-warp lists of rows whose cached neighbour failed
+    int src_off;      // [N] float4 (x,y,z,flag) -- the cloud being moved (initial coordinates X0)
+    int dst_off;      // [N] float4 (x,y,z,flag) -- the fixed cloud as stored (TMA landing zone)
+    int sorted_off;   // [N] float4 grid mode: dst rows in cell order, .w = (original row << 16 | sorted position)
+    int cells_off;    // [kCellWords] u32 grid mode: packed u16 run boundaries; run of cell i = [a[i], a[i+1])
+    int nn_off;       // [N] u32 correspondence word of each src row (see pack_nn)
+    int defer_off;    // [kWarps][defer_cap] u16 grid mode: per-warp lists of rows whose cached neighbour failed
     int defer_cap;
-    float* red;             // [kRedFloats] reduction scratch
-    float* bcast;           // [kBcastFloats] R, T, cache reference, pivots, flags
-    uint64_t* bar;          // TMA mbarrier
+    int red_off;      // [kRedFloats] float reduction scratch
+    __device__ __forceinline__ float4* src() const { return g_tile + src_off; }
+    __device__ __forceinline__ float4* dst() const { return g_tile + dst_off; }
+    __device__ __forceinline__ float4* sorted() const { return g_tile + sorted_off; }
+    __device__ __forceinline__ uint32_t* cells() const { return reinterpret_cast<uint32_t*>(g_tile + cells_off); }
+    __device__ __forceinline__ unsigned int* nn() const { return reinterpret_cast<unsigned int*>(g_tile + nn_off); }
+    __device__ __forceinline__ unsigned short* defer() const { return reinterpret_cast<unsigned short*>(g_tile + defer_off); }
+    __device__ __forceinline__ float* red() const { return reinterpret_cast<float*>(g_tile + red_off); }
+    __device__ __forceinline__ float* bcast() const { return red() + kRedFloats; }
+    __device__ __forceinline__ uint64_t* bar() const { return reinterpret_cast<uint64_t*>(bcast() + kBcastFloats); }
+    // the smaller cloud is the moved one (utils_match.py:139-146): exchange the roles of the two staged tiles
+    template <bool GRID>
+    __device__ __forceinline__ void swap_clouds() {
+        const int t = src_off; src_off = dst_off; dst_off = t;
+        if (GRID) nn_off = dst_off;      // the correspondence words alias the raw rows of the (new) fixed cloud
+        else sorted_off = dst_off;
+    }
 };
 
 __host__ __device__ inline int pair_defer_cap(int N) { return (N + kThreads - 1) / kThreads * 32; }
+__host__ __device__ inline int up16(int bytes) { return (bytes + 15) / 16; }
 
 __host__ __device__ inline size_t pair_smem_bytes(int N, bool grid) {
-    size_t b = (size_t)N * 16 * 2;                                        // src + dst
-    if (grid) b += (size_t)N * 16 + (size_t)kCellWords * 4 + (size_t)pair_defer_cap(N) * kWarps * 2;
-    else b += (size_t)N * 4;                                              // nn (grid mode: nn aliases the raw dst rows)
-    b = (b + 15) / 16 * 16;
-    return b + (size_t)(kRedFloats + kBcastFloats) * 4 + 16;
+    int u = 2 * N;                                                        // src + dst
+    if (grid) u += N + up16(kCellWords * 4) + up16(pair_defer_cap(N) * kWarps * 2);
+    else u += up16(N * 4);                                                // nn (grid mode: nn aliases the raw dst rows)
+    u += up16((kRedFloats + kBcastFloats) * 4 + 16);
+    return (size_t)u * 16;
 }
 
 template <bool GRID>
-__device__ __forceinline__ PairTiles carve_pair_tiles(unsigned char* base, int N) {
+__device__ __forceinline__ PairTiles carve_pair_tiles(int N) {
     PairTiles t;
-    t.src = reinterpret_cast<float4*>(base);
-    t.dst = t.src + N;
-    unsigned char* p = reinterpret_cast<unsigned char*>(t.dst + N);
+    t.src_off = 0;
+    t.dst_off = N;
+    int u = 2 * N;
     t.defer_cap = pair_defer_cap(N);
     if (GRID) {
-        t.sorted = reinterpret_cast<float4*>(p);
-        p += (size_t)N * 16;
-        t.cells = reinterpret_cast<uint32_t*>(p);
-        p += (size_t)kCellWords * 4;
-        t.defer = reinterpret_cast<unsigned short*>(p);
-        p += (size_t)t.defer_cap * kWarps * 2;
-        t.nn = reinterpret_cast<unsigned int*>(t.dst);      // the raw dst rows are dead once the grid is built
+        t.sorted_off = u; u += N;
+        t.cells_off = u; u += up16(kCellWords * 4);
+        t.defer_off = u; u += up16(t.defer_cap * kWarps * 2);
+        t.nn_off = t.dst_off;              // the raw dst rows are dead once the grid is built
     } else {
-        t.sorted = t.dst;
-        t.cells = nullptr;
-        t.defer = nullptr;
-        t.nn = reinterpret_cast<unsigned int*>(p);
-        p += (size_t)N * 4;
+        t.sorted_off = t.dst_off;
+        t.cells_off = 0;
+        t.defer_off = 0;
+        t.nn_off = u; u += up16(N * 4);
     }
-    p = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15));
-    t.red = reinterpret_cast<float*>(p);
-    t.bcast = t.red + kRedFloats;
-    t.bar = reinterpret_cast<uint64_t*>(t.bcast + kBcastFloats);
+    t.red_off = u;
     return t;
 }
 
@@ -99,11 +111,11 @@ __device__ __forceinline__ void load_pair_tiles(const PairTiles& t, const float*
                                                 uint32_t phase) {
     if (threadIdx.x == 0) {
         const uint32_t bytes = (uint32_t)N * 16u;
-        mbar_arrive_expect_tx(t.bar, 2u * bytes);
-        tma_load_1d(t.src, src_rows, bytes, t.bar);
-        tma_load_1d(t.dst, dst_rows, bytes, t.bar);
+        mbar_arrive_expect_tx(t.bar(), 2u * bytes);
+        tma_load_1d(t.src(), src_rows, bytes, t.bar());
+        tma_load_1d(t.dst(), dst_rows, bytes, t.bar());
     }
-    mbar_wait(t.bar, phase);
+    mbar_wait(t.bar(), phase);
 }
 
 // squared L2 exactly as the pinned oracle computes it: d = dx*dx; d += dy*dy; d += dz*dz  (no FMA contraction)
@@ -172,14 +184,14 @@ __device__ __forceinline__ int grid_cell(const GridInfo& g, float x, float y, fl
     return (ix * g.gy + iy) * g.gz + iz;
 }
 
-// Counting sort of dst[0, n_d) into tl.sorted by cell; fills the run boundaries in tl.cells.  All threads return the
+// Counting sort of dst[0, n_d) into tl.sorted() by cell; fills the run boundaries in tl.cells().  All threads return the
 // same GridInfo.  Uses the reduction scratch; ends with a block barrier.
-__device__ inline GridInfo build_grid(const PairTiles& tl, int n_d, float tau) {
+__device__ __forceinline__ GridInfo build_grid(const PairTiles& tl, int n_d, float tau, float cell_factor = kCellFactor) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float INF = __int_as_float(0x7f800000);
     float lo[3] = {INF, INF, INF}, hi[3] = {-INF, -INF, -INF};
     for (int j = tid; j < n_d; j += kThreads) {
-        const float4 p = tl.dst[j];
+        const float4 p = tl.dst()[j];
         lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
         hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
     }
@@ -191,7 +203,7 @@ __device__ inline GridInfo build_grid(const PairTiles& tl, int n_d, float tau) {
             hi[k] = fmaxf(hi[k], __shfl_xor_sync(FULL_MASK, hi[k], o));
         }
     }
-    float* scr = tl.red + kScrPart;
+    float* scr = tl.red() + kScrPart;
     if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -222,7 +234,7 @@ __device__ inline GridInfo build_grid(const PairTiles& tl, int n_d, float tau) {
                 ez = fminf(fmaxf(hi[2] - lo[2], 0.f), 1e6f);
     // cells of kCellFactor*tau: a query then overlaps <= 2 cells per axis while everything it does NOT inspect is at
     // least 0.4995 cells (~1.25 tau) away -- the head-room the correspondence cache needs to prove "still masked"
-    float c = kCellFactor * tau_pad;
+    float c = fmaxf(cell_factor, 2.002f) * tau_pad;
     g.gx = g.gy = g.gz = 1;
     bool fits = false;
     for (int k = 0; k < 40 && !fits; ++k) {
@@ -237,12 +249,12 @@ __device__ inline GridInfo build_grid(const PairTiles& tl, int n_d, float tau) {
     g.r = 0.4995f;   // >= tau_pad / c because c >= 2.002 * tau_pad
     const int G = g.gx * g.gy * g.gz;
 
-    uint32_t* w = tl.cells;
+    uint32_t* w = tl.cells();
     for (int i = tid; i < kCellWords; i += kThreads) w[i] = 0u;
     __syncthreads();
     // counts: entry e = cell + 1 (u16 halves of u32 words; a count never exceeds n_d < 65536 so halves do not carry)
     for (int j = tid; j < n_d; j += kThreads) {
-        const float4 p = tl.dst[j];
+        const float4 p = tl.dst()[j];
         const int e = grid_cell(g, p.x, p.y, p.z) + 1;
         atomicAdd(&w[e >> 1], 1u << ((e & 1) * 16));
     }
@@ -259,7 +271,7 @@ __device__ inline GridInfo build_grid(const PairTiles& tl, int n_d, float tau) {
         const unsigned int v = __shfl_up_sync(FULL_MASK, incl, o);
         if (lane >= o) incl += v;
     }
-    unsigned int* wtot = reinterpret_cast<unsigned int*>(tl.red + kScrPart) + 32;   // beyond the min/max scratch
+    unsigned int* wtot = reinterpret_cast<unsigned int*>(tl.red() + kScrPart) + 32;   // beyond the min/max scratch
     if (lane == 31) wtot[warp] = incl;
     __syncthreads();
     unsigned int run = incl - local;
@@ -272,13 +284,13 @@ __device__ inline GridInfo build_grid(const PairTiles& tl, int n_d, float tau) {
     __syncthreads();
     // scatter: the atomic turns "first position" into "one past the last", i.e. the first position of the next cell
     for (int j = tid; j < n_d; j += kThreads) {
-        const float4 p = tl.dst[j];
+        const float4 p = tl.dst()[j];
         const int e = grid_cell(g, p.x, p.y, p.z) + 1;
         const int sh = (e & 1) * 16;
         const unsigned int old = atomicAdd(&w[e >> 1], 1u << sh);
         const unsigned int pos = (old >> sh) & 0xffffu;
         // .w = (original row << 16) | sorted position: the low word of the 64-bit ranking key (d^2 bits, row, position)
-        tl.sorted[pos] = make_float4(p.x, p.y, p.z, __uint_as_float(((unsigned int)j << 16) | pos));
+        tl.sorted()[pos] = make_float4(p.x, p.y, p.z, __uint_as_float(((unsigned int)j << 16) | pos));
     }
     __syncthreads();
     return g;

@@ -45,7 +45,7 @@ typedef struct icpf_params {
                                  relative-RMSE test; 0: each pair independent (max_iterations / fixed point)   */
     int32_t nn_mode;          /* 0 auto (= 3 when the tiles fit), 1 brute force, 2 uniform grid (radius-bounded),
                                  3 grid + correspondence cache; all modes are result-identical                 */
-    int32_t reserved[2];
+    int32_t reserved[2];      /* [0]: tuning knob, grid cell size in 1/1000 of the gate radius (0 = default)     */
 } icpf_params;
 
 /* Histogram geometry of the translation initialisation.  The reference builds the bin starts with torch.arange in
