@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libicpflow_b200.so")
 EXPORTS = (
     "icpf_version", "icpf_error_string", "icpf_default_params", "icpf_workspace_bytes",
     "icpf_icp_f32", "icpf_nn_f32", "icpf_transform_points_f32", "icpf_host_kabsch", "icpf_profile_next_icp",
-    "icpf_hist_votes_f32", "icpf_hist_init_f32", "icpf_apply_icp_f32", "icpf_hist_icp_f32",
+    "icpf_host_kabsch_sequence", "icpf_hist_votes_f32", "icpf_hist_init_f32", "icpf_apply_icp_f32", "icpf_hist_icp_f32",
 )
 
 
@@ -99,6 +99,8 @@ def lib() -> ctypes.CDLL:
     L.icpf_profile_next_icp.argtypes = [vp, vp]
     L.icpf_host_kabsch.restype = None
     L.icpf_host_kabsch.argtypes = [vp, i32, vp]
+    L.icpf_host_kabsch_sequence.restype = None
+    L.icpf_host_kabsch_sequence.argtypes = [vp, i32, vp]
     _LIB = L
     return L
 

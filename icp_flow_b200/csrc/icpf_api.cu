@@ -152,6 +152,17 @@ void icpf_profile_next_icp(void* start_event, void* stop_event) {
     set_profile_events(static_cast<cudaEvent_t>(start_event), static_cast<cudaEvent_t>(stop_event));
 }
 
+void icpf_host_kabsch_sequence(const float* H, int32_t n, float* R) {
+    KabschState st;
+    st.warm = false;
+    for (int32_t i = 0; i < n; ++i) {
+        float h[9];
+        for (int k = 0; k < 9; ++k) h[k] = H[9 * i + k];
+        const Rot3 r = kabsch_rotation(h, &st);
+        for (int k = 0; k < 9; ++k) R[9 * i + k] = r.r[k];
+    }
+}
+
 void icpf_host_kabsch(const float* H, int32_t n, float* R) {
     for (int32_t i = 0; i < n; ++i) {
         float h[9];

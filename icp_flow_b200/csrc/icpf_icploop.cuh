@@ -136,6 +136,7 @@ __device__ __forceinline__ IcpResult icp_iterations(const PairTiles& tl, const G
         bc[B_PY] = pivx; bc[B_PY + 1] = pivy; bc[B_PY + 2] = pivz;
         bc[B_EXIT] = 0.f;
         bc[B_REFRESH] = 1.f;
+        reinterpret_cast<KabschState*>(bc + B_KABSCH)->warm = false;     // first solve of this pair starts cold
     }
     __syncthreads();
     if (tid < 12) bc[B_RC + tid] = bc[B_R + tid];      // cache reference = the transform of the first search
@@ -300,7 +301,7 @@ __device__ __forceinline__ IcpResult icp_iterations(const PairTiles& tl, const G
                 h[4] = __fdiv_rn(fmaf(-sx1, my1, total[11]), W); h[5] = __fdiv_rn(fmaf(-sx1, my2, total[12]), W);
                 h[6] = __fdiv_rn(fmaf(-sx2, my0, total[13]), W); h[7] = __fdiv_rn(fmaf(-sx2, my1, total[14]), W);
                 h[8] = __fdiv_rn(fmaf(-sx2, my2, total[15]), W);
-                const Rot3 rot = kabsch_rotation(h);
+                const Rot3 rot = kabsch_rotation(h, reinterpret_cast<KabschState*>(bc + B_KABSCH));
                 // centroids: mu = pivot + S / W   (zero-weight iteration: both are the pivots, T = 0 like the reference)
                 const float cx0 = bc[B_PX] + mx0, cx1 = bc[B_PX + 1] + mx1, cx2 = bc[B_PX + 2] + mx2;
                 const float cy0 = bc[B_PY] + my0, cy1 = bc[B_PY + 1] + my1, cy2 = bc[B_PY + 2] + my2;

@@ -22,6 +22,14 @@ ICPF_HD ICPF_INLINE float icpf_rsqrt(float x) {
 #endif
 }
 
+ICPF_HD ICPF_INLINE float icpf_fast_div(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fdividef(a, b);
+#else
+    return a / b;
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------ 3x3 Kabsch
 // Rotation of /root/reference/utils_icp_pytorch3d.py:339-363 in closed form.
 //
@@ -32,23 +40,36 @@ ICPF_HD ICPF_INLINE float icpf_rsqrt(float x) {
 // determinant-corrected product (the flipped singular vector is always the one of the smallest singular value) and
 // needs neither the third column nor a determinant, so rank-2 (planar cluster) inputs are handled exactly like the
 // reference.  H == 0 (no inliers) gives R = I, as torch.svd does for the zero matrix.
+//
+// Warm start: consecutive ICP iterations solve nearly the same problem, so the V of the previous solve already
+// orthogonalises H V to ~1e-3; the Jacobi sweeps then only polish (1-2 sweeps instead of 4-5).  The state is left
+// untouched when no rotation was needed, so an unchanged H reproduces the previous R bit for bit (the ICP loop's
+// fixed-point test relies on that); a slightly wider threshold for *starting* to rotate absorbs the rounding noise
+// of recomputing H V.  The inner arithmetic uses approximate divide / rsqrt: Jacobi is self-correcting and every
+// output vector is re-orthonormalised at the end.
 struct Rot3 {
     float r[9];  // row-major, row-vector convention: x' = x R
 };
 
+struct KabschState {
+    float v[9];   // right singular vectors of the previous solve, row-major (column c = v[c], v[3+c], v[6+c])
+    bool warm;
+};
+
 template <int p, int q>
-ICPF_HD ICPF_INLINE void jacobi_pair(float (&b)[9], float (&v)[9], bool& rotated) {
+ICPF_HD ICPF_INLINE void jacobi_pair(float (&b)[9], float (&v)[9], float thr2, bool& rotated) {
     // columns p,q of b (3x3 row-major): b[3*i+p]
     const float bp0 = b[p], bp1 = b[3 + p], bp2 = b[6 + p];
     const float bq0 = b[q], bq1 = b[3 + q], bq2 = b[6 + q];
     const float alpha = fmaf(bp2, bp2, fmaf(bp1, bp1, bp0 * bp0));
     const float beta = fmaf(bq2, bq2, fmaf(bq1, bq1, bq0 * bq0));
     const float gamma = fmaf(bp2, bq2, fmaf(bp1, bq1, bp0 * bq0));
-    // converged for this pair when the columns are orthogonal to working precision
-    if (!(fabsf(gamma) > 3e-7f * sqrtf(alpha * beta)) || gamma == 0.0f) return;
+    // converged for this pair when the columns are orthogonal to working precision: gamma^2 <= thr^2 alpha beta
+    if (!(gamma * gamma > thr2 * (alpha * beta))) return;
     rotated = true;
-    const float zeta = (beta - alpha) / (2.0f * gamma);
-    const float t = copysignf(1.0f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.0f)));
+    const float zeta = icpf_fast_div(beta - alpha, 2.0f * gamma);
+    const float az = fabsf(zeta);
+    const float t = copysignf(1.0f, zeta) * icpf_fast_div(1.0f, az + sqrtf(fmaf(az, az, 1.0f)));
     const float c = icpf_rsqrt(fmaf(t, t, 1.0f));
     const float s = c * t;
 #pragma unroll
@@ -78,9 +99,9 @@ ICPF_HD ICPF_INLINE void normalize3(float& x, float& y, float& z, float n2) {
     z *= inv;
 }
 
-ICPF_HD inline Rot3 kabsch_rotation(const float (&h)[9]) {
+ICPF_HD inline Rot3 kabsch_rotation(const float (&h)[9], KabschState* st = nullptr) {
     Rot3 out;
-    float b[9], v[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+    float b[9], v[9];
     // scale to unit magnitude so the thresholds below are relative (also avoids under/overflow of the squares)
     float amax = 0.f;
 #pragma unroll
@@ -91,40 +112,67 @@ ICPF_HD inline Rot3 kabsch_rotation(const float (&h)[9]) {
         return out;
     }
     const float sc = 1.0f / amax;
+    const bool warm = (st != nullptr) && st->warm;
+    if (warm) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) b[i] = h[i] * sc;
-
+        for (int i = 0; i < 9; ++i) v[i] = st->v[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float h0 = h[3 * i] * sc, h1 = h[3 * i + 1] * sc, h2 = h[3 * i + 2] * sc;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) b[3 * i + c] = fmaf(h2, v[6 + c], fmaf(h1, v[3 + c], h0 * v[c]));
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            b[i] = h[i] * sc;
+            v[i] = (i % 4 == 0) ? 1.f : 0.f;
+        }
+    }
+    const float kThr2 = 9e-14f;                 // (3e-7)^2
+    float thr2 = warm ? 3.6e-13f : kThr2;       // (6e-7)^2 to START rotating from a warm state
+    bool any = false;
     for (int sweep = 0; sweep < 12; ++sweep) {
         bool rotated = false;
-        jacobi_pair<0, 1>(b, v, rotated);
-        jacobi_pair<0, 2>(b, v, rotated);
-        jacobi_pair<1, 2>(b, v, rotated);
+        jacobi_pair<0, 1>(b, v, thr2, rotated);
+        jacobi_pair<0, 2>(b, v, thr2, rotated);
+        jacobi_pair<1, 2>(b, v, thr2, rotated);
         if (!rotated) break;
+        any = true;
+        thr2 = kThr2;
     }
     // squared column norms = squared singular values; pick the two dominant columns a, b_
     float n0 = fmaf(b[6], b[6], fmaf(b[3], b[3], b[0] * b[0]));
     float n1 = fmaf(b[7], b[7], fmaf(b[4], b[4], b[1] * b[1]));
     float n2 = fmaf(b[8], b[8], fmaf(b[5], b[5], b[2] * b[2]));
     // order the columns by decreasing norm with three register-level compare-swaps (no dynamic indexing)
-    if (n1 > n0) { swap_cols<0, 1>(b, v); float f = n0; n0 = n1; n1 = f; }
-    if (n2 > n0) { swap_cols<0, 2>(b, v); float f = n0; n0 = n2; n2 = f; }
-    if (n2 > n1) { swap_cols<1, 2>(b, v); float f = n1; n1 = n2; n2 = f; }
-    float ua0 = b[0], ua1 = b[3], ua2 = b[6];
-    normalize3(ua0, ua1, ua2, n0);
+    if (n1 > n0) { swap_cols<0, 1>(b, v); float f = n0; n0 = n1; n1 = f; any = true; }
+    if (n2 > n0) { swap_cols<0, 2>(b, v); float f = n0; n0 = n2; n2 = f; any = true; }
+    if (n2 > n1) { swap_cols<1, 2>(b, v); float f = n1; n1 = n2; n2 = f; any = true; }
     float va0 = v[0], va1 = v[3], va2 = v[6];
-    normalize3(va0, va1, va2, fmaf(va2, va2, fmaf(va1, va1, va0 * va0)));
-    float ub0 = b[1], ub1 = b[4], ub2 = b[7];
     float vb0 = v[1], vb1 = v[4], vb2 = v[7];
-    // Gram-Schmidt against the dominant pair (removes the accumulated fp32 drift of the Givens products)
+    if (any || !warm) {
+        // re-orthonormalise the right frame (removes the accumulated fp32 drift of the Givens products); a warm
+        // frame that needed no rotation is already clean and is used as stored
+        normalize3(va0, va1, va2, fmaf(va2, va2, fmaf(va1, va1, va0 * va0)));
+        const float e = fmaf(va2, vb2, fmaf(va1, vb1, va0 * vb0));
+        vb0 = fmaf(-e, va0, vb0); vb1 = fmaf(-e, va1, vb1); vb2 = fmaf(-e, va2, vb2);
+        normalize3(vb0, vb1, vb2, fmaf(vb2, vb2, fmaf(vb1, vb1, vb0 * vb0)));
+    }
+    // left vectors from fresh products H v (not from the incrementally rotated B): R is then a pure function of
+    // (H, stored frame), which is what makes an unchanged H reproduce R bit for bit
+    float ua0 = fmaf(h[2] * sc, va2, fmaf(h[1] * sc, va1, h[0] * sc * va0));
+    float ua1 = fmaf(h[5] * sc, va2, fmaf(h[4] * sc, va1, h[3] * sc * va0));
+    float ua2 = fmaf(h[8] * sc, va2, fmaf(h[7] * sc, va1, h[6] * sc * va0));
+    float ub0 = fmaf(h[2] * sc, vb2, fmaf(h[1] * sc, vb1, h[0] * sc * vb0));
+    float ub1 = fmaf(h[5] * sc, vb2, fmaf(h[4] * sc, vb1, h[3] * sc * vb0));
+    float ub2 = fmaf(h[8] * sc, vb2, fmaf(h[7] * sc, vb1, h[6] * sc * vb0));
+    normalize3(ua0, ua1, ua2, fmaf(ua2, ua2, fmaf(ua1, ua1, ua0 * ua0)));
     {
         const float d = fmaf(ua2, ub2, fmaf(ua1, ub1, ua0 * ub0));
         ub0 = fmaf(-d, ua0, ub0); ub1 = fmaf(-d, ua1, ub1); ub2 = fmaf(-d, ua2, ub2);
-        const float e = fmaf(va2, vb2, fmaf(va1, vb1, va0 * vb0));
-        vb0 = fmaf(-e, va0, vb0); vb1 = fmaf(-e, va1, vb1); vb2 = fmaf(-e, va2, vb2);
     }
     float nub = fmaf(ub2, ub2, fmaf(ub1, ub1, ub0 * ub0));
-    const float nvb = fmaf(vb2, vb2, fmaf(vb1, vb1, vb0 * vb0));
-    normalize3(vb0, vb1, vb2, nvb);
     if (!(nub > 1e-30f)) {
         // rank-1 cross-covariance: the rotation about u_a is not determined by the data (the reference returns
         // whatever LAPACK picks).  Choose the unit vector orthogonal to u_a closest to the image of v_b under the
@@ -150,6 +198,16 @@ ICPF_HD inline Rot3 kabsch_rotation(const float (&h)[9]) {
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) out.r[3 * i + j] = fmaf(uc[i], vc[j], fmaf(ub[i], vb[j], ua[i] * va[j]));
+    if (st != nullptr && (any || !warm)) {
+        // keep the re-orthonormalised frame for the next solve (only when something changed: see the header comment)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            st->v[3 * i] = va[i];
+            st->v[3 * i + 1] = vb[i];
+            st->v[3 * i + 2] = vc[i];
+        }
+        st->warm = true;
+    }
     return out;
 }
 

@@ -38,7 +38,8 @@ constexpr int kBcastFloats = 48;
 constexpr int kCellWords = (kGridMaxCells + 2 + 1) / 2 + 2;   // packed u16 entries 0..G (+pad), as u32 words
 
 // broadcast block written by thread 0 once per iteration
-enum : int { B_R = 0, B_T = 9, B_RC = 12, B_TC = 21, B_PX = 24, B_PY = 27, B_EXIT = 30, B_REFRESH = 31 };
+enum : int { B_R = 0, B_T = 9, B_RC = 12, B_TC = 21, B_PX = 24, B_PY = 27, B_EXIT = 30, B_REFRESH = 31,
+             B_KABSCH = 32 /* KabschState: 9 floats + flag */ };
 
 // Dynamic shared memory of every pair kernel.  Tiles are addressed as OFFSETS into this one array so that the
 // compiler always knows the address space (a run-time swap of two pointers degrades every access to a generic LD/ST).

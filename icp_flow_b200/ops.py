@@ -214,11 +214,13 @@ def transform_points_batch(xyz: torch.Tensor, pose: torch.Tensor) -> torch.Tenso
     return out
 
 
-def host_kabsch(H: torch.Tensor) -> torch.Tensor:
-    """CPU test hook: the kernels' closed-form Kabsch rotation for ``[n,3,3]`` cross-covariances (row convention)."""
+def host_kabsch(H: torch.Tensor, sequence: bool = False) -> torch.Tensor:
+    """CPU test hook: the kernels' closed-form Kabsch rotation for ``[n,3,3]`` cross-covariances (row convention).
+    ``sequence=True`` solves them in order with the warm start an ICP run uses between iterations."""
     h = H.detach().to(torch.float32).contiguous().cpu()
     out = torch.empty_like(h)
-    _lib.lib().icpf_host_kabsch(ctypes.c_void_p(h.data_ptr()), h.shape[0], ctypes.c_void_p(out.data_ptr()))
+    fn = _lib.lib().icpf_host_kabsch_sequence if sequence else _lib.lib().icpf_host_kabsch
+    fn(ctypes.c_void_p(h.data_ptr()), h.shape[0], ctypes.c_void_p(out.data_ptr()))
     return out
 
 

@@ -154,6 +154,8 @@ void icpf_profile_next_icp(void* start_event, void* stop_event);
 /* CPU-callable test hook: the closed-form 3x3 Kabsch rotation used inside the kernels, evaluated on the host
  * for `n` row-major cross-covariance matrices H (n*9 floats) -> R (n*9 floats).  Not part of the data path. */
 void icpf_host_kabsch(const float* H, int32_t n, float* R);
+/* Same, but the n matrices are solved as one ICP run would: each solve warm-starts from the previous one. */
+void icpf_host_kabsch_sequence(const float* H, int32_t n, float* R);
 
 #ifdef __cplusplus
 }

