@@ -139,8 +139,6 @@ __device__ __forceinline__ IcpResult icp_iterations(const PairTiles& tl, const G
         reinterpret_cast<KabschState*>(bc + B_KABSCH)->warm = false;     // first solve of this pair starts cold
     }
     __syncthreads();
-    if (tid < 12) bc[B_RC + tid] = bc[B_R + tid];      // cache reference = the transform of the first search
-    __syncthreads();
     float W_prev = 1.f;                                 // thread 0: clamp(sum of weights) of the previous iteration
     bool done = (n_s <= 0 || n_d <= 0 || max_it <= 0);  // engine-defined: nothing to align -> identity
 
@@ -150,14 +148,18 @@ __device__ __forceinline__ IcpResult icp_iterations(const PairTiles& tl, const G
         for (int i = 0; i < 9; ++i) R[i] = bc[B_R + i];
 #pragma unroll
         for (int i = 0; i < 3; ++i) T[i] = bc[B_T + i];
-        const bool refresh = !CACHE || (bc[B_REFRESH] != 0.f);
+        // The cache is re-anchored every iteration: bounds are kept relative to the row's position in the previous
+        // iteration, so the motion that counts is the step (R_k - R_{k-1}, T_k - T_{k-1}) thread 0 left in the
+        // broadcast block; a row is searched again only when its own bound is used up.
+        const bool refresh = !CACHE || (it == 0);
         float dr[9], dt[3];
         if (CACHE && !refresh) {
 #pragma unroll
-            for (int i = 0; i < 9; ++i) dr[i] = R[i] - bc[B_RC + i];
+            for (int i = 0; i < 9; ++i) dr[i] = bc[B_RC + i];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) dt[i] = T[i] - bc[B_TC + i];
+            for (int i = 0; i < 3; ++i) dt[i] = bc[B_TC + i];
         }
+        const float anchor_slack = 0.1f * g.pad;      // fp32 rounding of the two positions whose distance is m
         float sq = 0.f;
         int ndefer = 0;
         unsigned short* mylist = GRID ? tl.defer() + warp * tl.defer_cap : nullptr;
@@ -208,12 +210,14 @@ __device__ __forceinline__ IcpResult icp_iterations(const PairTiles& tl, const G
                     if (valid) {
                         const float bound = __half2float(__ushort_as_half((unsigned short)((wold >> 16) & 0x7fffu)));
                         const float m2 = moved_sq(dr, dt, x0);
+                        const float m = sqrtf(m2);
                         // (a) every other point is provably farther than tau: only the cached candidate can pass
-                        bool hit = bound > tau_hi + sqrtf(m2);
+                        bool hit = bound > tau_hi + m;
                         // (b) the cached candidate is provably still the strict nearest neighbour: (d_best + m) < B
                         if (pos >= 0) hit = hit || ((d2 + 2.f * sqrtf(d2 * m2) + m2) * 1.0002f < bound * bound);
                         if (hit) {
-                            nnw[q] = pack_nn(pos, bound, (pos >= 0) && (d2 <= tau2) && (x0.w > 0.f));
+                            // re-anchor: relative to the row's NEW position every other point is >= bound - m away
+                            nnw[q] = pack_nn(pos, bound - m - anchor_slack, (pos >= 0) && (d2 <= tau2) && (x0.w > 0.f));
                             need = false;
                         }
                     }
@@ -239,8 +243,7 @@ __device__ __forceinline__ IcpResult icp_iterations(const PairTiles& tl, const G
                     int pos;
                     apply_rt(R, T, x0.x, x0.y, x0.z, qx, qy, qz);
                     grid_search(g, cand, cell_runs, qx, qy, qz, d2, pos, d2nd, box);
-                    // re-express the bound relative to the cache reference position of this row
-                    const float bound = fminf(sqrtf(d2nd), box) * 0.9999f - g.pad - sqrtf(moved_sq(dr, dt, x0));
+                    const float bound = fminf(sqrtf(d2nd), box) * 0.9999f - g.pad;      // fresh, at the current position
                     nnw[q] = pack_nn(pos, bound, (pos >= 0) && (d2 <= tau2) && (x0.w > 0.f));
                 }
                 __syncwarp();
@@ -315,10 +318,6 @@ __device__ __forceinline__ IcpResult icp_iterations(const PairTiles& tl, const G
                 for (int i = 0; i < 9; ++i) same = same && (__float_as_uint(rot.r[i]) == __float_as_uint(bc[B_R + i]));
 #pragma unroll
                 for (int i = 0; i < 3; ++i) same = same && (__float_as_uint(t[i]) == __float_as_uint(bc[B_T + i]));
-#pragma unroll
-                for (int i = 0; i < 9; ++i) bc[B_R + i] = rot.r[i];
-#pragma unroll
-                for (int i = 0; i < 3; ++i) bc[B_T + i] = t[i];
                 if (!empty) {
                     bc[B_PX] = cx0; bc[B_PX + 1] = cx1; bc[B_PX + 2] = cx2;
                     bc[B_PY] = cy0; bc[B_PY + 1] = cy1; bc[B_PY + 2] = cy2;
@@ -328,16 +327,16 @@ __device__ __forceinline__ IcpResult icp_iterations(const PairTiles& tl, const G
                 if (CACHE) {
                     res.searches += refresh ? (float)n_s : total[17];
                     res.refreshes += refresh ? 1 : 0;
-                    // after a refresh the next iteration tests the cache; re-anchor it when too many rows fail
-                    const bool refresh_next = !refresh && (total[17] * 4.f > (float)n_s);
-                    bc[B_REFRESH] = refresh_next ? 1.f : 0.f;
-                    if (refresh_next) {
+                    // the step the rows take between this search and the next one
 #pragma unroll
-                        for (int i = 0; i < 9; ++i) bc[B_RC + i] = rot.r[i];
+                    for (int i = 0; i < 9; ++i) bc[B_RC + i] = rot.r[i] - bc[B_R + i];
 #pragma unroll
-                        for (int i = 0; i < 3; ++i) bc[B_TC + i] = t[i];
-                    }
+                    for (int i = 0; i < 3; ++i) bc[B_TC + i] = t[i] - bc[B_T + i];
                 }
+#pragma unroll
+                for (int i = 0; i < 9; ++i) bc[B_R + i] = rot.r[i];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) bc[B_T + i] = t[i];
                 bc[B_EXIT] = (early_exit && same) ? 1.f : 0.f;
             }
         }
