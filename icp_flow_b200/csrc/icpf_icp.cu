@@ -163,6 +163,7 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
     if (P == 0) return ICPF_OK;
     // nn_mode: 0 auto (grid + cache whenever the tiles fit in shared memory), 1 brute force, 2 grid, 3 grid + cache
     const size_t kMaxSmem = 227 * 1024;
+    if (N > kMaxRows) return ICPF_E_UNSUPPORTED;
     bool grid = prm.nn_mode != 1;
     if (grid && pair_smem_bytes(N, true) > kMaxSmem) {
         if (prm.nn_mode >= 2) return ICPF_E_UNSUPPORTED;

@@ -179,7 +179,7 @@ __device__ __forceinline__ IcpResult icp_iterations(const PairTiles& tl, const G
                     apply_rt(R, T, x0[k].x, x0[k].y, x0[k].z, qx[k], qy[k], qz[k]);
                     const unsigned int wold = (it > 0 && valid) ? nnw[q] : (kNnMasked | kNnNone);
                     if (!(wold & kNnMasked)) {
-                        const float4 c = cand[wold & 0xffffu];
+                        const float4 c = cand[wold & kNnPosMask];
                         sq += sqdist(qx[k], qy[k], qz[k], c.x, c.y, c.z);
                     }
                 }
@@ -198,7 +198,7 @@ __device__ __forceinline__ IcpResult icp_iterations(const PairTiles& tl, const G
                 float qx, qy, qz;
                 apply_rt(R, T, x0.x, x0.y, x0.z, qx, qy, qz);
                 const unsigned int wold = (it > 0 && valid) ? nnw[q] : (kNnMasked | kNnNone);
-                int pos = (wold & 0xffffu) == kNnNone ? -1 : (int)(wold & 0xffffu);
+                int pos = (wold & kNnPosMask) == kNnNone ? -1 : (int)(wold & kNnPosMask);
                 float d2 = INF;
                 if (pos >= 0 && (!(wold & kNnMasked) || (CACHE && !refresh))) {
                     const float4 c = cand[pos];
@@ -208,13 +208,13 @@ __device__ __forceinline__ IcpResult icp_iterations(const PairTiles& tl, const G
                 bool need = valid;
                 if (CACHE && !refresh) {
                     if (valid) {
-                        const float bound = __half2float(__ushort_as_half((unsigned short)((wold >> 16) & 0x7fffu)));
+                        const float bound = nn_bound(wold);
                         const float m2 = moved_sq(dr, dt, x0);
-                        const float m = sqrtf(m2);
+                        const float m = fast_sqrt(m2) * 1.0001f;
                         // (a) every other point is provably farther than tau: only the cached candidate can pass
                         bool hit = bound > tau_hi + m;
                         // (b) the cached candidate is provably still the strict nearest neighbour: (d_best + m) < B
-                        if (pos >= 0) hit = hit || ((d2 + 2.f * sqrtf(d2 * m2) + m2) * 1.0002f < bound * bound);
+                        if (pos >= 0) hit = hit || ((d2 + 2.0002f * fast_sqrt(d2 * m2) + m2) * 1.0002f < bound * bound);
                         if (hit) {
                             // re-anchor: relative to the row's NEW position every other point is >= bound - m away
                             nnw[q] = pack_nn(pos, bound - m - anchor_slack, (pos >= 0) && (d2 <= tau2) && (x0.w > 0.f));
@@ -262,7 +262,7 @@ __device__ __forceinline__ IcpResult icp_iterations(const PairTiles& tl, const G
                 const unsigned int w = (q < n_s) ? nnw[q] : kNnMasked;
                 if (w & kNnMasked) continue;
                 const float4 x = tl.src()[q];
-                const float4 y = cand[w & 0xffffu];
+                const float4 y = cand[w & kNnPosMask];
                 const float ax = x.x - px, ay = x.y - py, az = x.z - pz;
                 const float bx = y.x - ux, by = y.y - uy, bz = y.z - uz;
                 mom[0] += 1.f;
@@ -296,14 +296,15 @@ __device__ __forceinline__ IcpResult icp_iterations(const PairTiles& tl, const G
                 const float W = fmaxf(total[0], 1e-9f);
                 const float sx0 = total[1], sx1 = total[2], sx2 = total[3];
                 const float sy0 = total[4], sy1 = total[5], sy2 = total[6];
-                const float mx0 = __fdiv_rn(sx0, W), mx1 = __fdiv_rn(sx1, W), mx2 = __fdiv_rn(sx2, W);
-                const float my0 = __fdiv_rn(sy0, W), my1 = __fdiv_rn(sy1, W), my2 = __fdiv_rn(sy2, W);
+                const float iW = __frcp_rn(W);
+                const float mx0 = sx0 * iW, mx1 = sx1 * iW, mx2 = sx2 * iW;
+                const float my0 = sy0 * iW, my1 = sy1 * iW, my2 = sy2 * iW;
                 float h[9];
-                h[0] = __fdiv_rn(fmaf(-sx0, my0, total[7]), W);  h[1] = __fdiv_rn(fmaf(-sx0, my1, total[8]), W);
-                h[2] = __fdiv_rn(fmaf(-sx0, my2, total[9]), W);  h[3] = __fdiv_rn(fmaf(-sx1, my0, total[10]), W);
-                h[4] = __fdiv_rn(fmaf(-sx1, my1, total[11]), W); h[5] = __fdiv_rn(fmaf(-sx1, my2, total[12]), W);
-                h[6] = __fdiv_rn(fmaf(-sx2, my0, total[13]), W); h[7] = __fdiv_rn(fmaf(-sx2, my1, total[14]), W);
-                h[8] = __fdiv_rn(fmaf(-sx2, my2, total[15]), W);
+                h[0] = fmaf(-sx0, my0, total[7]) * iW;  h[1] = fmaf(-sx0, my1, total[8]) * iW;
+                h[2] = fmaf(-sx0, my2, total[9]) * iW;  h[3] = fmaf(-sx1, my0, total[10]) * iW;
+                h[4] = fmaf(-sx1, my1, total[11]) * iW; h[5] = fmaf(-sx1, my2, total[12]) * iW;
+                h[6] = fmaf(-sx2, my0, total[13]) * iW; h[7] = fmaf(-sx2, my1, total[14]) * iW;
+                h[8] = fmaf(-sx2, my2, total[15]) * iW;
                 const Rot3 rot = kabsch_rotation(h, reinterpret_cast<KabschState*>(bc + B_KABSCH));
                 // centroids: mu = pivot + S / W   (zero-weight iteration: both are the pivots, T = 0 like the reference)
                 const float cx0 = bc[B_PX] + mx0, cx1 = bc[B_PX + 1] + mx1, cx2 = bc[B_PX + 2] + mx2;
@@ -313,12 +314,21 @@ __device__ __forceinline__ IcpResult icp_iterations(const PairTiles& tl, const G
                 t[0] = empty ? 0.f : cy0 - fmaf(cx2, rot.r[6], fmaf(cx1, rot.r[3], cx0 * rot.r[0]));
                 t[1] = empty ? 0.f : cy1 - fmaf(cx2, rot.r[7], fmaf(cx1, rot.r[4], cx0 * rot.r[1]));
                 t[2] = empty ? 0.f : cy2 - fmaf(cx2, rot.r[8], fmaf(cx1, rot.r[5], cx0 * rot.r[2]));
-                bool same = it > 0;
+                // The pair has reached its fixed point only when the WHOLE state repeats: the transform, the pivots of
+                // the moment sums and the warm-start frame of the 3x3 solve -- then every later iteration is this one.
+                // (with no gated correspondence the pivots and the frame are left untouched, so only (R,T) = (I,0) counts)
+                // The pivots only have to be NEAR the centroids (so that S_x, S_y stay small); they follow them while
+                // they are more than a millimetre off and then stay put, which makes H a function of the
+                // correspondences alone once the alignment has settled.
+                const float off = fmaxf(fmaxf(fmaxf(fabsf(mx0), fabsf(mx1)), fabsf(mx2)),
+                                        fmaxf(fmaxf(fabsf(my0), fabsf(my1)), fabsf(my2)));
+                const bool move_pivot = !empty && (off > 1e-3f);
+                bool same = (it > 0) && !reinterpret_cast<KabschState*>(bc + B_KABSCH)->changed && !move_pivot;
 #pragma unroll
                 for (int i = 0; i < 9; ++i) same = same && (__float_as_uint(rot.r[i]) == __float_as_uint(bc[B_R + i]));
 #pragma unroll
                 for (int i = 0; i < 3; ++i) same = same && (__float_as_uint(t[i]) == __float_as_uint(bc[B_T + i]));
-                if (!empty) {
+                if (move_pivot) {
                     bc[B_PX] = cx0; bc[B_PX + 1] = cx1; bc[B_PX + 2] = cx2;
                     bc[B_PY] = cy0; bc[B_PY + 1] = cy1; bc[B_PY + 2] = cy2;
                 }
@@ -357,7 +367,7 @@ __device__ __forceinline__ IcpResult icp_iterations(const PairTiles& tl, const G
             const unsigned int w = (q < n_s) ? nnw[q] : kNnMasked;
             if (w & kNnMasked) continue;
             const float4 x = tl.src()[q];
-            const float4 c = cand[w & 0xffffu];
+            const float4 c = cand[w & kNnPosMask];
             float qx, qy, qz;
             apply_rt(res.r, res.t, x.x, x.y, x.z, qx, qy, qz);
             sq += sqdist(qx, qy, qz, c.x, c.y, c.z);

