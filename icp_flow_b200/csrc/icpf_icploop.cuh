@@ -135,7 +135,7 @@ __device__ __forceinline__ IcpResult icp_iterations(const PairTiles& tl, const G
         bc[B_PX] = pivx; bc[B_PX + 1] = pivy; bc[B_PX + 2] = pivz;
         bc[B_PY] = pivx; bc[B_PY + 1] = pivy; bc[B_PY + 2] = pivz;
         bc[B_EXIT] = 0.f;
-        bc[B_REFRESH] = 1.f;
+        *reinterpret_cast<int*>(bc + B_DEFER) = 0;
         reinterpret_cast<KabschState*>(bc + B_KABSCH)->warm = false;     // first solve of this pair starts cold
     }
     __syncthreads();
@@ -162,7 +162,11 @@ __device__ __forceinline__ IcpResult icp_iterations(const PairTiles& tl, const G
         const float anchor_slack = 0.1f * g.pad;      // fp32 rounding of the two positions whose distance is m
         float sq = 0.f;
         int ndefer = 0;
-        unsigned short* mylist = GRID ? tl.defer() + warp * tl.defer_cap : nullptr;
+        // rows whose cached neighbour failed are appended to ONE list per CTA (warp-aggregated atomic), so that the
+        // searches afterwards run with dense lanes: a few failing rows per warp would otherwise cost every warp a
+        // whole divergent search
+        unsigned short* dlist = GRID ? tl.defer() : nullptr;
+        int* dcount = reinterpret_cast<int*>(bc + B_DEFER);
 
         // ---------------- pass A: rmse numerator of the previous iteration + correspondence search of this one
         if (MODE == 1) {
@@ -222,8 +226,12 @@ __device__ __forceinline__ IcpResult icp_iterations(const PairTiles& tl, const G
                         }
                     }
                     const unsigned int vote = __ballot_sync(FULL_MASK, need);
-                    if (need) mylist[ndefer + __popc(vote & ((1u << lane) - 1u))] = (unsigned short)q;
-                    ndefer += __popc(vote);
+                    if (vote != 0u) {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(dcount, __popc(vote));
+                        base = __shfl_sync(FULL_MASK, base, 0);
+                        if (need) dlist[base + __popc(vote & ((1u << lane) - 1u))] = (unsigned short)q;
+                    }
                 } else if (need) {
                     float d2nd, box;
                     grid_search(g, cand, cell_runs, qx, qy, qz, d2, pos, d2nd, box);
@@ -235,9 +243,10 @@ __device__ __forceinline__ IcpResult icp_iterations(const PairTiles& tl, const G
             }
             if (CACHE && !refresh) {
                 // ---------------- deferred searches: dense lanes over the warp's compacted list
-                __syncwarp();
-                for (int i = lane; i < ndefer; i += 32) {
-                    const int q = mylist[i];
+                __syncthreads();
+                ndefer = *dcount;
+                for (int i = tid; i < ndefer; i += kThreads) {
+                    const int q = dlist[i];
                     const float4 x0 = tl.src()[q];
                     float qx, qy, qz, d2, d2nd, box;
                     int pos;
@@ -246,7 +255,7 @@ __device__ __forceinline__ IcpResult icp_iterations(const PairTiles& tl, const G
                     const float bound = fminf(sqrtf(d2nd), box) * 0.9999f - g.pad;      // fresh, at the current position
                     nnw[q] = pack_nn(pos, bound, (pos >= 0) && (d2 <= tau2) && (x0.w > 0.f));
                 }
-                __syncwarp();
+                __syncthreads();
             }
         }
 
@@ -278,7 +287,7 @@ __device__ __forceinline__ IcpResult icp_iterations(const PairTiles& tl, const G
         if ((lane & 1) == 0) part[warp * kSums + reduce16_slot(lane)] = msum;
         if (lane == 0) {
             part[warp * kSums + 16] = sq;
-            part[warp * kSums + 17] = (float)ndefer;
+            part[warp * kSums + 17] = (warp == 0) ? (float)ndefer : 0.f;
         }
         __syncthreads();
 
@@ -347,6 +356,7 @@ __device__ __forceinline__ IcpResult icp_iterations(const PairTiles& tl, const G
                 for (int i = 0; i < 9; ++i) bc[B_R + i] = rot.r[i];
 #pragma unroll
                 for (int i = 0; i < 3; ++i) bc[B_T + i] = t[i];
+                *reinterpret_cast<int*>(bc + B_DEFER) = 0;
                 bc[B_EXIT] = (early_exit && same) ? 1.f : 0.f;
             }
         }

@@ -38,7 +38,7 @@ constexpr int kBcastFloats = 48;
 constexpr int kCellWords = (kGridMaxCells + 2 + 1) / 2 + 2;   // packed u16 entries 0..G (+pad), as u32 words
 
 // broadcast block written by thread 0 once per iteration
-enum : int { B_R = 0, B_T = 9, B_RC = 12, B_TC = 21, B_PX = 24, B_PY = 27, B_EXIT = 30, B_REFRESH = 31,
+enum : int { B_R = 0, B_T = 9, B_RC = 12, B_TC = 21, B_PX = 24, B_PY = 27, B_EXIT = 30, B_DEFER = 31 /* int: rows queued for a search */,
              B_KABSCH = 32 /* KabschState: 9 floats + flag */ };
 
 // Dynamic shared memory of every pair kernel.  Tiles are addressed as OFFSETS into this one array so that the
@@ -52,7 +52,7 @@ struct PairTiles {
     int sorted_off;   // [N] float4 grid mode: dst rows in cell order, .w = (original row << 16 | sorted position)
     int cells_off;    // [kCellWords] u32 grid mode: packed u16 run boundaries; run of cell i = [a[i], a[i+1])
     int nn_off;       // [N] u32 correspondence word of each src row (see pack_nn)
-    int defer_off;    // [kWarps][defer_cap] u16 grid mode: per-warp lists of rows whose cached neighbour failed
+    int defer_off;    // [kWarps * defer_cap >= N] u16 grid mode: rows whose cached neighbour could not be proven
     int defer_cap;
     int red_off;      // [kRedFloats] float reduction scratch
     __device__ __forceinline__ float4* src() const { return g_tile + src_off; }
