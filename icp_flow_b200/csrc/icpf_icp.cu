@@ -33,7 +33,9 @@ struct IcpArgs {
     int* iters;            // [P] (never NULL inside the library)
     uint32_t* conv;        // [P,4]
     int* stats;            // [P,2] {full searches, cache refreshes} of the first pass
-    const int* batch;      // rerun mode: batch[0] = k*+1 (iterations the reference executed); NULL in the first pass
+    const int* batch;      // re-run pass: batch[0] = k*+1 (iterations the reference executed); NULL otherwise
+    const int* decided;    // second full pass: runs only while *decided == 0; NULL otherwise
+    int cap;               // first pass: iteration cap (<= max_it)
 };
 
 template <int MODE>
@@ -42,11 +44,15 @@ __global__ void __launch_bounds__(kThreads, 7) icp_pairs_kernel(IcpArgs a) {
     int max_it = a.max_it;
     bool early_exit = a.early_exit != 0;
     if (a.batch != nullptr) {
-        // second pass: only pairs that executed more iterations than the batch did need their state at k*
+        // re-run pass: only pairs that executed more iterations than the batch did need their state at k*
         const int batch_iters = a.batch[0];
         if (a.iters[p] <= batch_iters) return;
         max_it = batch_iters;
         early_exit = false;
+    } else if (a.decided != nullptr) {
+        if (*a.decided != 0) return;      // the capped first pass already found the batch stop
+    } else {
+        max_it = min(max_it, a.cap);
     }
     constexpr bool GRID = MODE >= 2;
     PairTiles tl = carve_pair_tiles<GRID>(a.N);
@@ -116,9 +122,12 @@ __global__ void __launch_bounds__(kThreads, 7) icp_pairs_kernel(IcpArgs a) {
 
 // AND of the per-pair convergence masks -> first iteration k* where every pair passes (utils_icp_pytorch3d.py:209).
 // batch[0] = iterations the reference loop would have executed, batch[1] = converged flag.
-__global__ void __launch_bounds__(256) icp_resolve_batch_kernel(const uint32_t* conv, int P, int max_it, int batch_stop,
-                                                                int* batch) {
+// `limit` = iterations the masks cover (the cap of the first pass, or max_it); `decided` (may be NULL) is set to 1 when
+// the answer is final and left 0 when the capped pass could not tell (a later full pass decides).
+__global__ void __launch_bounds__(256) icp_resolve_batch_kernel(const uint32_t* conv, int P, int max_it, int limit,
+                                                                int batch_stop, int* batch, int* decided) {
     __shared__ uint32_t s_and[4];
+    if (decided != nullptr && limit == max_it && *decided != 0) return;     // second resolve, nothing left to do
     if (threadIdx.x < 4) s_and[threadIdx.x] = 0xffffffffu;
     __syncthreads();
     uint32_t m[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
@@ -139,12 +148,18 @@ __global__ void __launch_bounds__(256) icp_resolve_batch_kernel(const uint32_t* 
                 if (s_and[i]) kstar = i * 32 + (__ffs(s_and[i]) - 1);
             }
         }
-        if (kstar >= 0 && kstar < max_it) {
+        if (kstar >= 0 && kstar < limit) {
             batch[0] = kstar + 1;
             batch[1] = 1;
-        } else {
+            if (decided) *decided = 1;
+        } else if (limit >= max_it) {
             batch[0] = max_it;
             batch[1] = 0;
+            if (decided) *decided = 1;
+        } else {
+            batch[0] = limit;          // provisional: no pair is re-run, the full pass follows
+            batch[1] = 0;
+            if (decided) *decided = 0;
         }
     }
 }
@@ -193,7 +208,14 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
     a.rel_thr = prm.relative_rmse_thr;
     a.early_exit = prm.early_exit;
     a.out_R = out_R; a.out_T = out_T; a.out_rmse = out_rmse; a.out_pose = out_pose;
-    a.iters = iters; a.conv = conv; a.batch = nullptr;
+    a.iters = iters; a.conv = conv; a.batch = nullptr; a.decided = nullptr;
+    // Pairs that never reach a bitwise fixed point (limit cycles of a few ulp, non-convergent clusters) would run all
+    // max_iterations in the first pass although the reference's batch stop fires after 10-25: cap the first pass and
+    // fall back to a full pass only when the batch stop was not found below the cap.
+    const int kFirstPassCap = 32;
+    const bool capped = prm.batch_stop && prm.early_exit && prm.max_iterations > kFirstPassCap;
+    a.cap = capped ? kFirstPassCap : prm.max_iterations;
+    int* decided = reinterpret_cast<int*>(ws + icp_ws_off_batch(P)) + 8;
     a.stats = reinterpret_cast<int*>(ws + icp_ws_off_stats(P));
     if (t_prof_start && t_prof_stop) cudaEventRecord(t_prof_start, stream);
     kernel<<<P, kThreads, smem, stream>>>(a);
@@ -204,9 +226,19 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
     }
     if (err != cudaSuccess) return (int)err;
 
-    icp_resolve_batch_kernel<<<1, 256, 0, stream>>>(conv, P, prm.max_iterations, prm.batch_stop, batch);
+    icp_resolve_batch_kernel<<<1, 256, 0, stream>>>(conv, P, prm.max_iterations, a.cap, prm.batch_stop, batch,
+                                                    capped ? decided : nullptr);
     err = cudaGetLastError();
     if (err != cudaSuccess) return (int)err;
+    if (capped) {
+        a.decided = decided;
+        kernel<<<P, kThreads, smem, stream>>>(a);
+        a.decided = nullptr;
+        icp_resolve_batch_kernel<<<1, 256, 0, stream>>>(conv, P, prm.max_iterations, prm.max_iterations, prm.batch_stop,
+                                                        batch, decided);
+        err = cudaGetLastError();
+        if (err != cudaSuccess) return (int)err;
+    }
 
     if (prm.batch_stop) {
         a.batch = batch;

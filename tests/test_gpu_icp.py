@@ -250,3 +250,21 @@ def test_grid_handles_large_and_flat_clusters():
     T = b.T.cpu().numpy()
     moved = src[:2, :, :3] @ b.R.cpu().numpy()[:2] + T[:2, None]
     assert np.abs(moved - dst[:2, :, :3]).max() < 0.02
+
+
+def test_batch_stop_beyond_the_first_pass_cap():
+    """The first pass is capped at 32 iterations; when the reference's batch stop lies beyond (here: never, because a
+    pair without inliers has rmse == 0 and a NaN relative rmse, SURVEY finding 1) a full pass must take over -- same results as
+    the oracle, which runs all 100 iterations like the reference."""
+    src, dst, _ = synth.make_pairs(12, 128, seed=77, ragged=True, residual_only=True, wrong_frac=0.0)
+    dst[0, :, :3] = np.where(dst[0, :, 3:4] > 0, dst[0, :, :3] + 5.0, dst[0, :, :3])   # no inliers: rmse == 0 -> NaN
+    ref = O.icp_loop(torch.from_numpy(src), torch.from_numpy(dst), 0.1, 100, 1e-6, diagnostics=True)
+    assert ref.iterations == 100 and not ref.converged
+    r = _run(src, dst, max_iterations=100, relative_rmse_thr=1e-6, early_exit=True, batch_stop=True)
+    assert r.batch.tolist() == [100, 0]
+    _assert_parity(src, r.R.cpu(), r.T.cpu(), ref.R, ref.T, ref, max_unstable_frac=0.35)
+    # and a batch whose stop iteration is found below the cap still agrees with the uncapped logic
+    ref2 = O.icp_loop(torch.from_numpy(src[1:]), torch.from_numpy(dst[1:]), 0.1, 100, 1e-6, diagnostics=True)
+    r2 = _run(src[1:], dst[1:], max_iterations=100, relative_rmse_thr=1e-6, early_exit=True, batch_stop=True)
+    assert r2.batch.tolist()[1] == int(ref2.converged) and abs(r2.batch.tolist()[0] - ref2.iterations) <= 2
+    _assert_parity(src[1:], r2.R.cpu(), r2.T.cpu(), ref2.R, ref2.T, ref2, max_unstable_frac=0.35)
