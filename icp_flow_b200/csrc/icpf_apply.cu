@@ -48,30 +48,40 @@ __device__ __forceinline__ float mean_nn_error(const float (&m)[12], const float
     return sum[0];
 }
 
+// BIG: clusters whose two row blocks do not fit shared memory are read from global memory (L1/L2) instead.
+template <bool BIG>
 __global__ void __launch_bounds__(kThreads) icp_finalize_kernel(FinalizeArgs a) {
     const int p = blockIdx.x, tid = threadIdx.x;
-    PairTiles tl = carve_pair_tiles<false>(a.N);
-    if (tid == 0) {
-        mbar_init(tl.bar(), 1);
-        fence_barrier_init();
+    __shared__ float s_scratch[kWarps * 4];
+    const float4* S;
+    const float4* D;
+    if constexpr (BIG) {
+        S = reinterpret_cast<const float4*>(a.src) + (size_t)p * a.N;
+        D = reinterpret_cast<const float4*>(a.dst) + (size_t)p * a.N;
+    } else {
+        PairTiles tl = carve_pair_tiles<false>(a.N);
+        if (tid == 0) {
+            mbar_init(tl.bar(), 1);
+            fence_barrier_init();
+        }
+        __syncthreads();
+        load_pair_tiles(tl, a.src + (size_t)p * a.N * 4, a.dst + (size_t)p * a.N * 4, a.N, 0);
+        S = tl.src();
+        D = tl.dst();
     }
-    __syncthreads();
-    load_pair_tiles(tl, a.src + (size_t)p * a.N * 4, a.dst + (size_t)p * a.N * 4, a.N, 0);
     float cnt[2] = {0.f, 0.f};
     for (int q = tid; q < a.N; q += kThreads) {
-        cnt[0] += (tl.src()[q].w > 0.f) ? 1.f : 0.f;
-        cnt[1] += (tl.dst()[q].w > 0.f) ? 1.f : 0.f;
+        cnt[0] += (S[q].w > 0.f) ? 1.f : 0.f;
+        cnt[1] += (D[q].w > 0.f) ? 1.f : 0.f;
     }
-    block_allreduce_sum<2, kWarps>(cnt, tl.red() + kScrPart);
+    block_allreduce_sum<2, kWarps>(cnt, s_scratch);
     __syncthreads();
     int n_s = (int)cnt[0], n_d = (int)cnt[1];
     const bool swapped = a.auto_swap && n_s > n_d;
     if (swapped) {
-        tl.swap_clouds<false>();
+        const float4* t = S; S = D; D = t;
         const int n = n_s; n_s = n_d; n_d = n;
     }
-    const float4* S = tl.src();
-    const float4* D = tl.dst();
     // M0 = init pose, Micp = [[R^T, T],[0,1]] (utils_icp.py:60-65), M = Micp * M0 (utils_icp.py:24)
     float m0[16], mi[16], mm[16];
 #pragma unroll
@@ -93,8 +103,8 @@ __global__ void __launch_bounds__(kThreads) icp_finalize_kernel(FinalizeArgs a) 
     float a0[12], a1[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) { a0[i] = m0[i]; a1[i] = mm[i]; }
-    const float e0 = __fdiv_rn(mean_nn_error(a0, S, n_s, D, n_d, tl.red() + kScrPart), (float)n_s);
-    const float e1 = __fdiv_rn(mean_nn_error(a1, S, n_s, D, n_d, tl.red() + kScrPart), (float)n_s);
+    const float e0 = __fdiv_rn(mean_nn_error(a0, S, n_s, D, n_d, s_scratch), (float)n_s);
+    const float e1 = __fdiv_rn(mean_nn_error(a1, S, n_s, D, n_d, s_scratch), (float)n_s);
     if (tid == 0) {
         const bool rolled = e1 >= e0;          // utils_icp.py:34-35 (NaN compares false: keep the ICP result)
         float out[16];
@@ -131,20 +141,20 @@ int launch_icp_finalize(const float* src, const float* dst, int P, int N, const 
                         const float* icp_T, int auto_swap, float* out_pose, float* out_err, int* out_flags,
                         cudaStream_t stream) {
     if (P == 0) return ICPF_OK;
-    const size_t smem = pair_smem_bytes(N, false);
-    if (smem > 227 * 1024) return ICPF_E_UNSUPPORTED;
-    cudaError_t err = cudaFuncSetAttribute(icp_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool big = pair_smem_bytes(N, false) > (size_t)227 * 1024;
+    const size_t smem = big ? 0 : pair_smem_bytes(N, false);
+    auto kernel = big ? icp_finalize_kernel<true> : icp_finalize_kernel<false>;
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
     FinalizeArgs a{src, dst, N, init_pose, icp_R, icp_T, auto_swap, out_pose, out_err, out_flags};
-    icp_finalize_kernel<<<P, kThreads, smem, stream>>>(a);
+    kernel<<<P, kThreads, smem, stream>>>(a);
     return (int)cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------ orchestration
 // workspace: [icp workspace][R P*9][T P*3][init pose P*16][cand idx P*5][votes P*5][histogram chunk]
 size_t path_workspace_bytes(int P, int N, int lx, int ly, int lz) {
-    (void)N;
-    size_t b = icp_workspace_bytes(P);
+    size_t b = icp_workspace_bytes(P) + icp_big_workspace_bytes(P, N);
     b += align_up((size_t)P * 9 * 4, 256) + align_up((size_t)P * 3 * 4, 256) + align_up((size_t)P * 16 * 4, 256);
     b += 2 * align_up((size_t)P * 5 * 4, 256);
     if (lx > 0 && ly > 0 && lz > 0) b += align_up((size_t)hist_chunk_pairs(P, lx, ly, lz) * lx * ly * lz * 4, 256);
@@ -170,10 +180,10 @@ struct PathWs {
     float* hist;
 };
 
-static PathWs carve_ws(void* workspace, int P) {
+static PathWs carve_ws(void* workspace, int P, int N) {
     PathWs w;
     unsigned char* p = static_cast<unsigned char*>(workspace);
-    w.icp = p; p += icp_workspace_bytes(P);
+    w.icp = p; p += icp_workspace_bytes(P) + icp_big_workspace_bytes(P, N);
     w.R = reinterpret_cast<float*>(p); p += align_up((size_t)P * 9 * 4, 256);
     w.T = reinterpret_cast<float*>(p); p += align_up((size_t)P * 3 * 4, 256);
     w.init = reinterpret_cast<float*>(p); p += align_up((size_t)P * 16 * 4, 256);
@@ -189,7 +199,7 @@ int launch_hist_init(const float* src, const float* dst, int P, int N, const icp
     if (P == 0) return ICPF_OK;
     if (workspace == nullptr || workspace_bytes < path_workspace_bytes(P, N, hb.len[0], hb.len[1], hb.len[2]))
         return ICPF_E_WORKSPACE;
-    PathWs w = carve_ws(workspace, P);
+    PathWs w = carve_ws(workspace, P, N);
     int* cand = out_cand ? out_cand : w.cand;
     float* votes = out_votes ? out_votes : w.votes;
     const int chunk = hist_chunk_pairs(P, hb.len[0], hb.len[1], hb.len[2]);
@@ -212,9 +222,9 @@ int launch_apply_icp(const float* src, const float* dst, const float* init_pose,
                      size_t workspace_bytes, cudaStream_t stream) {
     if (P == 0) return ICPF_OK;
     if (workspace == nullptr || workspace_bytes < path_workspace_bytes(P, N, 0, 0, 0)) return ICPF_E_WORKSPACE;
-    PathWs w = carve_ws(workspace, P);
+    PathWs w = carve_ws(workspace, P, N);
     int rc = launch_icp(src, dst, nullptr, nullptr, init_pose, auto_swap, P, N, prm, w.R, w.T, nullptr, nullptr,
-                        nullptr, nullptr, out_batch, w.icp, icp_workspace_bytes(P), stream);
+                        nullptr, nullptr, out_batch, w.icp, icp_workspace_bytes(P) + icp_big_workspace_bytes(P, N), stream);
     if (rc != ICPF_OK) return rc;
     return launch_icp_finalize(src, dst, P, N, init_pose, w.R, w.T, auto_swap, out_pose, out_err, out_flags, stream);
 }
@@ -225,7 +235,7 @@ int launch_hist_icp(const float* src, const float* dst, int P, int N, const icpf
     if (P == 0) return ICPF_OK;
     if (workspace == nullptr || workspace_bytes < path_workspace_bytes(P, N, hb.len[0], hb.len[1], hb.len[2]))
         return ICPF_E_WORKSPACE;
-    PathWs w = carve_ws(workspace, P);
+    PathWs w = carve_ws(workspace, P, N);
     float* init = out_init ? out_init : w.init;
     int rc = launch_hist_init(src, dst, P, N, hb, 1, init, nullptr, nullptr, nullptr, nullptr, workspace,
                               workspace_bytes, stream);

@@ -237,32 +237,42 @@ struct ScoreArgs {
     int* out_which;          // [P]   (may be NULL)
 };
 
+// BIG: clusters whose two row blocks do not fit shared memory are read from global memory (L1/L2) instead.
+template <bool BIG>
 __global__ void __launch_bounds__(kThreads) hist_score_kernel(ScoreArgs a) {
     __shared__ float s_t[kCand][3];
     __shared__ float s_sum[2][kCand];
     __shared__ float s_part[kWarps][2][kCand];
+    __shared__ float s_scratch[kWarps * 4];
     const int p = blockIdx.x, tid = threadIdx.x;
-    PairTiles tl = carve_pair_tiles<false>(a.N);
-    if (tid == 0) {
-        mbar_init(tl.bar(), 1);
-        fence_barrier_init();
+    const float4* S;
+    const float4* D;
+    if constexpr (BIG) {
+        S = reinterpret_cast<const float4*>(a.src) + (size_t)p * a.N;
+        D = reinterpret_cast<const float4*>(a.dst) + (size_t)p * a.N;
+    } else {
+        PairTiles tl = carve_pair_tiles<false>(a.N);
+        if (tid == 0) {
+            mbar_init(tl.bar(), 1);
+            fence_barrier_init();
+        }
+        __syncthreads();
+        load_pair_tiles(tl, a.src + (size_t)p * a.N * 4, a.dst + (size_t)p * a.N * 4, a.N, 0);
+        S = tl.src();
+        D = tl.dst();
     }
     if (tid < 2 * kCand) s_sum[tid / kCand][tid % kCand] = 0.f;
-    __syncthreads();
-    load_pair_tiles(tl, a.src + (size_t)p * a.N * 4, a.dst + (size_t)p * a.N * 4, a.N, 0);
     float cnt[2] = {0.f, 0.f};
     for (int q = tid; q < a.N; q += kThreads) {
-        cnt[0] += (tl.src()[q].w > 0.f) ? 1.f : 0.f;
-        cnt[1] += (tl.dst()[q].w > 0.f) ? 1.f : 0.f;
+        cnt[0] += (S[q].w > 0.f) ? 1.f : 0.f;
+        cnt[1] += (D[q].w > 0.f) ? 1.f : 0.f;
     }
-    block_allreduce_sum<2, kWarps>(cnt, tl.red() + kScrPart);
+    block_allreduce_sum<2, kWarps>(cnt, s_scratch);
     int n_s = (int)cnt[0], n_d = (int)cnt[1];
     if (a.auto_swap && n_s > n_d) {     // always register the smaller cloud onto the larger one (utils_match.py:139-146)
-        tl.swap_clouds<false>();
+        const float4* t = S; S = D; D = t;
         const int n = n_s; n_s = n_d; n_d = n;
     }
-    const float4* S = tl.src();
-    const float4* D = tl.dst();
     if (tid < kCand) {
         float tx = 0.f, ty = 0.f, tz = 0.f;
         if (tid < kTopK) {
@@ -356,13 +366,14 @@ int launch_hist_score(const float* src, const float* dst, int P, int N, const in
                       const float* bins_y, const float* bins_z, int lx, int ly, int lz, float half_bin, int auto_swap,
                       float* out_pose, float* out_scores, int* out_which, cudaStream_t stream) {
     if (P == 0) return ICPF_OK;
-    const size_t smem = pair_smem_bytes(N, false);
-    if (smem > 227 * 1024) return ICPF_E_UNSUPPORTED;
-    cudaError_t err = cudaFuncSetAttribute(hist_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool big = pair_smem_bytes(N, false) > (size_t)227 * 1024;
+    const size_t smem = big ? 0 : pair_smem_bytes(N, false);
+    auto kernel = big ? hist_score_kernel<true> : hist_score_kernel<false>;
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
     ScoreArgs a{src, dst, N, cand_idx, bins_x, bins_y, bins_z, lx, ly, lz, half_bin, auto_swap, out_pose, out_scores,
                 out_which};
-    hist_score_kernel<<<P, kThreads, smem, stream>>>(a);
+    kernel<<<P, kThreads, smem, stream>>>(a);
     return (int)cudaGetLastError();
 }
 

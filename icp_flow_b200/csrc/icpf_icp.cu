@@ -8,6 +8,8 @@
 //   kernel 2  AND-reduces the masks over the batch -> k* = first iteration at which the reference's `.all()` fires;
 //   kernel 3  re-runs (capped at k*+1 iterations) only the pairs that were still moving at k*.
 #include "icpf_internal.h"
+#include <type_traits>
+
 #include "icpf_icploop.cuh"
 
 namespace icpf {
@@ -36,10 +38,11 @@ struct IcpArgs {
     const int* batch;      // re-run pass: batch[0] = k*+1 (iterations the reference executed); NULL otherwise
     const int* decided;    // second full pass: runs only while *decided == 0; NULL otherwise
     int cap;               // first pass: iteration cap (<= max_it)
+    unsigned char* big_ws; // global-memory variant: per-pair workspace (pair_global_ws_bytes(N) each)
 };
 
-template <int MODE>
-__global__ void __launch_bounds__(kThreads, 7) icp_pairs_kernel(IcpArgs a) {
+template <int MODE, bool BIG>
+__global__ void __launch_bounds__(kThreads, BIG ? 4 : 7) icp_pairs_kernel(IcpArgs a) {
     const int p = blockIdx.x;
     int max_it = a.max_it;
     bool early_exit = a.early_exit != 0;
@@ -55,13 +58,27 @@ __global__ void __launch_bounds__(kThreads, 7) icp_pairs_kernel(IcpArgs a) {
         max_it = min(max_it, a.cap);
     }
     constexpr bool GRID = MODE >= 2;
-    PairTiles tl = carve_pair_tiles<GRID>(a.N);
-    if (threadIdx.x == 0) {
-        mbar_init(tl.bar(), 1);
-        fence_barrier_init();
+    typename std::conditional<BIG, PairTilesG, PairTiles>::type tl;
+    if constexpr (BIG) {
+        // rows stay in global memory; the workspace holds the sorted copy, the transformed src rows, nn words, list
+        const size_t n = (size_t)(a.N + kThreads - 1) / kThreads * kThreads;
+        unsigned char* w = a.big_ws + (size_t)p * pair_global_ws_bytes(a.N);
+        tl.src_p = const_cast<float4*>(reinterpret_cast<const float4*>(a.src) + (size_t)p * a.N);
+        tl.dst_p = const_cast<float4*>(reinterpret_cast<const float4*>(a.dst) + (size_t)p * a.N);
+        tl.sorted_p = reinterpret_cast<float4*>(w);
+        tl.nn_p = reinterpret_cast<unsigned int*>(w + n * 32);
+        tl.defer_p = reinterpret_cast<unsigned short*>(w + n * 36);
+        tl.defer_cap = (int)(n / kWarps);
+        if (!GRID) tl.sorted_p = tl.dst_p;
+    } else {
+        tl = carve_pair_tiles<GRID>(a.N);
+        if (threadIdx.x == 0) {
+            mbar_init(tl.bar(), 1);
+            fence_barrier_init();
+        }
+        __syncthreads();
+        load_pair_tiles(tl, a.src + (size_t)p * a.N * 4, a.dst + (size_t)p * a.N * 4, a.N, 0);
     }
-    __syncthreads();
-    load_pair_tiles(tl, a.src + (size_t)p * a.N * 4, a.dst + (size_t)p * a.N * 4, a.N, 0);
 
     // valid-row counts (knn `lengths`): number of rows with flag > 0  (utils_icp_pytorch3d.py:109-112)
     float cnt[2] = {0.f, 0.f};
@@ -72,7 +89,7 @@ __global__ void __launch_bounds__(kThreads, 7) icp_pairs_kernel(IcpArgs a) {
     block_allreduce_sum<2, kWarps>(cnt, tl.red() + kScrPart);
     int n_s = (int)cnt[0], n_d = (int)cnt[1];
     if (a.auto_swap && n_s > n_d) {
-        tl.swap_clouds<GRID>();
+        tl.template swap_clouds<GRID>();
         const int n = n_s; n_s = n_d; n_d = n;
     }
     const float4 piv = tl.dst()[0];      // first pivot of the moment sums: any point of the fixed cloud
@@ -84,7 +101,15 @@ __global__ void __launch_bounds__(kThreads, 7) icp_pairs_kernel(IcpArgs a) {
         float m[12];
 #pragma unroll
         for (int i = 0; i < 12; ++i) m[i] = tl.bcast()[i];
-        for (int q = threadIdx.x; q < n_s; q += kThreads) tl.src()[q] = transform_row(m, tl.src()[q]);
+        if constexpr (BIG) {
+            // the inputs are read-only: the moved cloud goes to the workspace
+            const size_t n = (size_t)(a.N + kThreads - 1) / kThreads * kThreads;
+            float4* moved = reinterpret_cast<float4*>(a.big_ws + (size_t)p * pair_global_ws_bytes(a.N) + n * 16);
+            for (int q = threadIdx.x; q < n_s; q += kThreads) moved[q] = transform_row(m, tl.src()[q]);
+            tl.src_p = moved;
+        } else {
+            for (int q = threadIdx.x; q < n_s; q += kThreads) tl.src()[q] = transform_row(m, tl.src()[q]);
+        }
         __syncthreads();
     }
 
@@ -164,6 +189,10 @@ __global__ void __launch_bounds__(256) icp_resolve_batch_kernel(const uint32_t* 
     }
 }
 
+size_t icp_big_workspace_bytes(int P, int N) {
+    return pair_needs_global(N) ? (size_t)P * pair_global_ws_bytes(N) : 0;
+}
+
 static thread_local cudaEvent_t t_prof_start = nullptr, t_prof_stop = nullptr;
 
 void set_profile_events(cudaEvent_t start, cudaEvent_t stop) {
@@ -179,22 +208,22 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
     // nn_mode: 0 auto (grid + cache whenever the tiles fit in shared memory), 1 brute force, 2 grid, 3 grid + cache
     const size_t kMaxSmem = 227 * 1024;
     if (N > kMaxRows) return ICPF_E_UNSUPPORTED;
-    bool grid = prm.nn_mode != 1;
-    if (grid && pair_smem_bytes(N, true) > kMaxSmem) {
-        if (prm.nn_mode >= 2) return ICPF_E_UNSUPPORTED;
-        grid = false;
-    }
-    const size_t smem = pair_smem_bytes(N, grid);
-    if (smem > kMaxSmem) return ICPF_E_UNSUPPORTED;
+    const bool grid = prm.nn_mode != 1;
+    // clusters whose tiles do not fit shared memory run the global-memory variant (same code, rows in L2)
+    const bool big = pair_needs_global(N);
+    const size_t smem = big ? pair_global_smem_bytes() : pair_smem_bytes(N, grid);
     // workspace: iters [P] | conv [P,4] | batch [2]
-    const size_t need = icp_workspace_bytes(P);
+    const size_t need = icp_workspace_bytes(P) + icp_big_workspace_bytes(P, N);
     if (workspace == nullptr || workspace_bytes < need) return ICPF_E_WORKSPACE;
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     int* iters = out_iters ? out_iters : reinterpret_cast<int*>(ws);
     uint32_t* conv = out_conv ? out_conv : reinterpret_cast<uint32_t*>(ws + icp_ws_off_conv(P));
     int* batch = out_batch ? out_batch : reinterpret_cast<int*>(ws + icp_ws_off_batch(P));
 
-    auto kernel = !grid ? icp_pairs_kernel<1> : (prm.nn_mode == 2 ? icp_pairs_kernel<2> : icp_pairs_kernel<3>);
+    auto kernel = big ? (!grid ? icp_pairs_kernel<1, true>
+                               : (prm.nn_mode == 2 ? icp_pairs_kernel<2, true> : icp_pairs_kernel<3, true>))
+                      : (!grid ? icp_pairs_kernel<1, false>
+                               : (prm.nn_mode == 2 ? icp_pairs_kernel<2, false> : icp_pairs_kernel<3, false>));
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
 
@@ -215,6 +244,7 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
     const int kFirstPassCap = 32;
     const bool capped = prm.batch_stop && prm.early_exit && prm.max_iterations > kFirstPassCap;
     a.cap = capped ? kFirstPassCap : prm.max_iterations;
+    a.big_ws = big ? ws + icp_workspace_bytes(P) : nullptr;
     int* decided = reinterpret_cast<int*>(ws + icp_ws_off_batch(P)) + 8;
     a.stats = reinterpret_cast<int*>(ws + icp_ws_off_stats(P));
     if (t_prof_start && t_prof_stop) cudaEventRecord(t_prof_start, stream);

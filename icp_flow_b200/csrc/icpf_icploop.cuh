@@ -104,12 +104,14 @@ __device__ __forceinline__ float moved_sq(const float (&dr)[9], const float (&dt
 //           always uses the exactly recomputed d_best^2, so the results are bit-identical to MODE 1/2.
 //   n_s / n_d : valid-row counts (knn `lengths`); tau2 = fp32(thres^2); pivot0 = any point near the clouds
 //   init_R / init_T (may be NULL) = init_transform of the reference: used for the first correspondence search only.
-template <int MODE>
-__device__ __forceinline__ IcpResult icp_iterations(const PairTiles& tl, const GridInfo& g, int n_s, int n_d, float tau2,
+template <int MODE, class Tiles>
+__device__ __forceinline__ IcpResult icp_iterations(const Tiles& tl, const GridInfo& g, int n_s, int n_d, float tau2,
                                            int max_it, float rel_thr, bool early_exit, const float* init_R,
                                            const float* init_T, float pivx, float pivy, float pivz) {
     constexpr bool GRID = MODE >= 2;
     constexpr bool CACHE = MODE == 3;
+    using NW = NnWord<Tiles::kPosBits>;
+    constexpr unsigned int kNnPosMask = NW::kPosMask, kNnNone = NW::kNone, kNnMasked = NW::kMasked;
     const float INF = __int_as_float(0x7f800000);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float4* __restrict__ cand = GRID ? tl.sorted() : tl.dst();
@@ -191,7 +193,7 @@ __device__ __forceinline__ IcpResult icp_iterations(const PairTiles& tl, const G
 #pragma unroll
                 for (int k = 0; k < QB; ++k) {
                     const int q = (b0 + k) * kThreads + tid;
-                    if (q < n_s) nnw[q] = pack_nn(bidx[k], 0.f, (best[k] <= tau2) && (x0[k].w > 0.f));
+                    if (q < n_s) nnw[q] = NW::pack(bidx[k], 0.f, (best[k] <= tau2) && (x0[k].w > 0.f));
                 }
             }
         } else {
@@ -212,7 +214,7 @@ __device__ __forceinline__ IcpResult icp_iterations(const PairTiles& tl, const G
                 bool need = valid;
                 if (CACHE && !refresh) {
                     if (valid) {
-                        const float bound = nn_bound(wold);
+                        const float bound = NW::bound(wold);
                         const float m2 = moved_sq(dr, dt, x0);
                         const float m = fast_sqrt(m2) * 1.0001f;
                         // (a) every other point is provably farther than tau: only the cached candidate can pass
@@ -221,7 +223,7 @@ __device__ __forceinline__ IcpResult icp_iterations(const PairTiles& tl, const G
                         if (pos >= 0) hit = hit || ((d2 + 2.0002f * fast_sqrt(d2 * m2) + m2) * 1.0002f < bound * bound);
                         if (hit) {
                             // re-anchor: relative to the row's NEW position every other point is >= bound - m away
-                            nnw[q] = pack_nn(pos, bound - m - anchor_slack, (pos >= 0) && (d2 <= tau2) && (x0.w > 0.f));
+                            nnw[q] = NW::pack(pos, bound - m - anchor_slack, (pos >= 0) && (d2 <= tau2) && (x0.w > 0.f));
                             need = false;
                         }
                     }
@@ -238,7 +240,7 @@ __device__ __forceinline__ IcpResult icp_iterations(const PairTiles& tl, const G
                     // g.pad (>= 1e-4 m, >= 16 ulp of the largest coordinate) covers the fp32 rounding of the
                     // transformed positions whose separation m is bounded analytically
                     const float bound = fminf(sqrtf(d2nd), box) * 0.9999f - g.pad;
-                    nnw[q] = pack_nn(pos, bound, (pos >= 0) && (d2 <= tau2) && (x0.w > 0.f));
+                    nnw[q] = NW::pack(pos, bound, (pos >= 0) && (d2 <= tau2) && (x0.w > 0.f));
                 }
             }
             if (CACHE && !refresh) {
@@ -253,7 +255,7 @@ __device__ __forceinline__ IcpResult icp_iterations(const PairTiles& tl, const G
                     apply_rt(R, T, x0.x, x0.y, x0.z, qx, qy, qz);
                     grid_search(g, cand, cell_runs, qx, qy, qz, d2, pos, d2nd, box);
                     const float bound = fminf(sqrtf(d2nd), box) * 0.9999f - g.pad;      // fresh, at the current position
-                    nnw[q] = pack_nn(pos, bound, (pos >= 0) && (d2 <= tau2) && (x0.w > 0.f));
+                    nnw[q] = NW::pack(pos, bound, (pos >= 0) && (d2 <= tau2) && (x0.w > 0.f));
                 }
                 __syncthreads();
             }

@@ -24,6 +24,7 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
 
 void set_profile_events(cudaEvent_t start, cudaEvent_t stop);
 
+size_t icp_big_workspace_bytes(int P, int N);     // 0 unless the clusters need the global-memory variant
 int hist_chunk_pairs(int P, int lx, int ly, int lz);
 size_t path_workspace_bytes(int P, int N, int lx, int ly, int lz);
 

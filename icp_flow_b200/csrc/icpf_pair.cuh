@@ -55,6 +55,7 @@ struct PairTiles {
     int defer_off;    // [kWarps * defer_cap >= N] u16 grid mode: rows whose cached neighbour could not be proven
     int defer_cap;
     int red_off;      // [kRedFloats] float reduction scratch
+    static constexpr int kPosBits = 13;
     __device__ __forceinline__ float4* src() const { return g_tile + src_off; }
     __device__ __forceinline__ float4* dst() const { return g_tile + dst_off; }
     __device__ __forceinline__ float4* sorted() const { return g_tile + sorted_off; }
@@ -83,6 +84,43 @@ __host__ __device__ inline size_t pair_smem_bytes(int N, bool grid) {
     u += up16((kRedFloats + kBcastFloats) * 4 + 16);
     return (size_t)u * 16;
 }
+
+// Large clusters (row blocks that do not fit shared memory, max_points up to 10 000): the same interface, but the rows
+// stay in global memory (L2-resident: one pair is 2 x 16 N bytes) and the sorted copy, the correspondence words and the
+// search list live in a caller-provided workspace; only the grid runs, the reduction scratch and the broadcast block
+// are in shared memory.
+struct PairTilesG {
+    float4* src_p;
+    float4* dst_p;
+    float4* sorted_p;
+    unsigned int* nn_p;
+    unsigned short* defer_p;
+    int defer_cap;
+    static constexpr int kPosBits = 14;
+    __device__ __forceinline__ float4* src() const { return src_p; }
+    __device__ __forceinline__ float4* dst() const { return dst_p; }
+    __device__ __forceinline__ float4* sorted() const { return sorted_p; }
+    __device__ __forceinline__ uint32_t* cells() const { return reinterpret_cast<uint32_t*>(g_tile); }
+    __device__ __forceinline__ unsigned int* nn() const { return nn_p; }
+    __device__ __forceinline__ unsigned short* defer() const { return defer_p; }
+    __device__ __forceinline__ float* red() const { return reinterpret_cast<float*>(g_tile + up16(kCellWords * 4)); }
+    __device__ __forceinline__ float* bcast() const { return red() + kRedFloats; }
+    template <bool GRID>
+    __device__ __forceinline__ void swap_clouds() {
+        float4* t = src_p; src_p = dst_p; dst_p = t;
+        if (!GRID) sorted_p = dst_p;
+    }
+};
+
+__host__ __device__ inline size_t pair_global_smem_bytes() {
+    return (size_t)(up16(kCellWords * 4) + up16((kRedFloats + kBcastFloats) * 4 + 16)) * 16;
+}
+// per-pair workspace of the global-memory variant: sorted rows | transformed src rows | nn words | search list
+__host__ __device__ inline size_t pair_global_ws_bytes(int N) {
+    const size_t n = (size_t)(N + kThreads - 1) / kThreads * kThreads;
+    return n * 16 + n * 16 + n * 4 + ((n * 2 + 15) / 16 * 16);
+}
+__host__ inline bool pair_needs_global(int N) { return pair_smem_bytes(N, true) > (size_t)227 * 1024; }
 
 template <bool GRID>
 __device__ __forceinline__ PairTiles carve_pair_tiles(int N) {
@@ -187,7 +225,8 @@ __device__ __forceinline__ int grid_cell(const GridInfo& g, float x, float y, fl
 
 // Counting sort of dst[0, n_d) into tl.sorted() by cell; fills the run boundaries in tl.cells().  All threads return the
 // same GridInfo.  Uses the reduction scratch; ends with a block barrier.
-__device__ __forceinline__ GridInfo build_grid(const PairTiles& tl, int n_d, float tau, float cell_factor = kCellFactor) {
+template <class Tiles>
+__device__ __forceinline__ GridInfo build_grid(const Tiles& tl, int n_d, float tau, float cell_factor = kCellFactor) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float INF = __int_as_float(0x7f800000);
     float lo[3] = {INF, INF, INF}, hi[3] = {-INF, -INF, -INF};
@@ -352,19 +391,24 @@ __device__ __forceinline__ void grid_search(const GridInfo& g, const float4* __r
     pos = (key == kNone) ? -1 : (int)((unsigned int)key & 0xffffu);
 }
 
-// correspondence word kept per src row: bits 0-12 sorted position of the best candidate (0x1fff none), bit 13
-// "masked out", bits 14-31 a lower bound on the distance of every OTHER dst point (the top 18 bits of the fp32
-// pattern without its sign: truncation rounds a positive value down, 2^-10 relative like fp16)
-constexpr unsigned int kNnPosMask = 0x1fffu;
-constexpr unsigned int kNnNone = 0x1fffu;
-constexpr unsigned int kNnMasked = 0x2000u;
-constexpr int kMaxRows = 8190;          // rows per cloud addressable by the 13-bit position
+// correspondence word kept per src row (PB = position bits: 13 for the shared-memory tiles, 14 for the large-cluster
+// variant): bits [0,PB) sorted position of the best candidate (all ones = none), bit PB "masked out", the remaining
+// high bits a lower bound on the distance of every OTHER dst point (the top bits of the fp32 pattern without its sign:
+// truncation rounds a positive value down; 10 / 9 mantissa bits)
+template <int PB> struct NnWord {
+    static constexpr unsigned int kPosMask = (1u << PB) - 1u;
+    static constexpr unsigned int kNone = kPosMask;
+    static constexpr unsigned int kMasked = 1u << PB;
+    static constexpr unsigned int kBoundMask = ~((1u << (PB + 1)) - 1u);
+    static constexpr int kMaxRows = (1 << PB) - 2;
+    __device__ __forceinline__ static unsigned int pack(int pos, float bound, bool used) {
+        const unsigned int b = (__float_as_uint(fmaxf(bound, 0.f)) << 1) & kBoundMask;
+        return (pos < 0 ? kNone : (unsigned int)pos) | b | (used ? 0u : kMasked);
+    }
+    __device__ __forceinline__ static float bound(unsigned int w) { return __uint_as_float((w & kBoundMask) >> 1); }
+};
+constexpr int kMaxRows = NnWord<14>::kMaxRows;      // rows per cloud the engine accepts
 
-__device__ __forceinline__ unsigned int pack_nn(int pos, float bound, bool used) {
-    const unsigned int b = (__float_as_uint(fmaxf(bound, 0.f)) << 1) & 0xffffc000u;
-    return (pos < 0 ? kNnNone : (unsigned int)pos) | b | (used ? 0u : kNnMasked);
-}
-__device__ __forceinline__ float nn_bound(unsigned int w) { return __uint_as_float((w & 0xffffc000u) >> 1); }
 __device__ __forceinline__ float fast_sqrt(float x) {      // ~2 ulp, callers keep slack; x >= 0
     const float y = fmaxf(x, 1e-30f);
     return y * rsqrtf(y);

@@ -217,3 +217,50 @@ def test_path_on_ragged_synthetic_batch_vs_oracle():
     err = _pose_err(src, T.cpu(), want)
     assert unstable.mean() <= 0.4
     assert err[~unstable].max() <= TOL, err
+
+
+def _repad(batch, N):
+    """Same clusters, padded to N rows (pad_segment convention)."""
+    P, n0, _ = batch.shape
+    out = np.full((P, N, 4), 1e8, np.float32)
+    out[:, :, 3] = 0.0
+    out[:, :n0] = batch
+    return out
+
+
+def test_padding_invariance_and_large_cluster_variant():
+    """Padded rows must not change anything, and clusters padded beyond what fits shared memory (max_points up to
+    10 000, BASELINE config C4) run the global-memory variant of the same kernels: bit-identical results."""
+    from icp_flow_b200 import synth
+    dev = _dev()
+    src, dst, _ = synth.make_pairs(12, 384, seed=17, ragged=True, residual_only=False, wrong_frac=0.1)
+    args = types.SimpleNamespace(thres_dist=0.1, translation_frame=2.5, chunk_size=50)
+    base, base_dbg = ops.hist_icp(args, torch.from_numpy(src).to(dev), torch.from_numpy(dst).to(dev), return_debug=True)
+    base_icp = ops.icp_batch(torch.from_numpy(src).to(dev), torch.from_numpy(dst).to(dev), ops.make_params())
+    for N in (1024, 5000, 10000):
+        s, d = torch.from_numpy(_repad(src, N)).to(dev), torch.from_numpy(_repad(dst, N)).to(dev)
+        T, dbg = ops.hist_icp(args, s, d, return_debug=True)
+        assert torch.equal(dbg["init"], base_dbg["init"]), N
+        assert torch.equal(T, base), N
+        r = ops.icp_batch(s, d, ops.make_params())
+        assert torch.equal(r.R, base_icp.R) and torch.equal(r.T, base_icp.T) and torch.equal(r.iterations, base_icp.iterations), N
+    with pytest.raises(RuntimeError, match="not supported"):
+        ops.icp_batch(torch.from_numpy(_repad(src, 20000)).to(dev), torch.from_numpy(_repad(dst, 20000)).to(dev),
+                      ops.make_params())
+
+
+def test_large_clusters_vs_oracle():
+    """Clusters of several thousand points (global-memory variant) against the CPU oracle."""
+    from icp_flow_b200 import synth
+    dev = _dev()
+    src, dst, _ = synth.make_pairs(3, 6000, seed=23, ragged=True, residual_only=True, wrong_frac=0.0, min_points=3000,
+                                   keep_density=False)
+    ref = O.icp_loop(torch.from_numpy(src), torch.from_numpy(dst), 0.1, 100, 1e-6, diagnostics=True)
+    r = ops.icp_batch(torch.from_numpy(src).to(dev), torch.from_numpy(dst).to(dev), ops.make_params())
+    pts = torch.from_numpy(src[:, :, :3]).double()
+    valid = torch.from_numpy(src[:, :, 3] > 0)
+    a = torch.bmm(pts, r.R.cpu().double()) + r.T.cpu().double()[:, None]
+    b = torch.bmm(pts, ref.R.double()) + ref.T.double()[:, None]
+    err = ((a - b).abs().amax(dim=2) * valid).amax(dim=1).numpy()
+    ok = ~O.unstable_pairs(ref).numpy()
+    assert ok.any() and err[ok].max() <= TOL, err
