@@ -104,7 +104,8 @@ int icpf_hist_votes_f32(const float* X, const float* Y, int32_t B, int32_t NX, i
     if (B == 0) return ICPF_OK;
     if (!X || !Y || !bins) return ICPF_E_NULL;
     if (!aligned16(X) || !aligned16(Y)) return ICPF_E_ALIGN;
-    return launch_hist_votes(X, Y, B, NX, NY, min_xyz, max_xyz, len_xyz, bins, 0, static_cast<cudaStream_t>(stream));
+    return launch_hist_votes(X, Y, B, NX, NY, min_xyz, max_xyz, len_xyz, bins, 0, nullptr,
+                             static_cast<cudaStream_t>(stream));
 }
 
 int icpf_hist_init_f32(const float* src, const float* dst, int32_t P, int32_t N, const icpf_hist_bins* bins,

@@ -156,7 +156,7 @@ int launch_icp_finalize(const float* src, const float* dst, int P, int N, const 
 size_t path_workspace_bytes(int P, int N, int lx, int ly, int lz) {
     size_t b = icp_workspace_bytes(P) + icp_big_workspace_bytes(P, N);
     b += align_up((size_t)P * 9 * 4, 256) + align_up((size_t)P * 3 * 4, 256) + align_up((size_t)P * 16 * 4, 256);
-    b += 2 * align_up((size_t)P * 5 * 4, 256);
+    b += 2 * align_up((size_t)P * 5 * 4, 256) + align_up((size_t)P * 4, 256);
     if (lx > 0 && ly > 0 && lz > 0) b += align_up((size_t)hist_chunk_pairs(P, lx, ly, lz) * lx * ly * lz * 4, 256);
     return b;
 }
@@ -177,6 +177,7 @@ struct PathWs {
     float* init;
     int* cand;
     float* votes;
+    int* need;      // [P] pairs that take the global-memory histogram path
     float* hist;
 };
 
@@ -189,6 +190,7 @@ static PathWs carve_ws(void* workspace, int P, int N) {
     w.init = reinterpret_cast<float*>(p); p += align_up((size_t)P * 16 * 4, 256);
     w.cand = reinterpret_cast<int*>(p); p += align_up((size_t)P * 5 * 4, 256);
     w.votes = reinterpret_cast<float*>(p); p += align_up((size_t)P * 5 * 4, 256);
+    w.need = reinterpret_cast<int*>(p); p += align_up((size_t)P * 4, 256);
     w.hist = reinterpret_cast<float*>(p);
     return w;
 }
@@ -202,15 +204,18 @@ int launch_hist_init(const float* src, const float* dst, int P, int N, const icp
     PathWs w = carve_ws(workspace, P, N);
     int* cand = out_cand ? out_cand : w.cand;
     float* votes = out_votes ? out_votes : w.votes;
+    // utils_hist.py:69: hist(dst, src, ...) -> votes dst_i - src_j.  Fused shared-memory kernel first; the pairs whose
+    // difference box does not fit are flagged and redone through the chunked global-memory histogram.
+    int rc = launch_hist_fused(dst, src, P, N, hb.min, hb.max, hb.len, auto_swap, cand, votes, w.need, stream);
+    if (rc != ICPF_OK) return rc;
     const int chunk = hist_chunk_pairs(P, hb.len[0], hb.len[1], hb.len[2]);
     for (int lo = 0; lo < P; lo += chunk) {
         const int n = (P - lo < chunk) ? (P - lo) : chunk;
-        // utils_hist.py:69: hist(dst, src, ...) -> votes dst_i - src_j
-        int rc = launch_hist_votes(dst + (size_t)lo * N * 4, src + (size_t)lo * N * 4, n, N, N, hb.min, hb.max, hb.len,
-                                   w.hist, auto_swap, stream);
+        rc = launch_hist_votes(dst + (size_t)lo * N * 4, src + (size_t)lo * N * 4, n, N, N, hb.min, hb.max, hb.len,
+                               w.hist, auto_swap, w.need + lo, stream);
         if (rc != ICPF_OK) return rc;
         rc = launch_hist_peaks(w.hist, n, hb.len[0], hb.len[1], hb.len[2], cand + (size_t)lo * 5,
-                               votes + (size_t)lo * 5, stream);
+                               votes + (size_t)lo * 5, w.need + lo, stream);
         if (rc != ICPF_OK) return rc;
     }
     return launch_hist_score(src, dst, P, N, cand, hb.bins_x, hb.bins_y, hb.bins_z, hb.len[0], hb.len[1], hb.len[2],

@@ -27,10 +27,12 @@ struct HistGeom {
 // call is hist(dst_, src_) with (src_, dst_) = (src, dst) swapped whenever src has more valid rows than dst.
 __global__ void __launch_bounds__(kVoteThreads) hist_votes_kernel(const float4* __restrict__ X,
                                                                   const float4* __restrict__ Y, int NX, int NY,
-                                                                  HistGeom gm, float* __restrict__ bins, int auto_swap) {
+                                                                  HistGeom gm, float* __restrict__ bins, int auto_swap,
+                                                                  const int* __restrict__ need) {
     __shared__ float4 tile[kVoteTile];
     __shared__ int s_cnt[2];
     const int b = blockIdx.y;
+    if (need != nullptr && need[b] == 0) return;      // this pair was handled by the fused shared-memory kernel
     const float4* xb = X + (size_t)b * NX;
     const float4* yb = Y + (size_t)b * NY;
     int nx = NX, ny = NY;
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(kVoteThreads) hist_votes_kernel(const float4* 
 }
 
 int launch_hist_votes(const float* X, const float* Y, int B, int NX, int NY, const float* mins, const float* maxs,
-                      const int* lens, float* bins, int auto_swap, cudaStream_t stream) {
+                      const int* lens, float* bins, int auto_swap, const int* need, cudaStream_t stream) {
     if (B == 0) return ICPF_OK;
     HistGeom gm{mins[0], mins[1], mins[2], maxs[0], maxs[1], maxs[2], lens[0], lens[1], lens[2]};
     const size_t bytes = (size_t)B * lens[0] * lens[1] * lens[2] * sizeof(float);
@@ -97,7 +99,7 @@ int launch_hist_votes(const float* X, const float* Y, int B, int NX, int NY, con
     dim3 grid((nmax + kVoteThreads - 1) / kVoteThreads, B);
     hist_votes_kernel<<<grid, kVoteThreads, 0, stream>>>(reinterpret_cast<const float4*>(X),
                                                          reinterpret_cast<const float4*>(Y), NX, NY, gm, bins,
-                                                         auto_swap);
+                                                         auto_swap, need);
     return (int)cudaGetLastError();
 }
 
@@ -113,13 +115,15 @@ __device__ __forceinline__ unsigned long long peak_key(float v, int idx) {
 
 __global__ void __launch_bounds__(kPeakThreads) hist_peaks_kernel(const float* __restrict__ bins, int lx, int ly,
                                                                   int lz, int* __restrict__ out_idx,
-                                                                  float* __restrict__ out_votes) {
+                                                                  float* __restrict__ out_votes,
+                                                                  const int* __restrict__ need) {
     extern __shared__ float sm[];
     float* colmax = sm;                 // [lx*ly] max over z
     float* rowmax = sm + lx * ly;       // [lx*ly] max over the y window
     __shared__ unsigned long long s_best[kPeakThreads / 32];
     __shared__ unsigned long long s_pick[kTopK];
     const int b = blockIdx.x, tid = threadIdx.x;
+    if (need != nullptr && need[b] == 0) return;      // handled by the fused kernel
     const float* hb = bins + (size_t)b * lx * ly * lz;
     const int ncol = lx * ly;
     for (int c = tid; c < ncol; c += kPeakThreads) {
@@ -208,13 +212,13 @@ __global__ void __launch_bounds__(kPeakThreads) hist_peaks_kernel(const float* _
 }
 
 int launch_hist_peaks(const float* bins, int B, int lx, int ly, int lz, int* out_idx, float* out_votes,
-                      cudaStream_t stream) {
+                      const int* need, cudaStream_t stream) {
     if (B == 0) return ICPF_OK;
     const size_t smem = (size_t)lx * ly * 2 * sizeof(float);
     if (smem > 200 * 1024) return ICPF_E_UNSUPPORTED;
     cudaError_t err = cudaFuncSetAttribute(hist_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
-    hist_peaks_kernel<<<B, kPeakThreads, smem, stream>>>(bins, lx, ly, lz, out_idx, out_votes);
+    hist_peaks_kernel<<<B, kPeakThreads, smem, stream>>>(bins, lx, ly, lz, out_idx, out_votes, need);
     return (int)cudaGetLastError();
 }
 

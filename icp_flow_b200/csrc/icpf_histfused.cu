@@ -1,0 +1,311 @@
+// icpf_histfused.cu -- votes + non-maximum suppression + top-5 of ONE pair inside ONE CTA, histogram in shared memory.
+//
+// The difference histogram of a pair only has support where differences X_i - Y_j exist: the box
+// [min X - max Y, max X - min Y], usually a few metres wide, while the reference allocates (and zero-fills, pools and
+// sorts) the full [lx, ly, lz] volume for every pair (135 x 135 x 3 fp32 = 219 KB at the default translation_frame;
+// utils_hist.py:69-77, hist_cuda.cu:59).  Here the CTA derives the bin range that box can reach, keeps exactly that
+// sub-histogram as u32 counters in shared memory (shared-memory atomics instead of L2 atomics), and runs the 11^3
+// max-pool / top-5 on it in place -- bins outside the box are zero by construction, so the result is identical to
+// pooling the full volume.  Pairs whose box needs more columns than fit are flagged and take the global-memory path
+// (icpf_hist.cu).  Vote arithmetic is the bit-compatible restatement of hist_cuda_core.cuh:48-60.
+#include "icpf_internal.h"
+#include "icpf_common.cuh"
+
+namespace icpf {
+
+constexpr int kFusedThreads = 256;
+constexpr int kFusedTile = 1024;       // Y rows staged per tile
+constexpr int kFusedTopK = 5;
+constexpr int kFusedNmsHalf = 5;
+
+struct FusedHistArgs {
+    const float4* X;         // the caller's dst  [P,N,4]   (votes X_i - Y_j; roles swap with auto_swap)
+    const float4* Y;         // the caller's src  [P,N,4]
+    int N;
+    float min_x, min_y, min_z, max_x, max_y, max_z;
+    int len_x, len_y, len_z;
+    int auto_swap;
+    int cap_cols;            // sub-histogram columns (x,y) that fit the dynamic shared memory
+    int* out_idx;            // [P,5]
+    float* out_votes;        // [P,5]
+    int* need_global;        // [P] 1 = this pair did not fit and must take the global path
+};
+
+__device__ __forceinline__ int vote_bin(float v, float mn, float range, float flen, int len) {
+    const int p = __float2int_rd(__fmul_rn(__fdiv_rn(__fsub_rn(v, mn), range), flen));
+    return min(p, len - 1);
+}
+
+__device__ __forceinline__ unsigned long long fused_peak_key(float v, int idx) {
+    return ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(0x7fffffff - idx);
+}
+
+__global__ void __launch_bounds__(kFusedThreads) hist_fused_kernel(FusedHistArgs a) {
+    extern __shared__ __align__(16) float4 fsm[];
+    __shared__ float s_red[kFusedThreads / 32][12];
+    __shared__ int s_cnt[2];
+    __shared__ int s_bad;
+    __shared__ unsigned long long s_best[kFusedThreads / 32];
+    __shared__ unsigned long long s_pick[kFusedTopK];
+    const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float INF = __int_as_float(0x7f800000);
+    const float4* xb = a.X + (size_t)p * a.N;
+    const float4* yb = a.Y + (size_t)p * a.N;
+    if (tid < 2) s_cnt[tid] = 0;
+    if (tid == 0) s_bad = 0;
+    __syncthreads();
+
+    // ---- valid counts (for the swap rule) and bounding boxes of the flagged rows
+    float lo[6] = {INF, INF, INF, INF, INF, INF}, hi[6] = {-INF, -INF, -INF, -INF, -INF, -INF};
+    int cx = 0, cy = 0;
+    for (int i = tid; i < a.N; i += kFusedThreads) {
+        const float4 u = xb[i], v = yb[i];
+        if (u.w > 0.f) {
+            ++cx;
+            lo[0] = fminf(lo[0], u.x); lo[1] = fminf(lo[1], u.y); lo[2] = fminf(lo[2], u.z);
+            hi[0] = fmaxf(hi[0], u.x); hi[1] = fmaxf(hi[1], u.y); hi[2] = fmaxf(hi[2], u.z);
+        }
+        if (v.w > 0.f) {
+            ++cy;
+            lo[3] = fminf(lo[3], v.x); lo[4] = fminf(lo[4], v.y); lo[5] = fminf(lo[5], v.z);
+            hi[3] = fmaxf(hi[3], v.x); hi[4] = fmaxf(hi[4], v.y); hi[5] = fmaxf(hi[5], v.z);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(FULL_MASK, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(FULL_MASK, hi[k], o));
+        }
+    }
+    cx = __reduce_add_sync(FULL_MASK, cx);
+    cy = __reduce_add_sync(FULL_MASK, cy);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            s_red[warp][k] = lo[k];
+            s_red[warp][6 + k] = hi[k];
+        }
+        atomicAdd(&s_cnt[0], cx);
+        atomicAdd(&s_cnt[1], cy);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        lo[k] = s_red[0][k];
+        hi[k] = s_red[0][6 + k];
+        for (int w = 1; w < kFusedThreads / 32; ++w) {
+            lo[k] = fminf(lo[k], s_red[w][k]);
+            hi[k] = fmaxf(hi[k], s_red[w][6 + k]);
+        }
+    }
+    // here X = dst and Y = src of the caller: swap when n_valid(src) > n_valid(dst)  (utils_match.py:139-146)
+    int kx = 0, ky = 3;      // offsets of the X / Y boxes in lo[] / hi[]
+    if (a.auto_swap && s_cnt[1] > s_cnt[0]) {
+        const float4* t = xb; xb = yb; yb = t;
+        kx = 3; ky = 0;
+    }
+    const float rx = __fsub_rn(a.max_x, a.min_x), ry = __fsub_rn(a.max_y, a.min_y), rz = __fsub_rn(a.max_z, a.min_z);
+    const float flx = (float)a.len_x, fly = (float)a.len_y, flz = (float)a.len_z;
+    // ---- bin range the differences can reach (x, y); +-1 bin of slack, clamped
+    int bx0 = 0, bx1 = -1, by0 = 0, by1 = -1;
+    {
+        const float dx0 = lo[kx] - hi[ky], dx1 = hi[kx] - lo[ky];
+        const float dy0 = lo[kx + 1] - hi[ky + 1], dy1 = hi[kx + 1] - lo[ky + 1];
+        const float dz0 = lo[kx + 2] - hi[ky + 2], dz1 = hi[kx + 2] - lo[ky + 2];
+        const bool any = (s_cnt[0] > 0) && (s_cnt[1] > 0) && (dx1 >= a.min_x) && (dx0 < a.max_x) && (dy1 >= a.min_y) &&
+                         (dy0 < a.max_y) && (dz1 >= a.min_z) && (dz0 < a.max_z);
+        if (any) {
+            bx0 = max(0, vote_bin(fmaxf(dx0, a.min_x), a.min_x, rx, flx, a.len_x) - 1);
+            bx1 = (dx1 >= a.max_x) ? a.len_x - 1 : min(a.len_x - 1, vote_bin(dx1, a.min_x, rx, flx, a.len_x) + 1);
+            by0 = max(0, vote_bin(fmaxf(dy0, a.min_y), a.min_y, ry, fly, a.len_y) - 1);
+            by1 = (dy1 >= a.max_y) ? a.len_y - 1 : min(a.len_y - 1, vote_bin(dy1, a.min_y, ry, fly, a.len_y) + 1);
+        }
+    }
+    const int wx = bx1 - bx0 + 1, wy = by1 - by0 + 1, lz = a.len_z;
+    const int ncol = (wx > 0 && wy > 0) ? wx * wy : 0;
+    if (ncol > a.cap_cols) {
+        if (tid == 0) a.need_global[p] = 1;
+        return;
+    }
+    if (tid == 0) a.need_global[p] = 0;
+    float4* tile = fsm;                                                      // [kFusedTile]
+    unsigned int* hist = reinterpret_cast<unsigned int*>(fsm + kFusedTile);    // [ncol * lz]
+    float* colmax = reinterpret_cast<float*>(hist + (size_t)a.cap_cols * lz);  // [ncol]
+    float* rowmax = colmax + a.cap_cols;                                       // [ncol]
+    for (int i = tid; i < ncol * lz; i += kFusedThreads) hist[i] = 0u;
+    __syncthreads();
+
+    // ---- votes (hist_cuda_core.cuh:48-60 restated; shared-memory atomics).
+    // Only |dz| < tau survives the z test -- about one pair in eight -- and fl(z_i - z_j) is monotone in z_j, so with
+    // the Y tile sorted by z the partners of an X row are ONE contiguous run found by two binary searches on the exact
+    // fp32 predicates; the inner loop then only touches pairs that pass the z test and every lane that iterates votes.
+    if (ncol > 0) {
+        for (int base = 0; base < a.N; base += kFusedTile) {
+            const int n = min(kFusedTile, a.N - base);
+            int npow = 1;
+            while (npow < n) npow <<= 1;
+            __syncthreads();
+            for (int j = tid; j < npow; j += kFusedThreads) {
+                float4 y = (j < n) ? yb[base + j] : make_float4(0.f, 0.f, INF, 0.f);
+                if (!(y.w > 0.f)) y.z = INF;          // unflagged rows sort to the end and never match
+                tile[j] = y;
+            }
+            __syncthreads();
+            for (int k = 2; k <= npow; k <<= 1) {     // bitonic sort by z
+                for (int st = k >> 1; st > 0; st >>= 1) {
+                    for (int t = tid; t < npow; t += kFusedThreads) {
+                        const int u = t ^ st;
+                        if (u > t) {
+                            const float4 p0 = tile[t], p1 = tile[u];
+                            const bool up = (t & k) == 0;
+                            if ((p0.z > p1.z) == up) { tile[t] = p1; tile[u] = p0; }
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            for (int i = tid; i < a.N; i += kFusedThreads) {
+                const float4 xi = xb[i];
+                if (!(xi.w > 0.f)) continue;
+                // first j with  fl(z_i - z_j) <  max_z   (predicate false..false true..true as z_j grows)
+                int lo_j = 0, hi_j = n;
+                while (lo_j < hi_j) {
+                    const int mid = (lo_j + hi_j) >> 1;
+                    if (__fsub_rn(xi.z, tile[mid].z) < a.max_z) hi_j = mid; else lo_j = mid + 1;
+                }
+                const int j0 = lo_j;
+                // first j with  fl(z_i - z_j) >= min_z  false  (true..true false..false)
+                hi_j = n;
+                while (lo_j < hi_j) {
+                    const int mid = (lo_j + hi_j) >> 1;
+                    if (__fsub_rn(xi.z, tile[mid].z) >= a.min_z) lo_j = mid + 1; else hi_j = mid;
+                }
+                for (int j = j0; j < lo_j; ++j) {
+                    const float4 yj = tile[j];
+                    const float vz = __fsub_rn(xi.z, yj.z);
+                    const float vx = __fsub_rn(xi.x, yj.x), vy = __fsub_rn(xi.y, yj.y);
+                    if (vx >= a.min_x && vx < a.max_x && vy >= a.min_y && vy < a.max_y && vz >= a.min_z && vz < a.max_z) {
+                        const int px = vote_bin(vx, a.min_x, rx, flx, a.len_x) - bx0;
+                        const int py = vote_bin(vy, a.min_y, ry, fly, a.len_y) - by0;
+                        const int pz = vote_bin(vz, a.min_z, rz, flz, a.len_z);
+                        if (px < 0 || px >= wx || py < 0 || py >= wy) {
+                            s_bad = 1;      // cannot happen (the range is conservative); fall back if it ever does
+                        } else {
+                            atomicAdd(&hist[(px * wy + py) * lz + pz], 1u);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (s_bad) {
+        if (tid == 0) a.need_global[p] = 1;
+        return;
+    }
+
+    // ---- 11^3 max-pool (separable; the z extent is always inside the window) + survivors == window max
+    for (int c = tid; c < ncol; c += kFusedThreads) {
+        unsigned int m = hist[c * lz];
+        for (int z = 1; z < lz; ++z) m = max(m, hist[c * lz + z]);
+        colmax[c] = (float)m;
+    }
+    __syncthreads();
+    for (int c = tid; c < ncol; c += kFusedThreads) {
+        const int x = c / wy, y = c - x * wy;
+        float m = colmax[c];
+        for (int d = max(0, y - kFusedNmsHalf); d <= min(wy - 1, y + kFusedNmsHalf); ++d) m = fmaxf(m, colmax[x * wy + d]);
+        rowmax[c] = m;
+    }
+    __syncthreads();
+    unsigned long long top[kFusedTopK];
+#pragma unroll
+    for (int k = 0; k < kFusedTopK; ++k) top[k] = 0ull;
+    for (int c = tid; c < ncol; c += kFusedThreads) {
+        const int x = c / wy, y = c - x * wy;
+        float m = rowmax[c];
+        for (int d = max(0, x - kFusedNmsHalf); d <= min(wx - 1, x + kFusedNmsHalf); ++d) m = fmaxf(m, rowmax[d * wy + y]);
+        if (!(m > 0.f)) continue;
+        for (int z = 0; z < lz; ++z) {
+            const float v = (float)hist[c * lz + z];
+            if (v == m) {
+                // flat index in the FULL volume: ties rank by it, exactly as on the global path
+                unsigned long long key = fused_peak_key(v, ((x + bx0) * a.len_y + (y + by0)) * lz + z);
+#pragma unroll
+                for (int k = 0; k < kFusedTopK; ++k) {
+                    if (key > top[k]) { const unsigned long long t = top[k]; top[k] = key; key = t; }
+                }
+            }
+        }
+    }
+    for (int round = 0; round < kFusedTopK; ++round) {
+        unsigned long long best = top[0];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(FULL_MASK, best, o);
+            best = other > best ? other : best;
+        }
+        if (lane == 0) s_best[warp] = best;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long m = s_best[0];
+            for (int w = 1; w < kFusedThreads / 32; ++w) m = s_best[w] > m ? s_best[w] : m;
+            s_pick[round] = m;
+        }
+        __syncthreads();
+        const unsigned long long win = s_pick[round];
+        if (win != 0ull && top[0] == win) {
+#pragma unroll
+            for (int k = 0; k + 1 < kFusedTopK; ++k) top[k] = top[k + 1];
+            top[kFusedTopK - 1] = 0ull;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        int picked[kFusedTopK];
+        int np = 0;
+        for (int k = 0; k < kFusedTopK; ++k) {
+            if (s_pick[k] != 0ull) {
+                picked[np] = 0x7fffffff - (int)(unsigned int)(s_pick[k] & 0xffffffffu);
+                a.out_votes[(size_t)p * kFusedTopK + np] = __uint_as_float((unsigned int)(s_pick[k] >> 32));
+                ++np;
+            }
+        }
+        int fill = 0;
+        const int npos = np;
+        while (np < kFusedTopK) {       // zero-vote fillers: lowest flat indices (see icpf_hist.cu)
+            bool used = false;
+            for (int k = 0; k < npos; ++k) used = used || (picked[k] == fill);
+            if (!used) {
+                picked[np] = fill;
+                a.out_votes[(size_t)p * kFusedTopK + np] = 0.f;
+                ++np;
+            }
+            ++fill;
+        }
+        for (int k = 0; k < kFusedTopK; ++k) a.out_idx[(size_t)p * kFusedTopK + k] = picked[k];
+    }
+}
+
+int launch_hist_fused(const float* X, const float* Y, int P, int N, const float* mins, const float* maxs,
+                      const int* lens, int auto_swap, int* out_idx, float* out_votes, int* need_global,
+                      cudaStream_t stream) {
+    if (P == 0) return ICPF_OK;
+    const size_t budget = 200 * 1024;
+    const size_t fixed = (size_t)kFusedTile * 16;
+    const size_t per_col = (size_t)lens[2] * 4 + 8;
+    int cap_cols = (int)((budget - fixed) / per_col);
+    if (cap_cols > lens[0] * lens[1]) cap_cols = lens[0] * lens[1];
+    const size_t smem = fixed + (size_t)cap_cols * per_col;
+    cudaError_t err = cudaFuncSetAttribute(hist_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return (int)err;
+    FusedHistArgs a{reinterpret_cast<const float4*>(X), reinterpret_cast<const float4*>(Y), N,
+                    mins[0], mins[1], mins[2], maxs[0], maxs[1], maxs[2], lens[0], lens[1], lens[2],
+                    auto_swap, cap_cols, out_idx, out_votes, need_global};
+    hist_fused_kernel<<<P, kFusedThreads, smem, stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace icpf

@@ -29,8 +29,11 @@ int hist_chunk_pairs(int P, int lx, int ly, int lz);
 size_t path_workspace_bytes(int P, int N, int lx, int ly, int lz);
 
 int launch_hist_votes(const float* X, const float* Y, int B, int NX, int NY, const float* mins, const float* maxs,
-                      const int* lens, float* bins, int auto_swap, cudaStream_t stream);
+                      const int* lens, float* bins, int auto_swap, const int* need, cudaStream_t stream);
 int launch_hist_peaks(const float* bins, int B, int lx, int ly, int lz, int* out_idx, float* out_votes,
+                      const int* need, cudaStream_t stream);
+int launch_hist_fused(const float* X, const float* Y, int P, int N, const float* mins, const float* maxs,
+                      const int* lens, int auto_swap, int* out_idx, float* out_votes, int* need_global,
                       cudaStream_t stream);
 int launch_hist_score(const float* src, const float* dst, int P, int N, const int* cand_idx, const float* bins_x,
                       const float* bins_y, const float* bins_z, int lx, int ly, int lz, float half_bin, int auto_swap,

@@ -264,3 +264,33 @@ def test_large_clusters_vs_oracle():
     err = ((a - b).abs().amax(dim=2) * valid).amax(dim=1).numpy()
     ok = ~O.unstable_pairs(ref).numpy()
     assert ok.any() and err[ok].max() <= TOL, err
+
+
+def test_histogram_global_fallback_for_wide_clusters():
+    """A cluster pair whose difference box spans more histogram columns than fit shared memory takes the
+    global-memory histogram path; both paths must agree with the oracle (peaks, votes, chosen translation)."""
+    dev = _dev()
+    rng = np.random.default_rng(3)
+    N = 512
+    src = np.full((3, N, 4), 1e8, np.float32); src[..., 3] = 0
+    dst = src.copy()
+    # pair 0: a 16 m x 16 m ground-like patch (difference box +-16 m -> clipped to the full 135 x 135 window)
+    big = np.stack([rng.uniform(0, 16, N), rng.uniform(0, 16, N), rng.uniform(0, 0.05, N)], 1) + [10.0, -30.0, 0.5]
+    # pairs 1, 2: compact clusters (fused shared-memory path)
+    small = np.stack([rng.uniform(0, 2, N), rng.uniform(0, 1, N), rng.uniform(0, 1.5, N)], 1) + [-20.0, 5.0, 0.2]
+    for k, pts in enumerate((big, small, small[::-1].copy())):
+        src[k, :, :3] = pts; src[k, :, 3] = 1
+        moved = pts + np.array([1.3, -0.7, 0.02]) + rng.normal(0, 0.005, pts.shape)
+        dst[k, :, :3] = moved; dst[k, :, 3] = 1
+    args = types.SimpleNamespace(thres_dist=0.1, translation_frame=6.666, chunk_size=50)
+    p = O.PathParams(thres_dist=0.1, translation_frame=6.666)
+    pose, dbg = ops.estimate_init_pose(args, torch.from_numpy(src).to(dev), torch.from_numpy(dst).to(dev), return_debug=True)
+    want, odbg = O.estimate_init_pose(torch.from_numpy(src), torch.from_numpy(dst), p, return_debug=True)
+    amb = O.ambiguous_topk_rows(torch.from_numpy(src), torch.from_numpy(dst), p).numpy()
+    assert torch.equal(dbg["votes"].cpu(), odbg["votes"])
+    for r in range(3):
+        pos = odbg["votes"][r] > 0
+        if not amb[r]:
+            assert sorted(dbg["flat_idx"].cpu().long()[r][pos].tolist()) == sorted(odbg["flat_idx"][r][pos].tolist()), r
+    assert np.abs(pose.cpu().numpy() - want.numpy())[~amb].max() <= 1e-6
+    assert np.abs(pose.cpu().numpy()[:, :3, 3] - np.array([1.3, -0.7, 0.0])).max() < 0.11
