@@ -191,6 +191,8 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nn-mode", type=int, default=0)
+    ap.add_argument("--gather", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="multi-GPU: fused peer-store all-gather from the kernel epilogue (p2p) or NCCL all_gather")
     ap.add_argument("--cell-factor", type=int, default=0, help="tuning: grid cell size in 1/1000 of the gate radius")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
@@ -234,6 +236,24 @@ def main():
     gathered = [torch.empty(n_gpus * P, 4, 4, device=dev, dtype=torch.float32) for _ in range(2)]
     launches_per_step = 3   # icp_pairs_kernel (first pass) + icp_resolve_batch_kernel + icp_pairs_kernel (re-run pass)
     comm_stream = torch.cuda.Stream() if world > 1 else None
+    peer = None
+    gather_kind = "none"
+    if world > 1:
+        gather_kind = "nccl"
+        if args.gather in ("auto", "p2p"):
+            try:
+                from icp_flow_b200.shard import PeerGather
+                peer = PeerGather(P, dev, slots=2)
+                gather_kind = "p2p"
+            except Exception as exc:          # symmetric memory unavailable on this box
+                if args.gather == "p2p":
+                    raise
+                if rank == 0:
+                    print(f"[bench] peer gather unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
+        ok = torch.tensor([1 if peer is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            peer, gather_kind = None, "nccl"
     computed = [torch.cuda.Event() for _ in range(2)]
     gathered_ev = [torch.cuda.Event() for _ in range(2)]
 
@@ -246,6 +266,17 @@ def main():
             torch.cuda.current_stream().wait_event(gathered_ev[s])
         if prof is not None:
             L.icpf_profile_next_icp(ctypes.c_void_p(prof[0].cuda_event), ctypes.c_void_p(prof[1].cuda_event))
+        if peer is not None:
+            # fused: the kernel epilogue stores the transforms into every rank's gathered buffer (NVLink peer memory);
+            # the cross-rank barrier that publishes them runs on the side stream, under the next batch's kernels
+            peer.arm(s)
+            outs[s] = out = ops.icp_batch(src_pool[i % pool_n], dst_pool[i % pool_n], params, out=outs[s], workspace=ws)
+            computed[s].record()
+            with torch.cuda.stream(comm_stream):
+                comm_stream.wait_event(computed[s])
+                peer.finish(s)
+                gathered_ev[s].record(comm_stream)
+            return out
         outs[s] = out = ops.icp_batch(src_pool[i % pool_n], dst_pool[i % pool_n], params, out=outs[s], workspace=ws)
         if world > 1:
             computed[s].record()
@@ -303,8 +334,13 @@ def main():
         # the public host-buffer call: H2D of this step's inputs, kernels, D2H of its transforms (double-buffered)
         nonlocal e2e_i
         s = e2e_i & 1
+        if peer is not None:
+            peer.arm(s)
         o = pipe.submit(host_src, host_dst, h_pose[s])
-        if world > 1:
+        if peer is not None:
+            with torch.cuda.stream(pipe.compute_stream):
+                peer.finish(s)
+        elif world > 1:
             with torch.cuda.stream(pipe.compute_stream):
                 dist.all_gather_into_tensor(gathered[s].view(n_gpus * P, 16), o.pose.view(P, 16))
         e2e_i += 1
@@ -342,7 +378,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(n_gpus), l2=f"rotating pool of {pool_n} input batches "
                            f"({pool_n * batch_bytes / 2**20:.0f} MiB > 2x 126 MiB L2): every step reads its inputs from HBM",
-                           nn_mode=args.nn_mode),
+                           nn_mode=args.nn_mode, gather=gather_kind),
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": batch_bytes, "d2h_bytes_per_step": P * 64,
                     "steps": e2e_steps},

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libicpflow_b200.so")
 EXPORTS = (
     "icpf_version", "icpf_error_string", "icpf_default_params", "icpf_workspace_bytes",
     "icpf_icp_f32", "icpf_nn_f32", "icpf_transform_points_f32", "icpf_host_kabsch", "icpf_profile_next_icp",
-    "icpf_host_kabsch_sequence", "icpf_hist_votes_f32", "icpf_hist_init_f32", "icpf_apply_icp_f32", "icpf_hist_icp_f32",
+    "icpf_host_kabsch_sequence", "icpf_peer_gather_next_icp", "icpf_hist_votes_f32", "icpf_hist_init_f32", "icpf_apply_icp_f32", "icpf_hist_icp_f32",
 )
 
 
@@ -95,6 +95,8 @@ def lib() -> ctypes.CDLL:
     L.icpf_hist_icp_f32.restype = ctypes.c_int
     L.icpf_hist_icp_f32.argtypes = [vp, vp, i32, i32, ctypes.POINTER(IcpfHistBins), ctypes.POINTER(IcpfParams), vp, vp,
                                     vp, vp, ctypes.c_size_t, vp]
+    L.icpf_peer_gather_next_icp.restype = ctypes.c_int
+    L.icpf_peer_gather_next_icp.argtypes = [vp, i32, i32]
     L.icpf_profile_next_icp.restype = None
     L.icpf_profile_next_icp.argtypes = [vp, vp]
     L.icpf_host_kabsch.restype = None

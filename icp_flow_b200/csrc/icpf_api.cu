@@ -149,6 +149,13 @@ int icpf_hist_icp_f32(const float* src, const float* dst, int32_t P, int32_t N, 
                            static_cast<cudaStream_t>(stream));
 }
 
+int icpf_peer_gather_next_icp(void* const* peer_pose_dev, int32_t world, int32_t row0) {
+    if (world < 0 || row0 < 0 || world > 64) return ICPF_E_PARAM;
+    if (world > 0 && peer_pose_dev == nullptr) return ICPF_E_NULL;
+    set_peer_gather(world > 0 ? reinterpret_cast<float* const*>(peer_pose_dev) : nullptr, world, row0);
+    return ICPF_OK;
+}
+
 void icpf_profile_next_icp(void* start_event, void* stop_event) {
     set_profile_events(static_cast<cudaEvent_t>(start_event), static_cast<cudaEvent_t>(stop_event));
 }

@@ -39,6 +39,9 @@ struct IcpArgs {
     const int* decided;    // second full pass: runs only while *decided == 0; NULL otherwise
     int cap;               // first pass: iteration cap (<= max_it)
     unsigned char* big_ws; // global-memory variant: per-pair workspace (pair_global_ws_bytes(N) each)
+    float* const* peer_pose;   // fused all-gather: DEVICE array of `peer_world` base pointers (peer-mapped [*,16]) or NULL
+    int peer_world;
+    int peer_row0;             // first row of this rank's block in the gathered buffer
 };
 
 template <int MODE, bool BIG>
@@ -131,6 +134,17 @@ __global__ void __launch_bounds__(kThreads, BIG ? 4 : 7) icp_pairs_kernel(IcpArg
         else v = tl.bcast()[B_R + col * 3 + row];
         a.out_pose[(size_t)p * 16 + threadIdx.x] = v;
     }
+    if (a.peer_pose != nullptr && threadIdx.x < 16) {
+        // Fused all-gather: the 64 B transform goes straight into every rank's gathered buffer through the
+        // NVLink-mapped peer pointers (plain st.global on peer addresses); a cross-rank barrier after the kernel makes
+        // the rows visible to their consumers.  No NCCL collective on the data path.
+        const int row = threadIdx.x >> 2, col = threadIdx.x & 3;
+        float v;
+        if (row == 3) v = (col == 3) ? 1.f : 0.f;
+        else if (col == 3) v = tl.bcast()[B_T + row];
+        else v = tl.bcast()[B_R + col * 3 + row];
+        for (int w = 0; w < a.peer_world; ++w) a.peer_pose[w][(size_t)(a.peer_row0 + p) * 16 + threadIdx.x] = v;
+    }
     if (threadIdx.x == 0) {
         if (a.out_rmse) a.out_rmse[p] = r.rmse;
         a.iters[p] = r.iters;
@@ -194,6 +208,14 @@ size_t icp_big_workspace_bytes(int P, int N) {
 }
 
 static thread_local cudaEvent_t t_prof_start = nullptr, t_prof_stop = nullptr;
+static thread_local float* const* t_peer_pose = nullptr;
+static thread_local int t_peer_world = 0, t_peer_row0 = 0;
+
+void set_peer_gather(float* const* peer_pose_dev, int world, int row0) {
+    t_peer_pose = peer_pose_dev;
+    t_peer_world = world;
+    t_peer_row0 = row0;
+}
 
 void set_profile_events(cudaEvent_t start, cudaEvent_t stop) {
     t_prof_start = start;
@@ -245,6 +267,8 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
     const bool capped = prm.batch_stop && prm.early_exit && prm.max_iterations > kFirstPassCap;
     a.cap = capped ? kFirstPassCap : prm.max_iterations;
     a.big_ws = big ? ws + icp_workspace_bytes(P) : nullptr;
+    a.peer_pose = t_peer_pose; a.peer_world = t_peer_world; a.peer_row0 = t_peer_row0;
+    t_peer_pose = nullptr;       // one-shot: applies to this call only
     int* decided = reinterpret_cast<int*>(ws + icp_ws_off_batch(P)) + 8;
     a.stats = reinterpret_cast<int*>(ws + icp_ws_off_stats(P));
     if (t_prof_start && t_prof_stop) cudaEventRecord(t_prof_start, stream);

@@ -23,6 +23,7 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
                size_t workspace_bytes, cudaStream_t stream);
 
 void set_profile_events(cudaEvent_t start, cudaEvent_t stop);
+void set_peer_gather(float* const* peer_pose_dev, int world, int row0);
 
 size_t icp_big_workspace_bytes(int P, int N);     // 0 unless the clusters need the global-memory variant
 int hist_chunk_pairs(int P, int lx, int ly, int lz);

@@ -52,3 +52,43 @@ def hist_icp_sharded(args, src: torch.Tensor, dst: torch.Tensor, group: Optional
     dist.all_reduce(counts, group=group)
     local = ops.hist_icp(args, src, dst)
     return gather_transforms(local, int(counts.item()), group)
+
+
+class PeerGather:
+    """Fused all-gather of the ICP transforms over NVLink peer memory (no NCCL collective on the data path).
+
+    Every rank owns a ``[world * pairs_per_rank, 4, 4]`` buffer allocated as torch symmetric memory; the ICP kernel's
+    epilogue stores each pair's 4x4 into row ``rank * pairs_per_rank + p`` of ALL ranks' buffers through the
+    peer-mapped pointers, and ``finish()`` runs the cross-rank barrier that makes the rows visible.
+    """
+
+    def __init__(self, pairs_per_rank: int, device, group=None, slots: int = 2):
+        import torch.distributed._symmetric_memory as symm
+
+        self.group = dist.group.WORLD if group is None else group
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.pairs = int(pairs_per_rank)
+        self.slots = []
+        for _ in range(slots):          # double-buffered so that a gather may overlap the next batch
+            buf = symm.empty(self.world * self.pairs, 16, dtype=torch.float32, device=device)
+            buf.zero_()
+            hdl = symm.rendezvous(buf, self.group)
+            self.slots.append((buf, hdl))
+
+    def arm(self, slot: int = 0):
+        """Route the next ``icp_batch`` call's transforms into slot ``slot`` of every rank."""
+        import ctypes
+        from . import _lib
+
+        buf, hdl = self.slots[slot]
+        code = _lib.lib().icpf_peer_gather_next_icp(ctypes.c_void_p(hdl.buffer_ptrs_dev), self.world,
+                                                     self.rank * self.pairs)
+        _lib.check(code, "icpf_peer_gather_next_icp")
+        return buf
+
+    def finish(self, slot: int = 0) -> torch.Tensor:
+        """Stream-ordered cross-rank barrier; afterwards the slot holds the transforms of every rank's pairs."""
+        buf, hdl = self.slots[slot]
+        hdl.barrier()
+        return buf.view(self.world * self.pairs, 4, 4)

@@ -146,6 +146,16 @@ int icpf_hist_icp_f32(const float* src, const float* dst, int32_t P, int32_t N, 
                       const icpf_params* params, float* out_pose, float* out_init, int32_t* out_batch,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * Fused all-gather of the transforms (multi-GPU): the next icpf_icp_f32 call on this host thread also stores every
+ * pair's 4x4 (64 B) directly into the gathered buffers of ALL ranks through peer-mapped pointers -- row (row0 + p) of
+ * each `[world * P, 16]` buffer -- from the kernel epilogue, instead of a separate NCCL all-gather.
+ *   peer_pose_dev  DEVICE array of `world` base pointers (e.g. torch symmetric memory `buffer_ptrs_dev`)
+ * The caller runs a cross-rank barrier on the stream afterwards (rows are visible once every rank's kernel has ended).
+ * One-shot: the setting applies to the next call only.
+ */
+int icpf_peer_gather_next_icp(void* const* peer_pose_dev, int32_t world, int32_t row0);
+
 /* Measurement hook (bench.py): when both handles are non-NULL the next icpf_icp_f32 call on this host thread records
  * `start_event` / `stop_event` (cudaEvent_t) on its stream immediately around the launch of the dominant kernel
  * (icp_pairs_kernel, first pass), then the hook clears itself.  No effect on results. */
