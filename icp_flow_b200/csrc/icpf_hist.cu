@@ -248,6 +248,9 @@ __global__ void __launch_bounds__(kThreads) hist_score_kernel(ScoreArgs a) {
     __shared__ float s_sum[2][kCand];
     __shared__ float s_part[kWarps][2][kCand];
     __shared__ float s_scratch[kWarps * 4];
+    __shared__ float s_box[kWarps][12];
+    __shared__ float s_lb[kCand];
+    __shared__ float s_score[kCand];
     const int p = blockIdx.x, tid = threadIdx.x;
     const float4* S;
     const float4* D;
@@ -290,74 +293,167 @@ __global__ void __launch_bounds__(kThreads) hist_score_kernel(ScoreArgs a) {
         s_t[tid][0] = tx; s_t[tid][1] = ty; s_t[tid][2] = tz;
     }
     __syncthreads();
-    float t[kCand][3];
-#pragma unroll
-    for (int k = 0; k < kCand; ++k) { t[k][0] = s_t[k][0]; t[k][1] = s_t[k][1]; t[k][2] = s_t[k][2]; }
     const float INF = __int_as_float(0x7f800000);
 
-    // forward: NN of (src_i + t_k) among the dst rows; backward: NN of dst_i among the (src_j + t_k)
-    float fsum[kCand], bsum[kCand];
-#pragma unroll
-    for (int k = 0; k < kCand; ++k) fsum[k] = bsum[k] = 0.f;
+    // ---- a cheap lower bound of every candidate's score: a point's NN distance is at least its distance to the
+    // other cloud's bounding box, so  score_k >= min(mean_i dist(src_i + t_k, bbox(dst)), mean_i dist(dst_i - t_k,
+    // bbox(src))).  Candidates whose bound exceeds an exactly evaluated score can never be the arg-min and are skipped
+    // (the zero-vote "filler" bins of pairs with fewer than five peaks sit metres away: result-identical, O(n) instead
+    // of O(n^2) for most candidates on real frames).
+    float blo[6] = {INF, INF, INF, INF, INF, INF}, bhi[6] = {-INF, -INF, -INF, -INF, -INF, -INF};
     for (int i = tid; i < n_s; i += kThreads) {
-        const float4 s = S[i];
-        float best[kCand], qx[kCand], qy[kCand], qz[kCand];
-#pragma unroll
-        for (int k = 0; k < kCand; ++k) {
-            best[k] = INF;
-            qx[k] = __fadd_rn(s.x, t[k][0]); qy[k] = __fadd_rn(s.y, t[k][1]); qz[k] = __fadd_rn(s.z, t[k][2]);
-        }
-        for (int j = 0; j < n_d; ++j) {
-            const float4 c = D[j];
-#pragma unroll
-            for (int k = 0; k < kCand; ++k) best[k] = fminf(best[k], sqdist(qx[k], qy[k], qz[k], c.x, c.y, c.z));
-        }
-#pragma unroll
-        for (int k = 0; k < kCand; ++k) fsum[k] += sqrtf(best[k]);
+        const float4 v = S[i];
+        blo[0] = fminf(blo[0], v.x); blo[1] = fminf(blo[1], v.y); blo[2] = fminf(blo[2], v.z);
+        bhi[0] = fmaxf(bhi[0], v.x); bhi[1] = fmaxf(bhi[1], v.y); bhi[2] = fmaxf(bhi[2], v.z);
     }
     for (int i = tid; i < n_d; i += kThreads) {
-        const float4 d = D[i];
-        float best[kCand];
-#pragma unroll
-        for (int k = 0; k < kCand; ++k) best[k] = INF;
-        for (int j = 0; j < n_s; ++j) {
-            const float4 c = S[j];
-#pragma unroll
-            for (int k = 0; k < kCand; ++k) {
-                const float cx = __fadd_rn(c.x, t[k][0]), cy = __fadd_rn(c.y, t[k][1]), cz = __fadd_rn(c.z, t[k][2]);
-                best[k] = fminf(best[k], sqdist(d.x, d.y, d.z, cx, cy, cz));
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < kCand; ++k) bsum[k] += sqrtf(best[k]);
+        const float4 v = D[i];
+        blo[3] = fminf(blo[3], v.x); blo[4] = fminf(blo[4], v.y); blo[5] = fminf(blo[5], v.z);
+        bhi[3] = fmaxf(bhi[3], v.x); bhi[4] = fmaxf(bhi[4], v.y); bhi[5] = fmaxf(bhi[5], v.z);
     }
 #pragma unroll
-    for (int k = 0; k < kCand; ++k) {
-        fsum[k] = warp_sum(fsum[k]);
-        bsum[k] = warp_sum(bsum[k]);
+    for (int k = 0; k < 6; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            blo[k] = fminf(blo[k], __shfl_xor_sync(FULL_MASK, blo[k], o));
+            bhi[k] = fmaxf(bhi[k], __shfl_xor_sync(FULL_MASK, bhi[k], o));
+        }
     }
     if ((tid & 31) == 0) {
 #pragma unroll
-        for (int k = 0; k < kCand; ++k) {
-            s_part[tid >> 5][0][k] = fsum[k];
-            s_part[tid >> 5][1][k] = bsum[k];
+        for (int k = 0; k < 6; ++k) {
+            s_box[tid >> 5][k] = blo[k];
+            s_box[tid >> 5][6 + k] = bhi[k];
         }
     }
     __syncthreads();
-    if (tid < 2 * kCand) {        // warps added in a fixed order: deterministic
-        float s = 0.f;
-        for (int w = 0; w < kWarps; ++w) s += s_part[w][tid / kCand][tid % kCand];
-        s_sum[tid / kCand][tid % kCand] = s;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        blo[k] = s_box[0][k];
+        bhi[k] = s_box[0][6 + k];
+        for (int w = 1; w < kWarps; ++w) {
+            blo[k] = fminf(blo[k], s_box[w][k]);
+            bhi[k] = fmaxf(bhi[k], s_box[w][6 + k]);
+        }
     }
-    __syncthreads();
+    {
+        float lf[kCand], lb[kCand];
+#pragma unroll
+        for (int k = 0; k < kCand; ++k) lf[k] = lb[k] = 0.f;
+        for (int i = tid; i < n_s; i += kThreads) {
+            const float4 v = S[i];
+#pragma unroll
+            for (int k = 0; k < kCand; ++k) {
+                const float x = v.x + s_t[k][0], y = v.y + s_t[k][1], z = v.z + s_t[k][2];
+                const float dx = fmaxf(fmaxf(blo[3] - x, x - bhi[3]), 0.f), dy = fmaxf(fmaxf(blo[4] - y, y - bhi[4]), 0.f),
+                            dz = fmaxf(fmaxf(blo[5] - z, z - bhi[5]), 0.f);
+                lf[k] += sqrtf(dx * dx + dy * dy + dz * dz);
+            }
+        }
+        for (int i = tid; i < n_d; i += kThreads) {
+            const float4 v = D[i];
+#pragma unroll
+            for (int k = 0; k < kCand; ++k) {
+                const float x = v.x - s_t[k][0], y = v.y - s_t[k][1], z = v.z - s_t[k][2];
+                const float dx = fmaxf(fmaxf(blo[0] - x, x - bhi[0]), 0.f), dy = fmaxf(fmaxf(blo[1] - y, y - bhi[1]), 0.f),
+                            dz = fmaxf(fmaxf(blo[2] - z, z - bhi[2]), 0.f);
+                lb[k] += sqrtf(dx * dx + dy * dy + dz * dz);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kCand; ++k) {
+            lf[k] = warp_sum(lf[k]);
+            lb[k] = warp_sum(lb[k]);
+        }
+        if ((tid & 31) == 0) {
+#pragma unroll
+            for (int k = 0; k < kCand; ++k) {
+                s_part[tid >> 5][0][k] = lf[k];
+                s_part[tid >> 5][1][k] = lb[k];
+            }
+        }
+        __syncthreads();
+        if (tid < kCand) {
+            float f = 0.f, bsum_ = 0.f;
+            for (int w = 0; w < kWarps; ++w) { f += s_part[w][0][tid]; bsum_ += s_part[w][1][tid]; }
+            // generous slack: the bound must stay below the exact fp32 score it is compared with
+            s_lb[tid] = fminf(f / (float)n_s, bsum_ / (float)n_d) * 0.9999f - 1e-5f;
+            s_score[tid] = INF;
+        }
+        __syncthreads();
+    }
+
+    // ---- exact scores: round 1 = the top peak and the zero translation, round 2 = whatever the bound cannot exclude
+    int list[kCand];
+    int nlist = 2;
+    list[0] = 0;
+    list[1] = kCand - 1;
+    for (int round = 0; round < 2; ++round) {
+        if (round == 1) {
+            const float best1 = fminf(s_score[0], s_score[kCand - 1]);
+            nlist = 0;
+            for (int k = 1; k < kCand - 1; ++k) {
+                if (!(s_lb[k] > best1)) list[nlist++] = k;      // NaN bounds are evaluated, never skipped
+            }
+        }
+        // forward: NN of (src_i + t_k) among the dst rows; backward: NN of dst_i among the (src_j + t_k)
+        for (int l0 = 0; l0 < nlist; l0 += 2) {
+            const int k0 = list[l0], k1 = (l0 + 1 < nlist) ? list[l0 + 1] : list[l0];
+            const float t0x = s_t[k0][0], t0y = s_t[k0][1], t0z = s_t[k0][2];
+            const float t1x = s_t[k1][0], t1y = s_t[k1][1], t1z = s_t[k1][2];
+            float f0 = 0.f, f1 = 0.f, b0 = 0.f, b1 = 0.f;
+            for (int i = tid; i < n_s; i += kThreads) {
+                const float4 v = S[i];
+                const float q0x = __fadd_rn(v.x, t0x), q0y = __fadd_rn(v.y, t0y), q0z = __fadd_rn(v.z, t0z);
+                const float q1x = __fadd_rn(v.x, t1x), q1y = __fadd_rn(v.y, t1y), q1z = __fadd_rn(v.z, t1z);
+                float m0 = INF, m1 = INF;
+#pragma unroll 4
+                for (int j = 0; j < n_d; ++j) {
+                    const float4 c = D[j];
+                    m0 = fminf(m0, sqdist(q0x, q0y, q0z, c.x, c.y, c.z));
+                    m1 = fminf(m1, sqdist(q1x, q1y, q1z, c.x, c.y, c.z));
+                }
+                f0 += sqrtf(m0);
+                f1 += sqrtf(m1);
+            }
+            for (int i = tid; i < n_d; i += kThreads) {
+                const float4 v = D[i];
+                float m0 = INF, m1 = INF;
+#pragma unroll 4
+                for (int j = 0; j < n_s; ++j) {
+                    const float4 c = S[j];
+                    m0 = fminf(m0, sqdist(v.x, v.y, v.z, __fadd_rn(c.x, t0x), __fadd_rn(c.y, t0y), __fadd_rn(c.z, t0z)));
+                    m1 = fminf(m1, sqdist(v.x, v.y, v.z, __fadd_rn(c.x, t1x), __fadd_rn(c.y, t1y), __fadd_rn(c.z, t1z)));
+                }
+                b0 += sqrtf(m0);
+                b1 += sqrtf(m1);
+            }
+            f0 = warp_sum(f0); f1 = warp_sum(f1); b0 = warp_sum(b0); b1 = warp_sum(b1);
+            __syncthreads();
+            if ((tid & 31) == 0) {
+                s_part[tid >> 5][0][0] = f0; s_part[tid >> 5][0][1] = f1;
+                s_part[tid >> 5][1][0] = b0; s_part[tid >> 5][1][1] = b1;
+            }
+            __syncthreads();
+            if (tid < 2) {        // warps added in a fixed order: deterministic
+                float f = 0.f, bb = 0.f;
+                for (int w = 0; w < kWarps; ++w) { f += s_part[w][0][tid]; bb += s_part[w][1][tid]; }
+                const float ef = __fdiv_rn(f, (float)n_s), eb = __fdiv_rn(bb, (float)n_d);
+                s_score[tid == 0 ? k0 : k1] = fminf(ef, eb);        // torch.minimum
+            }
+            __syncthreads();
+        }
+    }
     if (tid == 0) {
         int which = 0;
         float best = 0.f;
+        bool have = false;
         for (int k = 0; k < kCand; ++k) {
-            const float ef = __fdiv_rn(s_sum[0][k], (float)n_s), eb = __fdiv_rn(s_sum[1][k], (float)n_d);
-            const float e = fminf(ef, eb);        // torch.minimum
+            const float e = s_score[k];        // +inf for the candidates the bound excluded
             if (a.out_scores) a.out_scores[(size_t)p * kCand + k] = e;
-            if (k == 0 || e < best) { best = e; which = k; }      // errors.min(dim=-1): first minimum
+            const bool evaluated = (k == 0) || (k == kCand - 1) || !(s_lb[k] > fminf(s_score[0], s_score[kCand - 1]));
+            if (!evaluated) continue;
+            if (!have || e < best) { best = e; which = k; have = true; }      // errors.min(dim=-1): first minimum
         }
         if (a.out_which) a.out_which[p] = which;
         float* o = a.out_pose + (size_t)p * 16;

@@ -10,7 +10,8 @@
  *   - enqueue their work on `stream` (a cudaStream_t passed as void*) and return without synchronising,
  *   - never allocate or free device memory (the caller provides outputs and, where stated, a workspace),
  *   - return 0 on success, a negative ICPF_E_* code for argument errors, or a positive cudaError_t.
- * The `icpf_session_*` entry points take HOST buffers and own their device staging buffers.
+ * Host buffers are staged by the caller (icp_flow_b200.ops.IcpHostPipeline: pinned memory, double-buffered H2D on a
+ * copy stream overlapping the kernels of the previous batch).
  */
 #ifndef ICPFLOW_B200_H
 #define ICPFLOW_B200_H
