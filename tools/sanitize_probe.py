@@ -1,0 +1,19 @@
+"""Small end-to-end workload for compute-sanitizer (memcheck / racecheck / synccheck)."""
+import sys, os, types
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from icp_flow_b200 import ops, synth
+dev = torch.device("cuda:0")
+src, dst, _ = synth.make_pairs(6, 160, seed=3, ragged=True, residual_only=False, wrong_frac=0.2)
+s, d = torch.from_numpy(src).to(dev), torch.from_numpy(dst).to(dev)
+args = types.SimpleNamespace(thres_dist=0.1, translation_frame=2.0, chunk_size=50)
+T = ops.hist_icp(args, s, d)
+for mode in (1, 2, 3):
+    r = ops.icp_batch(s, d, ops.make_params(max_iterations=12, nn_mode=mode))
+idx, dist = ops.nearest_neighbor_batch(s, d)
+big = torch.full((2, 5000, 4), 1e8, device=dev); big[:, :, 3] = 0
+big[:, :160] = s[:2]
+big2 = big.clone(); big2[:, :160] = d[:2]
+T2 = ops.hist_icp(args, big, big2)
+torch.cuda.synchronize()
+print("ok", float(T.abs().sum()), float(T2.abs().sum()))
