@@ -77,6 +77,12 @@ void icpf_oracle_hist(const float *X, const float *Y, int64_t B, int64_t NX, int
                     float fy = (vy - min_y) / ry; fy = fy * fly;
                     float fz = (vz - min_z) / rz; fz = fz * flz;
                     int64_t px = (int64_t)floorf(fx), py = (int64_t)floorf(fy), pz = (int64_t)floorf(fz);
+                    /* For v one ulp below max, (v-min) rounds up to (max-min) and the reference kernel computes bin
+                     * index == len: an out-of-bounds write (hist_cuda_core.cuh:54-59 has no guard).  There is no
+                     * defined behaviour to restate; the oracle and the engine both clamp to the last bin. */
+                    if (px > lx - 1) px = lx - 1;
+                    if (py > ly - 1) py = ly - 1;
+                    if (pz > lz - 1) pz = lz - 1;
                     h[px * ly * lz + py * lz + pz] += 1.0f;
                 }
             }
