@@ -245,7 +245,6 @@ struct ScoreArgs {
 template <bool BIG>
 __global__ void __launch_bounds__(kThreads) hist_score_kernel(ScoreArgs a) {
     __shared__ float s_t[kCand][3];
-    __shared__ float s_sum[2][kCand];
     __shared__ float s_part[kWarps][2][kCand];
     __shared__ float s_scratch[kWarps * 4];
     __shared__ float s_box[kWarps][12];
@@ -268,7 +267,6 @@ __global__ void __launch_bounds__(kThreads) hist_score_kernel(ScoreArgs a) {
         S = tl.src();
         D = tl.dst();
     }
-    if (tid < 2 * kCand) s_sum[tid / kCand][tid % kCand] = 0.f;
     float cnt[2] = {0.f, 0.f};
     for (int q = tid; q < a.N; q += kThreads) {
         cnt[0] += (S[q].w > 0.f) ? 1.f : 0.f;

@@ -228,7 +228,6 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
                size_t workspace_bytes, cudaStream_t stream) {
     if (P == 0) return ICPF_OK;
     // nn_mode: 0 auto (grid + cache whenever the tiles fit in shared memory), 1 brute force, 2 grid, 3 grid + cache
-    const size_t kMaxSmem = 227 * 1024;
     if (N > kMaxRows) return ICPF_E_UNSUPPORTED;
     const bool grid = prm.nn_mode != 1;
     // clusters whose tiles do not fit shared memory run the global-memory variant (same code, rows in L2)

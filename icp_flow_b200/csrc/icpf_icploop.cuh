@@ -33,7 +33,7 @@ struct IcpResult {
     int iters;                    // iterations executed by this pair
     unsigned long long conv_lo;   // bit k: relative rmse <= thr at iteration k      (k < 64)
     unsigned long long conv_hi;   //                                                 (64 <= k < 128)
-    float searches;               // statistics: full searches executed, cache refresh iterations
+    float searches;               // statistics: rows searched (dense first iteration + deferred rows), dense passes
     int refreshes;
     float prev_rmse;
     bool have_prev;
@@ -153,7 +153,7 @@ __device__ __forceinline__ IcpResult icp_iterations(const Tiles& tl, const GridI
         // The cache is re-anchored every iteration: bounds are kept relative to the row's position in the previous
         // iteration, so the motion that counts is the step (R_k - R_{k-1}, T_k - T_{k-1}) thread 0 left in the
         // broadcast block; a row is searched again only when its own bound is used up.
-        const bool refresh = !CACHE || (it == 0);
+        const bool refresh = !CACHE || (it == 0);      // dense search of every row (always, without the cache)
         float dr[9], dt[3];
         if (CACHE && !refresh) {
 #pragma unroll

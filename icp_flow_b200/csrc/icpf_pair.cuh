@@ -12,10 +12,10 @@
 //
 // Correspondence search.  Only neighbours within thres_dist survive the gate, so inside the ICP loop a radius-bounded
 // search is result-identical to the reference's brute force (SURVEY.md finding 2): the dst cloud is counting-sorted
-// once per pair into a uniform grid in shared memory (cell >= 2*tau, <= kGridMaxCells cells, z fastest so that the
-// cells a query needs along z are one contiguous run), and each query inspects the <= 2x2 runs overlapping its
-// tau-box.  Candidates are ranked by (squared distance, original row index), i.e. exactly the reference's
-// "sequential scan, strict <" tie rule, so brute force (nn_mode 1) and grid (nn_mode 2) agree bit for bit.
+// once per pair into a uniform grid in shared memory (cell = kCellFactor * tau, <= kGridMaxCells cells, z fastest so
+// that the cells a query needs along z are one contiguous run), and each query inspects the <= 2x2 runs overlapping
+// its tau-box.  Candidates are ranked by (squared distance, original row index), i.e. exactly the reference's
+// "sequential scan, strict <" tie rule, so brute force (nn_mode 1), grid (2) and grid + cache (3) agree bit for bit.
 #pragma once
 
 #include <cuda_fp16.h>
@@ -38,7 +38,7 @@ constexpr int kBcastFloats = 48;
 constexpr int kCellWords = (kGridMaxCells + 2 + 1) / 2 + 2;   // packed u16 entries 0..G (+pad), as u32 words
 
 // broadcast block written by thread 0 once per iteration
-enum : int { B_R = 0, B_T = 9, B_RC = 12, B_TC = 21, B_PX = 24, B_PY = 27, B_EXIT = 30, B_DEFER = 31 /* int: rows queued for a search */,
+enum : int { B_R = 0, B_T = 9, B_RC = 12 /* last step R_k - R_{k-1} */, B_TC = 21 /* last step T_k - T_{k-1} */, B_PX = 24, B_PY = 27, B_EXIT = 30, B_DEFER = 31 /* int: rows queued for a search */,
              B_KABSCH = 32 /* KabschState: 9 floats + flag */ };
 
 // Dynamic shared memory of every pair kernel.  Tiles are addressed as OFFSETS into this one array so that the
