@@ -166,6 +166,7 @@ int hist_chunk_pairs(int P, int lx, int ly, int lz) {
     const size_t budget = (size_t)64 << 20;          // keep the live histograms L2-resident (126 MB L2)
     size_t c = budget / (per ? per : 1);
     if (c < 1) c = 1;
+    if (c > 32768) c = 32768;                        // gridDim.y of the vote kernel
     if (c > (size_t)P) c = (size_t)P;
     return (int)(c > 0 ? c : 1);
 }
