@@ -5,12 +5,12 @@ kernels reached through the C ABI in ``include/icpflow_b200.h`` (``libicpflow_b2
 CPU or PyTorch fallback: importing works anywhere (so the CPU test-suite can check the ABI), calling needs a GPU.
 """
 from .ops import (ICPSolution, SimilarityTransform, IcpBatchResult, apply_icp, estimate_init_pose, hist, hist_icp,
-                  icp_batch, iterative_closest_point, make_params, nearest_neighbor_batch, pytorch3d_icp,
-                  transform_points_batch)
+                  icp_batch, iterative_closest_point, make_params, match_eval, match_pairs, nearest_neighbor_batch,
+                  pytorch3d_icp, transform_points_batch)
 from .install import install, uninstall
 
 __all__ = [
     "ICPSolution", "SimilarityTransform", "IcpBatchResult", "apply_icp", "estimate_init_pose", "hist", "hist_icp",
-    "icp_batch", "iterative_closest_point", "make_params", "nearest_neighbor_batch", "pytorch3d_icp",
+    "icp_batch", "iterative_closest_point", "make_params", "match_eval", "match_pairs", "nearest_neighbor_batch", "pytorch3d_icp",
     "transform_points_batch", "install", "uninstall",
 ]

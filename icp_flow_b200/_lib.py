@@ -16,6 +16,7 @@ EXPORTS = (
     "icpf_version", "icpf_error_string", "icpf_default_params", "icpf_workspace_bytes",
     "icpf_icp_f32", "icpf_nn_f32", "icpf_transform_points_f32", "icpf_host_kabsch", "icpf_profile_next_icp",
     "icpf_host_kabsch_sequence", "icpf_peer_gather_next_icp", "icpf_hist_votes_f32", "icpf_hist_init_f32", "icpf_apply_icp_f32", "icpf_hist_icp_f32",
+    "icpf_match_eval_f32",
 )
 
 
@@ -45,6 +46,12 @@ class IcpfHistBins(ctypes.Structure):
         ("max", ctypes.c_float * 3),
         ("half_bin", ctypes.c_float),
     ]
+
+
+class IcpfMatchGates(ctypes.Structure):
+    """Mirror of ``struct icpf_match_gates``."""
+
+    _fields_ = [("translation_frame", ctypes.c_double), ("thres_iou", ctypes.c_double), ("thres_rot", ctypes.c_double)]
 
 
 class IcpfError(RuntimeError):
@@ -83,6 +90,9 @@ def lib() -> ctypes.CDLL:
     L.icpf_nn_f32.argtypes = [vp, vp, i32, i32, i32, i32, i32, i64p, vp, vp]
     L.icpf_transform_points_f32.restype = ctypes.c_int
     L.icpf_transform_points_f32.argtypes = [vp, vp, i32, i32, vp, vp]
+    L.icpf_match_eval_f32.restype = ctypes.c_int
+    L.icpf_match_eval_f32.argtypes = [vp, vp, vp, i32, i32, ctypes.c_double, vp, vp, vp, vp, vp, vp,
+                                      ctypes.POINTER(IcpfMatchGates), vp, vp]
     f3, i3 = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32)
     L.icpf_hist_votes_f32.restype = ctypes.c_int
     L.icpf_hist_votes_f32.argtypes = [vp, vp, i32, i32, i32, f3, f3, i3, vp, vp]

@@ -76,6 +76,22 @@ int icpf_transform_points_f32(const float* xyz, const float* pose, int32_t B, in
     return launch_transform_points(xyz, pose, B, N, out, static_cast<cudaStream_t>(stream));
 }
 
+int icpf_match_eval_f32(const float* src, const float* dst, const float* pose, int32_t P, int32_t N, double thres_dist,
+                        float* out_errors, float* out_inliers, float* out_ratios, float* out_ious,
+                        float* out_translations, float* out_rotations, const icpf_match_gates* gates,
+                        int32_t* out_accept, void* stream) {
+    if (P < 0 || N < 1) return ICPF_E_SHAPE;
+    if (P == 0) return ICPF_OK;
+    if (!src || !dst || !pose || !out_errors || !out_inliers || !out_ratios || !out_ious || !out_translations ||
+        !out_rotations)
+        return ICPF_E_NULL;
+    if (!aligned16(src) || !aligned16(dst)) return ICPF_E_ALIGN;
+    if ((gates == nullptr) != (out_accept == nullptr)) return ICPF_E_NULL;
+    if (!(thres_dist > 0.0)) return ICPF_E_PARAM;
+    return launch_match_eval(src, dst, pose, P, N, (float)thres_dist, out_errors, out_inliers, out_ratios, out_ious,
+                             out_translations, out_rotations, gates, out_accept, static_cast<cudaStream_t>(stream));
+}
+
 static int check_params(const icpf_params* params) {
     if (!params) return ICPF_E_NULL;
     if (params->max_iterations < 1 || params->max_iterations > ICPF_MAX_ITERATIONS) return ICPF_E_PARAM;

@@ -55,6 +55,9 @@ int launch_hist_icp(const float* src, const float* dst, int P, int N, const icpf
 int launch_nn(const float* src, const float* dst, int B, int Ns, int Nd, int src_stride, int dst_stride,
               int64_t* out_idx, float* out_dist, cudaStream_t stream);
 
+int launch_match_eval(const float* src, const float* dst, const float* pose, int P, int N, float thr, float* errors,
+                      float* inliers, float* ratios, float* ious, float* translations, float* rotations,
+                      const icpf_match_gates* gates, int* accept, cudaStream_t stream);
 int launch_transform_points(const float* xyz, const float* pose, int B, int N, float* out, cudaStream_t stream);
 
 }  // namespace icpf

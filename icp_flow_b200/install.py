@@ -4,6 +4,8 @@ The reference pipeline (``utils_track.track`` -> ``utils_match.match_pcds`` -> `
 only the hot-path entry points are rebound, exactly at the seams SURVEY.md section 8b lists:
 
     utils_match.hist_icp              <- icp_flow_b200.hist_icp            (sole caller: utils_match.py:92)
+    utils_match.match_eval            <- icp_flow_b200.match_eval          (sole caller: utils_match.py:93)
+    utils_match.match_pairs           <- icp_flow_b200.match_pairs         (callers: utils_match.py:38,55)
     utils_hist.estimate_init_pose     <- icp_flow_b200.estimate_init_pose
     utils_icp.apply_icp               <- icp_flow_b200.apply_icp
     utils_icp.pytorch3d_icp           <- icp_flow_b200.pytorch3d_icp
@@ -24,6 +26,8 @@ _SAVED = {}
 
 _BINDINGS = (
     ("utils_match", "hist_icp", ops.hist_icp),
+    ("utils_match", "match_eval", ops.match_eval),
+    ("utils_match", "match_pairs", ops.match_pairs),
     ("utils_match", "estimate_init_pose", ops.estimate_init_pose),
     ("utils_match", "apply_icp", ops.apply_icp),
     ("utils_hist", "estimate_init_pose", ops.estimate_init_pose),

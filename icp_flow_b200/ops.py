@@ -384,6 +384,89 @@ def hist_icp(args, src, dst, return_debug: bool = False):
     return out
 
 
+def match_eval(args, pcd1, pcd2, transformations, return_accept: bool = False):
+    """Drop-in for ``utils_match.match_eval(args, pcd1, pcd2, transformations)`` (utils_match.py:159-213): returns
+    ``(errors [P,2], inliers [P,2], ratios [P,2], ious [P,2], translations [P,3], rotations [P,3])`` of the registrations
+    ``transformations`` (``[P,4,4]``, pcd1 -> pcd2) from one fused launch.  ``return_accept`` appends the ``[P]`` int32
+    verdict of ``utils_check.check_transformation`` (needs args.translation_frame / thres_iou / thres_rot)."""
+    pcd1, pcd2 = _check_pair_batch(pcd1, pcd2)
+    P, N, _ = pcd1.shape
+    dev = pcd1.device
+    if transformations.shape != (P, 4, 4) or transformations.device != dev:
+        raise ValueError("transformations must be [P,4,4] on the device of the clouds")
+    pose = transformations.to(torch.float32).contiguous()
+    errors, inliers, ratios, ious = (torch.empty(P, 2, device=dev, dtype=torch.float32) for _ in range(4))
+    translations, rotations = (torch.empty(P, 3, device=dev, dtype=torch.float32) for _ in range(2))
+    gates, accept = None, None
+    if return_accept:
+        gates = ctypes.byref(_lib.IcpfMatchGates(float(args.translation_frame), float(args.thres_iou),
+                                                 float(args.thres_rot)))
+        accept = torch.empty(P, device=dev, dtype=torch.int32)
+    with torch.cuda.device(dev):
+        code = _lib.lib().icpf_match_eval_f32(_ptr(pcd1), _ptr(pcd2), _ptr(pose), P, N, float(args.thres_dist),
+                                              _ptr(errors), _ptr(inliers), _ptr(ratios), _ptr(ious),
+                                              _ptr(translations), _ptr(rotations), gates, _ptr(accept), _stream_ptr())
+    _lib.check(code, "icpf_match_eval_f32")
+    if return_accept:
+        return errors, inliers, ratios, ious, translations, rotations, accept
+    return errors, inliers, ratios, ious, translations, rotations
+
+
+def pad_segments(points, labels, wanted, max_points: int):
+    """The gather / ``pad_segment`` loop of match_pairs (utils_match.py:79-90, utils_helper.py:185-196) for a list of
+    cluster labels: ``[len(wanted), max_points, 4]`` rows (x,y,z,1) then (1e8,1e8,1e8,0).  Clusters larger than
+    ``max_points`` are subsampled by the reference with ``torch.randperm`` (global RNG); that policy is not reproduced
+    here -- such a cluster raises, the caller subsamples first."""
+    out = points.new_full((len(wanted), max_points, 4), 1e8)
+    out[:, :, 3] = 0.0
+    for k, lab in enumerate(wanted):
+        seg = points[labels == lab, 0:3]
+        if len(seg) > max_points:
+            raise ValueError(f"cluster {float(lab)} has {len(seg)} > max_points={max_points} rows; subsample it first")
+        out[k, : len(seg), 0:3] = seg
+        out[k, : len(seg), 3] = 1.0
+    return out
+
+
+def match_select(args, pairs, src_labels_unq, dst_labels_unq, evals, accept, transformations):
+    """The rejection loop and selection of match_pairs (utils_match.py:70-75, 94-135) without the per-pair Python loop:
+    accepted registrations are scattered into the ``[n_src, n_dst]`` matrices in one indexed store each, every src cluster
+    keeps its least-error dst cluster (``match_segments_descend``) if ``min(error) < thres_error``.  Device tensors in,
+    device tensors out; the only host sync is the data-dependent output length."""
+    errors, inliers, ratios, ious = evals[0:4]
+    dev = errors.device
+    ns, nd = len(src_labels_unq), len(dst_labels_unq)
+    pairs = pairs.to(dev)
+    si = torch.searchsorted(src_labels_unq.contiguous(), pairs[:, 0].to(src_labels_unq.dtype).contiguous())
+    di = torch.searchsorted(dst_labels_unq.contiguous(), pairs[:, 1].to(dst_labels_unq.dtype).contiguous())
+    si = torch.where(accept.to(dev).bool(), si, torch.full_like(si, ns))     # rejected pairs land in a spare row
+    m_err = torch.full((ns + 1, nd, 2), 1e8, device=dev)
+    m_inl, m_rat, m_iou = (torch.zeros((ns + 1, nd, 2), device=dev) for _ in range(3))
+    m_T = torch.zeros((ns + 1, nd, 4, 4), device=dev)
+    m_err[si, di], m_inl[si, di], m_rat[si, di], m_iou[si, di] = errors, inliers, ratios, ious
+    m_T[si, di] = transformations
+    e_min = m_err[:ns].min(-1)[0]
+    rows_i = torch.arange(ns, device=dev)
+    cols_i = torch.argmin(e_min, dim=1)
+    ok = e_min[rows_i, cols_i] < args.thres_error      # an all-rejected row holds 1e8 and drops out here
+    rows_i, cols_i = rows_i[ok], cols_i[ok]
+    rows = torch.cat([src_labels_unq[rows_i][:, None].float(), dst_labels_unq[cols_i][:, None].float(),
+                      m_err[rows_i, cols_i], m_inl[rows_i, cols_i], m_rat[rows_i, cols_i], m_iou[rows_i, cols_i]], dim=1)
+    return rows, m_T[rows_i, cols_i]
+
+
+def match_pairs(args, src_points, dst_points, src_labels, dst_labels, pairs):
+    """Drop-in for ``utils_match.match_pairs`` (utils_match.py:69-135): pad the candidate cluster pairs, register them
+    (``hist_icp``), score + gate them (``match_eval`` with the fused ``check_transformation``) and select one dst cluster
+    per src cluster.  Returns ``(rows [K,10], transformations [K,4,4])`` on the device of the inputs."""
+    assert len(pairs) > 0
+    segs_src = pad_segments(src_points, src_labels, pairs[:, 0], args.max_points)
+    segs_dst = pad_segments(dst_points, dst_labels, pairs[:, 1], args.max_points)
+    transformations = hist_icp(args, segs_src, segs_dst)
+    *evals, accept = match_eval(args, segs_src, segs_dst, transformations, return_accept=True)
+    return match_select(args, pairs, torch.unique(src_labels), torch.unique(dst_labels), evals, accept, transformations)
+
+
 class IcpHostPipeline:
     """Host-buffer front end of the ICP stage: pinned host inputs -> H2D -> kernels -> D2H of the 4x4 transforms.
 

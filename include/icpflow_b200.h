@@ -106,6 +106,34 @@ int icpf_nn_f32(const float* src, const float* dst, int32_t B, int32_t Ns, int32
 int icpf_transform_points_f32(const float* xyz, const float* pose, int32_t B, int32_t N, float* out, void* stream);
 
 /*
+ * Registration quality metrics of a batch of pairs -- replaces utils_match.match_eval (utils_match.py:159-213), the
+ * consumer of hist_icp's transforms in match_pairs (utils_match.py:93).  One fused launch instead of a transform, two
+ * knn_points passes and the masked reductions.
+ *   src, dst [P,N,4] (the clouds as given to hist_icp, NOT swapped), pose [P,16] row-major 4x4 (src -> dst)
+ *   out_errors [P,2]        mean NN distance of the valid rows: moved src -> dst, dst -> moved src
+ *   out_inliers [P,2]       number of valid rows with NN distance < (float)thres_dist (strict), as fp32 like the reference
+ *   out_ratios [P,2]        inliers / valid rows
+ *   out_ious [P,2]          inliers_a / (n_src + n_dst - inliers_b)
+ *   out_translations [P,3]  mean of the moved valid src rows - mean of the valid src rows
+ *   out_rotations [P,3]     ZYX Euler angles of pose[:3,:3] in degrees (pytorch3d matrix_to_euler_angles * 180 / pi)
+ * A cloud without valid rows gives NaN where the reference divides 0 by 0.
+ * gates / out_accept (both NULL or both set): out_accept [P] int32 = utils_check.check_transformation(args, translation,
+ * rotation, min(iou)) (utils_check.py:51-66) -- 0 when |translation| > translation_frame, min(iou) < thres_iou, or
+ * max(|pitch|,|roll|) > thres_rot * 90 degrees; the per-pair Python loop of match_pairs (utils_match.py:96-100) becomes
+ * one flag per pair written by the same launch.
+ */
+typedef struct icpf_match_gates {
+    double translation_frame;   /* args.translation_frame */
+    double thres_iou;           /* args.thres_iou */
+    double thres_rot;           /* args.thres_rot (fraction of 90 degrees) */
+} icpf_match_gates;
+
+int icpf_match_eval_f32(const float* src, const float* dst, const float* pose, int32_t P, int32_t N, double thres_dist,
+                        float* out_errors, float* out_inliers, float* out_ratios, float* out_ious,
+                        float* out_translations, float* out_rotations, const icpf_match_gates* gates,
+                        int32_t* out_accept, void* stream);
+
+/*
  * All-pairs difference histogram -- bit-compatible replacement of HIST.hist (hist_cuda/cpp/hist.cpp:25-27,
  * hist_cuda.cu:19-90, hist_cuda_core.cuh:23-64; python wrapper hist_cuda/hist.py:39-51).  Votes X_i - Y_j over rows
  * whose flags are both > 0.  X [B,NX,4], Y [B,NY,4] -> bins [B,len_x,len_y,len_z] fp32 counts (zero-filled here).

@@ -7,7 +7,7 @@ Run in the build container only (needs /root/reference):
 Every output array below is produced by calling the reference's own, unmodified functions
 (``utils_match.hist_icp``, ``utils_hist.estimate_init_pose``, ``utils_icp.apply_icp``,
 ``utils_icp_pytorch3d.iterative_closest_point``, ``utils_helper.nearest_neighbor_batch``,
-``utils_flow.flow_estimation_torch``) on torch CPU fp32 through ``oracle/ref_loader.py``; the inputs are
+``utils_match.match_eval``, ``utils_match.match_pairs``, ``utils_flow.flow_estimation_torch``) on torch CPU fp32 through ``oracle/ref_loader.py``; the inputs are
 stored next to them so the fixtures are self-contained on the GPU box.
 
 Fixtures
@@ -16,6 +16,7 @@ Fixtures
     c1_demo.npz           BASELINE config C1: demo.npz -> sklearn DBSCAN(eps .25, min 20) stand-in labels ->
                           first 32 static pairs with both clouds <= 256 points, N=256, F=2.0 (demo.sh)
     synth_hist.npz        24 ragged synthetic pairs, N=128, full hist_icp with F=3.333 (argparse default)
+    synth_match_dyn.npz   6 x 6 dynamic-stage candidate pairs through match_pairs (hist_icp + match_eval + gates + selection)
     synth_icp20.npz       32 synthetic residual-only pairs, N=256: ICP only, 20 forced iterations
                           (relative_rmse_thr=-1) and the reference stopping rule (1e-6, max 100)
 """
@@ -40,7 +41,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def _args(**kw):
     base = dict(thres_dist=0.1, translation_frame=3.333, chunk_size=50, max_points=256, min_cluster_size=20,
-                thres_box=0.1)
+                thres_box=0.1, thres_error=0.2, thres_iou=0.2, thres_rot=0.1)       # gates as in demo.sh
     base.update(kw)
     return types.SimpleNamespace(**base)
 
@@ -74,7 +75,58 @@ def _run_path(ref, args, src, dst):
     out["icp_converged"] = np.bool_(sol.converged)
     idx, dist = ref.utils_helper.nearest_neighbor_batch(a, c)
     out["nn_idx"], out["nn_dist"] = _np(idx), _np(dist)
+    # match_eval on the ORIGINAL (unswapped) clouds with the final transforms, as match_pairs calls it (utils_match.py:93)
+    ev = ref.utils_match.match_eval(args, src_t, dst_t, T)
+    for name, v in zip(("errors", "inliers", "ratios", "ious", "translations", "rotations"), ev):
+        out["eval_" + name] = _np(v)
     return out
+
+
+def clouds_from_batches(src_b, dst_b, pairs):
+    """Scan-level inputs of match_pairs (points + per-point labels) rebuilt from padded pair batches: the valid rows of
+    the FIRST batch entry that carries a label, in order -- so that ``points[labels == l]`` is that entry's cluster."""
+    out = []
+    for batch, col in ((src_b, 0), (dst_b, 1)):
+        pts, lab, seen = [], [], set()
+        for k, pr in enumerate(pairs):
+            l = float(pr[col])
+            if l in seen:
+                continue
+            seen.add(l)
+            rows = batch[k][batch[k][:, 3] > 0, 0:3]
+            pts.append(rows)
+            lab.append(np.full(len(rows), l, np.float32))
+        out += [np.concatenate(pts).astype(np.float32), np.concatenate(lab)]
+    return out
+
+
+def _run_match_pairs(ref, args, src_pts, src_lab, dst_pts, dst_lab, pairs):
+    rows, T = ref.utils_match.match_pairs(args, torch.from_numpy(src_pts), torch.from_numpy(dst_pts),
+                                          torch.from_numpy(src_lab), torch.from_numpy(dst_lab), torch.from_numpy(pairs))
+    return {"mp_rows": _np(rows), "mp_T": _np(T), "thres_error": np.float64(args.thres_error),
+            "thres_iou": np.float64(args.thres_iou), "thres_rot": np.float64(args.thres_rot),
+            "max_points": np.int64(args.max_points)}
+
+
+def gen_match_dyn(ref):
+    """Dynamic-stage shape of match_pairs (utils_match.py:46-57): every src cluster against every dst cluster.  Six
+    clusters re-centred onto a 1.2 m lattice so that wrong pairings are inside the histogram range and compete."""
+    n = 6
+    src, dst, meta = synth.make_pairs(n, 128, seed=99, ragged=True, residual_only=False)
+    for k in range(n):
+        vs, vd = src[k, :, 3] > 0, dst[k, :, 3] > 0
+        off = np.array([10.0 + 1.2 * k, -5.0 + 0.6 * (k % 2), 0.5], np.float32) - src[k, vs, :3].mean(0)
+        src[k, vs, :3] += off
+        dst[k, vd, :3] += off
+    ident = np.stack([np.arange(n), np.arange(n) + 100], 1).astype(np.float32)
+    src_pts, src_lab, dst_pts, dst_lab = clouds_from_batches(src, dst, ident)
+    pairs = np.stack([np.repeat(np.arange(n), n), np.tile(np.arange(n) + 100, n)], 1).astype(np.float32)
+    args = _args(translation_frame=3.333, max_points=128)
+    out = _run_match_pairs(ref, args, src_pts, src_lab, dst_pts, dst_lab, pairs)
+    np.savez_compressed(os.path.join(GOLDEN, "synth_match_dyn.npz"), src_points=src_pts, src_labels=src_lab,
+                        dst_points=dst_pts, dst_labels=dst_lab, pairs=pairs, thres_dist=np.float64(args.thres_dist),
+                        translation_frame=np.float64(args.translation_frame), chunk_size=np.int64(args.chunk_size), **out)
+    print("synth_match_dyn: candidate pairs", len(pairs), "selected", out["mp_rows"][:, :2].tolist())
 
 
 def gen_hist_test_vector(ref):
@@ -133,6 +185,10 @@ def gen_c1_demo(ref):
     pts, lab = src_t[sel], ls_t[sel]
     flow = ref.utils_flow.flow_estimation_torch(args, pts, None, lab, None, chosen.float(),
                                                 torch.from_numpy(out["T_hist_icp"]), torch.eye(4))
+    # match_pairs on the same 32 pairs (scan rebuilt from the padded batches so the fixture stays small)
+    mp_in = clouds_from_batches(_np(src_b), _np(dst_b), _np(chosen))
+    out.update(_run_match_pairs(ref, args, *mp_in, _np(chosen).astype(np.float32)))
+    print("c1_demo: match_pairs kept", len(out["mp_rows"]), "of", len(chosen))
     np.savez_compressed(os.path.join(GOLDEN, "c1_demo.npz"), src=_np(src_b), dst=_np(dst_b),
                         thres_dist=np.float64(args.thres_dist), translation_frame=np.float64(args.translation_frame),
                         chunk_size=np.int64(args.chunk_size), pair_labels=_np(chosen),
@@ -179,6 +235,7 @@ def main():
     gen_hist_test_vector(ref)
     gen_synth_icp20(ref)
     gen_synth_hist(ref)
+    gen_match_dyn(ref)
     gen_c1_demo(ref)
 
 

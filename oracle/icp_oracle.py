@@ -345,3 +345,125 @@ def flow_from_transforms(src_points: torch.Tensor, src_labels: torch.Tensor, pai
     per_point = torch.bmm(per_point, pose[None].expand(n, 4, 4))
     homo = torch.cat([src_points, src_points.new_ones(n, 1)], dim=-1)
     return torch.bmm(per_point, homo[:, :, None])[:, 0:3, 0] - src_points
+
+
+# ------------------------------------------------------------------------------------- match_eval (row f1)
+def euler_zyx_degrees(R: torch.Tensor) -> torch.Tensor:
+    """pytorch3d 0.7.4 ``matrix_to_euler_angles(R, "ZYX")`` in degrees, restated in closed form
+    (call site utils_match.py:184):  (atan2(m10, m00), asin(-m20), atan2(m21, m22))."""
+    z = torch.atan2(R[..., 1, 0], R[..., 0, 0])
+    y = torch.asin(-R[..., 2, 0])
+    x = torch.atan2(R[..., 2, 1], R[..., 2, 2])
+    return torch.stack([z, y, x], dim=-1) * 180.0 / 3.141592653589793
+
+
+def match_eval(pcd1: torch.Tensor, pcd2: torch.Tensor, transformations: torch.Tensor, p: PathParams):
+    """utils_match.py:159-213 -- quality metrics of a batch of registrations: mean NN errors in both directions,
+    inlier counts (strict ``< thres_dist``), inlier ratios, IoUs, mean translation of the moved cloud, ZYX Euler angles."""
+    moved = transform_points_batch(pcd1, transformations)
+    m1 = pcd1[:, :, -1] > 0.0
+    m2 = pcd2[:, :, -1] > 0.0
+    _, e12 = nearest_neighbor_batch(moved, pcd2)
+    _, e21 = nearest_neighbor_batch(pcd2, moved)
+    in1 = torch.logical_and(e12 < p.thres_dist, m1).float()
+    in2 = torch.logical_and(e21 < p.thres_dist, m2).float()
+    r1 = in1.sum(dim=1) / m1.sum(dim=1)
+    r2 = in2.sum(dim=1) / m2.sum(dim=1)
+    iou1 = in1.sum(dim=1) / (m1.sum(dim=1) + m2.sum(dim=1) - in2.sum(dim=1))
+    iou2 = in2.sum(dim=1) / (m1.sum(dim=1) + m2.sum(dim=1) - in1.sum(dim=1))
+    err1 = (e12 * m1).sum(1) / m1.sum(1)
+    err2 = (e21 * m2).sum(1) / m2.sum(1)
+    mean_moved = (moved[:, :, 0:3] * m1[:, :, None]).sum(dim=1) / m1.sum(dim=1, keepdim=True)
+    mean_orig = (pcd1[:, :, 0:3] * m1[:, :, None]).sum(dim=1) / m1.sum(dim=1, keepdim=True)
+    return (torch.stack([err1, err2], dim=1), torch.stack([in1.sum(1), in2.sum(1)], dim=1),
+            torch.stack([r1, r2], dim=1), torch.stack([iou1, iou2], dim=1), mean_moved - mean_orig,
+            euler_zyx_degrees(transformations[:, 0:3, 0:3]))
+
+
+@dataclasses.dataclass
+class MatchGates:
+    """The association thresholds ``match_pairs`` reads from ``args`` (main.py:97-110 defaults; demo.sh overrides
+    thres_error / thres_iou to 0.2)."""
+
+    max_points: int = 10000
+    thres_error: float = 0.1
+    thres_iou: float = 0.1
+    thres_rot: float = 0.1
+
+
+def check_transformation(translation: torch.Tensor, rotation: torch.Tensor, iou: torch.Tensor, p: PathParams,
+                         g: MatchGates) -> bool:
+    """utils_check.py:51-66 -- reject a registration that moves further than the frame budget, overlaps too little, or
+    pitches / rolls more than ``thres_rot * 90`` degrees."""
+    if torch.linalg.norm(translation) > p.translation_frame:
+        return False
+    if iou < g.thres_iou:
+        return False
+    if torch.abs(rotation[1:3]).max() > g.thres_rot * 90.0:
+        return False
+    return True
+
+
+def match_select(pairs, src_labels_unq, dst_labels_unq, evals, transformations, p: PathParams, g: MatchGates):
+    """utils_match.py:70-75,94-135 -- scatter the accepted registrations into [n_src, n_dst] matrices, keep for every
+    src cluster the dst cluster of least ``min(error)`` (``match_segments_descend``, utils_helper.py:108-115) if that
+    error is below ``thres_error``.  Returns (rows [K,10], transformations [K,4,4])."""
+    errors, inliers, ratios, ious, translations, rotations = evals
+    ns, nd = len(src_labels_unq), len(dst_labels_unq)
+    m_err = torch.zeros((ns, nd, 2)) + 1e8
+    m_inl, m_rat, m_iou = torch.zeros((ns, nd, 2)), torch.zeros((ns, nd, 2)), torch.zeros((ns, nd, 2))
+    m_T = torch.zeros((ns, nd, 4, 4))
+    matches = 0
+    for k in range(len(pairs)):
+        if not check_transformation(translations[k], rotations[k], min(ious[k]), p, g):
+            continue
+        si = torch.nonzero(src_labels_unq == pairs[k][0])
+        di = torch.nonzero(dst_labels_unq == pairs[k][1])
+        m_err[si, di, :], m_inl[si, di, :], m_rat[si, di, :], m_iou[si, di, :] = errors[k], inliers[k], ratios[k], ious[k]
+        m_T[si, di] = transformations[k]
+        matches += 1
+    if matches == 0:
+        return torch.zeros(0, 10), torch.zeros(0, 4, 4)
+    e_min = m_err.min(-1)[0]
+    si = torch.arange(0, ns)
+    di = torch.argmin(e_min, dim=1)
+    ok = e_min[si, di] < g.thres_error
+    si, di = si[ok], di[ok]
+    rows = torch.cat([src_labels_unq[si][:, None], dst_labels_unq[di][:, None], m_err[si, di], m_inl[si, di],
+                      m_rat[si, di], m_iou[si, di]], dim=1)
+    return rows, m_T[si, di]
+
+
+def match_pairs(src_points, dst_points, src_labels, dst_labels, pairs, p: PathParams, g: MatchGates,
+                return_debug: bool = False):
+    """utils_match.py:69-135 for clusters of at most ``max_points`` rows (``pad_segment`` subsamples larger ones with the
+    global torch RNG, which is outside what a restatement can pin)."""
+    assert len(pairs) > 0
+    segs_src = torch.stack([pad_cluster(src_points[src_labels == pr[0], 0:3], g.max_points) for pr in pairs])
+    segs_dst = torch.stack([pad_cluster(dst_points[dst_labels == pr[1], 0:3], g.max_points) for pr in pairs])
+    T = hist_icp(segs_src, segs_dst, p)
+    evals = match_eval(segs_src, segs_dst, T, p)
+    rows, T_sel = match_select(pairs, torch.unique(src_labels), torch.unique(dst_labels), evals, T, p, g)
+    if return_debug:
+        return rows, T_sel, {"segs_src": segs_src, "segs_dst": segs_dst, "T": T, "evals": evals}
+    return rows, T_sel
+
+
+def undetermined_pairs(src: torch.Tensor, dst: torch.Tensor, p: PathParams) -> torch.Tensor:
+    """Pairs whose ``hist_icp`` result the reference does not determine numerically -- a tied top-k peak set, an ICP
+    run that passes a discrete flip (``unstable_pairs``) or a roll-back decision inside fp32 noise.  Diagnostics for
+    the parity tests (the same three exclusions tests/test_gpu_path.py applies), not part of the reference."""
+    n_s = (src[:, :, -1] > 0.0).sum(dim=1)
+    n_d = (dst[:, :, -1] > 0.0).sum(dim=1)
+    swap = n_s > n_d
+    a, c = src.clone(), dst.clone()
+    a[swap] = dst[swap]
+    c[swap] = src[swap]
+    amb = ambiguous_topk_rows(a, c, p)
+    init = estimate_init_pose(a, c, p)
+    trace = icp_loop(transform_points_batch(a, init), c, p.thres_dist, p.max_iterations, p.relative_rmse_thr,
+                     diagnostics=True)
+    _, dbg = apply_icp(a, c, init, p, return_debug=True)
+    e0, e1 = dbg["error_init"], dbg["error_icp"]
+    tie = (e1 - e0).abs() <= 1e-5 * e0.clamp(min=1e-6)
+    return amb | unstable_pairs(trace) | tie

@@ -81,12 +81,15 @@ def _convert_pointclouds_to_tensor(pcl):
 
 
 def _matrix_to_euler_angles(matrix, convention):
-    """pytorch3d ``matrix_to_euler_angles`` restated with scipy (used by match_eval only, outside the path)."""
-    from scipy.spatial.transform import Rotation
-
-    m = matrix.detach().cpu().double().numpy()
-    ang = Rotation.from_matrix(m).as_euler(convention.upper())
-    return torch.as_tensor(ang, dtype=matrix.dtype)
+    """pytorch3d 0.7.4 ``matrix_to_euler_angles`` for the one convention the reference uses ("ZYX",
+    utils_match.py:184), restated from its published algorithm: central angle asin(-m20), the two outer angles by
+    atan2 -- (atan2(m10, m00), asin(-m20), atan2(m21, m22))."""
+    if convention != "ZYX":
+        raise NotImplementedError("oracle stub covers convention='ZYX' only")
+    z = torch.atan2(matrix[..., 1, 0], matrix[..., 0, 0])
+    y = torch.asin(-matrix[..., 2, 0])
+    x = torch.atan2(matrix[..., 2, 1], matrix[..., 2, 2])
+    return torch.stack([z, y, x], dim=-1)
 
 
 # --------------------------------------------------------------------------- hist_cuda leaf

@@ -35,3 +35,10 @@ print("finite", np.isfinite(T).all(), "orth err", np.abs(R @ R.transpose(0, 2, 1
 ok = ~meta["wrong"]
 t_err = np.abs(dbg["init"].cpu().numpy()[ok, :3, 3] - meta["translation"][ok]).max(axis=1)
 print("init translation within 0.15 m of ground truth on", float((t_err < 0.15).mean()), "of the true-match pairs")
+# row f1: match_eval (+ fused check_transformation) on the same batch
+eargs = types.SimpleNamespace(thres_dist=0.1, translation_frame=F, thres_iou=0.2, thres_rot=0.1)
+Tdev = torch.from_numpy(T).to(dev)
+t_eval, ev = timed(lambda: ops.match_eval(eargs, s, d, Tdev, return_accept=True))
+n_valid = float((s[:, :, 3] > 0).sum() + (d[:, :, 3] > 0).sum())
+print(f"match_eval {t_eval:.2f} ms -> {P / t_eval * 1e3:.0f} pairs/s; accepted {int(ev[6].sum())}/{P}; "
+      f"mean inlier ratio {float(ev[2].nanmean()):.3f}; brute-force candidates/s {float(((s[:, :, 3] > 0).sum(1).double() * (d[:, :, 3] > 0).sum(1).double()).sum()) * 2 / t_eval * 1e3:.3e}")
