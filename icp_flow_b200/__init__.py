@@ -5,12 +5,15 @@ kernels reached through the C ABI in ``include/icpflow_b200.h`` (``libicpflow_b2
 CPU or PyTorch fallback: importing works anywhere (so the CPU test-suite can check the ABI), calling needs a GPU.
 """
 from .ops import (ICPSolution, SimilarityTransform, IcpBatchResult, apply_icp, estimate_init_pose, hist, hist_icp,
-                  icp_batch, iterative_closest_point, make_params, match_eval, match_pairs, nearest_neighbor_batch,
+                  icp_batch, iterative_closest_point, make_params, match_eval, match_select, nearest_neighbor_batch,
                   pytorch3d_icp, transform_points_batch)
+from .scan import (ScanIndex, flow_estimation, flow_estimation_torch, match_pairs, match_pcds, pad_pairs,
+                   sanity_check, scan_index)
 from .install import install, uninstall
 
 __all__ = [
     "ICPSolution", "SimilarityTransform", "IcpBatchResult", "apply_icp", "estimate_init_pose", "hist", "hist_icp",
     "icp_batch", "iterative_closest_point", "make_params", "match_eval", "match_pairs", "nearest_neighbor_batch", "pytorch3d_icp",
-    "transform_points_batch", "install", "uninstall",
+    "transform_points_batch", "match_select", "ScanIndex", "scan_index", "sanity_check", "pad_pairs", "match_pcds",
+    "flow_estimation_torch", "flow_estimation", "install", "uninstall",
 ]

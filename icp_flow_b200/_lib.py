@@ -17,6 +17,8 @@ EXPORTS = (
     "icpf_icp_f32", "icpf_nn_f32", "icpf_transform_points_f32", "icpf_host_kabsch", "icpf_profile_next_icp",
     "icpf_host_kabsch_sequence", "icpf_peer_gather_next_icp", "icpf_hist_votes_f32", "icpf_hist_init_f32", "icpf_apply_icp_f32", "icpf_hist_icp_f32",
     "icpf_match_eval_f32",
+    "icpf_cluster_index_workspace_bytes", "icpf_cluster_index_f32", "icpf_sanity_check_f32", "icpf_gather_pairs_f32",
+    "icpf_flow_f32",
 )
 
 
@@ -113,6 +115,17 @@ def lib() -> ctypes.CDLL:
     L.icpf_host_kabsch.argtypes = [vp, i32, vp]
     L.icpf_host_kabsch_sequence.restype = None
     L.icpf_host_kabsch_sequence.argtypes = [vp, i32, vp]
+    L.icpf_cluster_index_workspace_bytes.restype = ctypes.c_size_t
+    L.icpf_cluster_index_workspace_bytes.argtypes = [i32, i32]
+    L.icpf_cluster_index_f32.restype = ctypes.c_int
+    L.icpf_cluster_index_f32.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp, vp, ctypes.c_size_t, vp]
+    L.icpf_sanity_check_f32.restype = ctypes.c_int
+    L.icpf_sanity_check_f32.argtypes = [vp, vp, i32, vp, vp, i32, vp, i32, i32, ctypes.c_double, ctypes.c_double, vp,
+                                        vp, vp, vp]
+    L.icpf_gather_pairs_f32.restype = ctypes.c_int
+    L.icpf_gather_pairs_f32.argtypes = [vp, i32, vp, vp, i32, vp, i32, vp, vp, i32, vp, i32, i32, vp, vp, vp, vp, vp]
+    L.icpf_flow_f32.restype = ctypes.c_int
+    L.icpf_flow_f32.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, vp]
     _LIB = L
     return L
 

@@ -165,6 +165,65 @@ int icpf_hist_icp_f32(const float* src, const float* dst, int32_t P, int32_t N, 
                            static_cast<cudaStream_t>(stream));
 }
 
+size_t icpf_cluster_index_workspace_bytes(int32_t n_points, int32_t n_labels) {
+    if (n_points < 0 || n_labels < 1 || n_labels > (1 << 20)) return 0;
+    return cluster_index_workspace_bytes(n_points, n_labels);
+}
+
+int icpf_cluster_index_f32(const float* points, int32_t point_stride, const float* labels, int32_t n_points,
+                           int32_t n_labels, int32_t* out_order, int32_t* out_offsets, float* out_stats,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+    if (n_points < 0 || n_labels < 1 || n_labels > (1 << 20)) return ICPF_E_SHAPE;
+    if (point_stride < 3) return ICPF_E_PARAM;
+    if (!out_offsets || !out_stats) return ICPF_E_NULL;
+    if (n_points > 0 && (!points || !labels || !out_order)) return ICPF_E_NULL;
+    return launch_cluster_index(points, point_stride, labels, n_points, n_labels, out_order, out_offsets, out_stats,
+                                workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int icpf_sanity_check_f32(const int32_t* src_offsets, const float* src_stats, int32_t n_src_labels,
+                          const int32_t* dst_offsets, const float* dst_stats, int32_t n_dst_labels,
+                          const int64_t* pairs, int32_t P, int32_t min_cluster_size, double translation_frame,
+                          double thres_box, int32_t* out_keep, int64_t* out_pairs, int32_t* out_count, void* stream) {
+    if (P < 0 || n_src_labels < 1 || n_dst_labels < 1) return ICPF_E_SHAPE;
+    if (!src_offsets || !src_stats || !dst_offsets || !dst_stats || !out_count) return ICPF_E_NULL;
+    if (P > 0 && (!pairs || !out_keep || !out_pairs)) return ICPF_E_NULL;
+    return launch_sanity_check(src_offsets, src_stats, n_src_labels, dst_offsets, dst_stats, n_dst_labels, pairs, P,
+                               min_cluster_size, (float)translation_frame, (float)thres_box, out_keep, out_pairs,
+                               out_count, static_cast<cudaStream_t>(stream));
+}
+
+int icpf_gather_pairs_f32(const float* src_points, int32_t src_stride, const int32_t* src_order,
+                          const int32_t* src_offsets, int32_t n_src_labels, const float* dst_points,
+                          int32_t dst_stride, const int32_t* dst_order, const int32_t* dst_offsets,
+                          int32_t n_dst_labels, const int64_t* pairs, int32_t P, int32_t max_points,
+                          const int32_t* sample_rows, const int64_t* sample_offsets, float* out_src, float* out_dst,
+                          void* stream) {
+    if (P < 0 || max_points < 1 || n_src_labels < 1 || n_dst_labels < 1) return ICPF_E_SHAPE;
+    if (src_stride < 3 || dst_stride < 3) return ICPF_E_PARAM;
+    if (P == 0) return ICPF_OK;
+    if (!src_points || !src_order || !src_offsets || !dst_points || !dst_order || !dst_offsets || !pairs || !out_src ||
+        !out_dst)
+        return ICPF_E_NULL;
+    if ((sample_rows == nullptr) != (sample_offsets == nullptr)) return ICPF_E_NULL;
+    if (!aligned16(out_src) || !aligned16(out_dst)) return ICPF_E_ALIGN;
+    return launch_gather_pairs(src_points, src_stride, src_order, src_offsets, n_src_labels, dst_points, dst_stride,
+                               dst_order, dst_offsets, n_dst_labels, pairs, P, max_points, sample_rows, sample_offsets,
+                               out_src, out_dst, static_cast<cudaStream_t>(stream));
+}
+
+int icpf_flow_f32(const float* points, int32_t point_stride, const float* labels, int32_t n_points,
+                  const float* pair_labels, int32_t pair_stride, const float* transforms, int32_t K, const float* pose,
+                  float* out_flow, void* stream) {
+    if (n_points < 0 || K < 0 || K > 65534) return ICPF_E_SHAPE;
+    if (point_stride < 3 || (K > 0 && pair_stride < 1)) return ICPF_E_PARAM;
+    if (n_points == 0) return ICPF_OK;
+    if (!points || !labels || !out_flow) return ICPF_E_NULL;
+    if (K > 0 && (!pair_labels || !transforms)) return ICPF_E_NULL;
+    return launch_flow(points, point_stride, labels, n_points, pair_labels, pair_stride, transforms, K, pose, out_flow,
+                       static_cast<cudaStream_t>(stream));
+}
+
 int icpf_peer_gather_next_icp(void* const* peer_pose_dev, int32_t world, int32_t row0) {
     if (world < 0 || row0 < 0 || world > 64) return ICPF_E_PARAM;
     if (world > 0 && peer_pose_dev == nullptr) return ICPF_E_NULL;

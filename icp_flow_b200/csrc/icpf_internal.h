@@ -60,4 +60,20 @@ int launch_match_eval(const float* src, const float* dst, const float* pose, int
                       const icpf_match_gates* gates, int* accept, cudaStream_t stream);
 int launch_transform_points(const float* xyz, const float* pose, int B, int N, float* out, cudaStream_t stream);
 
+
+// scan-level callers (icpf_scan.cu)
+size_t cluster_index_workspace_bytes(int n, int n_labels);
+int launch_cluster_index(const float* points, int stride, const float* labels, int n, int n_labels, int* order,
+                         int* offsets, float* stats, void* ws, size_t ws_bytes, cudaStream_t stream);
+int launch_sanity_check(const int* src_offsets, const float* src_stats, int n_src, const int* dst_offsets,
+                        const float* dst_stats, int n_dst, const int64_t* pairs, int P, int min_cluster_size,
+                        float translation_frame, float thres_box, int* out_keep, int64_t* out_pairs, int* out_count,
+                        cudaStream_t stream);
+int launch_gather_pairs(const float* src_points, int src_stride, const int* src_order, const int* src_offsets, int n_src,
+                        const float* dst_points, int dst_stride, const int* dst_order, const int* dst_offsets, int n_dst,
+                        const int64_t* pairs, int P, int max_points, const int* sample_rows,
+                        const int64_t* sample_offsets, float* out_src, float* out_dst, cudaStream_t stream);
+int launch_flow(const float* points, int stride, const float* labels, int n, const float* pair_labels, int pair_stride,
+                const float* transforms, int K, const float* pose, float* flow, cudaStream_t stream);
+
 }  // namespace icpf

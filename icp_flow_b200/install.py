@@ -6,6 +6,9 @@ only the hot-path entry points are rebound, exactly at the seams SURVEY.md secti
     utils_match.hist_icp              <- icp_flow_b200.hist_icp            (sole caller: utils_match.py:92)
     utils_match.match_eval            <- icp_flow_b200.match_eval          (sole caller: utils_match.py:93)
     utils_match.match_pairs           <- icp_flow_b200.match_pairs         (callers: utils_match.py:38,55)
+    utils_match.match_pcds            <- icp_flow_b200.match_pcds          (caller: utils_track.py:32; also rebound there)
+    utils_check.sanity_check          <- icp_flow_b200.sanity_check        (callers: utils_match.py:35,51)
+    utils_flow.flow_estimation_torch  <- icp_flow_b200.flow_estimation_torch (caller: demo.py:222)
     utils_hist.estimate_init_pose     <- icp_flow_b200.estimate_init_pose
     utils_icp.apply_icp               <- icp_flow_b200.apply_icp
     utils_icp.pytorch3d_icp           <- icp_flow_b200.pytorch3d_icp
@@ -20,14 +23,18 @@ from __future__ import annotations
 import importlib
 import sys
 
-from . import ops
+from . import ops, scan
 
 _SAVED = {}
 
 _BINDINGS = (
     ("utils_match", "hist_icp", ops.hist_icp),
     ("utils_match", "match_eval", ops.match_eval),
-    ("utils_match", "match_pairs", ops.match_pairs),
+    ("utils_match", "match_pairs", scan.match_pairs),
+    ("utils_match", "match_pcds", scan.match_pcds),
+    ("utils_match", "sanity_check", scan.sanity_check),
+    ("utils_check", "sanity_check", scan.sanity_check),
+    ("utils_flow", "flow_estimation_torch", scan.flow_estimation_torch),
     ("utils_match", "estimate_init_pose", ops.estimate_init_pose),
     ("utils_match", "apply_icp", ops.apply_icp),
     ("utils_hist", "estimate_init_pose", ops.estimate_init_pose),
@@ -35,6 +42,12 @@ _BINDINGS = (
     ("utils_icp", "pytorch3d_icp", ops.pytorch3d_icp),
     ("utils_icp", "iterative_closest_point", ops.iterative_closest_point),
     ("utils_icp_pytorch3d", "iterative_closest_point", ops.iterative_closest_point),
+)
+
+# names other reference modules copied with `from ... import ...`: rebound only where the module is already loaded
+_LOADED_ONLY = (
+    ("utils_track", "match_pcds", scan.match_pcds),
+    ("demo", "flow_estimation_torch", scan.flow_estimation_torch),
 )
 
 _HELPERS = (
@@ -52,6 +65,11 @@ def install(patch_helpers: bool = False):
     for mod_name, attr, fn in todo:
         mod = sys.modules.get(mod_name) or importlib.import_module(mod_name)
         if hasattr(mod, attr):
+            _SAVED.setdefault((mod_name, attr), getattr(mod, attr))
+            setattr(mod, attr, fn)
+    for mod_name, attr, fn in _LOADED_ONLY:
+        mod = sys.modules.get(mod_name)
+        if mod is not None and hasattr(mod, attr):
             _SAVED.setdefault((mod_name, attr), getattr(mod, attr))
             setattr(mod, attr, fn)
     return sorted({m for m, _, _ in todo})

@@ -412,22 +412,6 @@ def match_eval(args, pcd1, pcd2, transformations, return_accept: bool = False):
     return errors, inliers, ratios, ious, translations, rotations
 
 
-def pad_segments(points, labels, wanted, max_points: int):
-    """The gather / ``pad_segment`` loop of match_pairs (utils_match.py:79-90, utils_helper.py:185-196) for a list of
-    cluster labels: ``[len(wanted), max_points, 4]`` rows (x,y,z,1) then (1e8,1e8,1e8,0).  Clusters larger than
-    ``max_points`` are subsampled by the reference with ``torch.randperm`` (global RNG); that policy is not reproduced
-    here -- such a cluster raises, the caller subsamples first."""
-    out = points.new_full((len(wanted), max_points, 4), 1e8)
-    out[:, :, 3] = 0.0
-    for k, lab in enumerate(wanted):
-        seg = points[labels == lab, 0:3]
-        if len(seg) > max_points:
-            raise ValueError(f"cluster {float(lab)} has {len(seg)} > max_points={max_points} rows; subsample it first")
-        out[k, : len(seg), 0:3] = seg
-        out[k, : len(seg), 3] = 1.0
-    return out
-
-
 def match_select(args, pairs, src_labels_unq, dst_labels_unq, evals, accept, transformations):
     """The rejection loop and selection of match_pairs (utils_match.py:70-75, 94-135) without the per-pair Python loop:
     accepted registrations are scattered into the ``[n_src, n_dst]`` matrices in one indexed store each, every src cluster
@@ -453,18 +437,6 @@ def match_select(args, pairs, src_labels_unq, dst_labels_unq, evals, accept, tra
     rows = torch.cat([src_labels_unq[rows_i][:, None].float(), dst_labels_unq[cols_i][:, None].float(),
                       m_err[rows_i, cols_i], m_inl[rows_i, cols_i], m_rat[rows_i, cols_i], m_iou[rows_i, cols_i]], dim=1)
     return rows, m_T[rows_i, cols_i]
-
-
-def match_pairs(args, src_points, dst_points, src_labels, dst_labels, pairs):
-    """Drop-in for ``utils_match.match_pairs`` (utils_match.py:69-135): pad the candidate cluster pairs, register them
-    (``hist_icp``), score + gate them (``match_eval`` with the fused ``check_transformation``) and select one dst cluster
-    per src cluster.  Returns ``(rows [K,10], transformations [K,4,4])`` on the device of the inputs."""
-    assert len(pairs) > 0
-    segs_src = pad_segments(src_points, src_labels, pairs[:, 0], args.max_points)
-    segs_dst = pad_segments(dst_points, dst_labels, pairs[:, 1], args.max_points)
-    transformations = hist_icp(args, segs_src, segs_dst)
-    *evals, accept = match_eval(args, segs_src, segs_dst, transformations, return_accept=True)
-    return match_select(args, pairs, torch.unique(src_labels), torch.unique(dst_labels), evals, accept, transformations)
 
 
 class IcpHostPipeline:

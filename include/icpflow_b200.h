@@ -176,6 +176,68 @@ int icpf_hist_icp_f32(const float* src, const float* dst, int32_t P, int32_t N, 
                       void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * ---------------------------------------------------------------------------------------------------------------
+ * Scan-level callers of the path.  A scan is `points` [n, stride >= 3] fp32 rows
+ * (x, y, z, ...) plus one fp32 label per point, as the reference holds them (main.py:205-208): cluster labels are the
+ * non-negative integers, ground / unclustered points carry -1e8 / -1.
+ * ---------------------------------------------------------------------------------------------------------------
+ */
+
+/*
+ * Cluster index of one scan -- replaces the per-use boolean masks `points[labels == l]` of sanity_check
+ * (utils_check.py:24-25) and match_pairs (utils_match.py:85-86) by one stable counting sort.
+ *   labels [n] fp32; a label l is indexed when it is an integer with 0 <= l < n_labels
+ *   out_order   [n] int32    point rows grouped by label, scan order kept inside a label (first out_offsets[n_labels] valid)
+ *   out_offsets [n_labels+1] int32   rows of label l = out_order[out_offsets[l] .. out_offsets[l+1])
+ *   out_stats   [n_labels,8] fp32    {mean x, mean y, mean z (fp64 sums rounded once), the three |max - min| extents
+ *                                     sorted ascending (get_bbox_tensor, utils_helper.py:166-170), 0, 0}
+ *   workspace   icpf_cluster_index_workspace_bytes(n, n_labels)
+ */
+size_t icpf_cluster_index_workspace_bytes(int32_t n_points, int32_t n_labels);
+int icpf_cluster_index_f32(const float* points, int32_t point_stride, const float* labels, int32_t n_points,
+                           int32_t n_labels, int32_t* out_order, int32_t* out_offsets, float* out_stats,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Candidate-pair filter -- replaces utils_check.sanity_check (utils_check.py:21-49), a Python loop with two scan-wide
+ * masks and several host syncs per candidate pair, by one launch on the statistics of the two cluster indices.
+ *   pairs [P,2] int64 (src label, dst label) as the reference's `pairs` tensor (utils_match.py:32,50)
+ *   a pair is kept when both labels are >= 0, min(len) >= min_cluster_size, |mean_dst - mean_src|_xy <= translation_frame
+ *   and, per sorted bounding-box extent, min >= thres_box * max   (all comparisons in fp32 like the reference)
+ *   out_keep [P] int32 0/1; out_pairs [P,2] int64 the kept pairs in input order; out_count [1] int32 their number
+ */
+int icpf_sanity_check_f32(const int32_t* src_offsets, const float* src_stats, int32_t n_src_labels,
+                          const int32_t* dst_offsets, const float* dst_stats, int32_t n_dst_labels,
+                          const int64_t* pairs, int32_t P, int32_t min_cluster_size, double translation_frame,
+                          double thres_box, int32_t* out_keep, int64_t* out_pairs, int32_t* out_count, void* stream);
+
+/*
+ * Padded pair batch -- replaces the gather loop of match_pairs (utils_match.py:81-91) and pad_segment
+ * (utils_helper.py:185-196): out_src / out_dst [P, max_points, 4] rows (x, y, z, 1) in scan order, then
+ * (1e8, 1e8, 1e8, 0).  Clusters with more than max_points rows: the reference keeps torch.randperm(len)[:max_points];
+ * the caller draws that permutation (same call, same order, so the same RNG stream) and passes it --
+ *   sample_rows     int32 positions inside the cluster, max_points per sampled cluster (may be NULL)
+ *   sample_offsets  [P,2] int64 start of the (pair, side) sample inside sample_rows, -1 = none (may be NULL)
+ * -- a larger cluster without a sample keeps its first max_points rows.
+ */
+int icpf_gather_pairs_f32(const float* src_points, int32_t src_stride, const int32_t* src_order,
+                          const int32_t* src_offsets, int32_t n_src_labels, const float* dst_points,
+                          int32_t dst_stride, const int32_t* dst_order, const int32_t* dst_offsets,
+                          int32_t n_dst_labels, const int64_t* pairs, int32_t P, int32_t max_points,
+                          const int32_t* sample_rows, const int64_t* sample_offsets, float* out_src, float* out_dst,
+                          void* stream);
+
+/*
+ * Scene flow from the matched transforms -- replaces utils_flow.flow_estimation_torch (utils_flow.py:57-69):
+ *   flow_i = (T_k * pose) p_i - p_i  with k the (last) row whose pair_labels[k] equals labels[i], T = identity otherwise.
+ *   pair_labels  fp32, row k at pair_labels[k * pair_stride]  (column 0 of the [K,10] `pairs` rows: pair_stride = 10)
+ *   transforms [K,16] row-major 4x4; pose [16] DEVICE row-major 4x4 (NULL = identity); out_flow [n,3]
+ */
+int icpf_flow_f32(const float* points, int32_t point_stride, const float* labels, int32_t n_points,
+                  const float* pair_labels, int32_t pair_stride, const float* transforms, int32_t K, const float* pose,
+                  float* out_flow, void* stream);
+
+/*
  * Fused all-gather of the transforms (multi-GPU): the next icpf_icp_f32 call on this host thread also stores every
  * pair's 4x4 (64 B) directly into the gathered buffers of ALL ranks through peer-mapped pointers -- row (row0 + p) of
  * each `[world * P, 16]` buffer -- from the kernel epilogue, instead of a separate NCCL all-gather.

@@ -17,6 +17,9 @@ Fixtures
                           first 32 static pairs with both clouds <= 256 points, N=256, F=2.0 (demo.sh)
     synth_hist.npz        24 ragged synthetic pairs, N=128, full hist_icp with F=3.333 (argparse default)
     synth_match_dyn.npz   6 x 6 dynamic-stage candidate pairs through match_pairs (hist_icp + match_eval + gates + selection)
+    frame_demo.npz        a whole frame pair through match_pcds (sanity_check, gather + pad_segment incl. the randperm
+                          subsampling, both stages) and flow_estimation_torch: the demo.npz scene with the DBSCAN
+                          stand-in labels, its largest cluster relabelled as ground (-1e8) and thinned, max_points=512
     synth_icp20.npz       32 synthetic residual-only pairs, N=256: ICP only, 20 forced iterations
                           (relative_rmse_thr=-1) and the reference stopping rule (1e-6, max 100)
 """
@@ -228,6 +231,66 @@ def gen_synth_icp20(ref):
     np.savez_compressed(os.path.join(GOLDEN, "synth_icp20.npz"), thres_dist=np.float64(0.1), **res)
 
 
+def gen_frame_demo(ref):
+    """Rows f2 / f3: the reference's own match_pcds + flow_estimation_torch on a whole frame pair (torch CPU fp32,
+    torch.manual_seed(0) right before match_pcds so that the randperm subsampling of oversized clusters is reproducible
+    by anyone making the same calls in the same order)."""
+    from sklearn.cluster import DBSCAN
+
+    d = np.load(os.path.join(ref_loader.REFERENCE_ROOT, "demo.npz"))
+    pc_src = d["pc1"][d["pc1_flows_valid_idx"]].astype(np.float32)
+    pc_dst = d["pc2"][d["pc2_flows_valid_idx"]].astype(np.float32)
+    fused = np.concatenate([pc_dst, pc_src], axis=0)
+    labels = DBSCAN(eps=0.25, min_samples=20).fit_predict(fused[:, :3]).astype(np.int64)
+    big = np.bincount(labels[labels >= 0]).argmax()
+    rng = np.random.default_rng(7)
+    scans = []
+    for pts, lab in ((pc_src, labels[len(pc_dst):]), (pc_dst, labels[: len(pc_dst)])):
+        lab = lab.astype(np.float32)
+        keep = np.ones(len(pts), bool)
+        for value, relabel, quota in ((big, -1e8, 3000), (-1, -1.0, 1500)):     # thin what is not a cluster
+            idx = np.flatnonzero(lab == value)
+            lab[idx] = relabel
+            keep[rng.permutation(idx)[quota:]] = False
+        scans.append((pts[keep], lab[keep]))
+    (src_pts, src_lab), (dst_pts, dst_lab) = scans
+    args = _args(translation_frame=2.0, max_points=512)                        # demo.sh gates
+    tens = [torch.from_numpy(x) for x in (src_pts, dst_pts, src_lab, dst_lab)]
+    calls = []
+    real_sanity = ref.utils_match.sanity_check
+
+    def spy(a, sp, dp, sl, dl, pairs):
+        out = real_sanity(a, sp, dp, sl, dl, pairs)
+        calls.append((_np(pairs).astype(np.int64).reshape(-1, 2), _np(out).astype(np.int64).reshape(-1, 2)))
+        return out
+
+    ref.utils_match.sanity_check = spy
+    try:
+        torch.manual_seed(0)
+        rows, T = ref.utils_match.match_pcds(args, *tens)
+    finally:
+        ref.utils_match.sanity_check = real_sanity
+    yaw = np.deg2rad(1.0)
+    pose = np.eye(4, dtype=np.float32)
+    pose[:2, :2] = [[np.cos(yaw), -np.sin(yaw)], [np.sin(yaw), np.cos(yaw)]]
+    pose[:3, 3] = [0.3, -0.1, 0.02]
+    flow = ref.utils_flow.flow_estimation_torch(args, tens[0], tens[1], tens[2], tens[3], rows, T, torch.from_numpy(pose))
+    (cand_sta, kept_sta), (cand_dyn, kept_dyn) = calls
+    np.savez_compressed(os.path.join(GOLDEN, "frame_demo.npz"), src_points=src_pts, src_labels=src_lab,
+                        dst_points=dst_pts, dst_labels=dst_lab, thres_dist=np.float64(args.thres_dist),
+                        translation_frame=np.float64(args.translation_frame), chunk_size=np.int64(args.chunk_size),
+                        max_points=np.int64(args.max_points), min_cluster_size=np.int64(args.min_cluster_size),
+                        thres_box=np.float64(args.thres_box), thres_error=np.float64(args.thres_error),
+                        thres_iou=np.float64(args.thres_iou), thres_rot=np.float64(args.thres_rot),
+                        static_candidates=cand_sta, static_kept=kept_sta,
+                        dynamic_candidates_shape=np.array(cand_dyn.shape), dynamic_kept=kept_dyn,
+                        rows=_np(rows), T=_np(T), pose=pose, flow_stride=np.int64(4), flow=_np(flow)[::4])
+    sizes = np.bincount(src_lab[src_lab >= 0].astype(np.int64))
+    print("frame_demo: points", len(src_pts), len(dst_pts), "static kept", len(kept_sta), "of", len(cand_sta),
+          "dynamic kept", len(kept_dyn), "of", len(cand_dyn), "matched", len(rows), "oversized src clusters",
+          int((sizes > args.max_points).sum()))
+
+
 def main():
     torch.set_num_threads(os.cpu_count() or 1)
     os.makedirs(GOLDEN, exist_ok=True)
@@ -237,6 +300,7 @@ def main():
     gen_synth_hist(ref)
     gen_match_dyn(ref)
     gen_c1_demo(ref)
+    gen_frame_demo(ref)
 
 
 if __name__ == "__main__":

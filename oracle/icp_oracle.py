@@ -389,6 +389,8 @@ class MatchGates:
     thres_error: float = 0.1
     thres_iou: float = 0.1
     thres_rot: float = 0.1
+    min_cluster_size: int = 30      # main.py:79 (demo.sh: 20)
+    thres_box: float = 0.1          # main.py:101
 
 
 def check_transformation(translation: torch.Tensor, rotation: torch.Tensor, iou: torch.Tensor, p: PathParams,
@@ -447,6 +449,104 @@ def match_pairs(src_points, dst_points, src_labels, dst_labels, pairs, p: PathPa
     if return_debug:
         return rows, T_sel, {"segs_src": segs_src, "segs_dst": segs_dst, "T": T, "evals": evals}
     return rows, T_sel
+
+
+# ------------------------------------------------------------------------------- batch construction (row f2)
+def cluster_bbox(points: torch.Tensor):
+    """utils_helper.py:166-170 (get_bbox_tensor): the three axis extents |max - min|, sorted ascending."""
+    x = torch.abs(points[:, 0].max() - points[:, 0].min())
+    y = torch.abs(points[:, 1].max() - points[:, 1].min())
+    z = torch.abs(points[:, 2].max() - points[:, 2].min())
+    return sorted([x, y, z])
+
+
+def sanity_check(src_points, dst_points, src_labels, dst_labels, pairs, p: PathParams, g: MatchGates):
+    """utils_check.py:21-49 -- keep a candidate pair when both clusters have >= min_cluster_size points, no label is
+    negative, the xy centroid offset is within translation_frame and each sorted bbox extent pair satisfies
+    min >= thres_box * max.  Returns the kept rows of ``pairs`` (``[K,2]``, ``zeros((0,2))`` when none)."""
+    keep = []
+    for pair in pairs:
+        src = src_points[src_labels == pair[0]]
+        dst = dst_points[dst_labels == pair[1]]
+        if min(len(src), len(dst)) < g.min_cluster_size:
+            continue
+        if min(pair[0], pair[1]) < 0:
+            continue
+        if torch.linalg.norm((dst.mean(0) - src.mean(0))[0:2]) > p.translation_frame:
+            continue
+        sb, db = cluster_bbox(src), cluster_bbox(dst)
+        if any(min(sb[k], db[k]) < g.thres_box * max(sb[k], db[k]) for k in range(3)):
+            continue
+        keep.append(pair)
+    return torch.vstack(keep) if len(keep) > 0 else torch.zeros((0, 2))
+
+
+def pad_cluster_sampled(points: torch.Tensor, max_points: int) -> torch.Tensor:
+    """utils_helper.py:185-201 (pad_segment + random_choice) including the subsampling branch: a cluster with more than
+    ``max_points`` rows keeps ``torch.randperm(len)[:max_points]`` -- the global torch RNG, so a comparison has to seed
+    it and make the calls in the reference's order (pair by pair, src before dst, utils_match.py:84-88)."""
+    if len(points) > max_points:
+        points = points[torch.randperm(len(points))[0:max_points], :]
+    return pad_cluster(points, max_points)
+
+
+def match_pairs_sampled(src_points, dst_points, src_labels, dst_labels, pairs, p: PathParams, g: MatchGates,
+                        return_debug: bool = False):
+    """``match_pairs`` (utils_match.py:69-135) with the reference's subsampling of oversized clusters."""
+    assert len(pairs) > 0
+    segs_src, segs_dst = [], []
+    for pr in pairs:                                    # one loop: the RNG is consumed src, dst, src, dst, ...
+        segs_src.append(pad_cluster_sampled(src_points[src_labels == pr[0], 0:3], g.max_points))
+        segs_dst.append(pad_cluster_sampled(dst_points[dst_labels == pr[1], 0:3], g.max_points))
+    segs_src, segs_dst = torch.stack(segs_src), torch.stack(segs_dst)
+    T = hist_icp(segs_src, segs_dst, p)
+    evals = match_eval(segs_src, segs_dst, T, p)
+    rows, T_sel = match_select(pairs, torch.unique(src_labels), torch.unique(dst_labels), evals, T, p, g)
+    if return_debug:
+        return rows, T_sel, {"segs_src": segs_src, "segs_dst": segs_dst, "T": T, "evals": evals, "pairs": pairs}
+    return rows, T_sel
+
+
+def setdiff1d(t1: torch.Tensor, t2: torch.Tensor) -> torch.Tensor:
+    """utils_helper.py:172-183: elements of t1 that are not in t2 (t2 assumed a subset of t1)."""
+    t12, counts = torch.cat([torch.unique(t1), torch.unique(t2)]).unique(return_counts=True)
+    return t12[torch.where(counts.eq(1))]
+
+
+def match_pcds(src_points, dst_points, src_labels, dst_labels, p: PathParams, g: MatchGates, return_debug: bool = False):
+    """utils_match.py:26-66 -- static stage (label l against label l), then every unmatched src cluster against every
+    unmatched dst cluster; both filtered by ``sanity_check`` and resolved by ``match_pairs``."""
+    src_unq = torch.unique(src_labels).long()
+    dst_unq = torch.unique(dst_labels).long()
+    labels_unq = torch.unique(torch.cat([src_unq, dst_unq], dim=0))
+    dbg = {}
+    pairs = torch.stack([labels_unq, labels_unq], dim=1)
+    pairs = pairs[pairs.min(dim=1)[0] >= 0]
+    pairs_true = sanity_check(src_points, dst_points, src_labels, dst_labels, pairs, p, g)
+    dbg["static_candidates"], dbg["static_kept"] = pairs, pairs_true
+    if len(pairs_true) > 0:
+        rows_sta, T_sta, dbg["static"] = match_pairs_sampled(src_points, dst_points, src_labels, dst_labels, pairs_true,
+                                                             p, g, return_debug=True)
+    else:
+        rows_sta, T_sta = torch.zeros(0, 10), torch.zeros(0, 4, 4)
+    if len(rows_sta) < len(labels_unq):
+        if len(rows_sta) > 0:
+            src_unq = setdiff1d(src_unq, rows_sta[:, 0])
+            dst_unq = setdiff1d(dst_unq, rows_sta[:, 1])
+        pairs = torch.stack([src_unq.repeat_interleave(len(dst_unq)), dst_unq.repeat(len(src_unq))], dim=1)
+        pairs_true = sanity_check(src_points, dst_points, src_labels, dst_labels, pairs, p, g)
+    else:
+        pairs, pairs_true = torch.zeros(0, 2), torch.zeros(0, 2)
+    dbg["dynamic_candidates"], dbg["dynamic_kept"] = pairs, pairs_true
+    if len(pairs_true) > 0:
+        rows_dyn, T_dyn, dbg["dynamic"] = match_pairs_sampled(src_points, dst_points, src_labels, dst_labels,
+                                                              pairs_true, p, g, return_debug=True)
+    else:
+        rows_dyn, T_dyn = torch.zeros(0, 10), torch.zeros(0, 4, 4)
+    rows, T = torch.cat([rows_sta, rows_dyn], dim=0), torch.cat([T_sta, T_dyn], dim=0)
+    if return_debug:
+        return rows, T, dbg
+    return rows, T
 
 
 def undetermined_pairs(src: torch.Tensor, dst: torch.Tensor, p: PathParams) -> torch.Tensor:

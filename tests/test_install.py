@@ -24,6 +24,12 @@ def test_install_rebinds_reference_seams():
         assert ref.utils_icp.pytorch3d_icp is ops.pytorch3d_icp
         assert ref.utils_icp_pytorch3d.iterative_closest_point is ops.iterative_closest_point
         assert ref.utils_helper.nearest_neighbor_batch is orig[4]                 # helpers only on request
+        # scan-level seams (rows f1-f3): pair enumeration, candidate filter, batch construction, flow recovery
+        assert ref.utils_match.match_pcds is icp_flow_b200.match_pcds
+        assert ref.utils_match.match_pairs is icp_flow_b200.match_pairs
+        assert ref.utils_match.sanity_check is icp_flow_b200.sanity_check        # re-imported name inside utils_match
+        assert ref.utils_check.sanity_check is icp_flow_b200.sanity_check
+        assert ref.utils_flow.flow_estimation_torch is icp_flow_b200.flow_estimation_torch
         icp_flow_b200.install(patch_helpers=True)
         assert ref.utils_match.nearest_neighbor_batch is ops.nearest_neighbor_batch
     finally:
@@ -51,5 +57,12 @@ def test_signatures_match_the_reference():
     assert params(ops.pytorch3d_icp) == params(ref.utils_icp.pytorch3d_icp)
     assert params(ops.nearest_neighbor_batch) == params(ref.utils_helper.nearest_neighbor_batch)
     assert params(ops.transform_points_batch) == params(ref.utils_helper.transform_points_batch)
+    import icp_flow_b200 as E
+    assert params(E.sanity_check) == params(ref.utils_check.sanity_check)
+    assert params(E.match_pairs) == params(ref.utils_match.match_pairs)
+    assert params(E.match_pcds) == params(ref.utils_match.match_pcds)
+    assert params(E.match_eval, 4) == params(ref.utils_match.match_eval)
+    assert params(E.flow_estimation_torch) == params(ref.utils_flow.flow_estimation_torch)
+    assert params(E.flow_estimation, 8) == params(ref.utils_flow.flow_estimation)
     import hist_cuda.hist as ref_hist          # the stub keeps the reference's signature (hist_cuda/hist.py:39)
     assert [p for p, _ in params(ops.hist)] == [p for p, _ in params(ref_hist.hist)]

@@ -210,7 +210,8 @@ def test_engine_match_pairs_vs_reference_golden(golden, name):
     args = types.SimpleNamespace(thres_dist=p.thres_dist, translation_frame=p.translation_frame, chunk_size=p.chunk_size,
                                  max_points=gates.max_points, thres_error=gates.thres_error, thres_iou=gates.thres_iou,
                                  thres_rot=gates.thres_rot)
-    rows, T = ops.match_pairs(args, *(torch.from_numpy(x).to(dev) for x in (sp, dp, sl, dl, pairs)))
+    import icp_flow_b200
+    rows, T = icp_flow_b200.match_pairs(args, *(torch.from_numpy(x).to(dev) for x in (sp, dp, sl, dl, pairs)))
     rows, T = rows.cpu().numpy(), T.cpu().numpy()
     ref_rows, ref_T = g["mp_rows"], g["mp_T"]
     assert rows.shape[1] == 10
