@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libicpflow_b200.so")
+# ICPF_LIB_PATH: an experimental build of the same ABI (tools/ab_kernel.py); the product path is the in-tree library
+LIB_PATH = os.environ.get("ICPF_LIB_PATH") or os.path.join(_HERE, "libicpflow_b200.so")
 
 # every symbol include/icpflow_b200.h declares (checked by tests/test_abi.py against the header text)
 EXPORTS = (

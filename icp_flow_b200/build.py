@@ -40,14 +40,15 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build_library(force: bool = False, verbose: bool = False, extra_flags=(), out: str = OUT) -> str:
+    """``extra_flags`` / ``out`` build an experimental variant next to the product library (tools/ab_kernel.py)."""
+    if not force and out == OUT and not _stale():
         return OUT
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + sources()
+    cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + sources()
     env = dict(os.environ)
     # the image exports CC=/opt/gcc/bin/gcc, a wrapper without OpenMP specs; nvcc only needs a plain host g++
     subprocess.check_call(cmd, env=env)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

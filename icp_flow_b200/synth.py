@@ -78,3 +78,63 @@ def make_pairs(num_pairs: int, max_points: int, seed: int = 1234, *, ragged: boo
         yaw[p], trans[p], wrong[p] = ang, t, is_wrong
     meta = {"yaw": yaw, "translation": trans, "wrong": wrong}
     return src, dst, meta
+
+
+def make_scene(num_clusters: int = 200, num_points: int = 150_000, seed: int = 4, *, dynamic_frac: float = 0.15,
+               median_size: int = 80, sigma: float = 1.3, max_size: int = 12_000, noise: float = 0.01,
+               density: float = 40.0):
+    """A "Waymo-shape" frame pair (BASELINE config C4): ``num_clusters`` box-shell clusters with a
+    log-normal size distribution (median ~80, p90 ~450, a few of several thousand points) on a 100 m x 100 m lattice,
+    the rest of the ``num_points`` budget as ground (label -1e8) and unclustered (-1) points, scan order shuffled.
+
+    Static clusters keep their label in both scans and move by a residual (<= 5 cm, <= 3 deg yaw); ``dynamic_frac`` of
+    the clusters move by up to 1.5 m and carry a DIFFERENT label in the dst scan, so that only the all-against-all
+    dynamic stage of ``match_pcds`` can pair them.  Returns ``(src_points, src_labels, dst_points, dst_labels, meta)``
+    with fp32 points ``[n,3]``, fp32 labels ``[n]`` and ``meta`` = per src label the dst label and the 4x4 motion.
+    """
+    rng = np.random.default_rng(seed)
+    K = int(num_clusters)
+    sizes = np.clip(np.exp(rng.normal(np.log(median_size), sigma, size=K)).astype(int), 30, max_size)
+    side = int(np.ceil(np.sqrt(K)))
+    pitch = 100.0 / side
+    dynamic = rng.uniform(size=K) < dynamic_frac
+    src_pts, src_lab, dst_pts, dst_lab = [], [], [], []
+    dst_label_of = np.arange(K)
+    dst_label_of[dynamic] = K + np.arange(int(dynamic.sum()))            # moved objects get a fresh label
+    motion = np.tile(np.eye(4), (K, 1, 1))
+    for k in range(K):
+        n = int(sizes[k])
+        scale = np.sqrt(n / 512.0 * 15.0 / density)                     # `density` points / m^2 whatever the size
+        extents = np.array([rng.uniform(1.5, 5.0), rng.uniform(0.8, 2.2), rng.uniform(0.8, 2.0)]) * scale
+        extents = np.minimum(extents, [pitch - 3.5, pitch - 3.5, 4.0])
+        centre = np.array([-50.0 + pitch * (k % side + 0.5), -50.0 + pitch * (k // side + 0.5), rng.uniform(0.5, 2.0)])
+        a = _shell_points(rng, extents, n)
+        b = _shell_points(rng, extents, max(30, int(n * rng.uniform(0.85, 1.15))))
+        ang = np.deg2rad(rng.uniform(-3.0, 3.0))
+        t = rng.uniform(-0.05, 0.05, size=3)
+        if dynamic[k]:
+            t[:2] = rng.uniform(-1.0, 1.0, size=2)
+        c, s = np.cos(ang), np.sin(ang)
+        Rz = np.array([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]])
+        b = b @ Rz.T + t + rng.normal(0.0, noise, size=b.shape)
+        src_pts.append(a + centre)
+        dst_pts.append(b + centre)
+        src_lab.append(np.full(len(a), k, np.float32))
+        dst_lab.append(np.full(len(b), dst_label_of[k], np.float32))
+        motion[k, :3, :3] = Rz
+        motion[k, :3, 3] = centre + t - Rz @ centre                     # p' = Rz (p - c) + c + t
+    scans = []
+    for pts, lab in ((src_pts, src_lab), (dst_pts, dst_lab)):
+        pts, lab = np.concatenate(pts), np.concatenate(lab)
+        rest = max(0, int(num_points) - len(pts))
+        n_ground = int(rest * 0.9)
+        ground = np.stack([rng.uniform(-55, 55, n_ground), rng.uniform(-55, 55, n_ground),
+                           rng.normal(0.0, 0.03, n_ground)], 1)
+        loose = np.stack([rng.uniform(-55, 55, rest - n_ground), rng.uniform(-55, 55, rest - n_ground),
+                          rng.uniform(0.2, 3.0, rest - n_ground)], 1)
+        pts = np.concatenate([pts, ground, loose])
+        lab = np.concatenate([lab, np.full(n_ground, -1e8, np.float32), np.full(rest - n_ground, -1.0, np.float32)])
+        perm = rng.permutation(len(pts))
+        scans += [pts[perm].astype(np.float32), lab[perm].astype(np.float32)]
+    meta = {"dst_label": dst_label_of, "motion": motion, "dynamic": dynamic, "sizes": sizes}
+    return scans[0], scans[1], scans[2], scans[3], meta
