@@ -6,6 +6,7 @@
 //   icp_finalize: compose ICP with the init pose, mean NN error before/after, roll back, undo the swap
 #include "icpf_internal.h"
 #include "icpf_pair.cuh"
+#include "icpf_gridnn.cuh"
 
 namespace icpf {
 
@@ -17,30 +18,44 @@ struct FinalizeArgs {
     const float* icp_R;      // [P,9]  row-vector convention
     const float* icp_T;      // [P,3]
     int auto_swap;
+    float tau;               // thres_dist: only sizes the cells of the NN grid
     float* out_pose;         // [P,16]
     float* out_err;          // [P,2] {error_init, error_icp} (may be NULL)
     int* out_flags;          // [P]   bit 0 rolled back, bit 1 swapped (may be NULL)
 };
 
 // mean over the valid rows of S of the unbounded NN distance of (pose * S_i) among D[0, n_d)   (utils_icp.py:28-33)
+// Rows are accumulated per thread in increasing row order (q = tid, tid + kThreads, ...) whichever search is used; the
+// grid search (icpf_gridnn.cuh) returns the same minimum as the full scan, so both variants produce the same bits.
+template <bool GRIDNN>
 __device__ __forceinline__ float mean_nn_error(const float (&m)[12], const float4* S, int n_s, const float4* D, int n_d,
-                                      float* scratch) {
+                                               float* scratch, const GridInfo& g, const float4* sorted,
+                                               const unsigned short* runs) {
     float sum[1] = {0.f};
-    constexpr int QB = 4;
-    for (int q0 = threadIdx.x; q0 < n_s; q0 += kThreads * QB) {
-        float qx[QB], qy[QB], qz[QB], best[QB];
-        int bidx[QB];
-#pragma unroll
-        for (int k = 0; k < QB; ++k) {
-            const int q = q0 + k * kThreads;
-            const float4 s = transform_row(m, q < n_s ? S[q] : make_float4(0.f, 0.f, 0.f, 0.f));
-            qx[k] = s.x; qy[k] = s.y; qz[k] = s.z;
+    if (GRIDNN && n_d > 0) {
+        for (int q = threadIdx.x; q < n_s; q += kThreads) {
+            const float4 raw = S[q];
+            const float4 s = transform_row(m, raw);
+            const float best = nn_unbounded_grid<false>(g, sorted, runs, n_d, s.x, s.y, s.z, s.x, s.y, s.z, 0.f, 0.f, 0.f);
+            if (raw.w > 0.f) sum[0] += sqrtf(best);
         }
-        nn_brute<QB>(D, n_d, qx, qy, qz, best, bidx);
+    } else {
+        constexpr int QB = 4;
+        for (int q0 = threadIdx.x; q0 < n_s; q0 += kThreads * QB) {
+            float qx[QB], qy[QB], qz[QB], best[QB];
+            int bidx[QB];
 #pragma unroll
-        for (int k = 0; k < QB; ++k) {
-            const int q = q0 + k * kThreads;
-            if (q < n_s && S[q].w > 0.f) sum[0] += sqrtf(best[k]);
+            for (int k = 0; k < QB; ++k) {
+                const int q = q0 + k * kThreads;
+                const float4 s = transform_row(m, q < n_s ? S[q] : make_float4(0.f, 0.f, 0.f, 0.f));
+                qx[k] = s.x; qy[k] = s.y; qz[k] = s.z;
+            }
+            nn_brute<QB>(D, n_d, qx, qy, qz, best, bidx);
+#pragma unroll
+            for (int k = 0; k < QB; ++k) {
+                const int q = q0 + k * kThreads;
+                if (q < n_s && S[q].w > 0.f) sum[0] += sqrtf(best[k]);
+            }
         }
     }
     block_allreduce_sum<1, kWarps>(sum, scratch);
@@ -48,27 +63,15 @@ __device__ __forceinline__ float mean_nn_error(const float (&m)[12], const float
     return sum[0];
 }
 
-// BIG: clusters whose two row blocks do not fit shared memory are read from global memory (L1/L2) instead.
-template <bool BIG>
+// GRIDNN: the fixed cloud is counting-sorted into a uniform grid in shared memory and the two error passes are grid
+// searches (same minima as the full scans, same bits); the rows in storage order are streamed from global memory.
+// !GRIDNN (the grid does not fit shared memory): full scans over the rows in global memory.
+template <bool GRIDNN>
 __global__ void __launch_bounds__(kThreads) icp_finalize_kernel(FinalizeArgs a) {
     const int p = blockIdx.x, tid = threadIdx.x;
     __shared__ float s_scratch[kWarps * 4];
-    const float4* S;
-    const float4* D;
-    if constexpr (BIG) {
-        S = reinterpret_cast<const float4*>(a.src) + (size_t)p * a.N;
-        D = reinterpret_cast<const float4*>(a.dst) + (size_t)p * a.N;
-    } else {
-        PairTiles tl = carve_pair_tiles<false>(a.N);
-        if (tid == 0) {
-            mbar_init(tl.bar(), 1);
-            fence_barrier_init();
-        }
-        __syncthreads();
-        load_pair_tiles(tl, a.src + (size_t)p * a.N * 4, a.dst + (size_t)p * a.N * 4, a.N, 0);
-        S = tl.src();
-        D = tl.dst();
-    }
+    const float4* S = reinterpret_cast<const float4*>(a.src) + (size_t)p * a.N;
+    const float4* D = reinterpret_cast<const float4*>(a.dst) + (size_t)p * a.N;
     float cnt[2] = {0.f, 0.f};
     for (int q = tid; q < a.N; q += kThreads) {
         cnt[0] += (S[q].w > 0.f) ? 1.f : 0.f;
@@ -81,6 +84,17 @@ __global__ void __launch_bounds__(kThreads) icp_finalize_kernel(FinalizeArgs a) 
     if (swapped) {
         const float4* t = S; S = D; D = t;
         const int n = n_s; n_s = n_d; n_d = n;
+    }
+    // NN grid over the fixed cloud (after the role swap), shared by the two error passes
+    GridInfo g;
+    const float4* sorted = nullptr;
+    const unsigned short* runs = nullptr;
+    if constexpr (GRIDNN) {
+        float4* extra = g_tile;
+        GridTiles td{D, extra, reinterpret_cast<uint32_t*>(extra + a.N), reinterpret_cast<float*>(extra + gridnn_units(a.N))};
+        if (n_d > 0) g = build_grid(td, n_d, a.tau);
+        sorted = td.sorted_p;
+        runs = reinterpret_cast<const unsigned short*>(td.cells_p);
     }
     // M0 = init pose, Micp = [[R^T, T],[0,1]] (utils_icp.py:60-65), M = Micp * M0 (utils_icp.py:24)
     float m0[16], mi[16], mm[16];
@@ -103,8 +117,8 @@ __global__ void __launch_bounds__(kThreads) icp_finalize_kernel(FinalizeArgs a) 
     float a0[12], a1[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) { a0[i] = m0[i]; a1[i] = mm[i]; }
-    const float e0 = __fdiv_rn(mean_nn_error(a0, S, n_s, D, n_d, s_scratch), (float)n_s);
-    const float e1 = __fdiv_rn(mean_nn_error(a1, S, n_s, D, n_d, s_scratch), (float)n_s);
+    const float e0 = __fdiv_rn(mean_nn_error<GRIDNN>(a0, S, n_s, D, n_d, s_scratch, g, sorted, runs), (float)n_s);
+    const float e1 = __fdiv_rn(mean_nn_error<GRIDNN>(a1, S, n_s, D, n_d, s_scratch, g, sorted, runs), (float)n_s);
     if (tid == 0) {
         const bool rolled = e1 >= e0;          // utils_icp.py:34-35 (NaN compares false: keep the ICP result)
         float out[16];
@@ -138,15 +152,16 @@ __global__ void __launch_bounds__(kThreads) icp_finalize_kernel(FinalizeArgs a) 
 }
 
 int launch_icp_finalize(const float* src, const float* dst, int P, int N, const float* init_pose, const float* icp_R,
-                        const float* icp_T, int auto_swap, float* out_pose, float* out_err, int* out_flags,
+                        const float* icp_T, int auto_swap, float tau, float* out_pose, float* out_err, int* out_flags,
                         cudaStream_t stream) {
     if (P == 0) return ICPF_OK;
-    const bool big = pair_smem_bytes(N, false) > (size_t)227 * 1024;
-    const size_t smem = big ? 0 : pair_smem_bytes(N, false);
-    auto kernel = big ? icp_finalize_kernel<true> : icp_finalize_kernel<false>;
+    const size_t with_grid = ((size_t)gridnn_units(N) + up16(kRedFloats * 4)) * 16;
+    const bool gridnn = with_grid <= (size_t)227 * 1024 && tau > 0.f;
+    const size_t smem = gridnn ? with_grid : 0;
+    auto kernel = gridnn ? icp_finalize_kernel<true> : icp_finalize_kernel<false>;
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
-    FinalizeArgs a{src, dst, N, init_pose, icp_R, icp_T, auto_swap, out_pose, out_err, out_flags};
+    FinalizeArgs a{src, dst, N, init_pose, icp_R, icp_T, auto_swap, tau, out_pose, out_err, out_flags};
     kernel<<<P, kThreads, smem, stream>>>(a);
     return (int)cudaGetLastError();
 }
@@ -219,8 +234,10 @@ int launch_hist_init(const float* src, const float* dst, int P, int N, const icp
                                votes + (size_t)lo * 5, w.need + lo, stream);
         if (rc != ICPF_OK) return rc;
     }
+    // bin width of the z axis = thres_dist (utils_hist.py:65: arange(-tau, 2 tau - eps, tau)); it only sizes NN-grid cells
+    const float tau = hb.len[2] > 1 ? (hb.max[2] - hb.min[2]) / (float)(hb.len[2] - 1) : 0.1f;
     return launch_hist_score(src, dst, P, N, cand, hb.bins_x, hb.bins_y, hb.bins_z, hb.len[0], hb.len[1], hb.len[2],
-                             hb.half_bin, auto_swap, out_pose, out_scores, out_which, stream);
+                             hb.half_bin, tau, auto_swap, out_pose, out_scores, out_which, stream);
 }
 
 int launch_apply_icp(const float* src, const float* dst, const float* init_pose, int P, int N, const icpf_params& prm,
@@ -232,7 +249,8 @@ int launch_apply_icp(const float* src, const float* dst, const float* init_pose,
     int rc = launch_icp(src, dst, nullptr, nullptr, init_pose, auto_swap, P, N, prm, w.R, w.T, nullptr, nullptr,
                         nullptr, nullptr, out_batch, w.icp, icp_workspace_bytes(P) + icp_big_workspace_bytes(P, N), stream);
     if (rc != ICPF_OK) return rc;
-    return launch_icp_finalize(src, dst, P, N, init_pose, w.R, w.T, auto_swap, out_pose, out_err, out_flags, stream);
+    return launch_icp_finalize(src, dst, P, N, init_pose, w.R, w.T, auto_swap, (float)prm.thres_dist, out_pose, out_err,
+                               out_flags, stream);
 }
 
 int launch_hist_icp(const float* src, const float* dst, int P, int N, const icpf_hist_bins& hb, const icpf_params& prm,

@@ -1,0 +1,105 @@
+// icpf_gridnn.cuh -- exact UNBOUNDED nearest-neighbour distance through the uniform grid of icpf_pair.cuh.
+//
+// nearest_neighbor_batch (utils_helper.py:20-30) has no radius: the reference scans every row of the other cloud for
+// every query (12 passes in estimate_init_pose, 2 in apply_icp, 2 in match_eval).  The quantity those callers consume is
+// min_j d(q, c_j) -- a minimum, so the visiting order is irrelevant and any search that provably saw the minimiser
+// returns the SAME bits as the full scan as long as each candidate distance is evaluated with the same arithmetic.
+// Search: the block of cells that just covers the gate radius first; if the best candidate found is farther than the
+// nearest un-inspected face (`box`), one more block sized to contain the ball of that candidate (which then proves it);
+// a query that found nothing within kUnbMaxR cells falls back to the full scan (far clouds: wrong candidate
+// translations, unrelated clusters), so the worst case is the reference's scan plus a bounded overhead.
+#pragma once
+
+#include "icpf_pair.cuh"
+
+namespace icpf {
+
+// lets build_grid() sort an arbitrary row block: rows -> sorted (cell order) + packed run boundaries
+struct GridTiles {
+    const float4* rows_p;
+    float4* sorted_p;
+    uint32_t* cells_p;
+    float* red_p;
+    __device__ __forceinline__ float4* dst() const { return const_cast<float4*>(rows_p); }
+    __device__ __forceinline__ float4* sorted() const { return sorted_p; }
+    __device__ __forceinline__ uint32_t* cells() const { return cells_p; }
+    __device__ __forceinline__ float* red() const { return red_p; }
+};
+
+// float4 units of shared memory one grid over N rows needs (sorted copy + run boundaries)
+__host__ __device__ inline int gridnn_units(int N) { return N + up16(kCellWords * 4); }
+
+constexpr float kUnbMaxR = 3.5f;      // widest block (half-width in cells) tried before the full scan
+
+// min over the block of half-width r (cells) around the look-up position l of sqdist(e, c + s), c the grid's rows.
+//   box  lower bound (m) on the distance from l to every row NOT inspected (+inf when the block covers the grid)
+template <bool SHIFT>
+__device__ __forceinline__ void grid_block_min(const GridInfo& g, const float4* __restrict__ sorted,
+                                               const unsigned short* __restrict__ a, float lx, float ly, float lz,
+                                               float ex, float ey, float ez, float sx, float sy, float sz, float r,
+                                               float& dmin, float& box) {
+    const float INF = __int_as_float(0x7f800000);
+    const float fx = (lx - g.ox) * g.inv_c, fy = (ly - g.oy) * g.inv_c, fz = (lz - g.oz) * g.inv_c;
+    const float x0 = floorf(fx - r), x1 = floorf(fx + r);
+    const float y0 = floorf(fy - r), y1 = floorf(fy + r);
+    const float z0 = floorf(fz - r), z1 = floorf(fz + r);
+    const float hx = (float)(g.gx - 1), hy = (float)(g.gy - 1), hz = (float)(g.gz - 1);
+    if (!(x1 >= 0.f && y1 >= 0.f && z1 >= 0.f && x0 <= hx && y0 <= hy && z0 <= hz)) {
+        // the block misses the grid (or the position is NaN): all rows lie inside [0, g]^3 cell coordinates
+        const float gapx = fmaxf(-fx, fx - (hx + 1.f)), gapy = fmaxf(-fy, fy - (hy + 1.f)),
+                    gapz = fmaxf(-fz, fz - (hz + 1.f));
+        box = fmaxf(fmaxf(gapx, fmaxf(gapy, gapz)) * g.c - g.pad, 0.f);
+        return;
+    }
+    const float bx = fminf(x0 < 0.f ? INF : fx - x0, x1 > hx ? INF : x1 + 1.f - fx);
+    const float by = fminf(y0 < 0.f ? INF : fy - y0, y1 > hy ? INF : y1 + 1.f - fy);
+    const float bz = fminf(z0 < 0.f ? INF : fz - z0, z1 > hz ? INF : z1 + 1.f - fz);
+    box = fmaxf(fminf(bx, fminf(by, bz)) * g.c - g.pad, 0.f);
+    const int ix0 = max(0, (int)x0), ix1 = min(g.gx - 1, (int)x1);
+    const int iy0 = max(0, (int)y0), iy1 = min(g.gy - 1, (int)y1);
+    const int iz0 = max(0, (int)z0), iz1 = min(g.gz - 1, (int)z1);
+    for (int ix = ix0; ix <= ix1; ++ix) {
+        for (int iy = iy0; iy <= iy1; ++iy) {
+            const int base = (ix * g.gy + iy) * g.gz;
+            const int s = a[base + iz0], e = a[base + iz1 + 1];
+            for (int j = s; j < e; ++j) {
+                const float4 c = sorted[j];
+                const float d = SHIFT ? sqdist(ex, ey, ez, __fadd_rn(c.x, sx), __fadd_rn(c.y, sy), __fadd_rn(c.z, sz))
+                                      : sqdist(ex, ey, ez, c.x, c.y, c.z);
+                dmin = fminf(dmin, d);
+            }
+        }
+    }
+}
+
+// Exact  min_j sqdist(e, rows_j (+ s))  over ALL n rows of the grid -- the value of the reference's full scan.
+//   l = where e sits relative to the un-shifted rows (e - s up to rounding; only used to pick cells, the slack g.pad
+//   absorbs its rounding);  SHIFT = candidates are evaluated as fadd(row, s), the arithmetic of the scan it replaces.
+template <bool SHIFT>
+__device__ __forceinline__ float nn_unbounded_grid(const GridInfo& g, const float4* __restrict__ sorted,
+                                                   const unsigned short* __restrict__ a, int n, float lx, float ly,
+                                                   float lz, float ex, float ey, float ez, float sx, float sy,
+                                                   float sz) {
+    const float INF = __int_as_float(0x7f800000);
+    float dmin = INF, box = 0.f;
+    float r = g.r;
+    for (int lvl = 0; lvl < 3; ++lvl) {
+        grid_block_min<SHIFT>(g, sorted, a, lx, ly, lz, ex, ey, ez, sx, sy, sz, r, dmin, box);
+        // proven when every row that was not inspected is farther than the best one that was
+        if (sqrtf(dmin) * 1.0001f + 1e-6f <= box) return dmin;
+        // next block: just large enough to contain the ball of the best candidate so far (that block proves it)
+        const float want = (dmin < INF) ? sqrtf(dmin) * g.inv_c * 1.001f + 0.02f : r + 1.0f;
+        if (!(want <= kUnbMaxR) || !(want > r)) break;
+        r = want;
+    }
+    // far query (or NaN): the full scan
+    for (int j = 0; j < n; ++j) {
+        const float4 c = sorted[j];
+        const float d = SHIFT ? sqdist(ex, ey, ez, __fadd_rn(c.x, sx), __fadd_rn(c.y, sy), __fadd_rn(c.z, sz))
+                              : sqdist(ex, ey, ez, c.x, c.y, c.z);
+        dmin = fminf(dmin, d);
+    }
+    return dmin;
+}
+
+}  // namespace icpf

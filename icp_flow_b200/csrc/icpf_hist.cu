@@ -11,6 +11,7 @@
 // L2-resident histogram (exact: counts stay far below 2^24), cheap rejects first (|dz| < tau discards most pairs).
 #include "icpf_internal.h"
 #include "icpf_pair.cuh"
+#include "icpf_gridnn.cuh"
 
 namespace icpf {
 
@@ -235,14 +236,19 @@ struct ScoreArgs {
     const float* bins_z;     // [lz]
     int lx, ly, lz;
     float half_bin;          // args.thres_dist // 2  (utils_hist.py:78; 0.0 for tau = 0.1)
+    float tau;               // bin width = thres_dist: only sizes the cells of the NN grids
     int auto_swap;
     float* out_pose;         // [P,16]
     float* out_scores;       // [P,6] (may be NULL)
     int* out_which;          // [P]   (may be NULL)
 };
 
-// BIG: clusters whose two row blocks do not fit shared memory are read from global memory (L1/L2) instead.
-template <bool BIG>
+// GRIDNN: both clouds are counting-sorted into uniform grids in shared memory (icpf_gridnn.cuh) and the exact scores
+// come from grid searches instead of full scans -- the same minima, hence the same bits, at O(n) instead of O(n^2).
+// The rows in storage order (they fix the order of the sums) are streamed from global memory, coalesced and
+// L2-resident, so a pair costs 2 (N + 257) * 16 B of shared memory (N = 1024: 41 KB, 5 CTAs per SM).
+// !GRIDNN (clusters whose grids do not fit shared memory, N > ~7000): full scans over the rows in global memory.
+template <bool GRIDNN>
 __global__ void __launch_bounds__(kThreads) hist_score_kernel(ScoreArgs a) {
     __shared__ float s_t[kCand][3];
     __shared__ float s_part[kWarps][2][kCand];
@@ -251,22 +257,8 @@ __global__ void __launch_bounds__(kThreads) hist_score_kernel(ScoreArgs a) {
     __shared__ float s_lb[kCand];
     __shared__ float s_score[kCand];
     const int p = blockIdx.x, tid = threadIdx.x;
-    const float4* S;
-    const float4* D;
-    if constexpr (BIG) {
-        S = reinterpret_cast<const float4*>(a.src) + (size_t)p * a.N;
-        D = reinterpret_cast<const float4*>(a.dst) + (size_t)p * a.N;
-    } else {
-        PairTiles tl = carve_pair_tiles<false>(a.N);
-        if (tid == 0) {
-            mbar_init(tl.bar(), 1);
-            fence_barrier_init();
-        }
-        __syncthreads();
-        load_pair_tiles(tl, a.src + (size_t)p * a.N * 4, a.dst + (size_t)p * a.N * 4, a.N, 0);
-        S = tl.src();
-        D = tl.dst();
-    }
+    const float4* S = reinterpret_cast<const float4*>(a.src) + (size_t)p * a.N;
+    const float4* D = reinterpret_cast<const float4*>(a.dst) + (size_t)p * a.N;
     float cnt[2] = {0.f, 0.f};
     for (int q = tid; q < a.N; q += kThreads) {
         cnt[0] += (S[q].w > 0.f) ? 1.f : 0.f;
@@ -381,76 +373,187 @@ __global__ void __launch_bounds__(kThreads) hist_score_kernel(ScoreArgs a) {
         __syncthreads();
     }
 
-    // ---- exact scores: round 1 = the top peak and the zero translation, round 2 = whatever the bound cannot exclude
-    int list[kCand];
-    int nlist = 2;
-    list[0] = 0;
-    list[1] = kCand - 1;
-    for (int round = 0; round < 2; ++round) {
-        if (round == 1) {
+    // ---- NN grids over both clouds (after the role swap), built once per pair
+    GridInfo gS, gD;
+    const float4* sortS = nullptr;
+    const float4* sortD = nullptr;
+    const unsigned short* runS = nullptr;
+    const unsigned short* runD = nullptr;
+    const bool use_grid = GRIDNN && n_s > 0 && n_d > 0;
+    if constexpr (GRIDNN) {
+        float4* extra = g_tile;
+        float* grid_scratch = reinterpret_cast<float*>(extra + 2 * gridnn_units(a.N));
+        GridTiles td{D, extra, reinterpret_cast<uint32_t*>(extra + a.N), grid_scratch};
+        GridTiles ts{S, extra + gridnn_units(a.N), reinterpret_cast<uint32_t*>(extra + gridnn_units(a.N) + a.N),
+                     grid_scratch};
+        if (use_grid) {
+            gD = build_grid(td, n_d, a.tau);
+            gS = build_grid(ts, n_s, a.tau);
+        }
+        sortD = td.sorted_p; runD = reinterpret_cast<const unsigned short*>(td.cells_p);
+        sortS = ts.sorted_p; runS = reinterpret_cast<const unsigned short*>(ts.cells_p);
+    }
+
+    // ---- exact scores
+    __shared__ unsigned char s_eval[kCand];      // 1: s_score[k] is the exact score, 0: k is provably not the arg-min
+    if (tid < kCand) s_eval[tid] = 0;
+    __syncthreads();
+    if (GRIDNN && use_grid) {
+        // One candidate at a time through the NN grids.  The top peak is evaluated in full; every other candidate that
+        // its bounding-box bound cannot exclude is evaluated with EARLY TERMINATION: score_k = min(mean_f, mean_b) and
+        // both means are sums of non-negative terms, so as soon as the partial sums prove mean_f > best and
+        // mean_b > best the candidate cannot be the arg-min and its exact value is never needed (the zero translation
+        // of a cluster that moved by metres is dismissed after its first 128 rows).  A candidate that survives has the
+        // exact score of the full evaluation, accumulated in the same order -> the selected translation is the same.
+        __shared__ float s_chk[kWarps];
+        const int lane = tid & 31, warp = tid >> 5;
+        auto block_total = [&](float v) -> float {       // uniform: every thread gets the same total
+            __syncthreads();
+            v = warp_sum(v);
+            if (lane == 0) s_chk[warp] = v;
+            __syncthreads();
+            float t = s_chk[0];
+            for (int w = 1; w < kWarps; ++w) t += s_chk[w];
+            return t;
+        };
+        // mean over the rows of Q of the NN distance in the other cloud; stops (returns true in `exceeded`) once the
+        // partial sum proves mean > limit.  BACK: rows of D against (S + t), else rows of (S + t) against D.
+        auto mean_nn = [&](bool back, float tx, float ty, float tz, float limit, bool can_stop, bool& exceeded) -> float {
+            const int nq = back ? n_d : n_s;
+            float acc = 0.f;
+            exceeded = false;
+            int chunk = 0;
+            for (int i0 = 0; i0 < nq; i0 += kThreads, ++chunk) {
+                const int i = i0 + tid;
+                if (i < nq) {
+                    float m;
+                    if (back) {
+                        const float4 v = D[i];
+                        m = nn_unbounded_grid<true>(gS, sortS, runS, n_s, v.x - tx, v.y - ty, v.z - tz, v.x, v.y, v.z,
+                                                    tx, ty, tz);
+                    } else {
+                        const float4 v = S[i];
+                        const float qx = __fadd_rn(v.x, tx), qy = __fadd_rn(v.y, ty), qz = __fadd_rn(v.z, tz);
+                        m = nn_unbounded_grid<false>(gD, sortD, runD, n_d, qx, qy, qz, qx, qy, qz, 0.f, 0.f, 0.f);
+                    }
+                    acc += sqrtf(m);
+                }
+                // checks after chunks 0, 1, 3, 7, ... (never after the last one)
+                if (can_stop && ((chunk + 1) & chunk) == 0 && i0 + kThreads < nq) {
+                    if (block_total(acc) * 0.999f > limit * (float)nq) {
+                        exceeded = true;
+                        break;
+                    }
+                }
+            }
+            if (exceeded) return 0.f;
+            // the deterministic final sum of the full evaluation: lanes by butterfly, warps in order
+            acc = warp_sum(acc);
+            __syncthreads();
+            if (lane == 0) s_chk[warp] = acc;
+            __syncthreads();
+            float t = 0.f;
+            for (int w = 0; w < kWarps; ++w) t += s_chk[w];
+            return __fdiv_rn(t, (float)nq);
+        };
+        float best = INF;
+        const int order[kCand] = {0, kCand - 1, 1, 2, 3, 4};
+        for (int o = 0; o < kCand; ++o) {
+            const int k = order[o];
+            const bool first = (o == 0);
+            if (!first && s_lb[k] > best) continue;                 // (NaN bounds are evaluated, never skipped)
+            const float tx = s_t[k][0], ty = s_t[k][1], tz = s_t[k][2];
+            bool fx, bx;
+            const float ef = mean_nn(false, tx, ty, tz, best, !first, fx);
+            // the backward mean matters only below min(best, ef)
+            const float eb = mean_nn(true, tx, ty, tz, fx ? best : fminf(best, ef), !first, bx);
+            float score = INF;
+            bool exact = false;
+            if (!fx && !bx) { score = fminf(ef, eb); exact = true; }          // torch.minimum
+            else if (!fx && bx) { if (ef <= best) { score = ef; exact = true; } }   // mean_b > ef: the minimum is ef
+            else if (fx && !bx) { if (eb <= best) { score = eb; exact = true; } }   // mean_f > best >= eb
+            if (exact) {
+                if (tid == 0) { s_score[k] = score; s_eval[k] = 1; }
+                best = fminf(best, score);
+            }
+        }
+        __syncthreads();
+    } else {
+        // full scans, two candidates per sweep: round 1 = the top peak and the zero translation, round 2 = whatever the bound cannot exclude
+        int list[kCand];
+        int nlist = 2;
+        list[0] = 0;
+        list[1] = kCand - 1;
+        for (int round = 0; round < 2; ++round) {
+            if (round == 1) {
+                const float best1 = fminf(s_score[0], s_score[kCand - 1]);
+                nlist = 0;
+                for (int k = 1; k < kCand - 1; ++k) {
+                    if (!(s_lb[k] > best1)) list[nlist++] = k;      // NaN bounds are evaluated, never skipped
+                }
+            }
+            // forward: NN of (src_i + t_k) among the dst rows; backward: NN of dst_i among the (src_j + t_k)
+            for (int l0 = 0; l0 < nlist; l0 += 2) {
+                const int k0 = list[l0], k1 = (l0 + 1 < nlist) ? list[l0 + 1] : list[l0];
+                const float t0x = s_t[k0][0], t0y = s_t[k0][1], t0z = s_t[k0][2];
+                const float t1x = s_t[k1][0], t1y = s_t[k1][1], t1z = s_t[k1][2];
+                float f0 = 0.f, f1 = 0.f, b0 = 0.f, b1 = 0.f;
+                for (int i = tid; i < n_s; i += kThreads) {
+                    const float4 v = S[i];
+                    const float q0x = __fadd_rn(v.x, t0x), q0y = __fadd_rn(v.y, t0y), q0z = __fadd_rn(v.z, t0z);
+                    const float q1x = __fadd_rn(v.x, t1x), q1y = __fadd_rn(v.y, t1y), q1z = __fadd_rn(v.z, t1z);
+                    float m0 = INF, m1 = INF;
+#pragma unroll 4
+                    for (int j = 0; j < n_d; ++j) {
+                        const float4 c = D[j];
+                        m0 = fminf(m0, sqdist(q0x, q0y, q0z, c.x, c.y, c.z));
+                        m1 = fminf(m1, sqdist(q1x, q1y, q1z, c.x, c.y, c.z));
+                    }
+                    f0 += sqrtf(m0);
+                    f1 += sqrtf(m1);
+                }
+                for (int i = tid; i < n_d; i += kThreads) {
+                    const float4 v = D[i];
+                    float m0 = INF, m1 = INF;
+#pragma unroll 4
+                    for (int j = 0; j < n_s; ++j) {
+                        const float4 c = S[j];
+                        m0 = fminf(m0, sqdist(v.x, v.y, v.z, __fadd_rn(c.x, t0x), __fadd_rn(c.y, t0y), __fadd_rn(c.z, t0z)));
+                        m1 = fminf(m1, sqdist(v.x, v.y, v.z, __fadd_rn(c.x, t1x), __fadd_rn(c.y, t1y), __fadd_rn(c.z, t1z)));
+                    }
+                    b0 += sqrtf(m0);
+                    b1 += sqrtf(m1);
+                }
+                f0 = warp_sum(f0); f1 = warp_sum(f1); b0 = warp_sum(b0); b1 = warp_sum(b1);
+                __syncthreads();
+                if ((tid & 31) == 0) {
+                    s_part[tid >> 5][0][0] = f0; s_part[tid >> 5][0][1] = f1;
+                    s_part[tid >> 5][1][0] = b0; s_part[tid >> 5][1][1] = b1;
+                }
+                __syncthreads();
+                if (tid < 2) {        // warps added in a fixed order: deterministic
+                    float f = 0.f, bb = 0.f;
+                    for (int w = 0; w < kWarps; ++w) { f += s_part[w][0][tid]; bb += s_part[w][1][tid]; }
+                    const float ef = __fdiv_rn(f, (float)n_s), eb = __fdiv_rn(bb, (float)n_d);
+                    s_score[tid == 0 ? k0 : k1] = fminf(ef, eb);        // torch.minimum
+                }
+                __syncthreads();
+            }
+        }
+        if (tid == 0) {
             const float best1 = fminf(s_score[0], s_score[kCand - 1]);
-            nlist = 0;
-            for (int k = 1; k < kCand - 1; ++k) {
-                if (!(s_lb[k] > best1)) list[nlist++] = k;      // NaN bounds are evaluated, never skipped
-            }
+            for (int k = 0; k < kCand; ++k) s_eval[k] = (k == 0) || (k == kCand - 1) || !(s_lb[k] > best1);
         }
-        // forward: NN of (src_i + t_k) among the dst rows; backward: NN of dst_i among the (src_j + t_k)
-        for (int l0 = 0; l0 < nlist; l0 += 2) {
-            const int k0 = list[l0], k1 = (l0 + 1 < nlist) ? list[l0 + 1] : list[l0];
-            const float t0x = s_t[k0][0], t0y = s_t[k0][1], t0z = s_t[k0][2];
-            const float t1x = s_t[k1][0], t1y = s_t[k1][1], t1z = s_t[k1][2];
-            float f0 = 0.f, f1 = 0.f, b0 = 0.f, b1 = 0.f;
-            for (int i = tid; i < n_s; i += kThreads) {
-                const float4 v = S[i];
-                const float q0x = __fadd_rn(v.x, t0x), q0y = __fadd_rn(v.y, t0y), q0z = __fadd_rn(v.z, t0z);
-                const float q1x = __fadd_rn(v.x, t1x), q1y = __fadd_rn(v.y, t1y), q1z = __fadd_rn(v.z, t1z);
-                float m0 = INF, m1 = INF;
-#pragma unroll 4
-                for (int j = 0; j < n_d; ++j) {
-                    const float4 c = D[j];
-                    m0 = fminf(m0, sqdist(q0x, q0y, q0z, c.x, c.y, c.z));
-                    m1 = fminf(m1, sqdist(q1x, q1y, q1z, c.x, c.y, c.z));
-                }
-                f0 += sqrtf(m0);
-                f1 += sqrtf(m1);
-            }
-            for (int i = tid; i < n_d; i += kThreads) {
-                const float4 v = D[i];
-                float m0 = INF, m1 = INF;
-#pragma unroll 4
-                for (int j = 0; j < n_s; ++j) {
-                    const float4 c = S[j];
-                    m0 = fminf(m0, sqdist(v.x, v.y, v.z, __fadd_rn(c.x, t0x), __fadd_rn(c.y, t0y), __fadd_rn(c.z, t0z)));
-                    m1 = fminf(m1, sqdist(v.x, v.y, v.z, __fadd_rn(c.x, t1x), __fadd_rn(c.y, t1y), __fadd_rn(c.z, t1z)));
-                }
-                b0 += sqrtf(m0);
-                b1 += sqrtf(m1);
-            }
-            f0 = warp_sum(f0); f1 = warp_sum(f1); b0 = warp_sum(b0); b1 = warp_sum(b1);
-            __syncthreads();
-            if ((tid & 31) == 0) {
-                s_part[tid >> 5][0][0] = f0; s_part[tid >> 5][0][1] = f1;
-                s_part[tid >> 5][1][0] = b0; s_part[tid >> 5][1][1] = b1;
-            }
-            __syncthreads();
-            if (tid < 2) {        // warps added in a fixed order: deterministic
-                float f = 0.f, bb = 0.f;
-                for (int w = 0; w < kWarps; ++w) { f += s_part[w][0][tid]; bb += s_part[w][1][tid]; }
-                const float ef = __fdiv_rn(f, (float)n_s), eb = __fdiv_rn(bb, (float)n_d);
-                s_score[tid == 0 ? k0 : k1] = fminf(ef, eb);        // torch.minimum
-            }
-            __syncthreads();
-        }
+        __syncthreads();
     }
     if (tid == 0) {
         int which = 0;
         float best = 0.f;
         bool have = false;
         for (int k = 0; k < kCand; ++k) {
-            const float e = s_score[k];        // +inf for the candidates the bound excluded
+            const float e = s_eval[k] ? s_score[k] : INF;        // +inf for the candidates that were excluded
             if (a.out_scores) a.out_scores[(size_t)p * kCand + k] = e;
-            const bool evaluated = (k == 0) || (k == kCand - 1) || !(s_lb[k] > fminf(s_score[0], s_score[kCand - 1]));
-            if (!evaluated) continue;
+            if (!s_eval[k]) continue;
             if (!have || e < best) { best = e; which = k; have = true; }      // errors.min(dim=-1): first minimum
         }
         if (a.out_which) a.out_which[p] = which;
@@ -461,16 +564,17 @@ __global__ void __launch_bounds__(kThreads) hist_score_kernel(ScoreArgs a) {
 }
 
 int launch_hist_score(const float* src, const float* dst, int P, int N, const int* cand_idx, const float* bins_x,
-                      const float* bins_y, const float* bins_z, int lx, int ly, int lz, float half_bin, int auto_swap,
-                      float* out_pose, float* out_scores, int* out_which, cudaStream_t stream) {
+                      const float* bins_y, const float* bins_z, int lx, int ly, int lz, float half_bin, float tau,
+                      int auto_swap, float* out_pose, float* out_scores, int* out_which, cudaStream_t stream) {
     if (P == 0) return ICPF_OK;
-    const bool big = pair_smem_bytes(N, false) > (size_t)227 * 1024;
-    const size_t smem = big ? 0 : pair_smem_bytes(N, false);
-    auto kernel = big ? hist_score_kernel<true> : hist_score_kernel<false>;
+    const size_t with_grids = ((size_t)2 * gridnn_units(N) + up16(kRedFloats * 4)) * 16;
+    const bool gridnn = with_grids <= (size_t)227 * 1024 && tau > 0.f;
+    const size_t smem = gridnn ? with_grids : 0;
+    auto kernel = gridnn ? hist_score_kernel<true> : hist_score_kernel<false>;
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
-    ScoreArgs a{src, dst, N, cand_idx, bins_x, bins_y, bins_z, lx, ly, lz, half_bin, auto_swap, out_pose, out_scores,
-                out_which};
+    ScoreArgs a{src, dst, N, cand_idx, bins_x, bins_y, bins_z, lx, ly, lz, half_bin, tau, auto_swap, out_pose,
+                out_scores, out_which};
     kernel<<<P, kThreads, smem, stream>>>(a);
     return (int)cudaGetLastError();
 }

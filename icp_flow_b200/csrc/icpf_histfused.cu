@@ -11,9 +11,10 @@
 #include "icpf_internal.h"
 #include "icpf_common.cuh"
 
+#include <string.h>
+
 namespace icpf {
 
-constexpr int kFusedThreads = 256;
 constexpr int kFusedTile = 1024;       // Y rows staged per tile
 constexpr int kFusedTopK = 5;
 constexpr int kFusedNmsHalf = 5;
@@ -36,10 +37,28 @@ __device__ __forceinline__ int vote_bin(float v, float mn, float range, float fl
     return min(p, len - 1);
 }
 
+// The same bin with the IEEE division (~25 instructions, three per vote: 40 % of the kernel) replaced by Markstein's
+// correction step: with y = RN(1/b), q0 = RN(x y) and the exact remainder r = x - q0 b (one FMA), RN(q0 + r y) is the
+// correctly rounded quotient x / b for every x whenever the significand of b is not all ones (Markstein 1990; the
+// fast path of every IEEE-compliant software division).  launch_hist_fused() checks that condition and the exponent
+// range on the host and selects the plain division otherwise; tools/check_fastdiv.cu compares the two bit for bit for
+// ALL dividends in [0, b) for the divisors the reference's settings produce.
+__device__ __forceinline__ int vote_bin_fast(float v, float mn, float range, float inv_range, float flen, int len) {
+    const float x = __fsub_rn(v, mn);
+    const float q0 = __fmul_rn(x, inv_range);
+    const float q = __fmaf_rn(__fmaf_rn(-q0, range, x), inv_range, q0);
+    const int p = __float2int_rd(__fmul_rn(q, flen));
+    return min(p, len - 1);
+}
+
 __device__ __forceinline__ unsigned long long fused_peak_key(float v, int idx) {
     return ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(0x7fffffff - idx);
 }
 
+// kFusedThreads: the sub-histogram of the widest pair fixes the shared memory of the launch (~200 KB at the default
+// 135 x 135 x 3 bins), i.e. ONE CTA per SM whatever its size -- so large clusters run 1024 threads (32 warps per SM
+// instead of 8) and small ones 256.
+template <int kFusedThreads, bool FASTDIV>
 __global__ void __launch_bounds__(kFusedThreads) hist_fused_kernel(FusedHistArgs a) {
     extern __shared__ __align__(16) float4 fsm[];
     __shared__ float s_red[kFusedThreads / 32][12];
@@ -108,6 +127,7 @@ __global__ void __launch_bounds__(kFusedThreads) hist_fused_kernel(FusedHistArgs
     }
     const float rx = __fsub_rn(a.max_x, a.min_x), ry = __fsub_rn(a.max_y, a.min_y), rz = __fsub_rn(a.max_z, a.min_z);
     const float flx = (float)a.len_x, fly = (float)a.len_y, flz = (float)a.len_z;
+    const float irx = __frcp_rn(rx), iry = __frcp_rn(ry), irz = __frcp_rn(rz);
     // ---- bin range the differences can reach (x, y); +-1 bin of slack, clamped
     int bx0 = 0, bx1 = -1, by0 = 0, by1 = -1;
     {
@@ -187,9 +207,12 @@ __global__ void __launch_bounds__(kFusedThreads) hist_fused_kernel(FusedHistArgs
                     const float vz = __fsub_rn(xi.z, yj.z);
                     const float vx = __fsub_rn(xi.x, yj.x), vy = __fsub_rn(xi.y, yj.y);
                     if (vx >= a.min_x && vx < a.max_x && vy >= a.min_y && vy < a.max_y && vz >= a.min_z && vz < a.max_z) {
-                        const int px = vote_bin(vx, a.min_x, rx, flx, a.len_x) - bx0;
-                        const int py = vote_bin(vy, a.min_y, ry, fly, a.len_y) - by0;
-                        const int pz = vote_bin(vz, a.min_z, rz, flz, a.len_z);
+                        const int px = (FASTDIV ? vote_bin_fast(vx, a.min_x, rx, irx, flx, a.len_x)
+                                                : vote_bin(vx, a.min_x, rx, flx, a.len_x)) - bx0;
+                        const int py = (FASTDIV ? vote_bin_fast(vy, a.min_y, ry, iry, fly, a.len_y)
+                                                : vote_bin(vy, a.min_y, ry, fly, a.len_y)) - by0;
+                        const int pz = FASTDIV ? vote_bin_fast(vz, a.min_z, rz, irz, flz, a.len_z)
+                                               : vote_bin(vz, a.min_z, rz, flz, a.len_z);
                         if (px < 0 || px >= wx || py < 0 || py >= wy) {
                             s_bad = 1;      // cannot happen (the range is conservative); fall back if it ever does
                         } else {
@@ -299,12 +322,28 @@ int launch_hist_fused(const float* X, const float* Y, int P, int N, const float*
     int cap_cols = (int)((budget - fixed) / per_col);
     if (cap_cols > lens[0] * lens[1]) cap_cols = lens[0] * lens[1];
     const size_t smem = fixed + (size_t)cap_cols * per_col;
-    cudaError_t err = cudaFuncSetAttribute(hist_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool wide = N >= 512;
+#ifndef ICPF_FUSED_WIDE
+#define ICPF_FUSED_WIDE 1024
+#endif
+    // Markstein's division needs a divisor whose significand is not all ones and quotients / remainders far from the
+    // under- and overflow thresholds (dividends are differences of coordinates, |x| < range)
+    bool fastdiv = true;
+    for (int k = 0; k < 3; ++k) {
+        const float r = maxs[k] - mins[k];
+        uint32_t u;
+        memcpy(&u, &r, 4);
+        const int e = (int)((u >> 23) & 0xffu);
+        fastdiv = fastdiv && (u & 0x7fffffu) != 0x7fffffu && e > 127 - 40 && e < 127 + 40;
+    }
+    auto kernel = wide ? (fastdiv ? hist_fused_kernel<ICPF_FUSED_WIDE, true> : hist_fused_kernel<ICPF_FUSED_WIDE, false>)
+                       : (fastdiv ? hist_fused_kernel<256, true> : hist_fused_kernel<256, false>);
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
     FusedHistArgs a{reinterpret_cast<const float4*>(X), reinterpret_cast<const float4*>(Y), N,
                     mins[0], mins[1], mins[2], maxs[0], maxs[1], maxs[2], lens[0], lens[1], lens[2],
                     auto_swap, cap_cols, out_idx, out_votes, need_global};
-    hist_fused_kernel<<<P, kFusedThreads, smem, stream>>>(a);
+    kernel<<<P, wide ? ICPF_FUSED_WIDE : 256, smem, stream>>>(a);
     return (int)cudaGetLastError();
 }
 

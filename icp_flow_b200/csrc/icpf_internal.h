@@ -37,10 +37,10 @@ int launch_hist_fused(const float* X, const float* Y, int P, int N, const float*
                       const int* lens, int auto_swap, int* out_idx, float* out_votes, int* need_global,
                       cudaStream_t stream);
 int launch_hist_score(const float* src, const float* dst, int P, int N, const int* cand_idx, const float* bins_x,
-                      const float* bins_y, const float* bins_z, int lx, int ly, int lz, float half_bin, int auto_swap,
-                      float* out_pose, float* out_scores, int* out_which, cudaStream_t stream);
+                      const float* bins_y, const float* bins_z, int lx, int ly, int lz, float half_bin, float tau,
+                      int auto_swap, float* out_pose, float* out_scores, int* out_which, cudaStream_t stream);
 int launch_icp_finalize(const float* src, const float* dst, int P, int N, const float* init_pose, const float* icp_R,
-                        const float* icp_T, int auto_swap, float* out_pose, float* out_err, int* out_flags,
+                        const float* icp_T, int auto_swap, float tau, float* out_pose, float* out_err, int* out_flags,
                         cudaStream_t stream);
 int launch_hist_init(const float* src, const float* dst, int P, int N, const icpf_hist_bins& hb, int auto_swap,
                      float* out_pose, int* out_cand, float* out_votes, float* out_scores, int* out_which,

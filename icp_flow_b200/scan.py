@@ -182,8 +182,31 @@ def pad_pairs(si: ScanIndex, di: ScanIndex, pairs: torch.Tensor, max_points: int
     return segs_src, segs_dst
 
 
+# The reference pads every cluster of a frame to args.max_points rows (default 10 000).  The path's results do not depend
+# on the padding (rows beyond the valid prefix are never a nearest neighbour and never counted; padding-invariance is a
+# tested, bit-exact property), so a batch is padded only up to its own largest cluster, rounded up to PAD_QUANTUM rows:
+# the clusters of a real frame then run the shared-memory kernels instead of the large-cluster variants.
+ADAPTIVE_PAD = True
+PAD_QUANTUM = 256
+
+
+def batch_rows(si: ScanIndex, di: ScanIndex, pairs: torch.Tensor, max_points: int) -> int:
+    """Rows to pad this batch to: min(max_points, largest cluster of the batch rounded up to PAD_QUANTUM)."""
+    max_points = int(max_points)
+    if not ADAPTIVE_PAD or len(pairs) == 0:
+        return max_points
+    ph = _pairs_i64(pairs, si.points.device).cpu().numpy()
+    top = 1
+    for col, idx in ((0, si), (1, di)):
+        lab = ph[:, col]
+        ok = (lab >= 0) & (lab < idx.n_labels)
+        if ok.any():
+            top = max(top, int(idx.counts_host[lab[ok]].max()))
+    return min(max_points, (top + PAD_QUANTUM - 1) // PAD_QUANTUM * PAD_QUANTUM)
+
+
 def _match_pairs_indexed(args, si: ScanIndex, di: ScanIndex, pairs, src_unq, dst_unq):
-    segs_src, segs_dst = pad_pairs(si, di, pairs, args.max_points)
+    segs_src, segs_dst = pad_pairs(si, di, pairs, batch_rows(si, di, pairs, args.max_points))
     transformations = hist_icp(args, segs_src, segs_dst)
     *evals, accept = match_eval(args, segs_src, segs_dst, transformations, return_accept=True)
     return match_select(args, _pairs_i64(pairs, si.points.device), src_unq, dst_unq, evals, accept, transformations)

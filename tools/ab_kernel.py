@@ -69,6 +69,19 @@ def one():
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record(); r = ops.icp_batch(s, d, ops.make_params()); t1.record(); torch.cuda.synchronize()
     res["big_ms"] = t0.elapsed_time(t1)
+    # histogram initialisation on a C3-shaped batch (1024 pairs x 1024 points, 135 x 135 x 3 bins)
+    import types
+    s, d, _ = synth.make_pairs(1024, 1024, seed=99, ragged=False, residual_only=False)
+    s, d = torch.from_numpy(s).to(dev), torch.from_numpy(d).to(dev)
+    args = types.SimpleNamespace(thres_dist=0.1, translation_frame=6.666, chunk_size=50)
+    init = ops.estimate_init_pose(args, s, d, auto_swap=True)
+    torch.cuda.synchronize()
+    t0.record(); init = ops.estimate_init_pose(args, s, d, auto_swap=True); t1.record(); torch.cuda.synchronize()
+    res["init_ms"] = t0.elapsed_time(t1)
+    res["h_init"] = h(init)
+    t0.record(); T = ops.hist_icp(args, s, d); t1.record(); torch.cuda.synchronize()
+    res["hist_icp_ms"] = t0.elapsed_time(t1)
+    res["h_hist_icp"] = h(T)
     print("AB " + json.dumps(res))
 
 
