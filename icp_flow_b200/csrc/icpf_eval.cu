@@ -9,6 +9,7 @@
 // no valid row at all, so the candidates are the valid prefix -- or all rows when it is empty.
 #include "icpf_internal.h"
 #include "icpf_pair.cuh"
+#include "icpf_gridnn.cuh"
 
 namespace icpf {
 
@@ -27,6 +28,7 @@ struct EvalArgs {
     float* ious;
     float* translations;
     float* rotations;
+    float tau;              // thres_dist: only sizes the cells of the NN grids
     int* accept;            // optional: check_transformation verdict (utils_check.py:51-66)
     float gate_translation, gate_iou, gate_rot;
 };
@@ -76,9 +78,28 @@ __device__ __forceinline__ void eval_direction(const float (&m)[12], const float
     }
 }
 
+// Same sums through the NN grids (icpf_gridnn.cuh): the minimum over the inspected rows is the minimum of the full scan,
+// and every thread accumulates its rows in the same increasing order, so both variants write the same bits.
+template <bool MOVE_Q>
+__device__ __forceinline__ void eval_direction_grid(const float (&m)[12], const float4* __restrict__ Q, int n_q,
+                                                    const GridInfo& g, const float4* __restrict__ sorted,
+                                                    const unsigned short* __restrict__ runs, int n_c, float thr,
+                                                    float& err, float& inl) {
+    for (int q = threadIdx.x; q < n_q; q += kThreads) {
+        float4 r = Q[q];
+        if (MOVE_Q) r = transform_row(m, r);
+        const float e = sqrtf(nn_unbounded_grid<false>(g, sorted, runs, n_c, r.x, r.y, r.z, r.x, r.y, r.z, 0.f, 0.f, 0.f));
+        err += e;
+        inl += (e < thr) ? 1.f : 0.f;
+    }
+}
+
+// GRIDNN: dst and the MOVED src are counting-sorted into uniform grids in shared memory (2 (N + 257) * 16 B per pair);
+// !GRIDNN (grids do not fit): full scans through a staged tile.
+template <bool GRIDNN>
 __global__ void __launch_bounds__(kThreads) match_eval_kernel(EvalArgs a) {
     const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    __shared__ float4 tile[kEvTile];
+    __shared__ float4 tile[GRIDNN ? 1 : kEvTile];
     __shared__ float s_scratch[kWarps * 8];
     __shared__ double s_mean[kWarps][6];
     const float4* S = reinterpret_cast<const float4*>(a.src) + (size_t)p * a.N;
@@ -111,8 +132,22 @@ __global__ void __launch_bounds__(kThreads) match_eval_kernel(EvalArgs a) {
     const int n_s = (int)cnt[0], n_d = (int)cnt[1];
 
     float acc[4] = {0.f, 0.f, 0.f, 0.f};   // err(src->dst), inliers(src), err(dst->src), inliers(dst)
-    eval_direction<true>(m, S, n_s, D, n_d > 0 ? n_d : a.N, a.thr, tile, acc[0], acc[1]);
-    eval_direction<false>(m, D, n_d, S, n_s > 0 ? n_s : a.N, a.thr, tile, acc[2], acc[3]);
+    if (GRIDNN && n_s > 0 && n_d > 0) {
+        float4* extra = g_tile;
+        float* scratch = reinterpret_cast<float*>(extra + 2 * gridnn_units(a.N));
+        GridTiles td{D, extra, reinterpret_cast<uint32_t*>(extra + a.N), scratch};
+        GridTiles ts{S, extra + gridnn_units(a.N), reinterpret_cast<uint32_t*>(extra + gridnn_units(a.N) + a.N), scratch};
+        const GridInfo gD = build_grid(td, n_d, a.tau);
+        // the candidates of the second direction are the rows of pcd1 under the pose: sorted as they are moved
+        const GridInfo gS = build_grid_rows(ts, n_s, a.tau, kCellFactor, [&](int j) { return transform_row(m, S[j]); });
+        eval_direction_grid<true>(m, S, n_s, gD, td.sorted_p, reinterpret_cast<const unsigned short*>(td.cells_p), n_d,
+                                  a.thr, acc[0], acc[1]);
+        eval_direction_grid<false>(m, D, n_d, gS, ts.sorted_p, reinterpret_cast<const unsigned short*>(ts.cells_p), n_s,
+                                   a.thr, acc[2], acc[3]);
+    } else {
+        eval_direction<true>(m, S, n_s, D, n_d > 0 ? n_d : a.N, a.thr, tile, acc[0], acc[1]);
+        eval_direction<false>(m, D, n_d, S, n_s > 0 ? n_s : a.N, a.thr, tile, acc[2], acc[3]);
+    }
     __syncthreads();
     block_allreduce_sum<4, kWarps>(acc, s_scratch);
 
@@ -163,14 +198,20 @@ int launch_match_eval(const float* src, const float* dst, const float* pose, int
                       float* inliers, float* ratios, float* ious, float* translations, float* rotations,
                       const icpf_match_gates* gates, int* accept, cudaStream_t stream) {
     if (P == 0) return ICPF_OK;
-    EvalArgs a{src, dst, pose, N, thr, errors, inliers, ratios, ious, translations, rotations, nullptr, 0.f, 0.f, 0.f};
+    EvalArgs a{src, dst, pose, N, thr, errors, inliers, ratios, ious, translations, rotations, thr, nullptr, 0.f, 0.f, 0.f};
     if (gates) {
         a.accept = accept;
         a.gate_translation = (float)gates->translation_frame;
         a.gate_iou = (float)gates->thres_iou;
         a.gate_rot = (float)(gates->thres_rot * 90.0);
     }
-    match_eval_kernel<<<P, kThreads, 0, stream>>>(a);
+    const size_t with_grids = ((size_t)2 * gridnn_units(N) + up16(kRedFloats * 4)) * 16;
+    const bool gridnn = with_grids <= (size_t)227 * 1024;
+    auto kernel = gridnn ? match_eval_kernel<true> : match_eval_kernel<false>;
+    const size_t smem = gridnn ? with_grids : 0;
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return (int)err;
+    kernel<<<P, kThreads, smem, stream>>>(a);
     return (int)cudaGetLastError();
 }
 

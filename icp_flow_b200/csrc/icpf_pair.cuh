@@ -225,13 +225,14 @@ __device__ __forceinline__ int grid_cell(const GridInfo& g, float x, float y, fl
 
 // Counting sort of dst[0, n_d) into tl.sorted() by cell; fills the run boundaries in tl.cells().  All threads return the
 // same GridInfo.  Uses the reduction scratch; ends with a block barrier.
-template <class Tiles>
-__device__ __forceinline__ GridInfo build_grid(const Tiles& tl, int n_d, float tau, float cell_factor = kCellFactor) {
+// `row(j)` yields row j of the cloud being sorted (the stored row, or a row moved on the fly).
+template <class Tiles, class RowFn>
+__device__ __forceinline__ GridInfo build_grid_rows(const Tiles& tl, int n_d, float tau, float cell_factor, RowFn row) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float INF = __int_as_float(0x7f800000);
     float lo[3] = {INF, INF, INF}, hi[3] = {-INF, -INF, -INF};
     for (int j = tid; j < n_d; j += kThreads) {
-        const float4 p = tl.dst()[j];
+        const float4 p = row(j);
         lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
         hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
     }
@@ -294,7 +295,7 @@ __device__ __forceinline__ GridInfo build_grid(const Tiles& tl, int n_d, float t
     __syncthreads();
     // counts: entry e = cell + 1 (u16 halves of u32 words; a count never exceeds n_d < 65536 so halves do not carry)
     for (int j = tid; j < n_d; j += kThreads) {
-        const float4 p = tl.dst()[j];
+        const float4 p = row(j);
         const int e = grid_cell(g, p.x, p.y, p.z) + 1;
         atomicAdd(&w[e >> 1], 1u << ((e & 1) * 16));
     }
@@ -324,7 +325,7 @@ __device__ __forceinline__ GridInfo build_grid(const Tiles& tl, int n_d, float t
     __syncthreads();
     // scatter: the atomic turns "first position" into "one past the last", i.e. the first position of the next cell
     for (int j = tid; j < n_d; j += kThreads) {
-        const float4 p = tl.dst()[j];
+        const float4 p = row(j);
         const int e = grid_cell(g, p.x, p.y, p.z) + 1;
         const int sh = (e & 1) * 16;
         const unsigned int old = atomicAdd(&w[e >> 1], 1u << sh);
@@ -334,6 +335,12 @@ __device__ __forceinline__ GridInfo build_grid(const Tiles& tl, int n_d, float t
     }
     __syncthreads();
     return g;
+}
+
+template <class Tiles>
+__device__ __forceinline__ GridInfo build_grid(const Tiles& tl, int n_d, float tau, float cell_factor = kCellFactor) {
+    const float4* rows = tl.dst();
+    return build_grid_rows(tl, n_d, tau, cell_factor, [rows](int j) { return rows[j]; });
 }
 
 // Radius-bounded NN: best candidate among the cells overlapping the padded tau-box of q, ranked by the 64-bit key
