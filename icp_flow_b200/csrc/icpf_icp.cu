@@ -57,6 +57,19 @@ __global__ void __launch_bounds__(kThreads, BIG ? 4 : 7) icp_pairs_kernel(IcpArg
         early_exit = false;
     } else if (a.decided != nullptr) {
         if (*a.decided != 0) return;      // the capped first pass already found the batch stop
+        if (a.iters[p] < a.cap) {
+            // This pair stopped at its bitwise fixed point below the cap: every later iteration repeats that state, so
+            // its transform stands and its convergence history continues the way the tail of the capped pass went
+            // (icpf_icploop.cuh, tail rule) -- only the pairs still moving at the cap are run again.
+            if (threadIdx.x == 0 && a.cap >= 1) {
+                uint32_t* c = a.conv + (size_t)p * 4;
+                const int last = a.cap - 1;
+                if ((c[last >> 5] >> (last & 31)) & 1u) {
+                    for (int k = a.cap; k < max_it && k < 128; ++k) c[k >> 5] |= 1u << (k & 31);
+                }
+            }
+            return;
+        }
     } else {
         max_it = min(max_it, a.cap);
     }

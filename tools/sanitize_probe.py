@@ -17,3 +17,14 @@ big2 = big.clone(); big2[:, :160] = d[:2]
 T2 = ops.hist_icp(args, big, big2)
 torch.cuda.synchronize()
 print("ok", float(T.abs().sum()), float(T2.abs().sum()))
+# rows f1-f3: a small scene through the cluster index, sanity_check, gather/pad (with an oversized cluster), match_eval
+# (NN grids), selection and flow
+import icp_flow_b200 as E
+sp, sl, dp, dl, meta = synth.make_scene(num_clusters=12, num_points=6000, seed=2, max_size=700)
+t = [torch.from_numpy(x).to(dev) for x in (sp, dp, sl, dl)]
+fargs = types.SimpleNamespace(thres_dist=0.1, translation_frame=3.34, chunk_size=50, min_cluster_size=30, thres_box=0.1,
+                              max_points=256, thres_error=0.2, thres_iou=0.2, thres_rot=0.1)
+rows, Tm = E.match_pcds(fargs, *t)
+flow = E.flow_estimation_torch(fargs, t[0], t[1], t[2], t[3], rows, Tm, torch.eye(4, device=dev))
+torch.cuda.synchronize()
+print("frame ok", len(rows), float(flow.abs().sum()))
