@@ -185,6 +185,49 @@ def workload_config(n_gpus: int):
             "parallelism": f"pairs sharded over {n_gpus} GPU(s), all-gather of 4x4 transforms"}
 
 
+# ---------------------------------------------------------------------------------------------- secondary configs
+def time_secondary(dev):
+    """Not the headline metric: the two other single-GPU BASELINE configs, timed with CUDA events / wall clock so that
+    they are measured in the same run.  C3 at a quarter of its pair count (1024 of 4096 pairs x 1024 points, full
+    hist_icp with the 135 x 135 x 3 histogram) and C4 (Waymo-shape frame pair through match_pcds + flow)."""
+    import types
+    import torch
+    import icp_flow_b200 as E
+    from icp_flow_b200 import scan, synth
+    out = {}
+    s, d, _ = synth.make_pairs(1024, 1024, seed=99, ragged=False, residual_only=False)
+    s, d = torch.from_numpy(s).to(dev), torch.from_numpy(d).to(dev)
+    args = types.SimpleNamespace(thres_dist=THRES, translation_frame=6.666, chunk_size=50)
+    for _ in range(2):
+        E.hist_icp(args, s, d)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        E.hist_icp(args, s, d)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    out["c3_hist_icp"] = {"pairs": 1024, "points": 1024, "bins": [135, 135, 3], "ms": ms, "pairs_per_s": 1024 / ms * 1e3}
+    sp, sl, dp, dl, _ = synth.make_scene()
+    t = [torch.from_numpy(x).to(dev) for x in (sp, dp, sl, dl)]
+    fargs = types.SimpleNamespace(thres_dist=THRES, translation_frame=3.34, chunk_size=50, min_cluster_size=30,
+                                  thres_box=0.1, max_points=10000, thres_error=0.2, thres_iou=0.2, thres_rot=0.1)
+    pose = torch.eye(4, device=dev)
+    best, matched = 1e9, 0
+    for _ in range(4):
+        scan.clear_cache()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rows, T = E.match_pcds(fargs, *t)
+        E.flow_estimation_torch(fargs, t[0], t[1], t[2], t[3], rows, T, pose)
+        torch.cuda.synchronize()
+        best, matched = min(best, time.perf_counter() - t0), len(rows)
+    out["c4_frame"] = {"points": [len(sp), len(dp)], "clusters": 200, "max_points": 10000, "matched_pairs": matched,
+                       "ms": best * 1e3, "what": "cluster index + match_pcds (both stages) + flow, wall clock"}
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- engine arm
 def main():
     ap = argparse.ArgumentParser()
@@ -193,6 +236,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C3 / C4 side measurements (N=1 only)")
     ap.add_argument("--nn-mode", type=int, default=0)
     ap.add_argument("--gather", default="auto", choices=["auto", "p2p", "nccl"],
                     help="multi-GPU: fused peer-store all-gather from the kernel epilogue (p2p) or NCCL all_gather")
@@ -393,6 +437,11 @@ def main():
             "nn_search": {"full_search_fraction": stats[0] / float(P * ICP_ITERS * N),
                           "cache_refreshes_per_pair": stats[1] / float(P)},
         }
+        if n_gpus == 1 and not args.no_secondary:
+            try:
+                line["secondary"] = time_secondary(dev)
+            except Exception as exc:      # side measurements must never cost the headline line
+                line["secondary"] = {"error": f"{type(exc).__name__}: {exc}"}
         if n_gpus == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = time_cpu_oracle()[0]
         print(json.dumps(line))
