@@ -172,12 +172,14 @@ size_t path_workspace_bytes(int P, int N, int lx, int ly, int lz) {
     size_t b = icp_workspace_bytes(P) + icp_big_workspace_bytes(P, N);
     b += align_up((size_t)P * 9 * 4, 256) + align_up((size_t)P * 3 * 4, 256) + align_up((size_t)P * 16 * 4, 256);
     b += 2 * align_up((size_t)P * 5 * 4, 256) + align_up((size_t)P * 4, 256);
-    if (lx > 0 && ly > 0 && lz > 0) b += align_up((size_t)hist_chunk_pairs(P, lx, ly, lz) * lx * ly * lz * 4, 256);
+    // histogram chunk [chunk, lx, ly, lz] (+ [chunk, 2, lx, ly] max planes when they do not fit shared memory)
+    if (lx > 0 && ly > 0 && lz > 0)
+        b += align_up((size_t)hist_chunk_pairs(P, lx, ly, lz) * ((size_t)lx * ly * lz + hist_peaks_scratch_floats(lx, ly)) * 4, 256);
     return b;
 }
 
 int hist_chunk_pairs(int P, int lx, int ly, int lz) {
-    const size_t per = (size_t)lx * ly * lz * 4;
+    const size_t per = ((size_t)lx * ly * lz + hist_peaks_scratch_floats(lx, ly)) * 4;
     const size_t budget = (size_t)64 << 20;          // keep the live histograms L2-resident (126 MB L2)
     size_t c = budget / (per ? per : 1);
     if (c < 1) c = 1;
@@ -231,7 +233,8 @@ int launch_hist_init(const float* src, const float* dst, int P, int N, const icp
                                w.hist, auto_swap, w.need + lo, stream);
         if (rc != ICPF_OK) return rc;
         rc = launch_hist_peaks(w.hist, n, hb.len[0], hb.len[1], hb.len[2], cand + (size_t)lo * 5,
-                               votes + (size_t)lo * 5, w.need + lo, stream);
+                               votes + (size_t)lo * 5, w.need + lo,
+                               w.hist + (size_t)chunk * hb.len[0] * hb.len[1] * hb.len[2], stream);
         if (rc != ICPF_OK) return rc;
     }
     // bin width of the z axis = thres_dist (utils_hist.py:65: arange(-tau, 2 tau - eps, tau)); it only sizes NN-grid cells

@@ -114,17 +114,20 @@ __device__ __forceinline__ unsigned long long peak_key(float v, int idx) {
     return ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(0x7fffffff - idx);
 }
 
+// `scratch` (may be NULL): [B, 2, lx*ly] floats in global memory for windows whose two max planes do not fit shared
+// memory (translation_frame beyond ~8 m: the reference widens it with the frame gap, main.py:200).
 __global__ void __launch_bounds__(kPeakThreads) hist_peaks_kernel(const float* __restrict__ bins, int lx, int ly,
                                                                   int lz, int* __restrict__ out_idx,
                                                                   float* __restrict__ out_votes,
-                                                                  const int* __restrict__ need) {
+                                                                  const int* __restrict__ need,
+                                                                  float* __restrict__ scratch) {
     extern __shared__ float sm[];
-    float* colmax = sm;                 // [lx*ly] max over z
-    float* rowmax = sm + lx * ly;       // [lx*ly] max over the y window
     __shared__ unsigned long long s_best[kPeakThreads / 32];
     __shared__ unsigned long long s_pick[kTopK];
     const int b = blockIdx.x, tid = threadIdx.x;
     if (need != nullptr && need[b] == 0) return;      // handled by the fused kernel
+    float* colmax = scratch ? scratch + (size_t)b * 2 * lx * ly : sm;      // [lx*ly] max over z
+    float* rowmax = colmax + (size_t)lx * ly;                               // [lx*ly] max over the y window
     const float* hb = bins + (size_t)b * lx * ly * lz;
     const int ncol = lx * ly;
     for (int c = tid; c < ncol; c += kPeakThreads) {
@@ -212,14 +215,20 @@ __global__ void __launch_bounds__(kPeakThreads) hist_peaks_kernel(const float* _
     }
 }
 
+size_t hist_peaks_scratch_floats(int lx, int ly) {
+    return ((size_t)lx * ly * 2 * sizeof(float) > (size_t)200 * 1024) ? (size_t)lx * ly * 2 : 0;
+}
+
 int launch_hist_peaks(const float* bins, int B, int lx, int ly, int lz, int* out_idx, float* out_votes,
-                      const int* need, cudaStream_t stream) {
+                      const int* need, float* scratch, cudaStream_t stream) {
     if (B == 0) return ICPF_OK;
-    const size_t smem = (size_t)lx * ly * 2 * sizeof(float);
-    if (smem > 200 * 1024) return ICPF_E_UNSUPPORTED;
+    const bool global = hist_peaks_scratch_floats(lx, ly) > 0;
+    if (global && scratch == nullptr) return ICPF_E_WORKSPACE;
+    const size_t smem = global ? 0 : (size_t)lx * ly * 2 * sizeof(float);
     cudaError_t err = cudaFuncSetAttribute(hist_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
-    hist_peaks_kernel<<<B, kPeakThreads, smem, stream>>>(bins, lx, ly, lz, out_idx, out_votes, need);
+    hist_peaks_kernel<<<B, kPeakThreads, smem, stream>>>(bins, lx, ly, lz, out_idx, out_votes, need,
+                                                         global ? scratch : nullptr);
     return (int)cudaGetLastError();
 }
 

@@ -31,8 +31,9 @@ size_t path_workspace_bytes(int P, int N, int lx, int ly, int lz);
 
 int launch_hist_votes(const float* X, const float* Y, int B, int NX, int NY, const float* mins, const float* maxs,
                       const int* lens, float* bins, int auto_swap, const int* need, cudaStream_t stream);
+size_t hist_peaks_scratch_floats(int lx, int ly);      // per pair, 0 when the max planes fit shared memory
 int launch_hist_peaks(const float* bins, int B, int lx, int ly, int lz, int* out_idx, float* out_votes,
-                      const int* need, cudaStream_t stream);
+                      const int* need, float* scratch, cudaStream_t stream);
 int launch_hist_fused(const float* X, const float* Y, int P, int N, const float* mins, const float* maxs,
                       const int* lens, int auto_swap, int* out_idx, float* out_votes, int* need_global,
                       cudaStream_t stream);

@@ -288,9 +288,12 @@ def test_large_clusters_vs_oracle():
     assert ok.any() and err[ok].max() <= TOL, err
 
 
-def test_histogram_global_fallback_for_wide_clusters():
+@pytest.mark.parametrize("frame", [6.666, 10.0])
+def test_histogram_global_fallback_for_wide_clusters(frame):
     """A cluster pair whose difference box spans more histogram columns than fit shared memory takes the
-    global-memory histogram path; both paths must agree with the oracle (peaks, votes, chosen translation)."""
+    global-memory histogram path; both paths must agree with the oracle (peaks, votes, chosen translation).
+    translation_frame 6.666: the whole 135 x 135 window fits the u16 sub-histogram (fused path even for the 16 m patch);
+    10.0: 201 x 201 columns do not fit, the wide pair takes the global-memory kernels."""
     dev = _dev()
     rng = np.random.default_rng(3)
     N = 512
@@ -304,8 +307,8 @@ def test_histogram_global_fallback_for_wide_clusters():
         src[k, :, :3] = pts; src[k, :, 3] = 1
         moved = pts + np.array([1.3, -0.7, 0.02]) + rng.normal(0, 0.005, pts.shape)
         dst[k, :, :3] = moved; dst[k, :, 3] = 1
-    args = types.SimpleNamespace(thres_dist=0.1, translation_frame=6.666, chunk_size=50)
-    p = O.PathParams(thres_dist=0.1, translation_frame=6.666)
+    args = types.SimpleNamespace(thres_dist=0.1, translation_frame=frame, chunk_size=50)
+    p = O.PathParams(thres_dist=0.1, translation_frame=frame)
     pose, dbg = ops.estimate_init_pose(args, torch.from_numpy(src).to(dev), torch.from_numpy(dst).to(dev), return_debug=True)
     want, odbg = O.estimate_init_pose(torch.from_numpy(src), torch.from_numpy(dst), p, return_debug=True)
     amb = O.ambiguous_topk_rows(torch.from_numpy(src), torch.from_numpy(dst), p).numpy()
