@@ -12,6 +12,7 @@
 #include "icpf_common.cuh"
 
 #include <string.h>
+#include <type_traits>
 
 namespace icpf {
 
@@ -29,7 +30,8 @@ struct FusedHistArgs {
     int cap_cols;            // sub-histogram columns (x,y) that fit the dynamic shared memory
     int* out_idx;            // [P,5]
     float* out_votes;        // [P,5]
-    int* need_global;        // [P] 1 = this pair did not fit and must take the global path
+    int* need_global;        // [P] 1 = this pair did not fit and must take the next (wider / global) path
+    int only_flagged;        // 1: second tier -- handle only the pairs the first tier flagged
 };
 
 __device__ __forceinline__ int vote_bin(float v, float mn, float range, float flen, int len) {
@@ -58,7 +60,11 @@ __device__ __forceinline__ unsigned long long fused_peak_key(float v, int idx) {
 // kFusedThreads: the sub-histogram of the widest pair fixes the shared memory of the launch (~200 KB at the default
 // 135 x 135 x 3 bins), i.e. ONE CTA per SM whatever its size -- so large clusters run 1024 threads (32 warps per SM
 // instead of 8) and small ones 256.
-template <int kFusedThreads, bool FASTDIV>
+// COUNT16: second tier for pairs whose sub-histogram does not fit as u32 counters -- u16 counters and max planes (10 B
+// per column at three z bins: the whole 135 x 135 window of the default translation_frame fits).  A counter that is
+// about to wrap is caught on the increment that wraps it (the atomic returns the old value) and sends the pair on to
+// the exact global-memory path.
+template <int kFusedThreads, bool FASTDIV, bool COUNT16>
 __global__ void __launch_bounds__(kFusedThreads) hist_fused_kernel(FusedHistArgs a) {
     extern __shared__ __align__(16) float4 fsm[];
     __shared__ float s_red[kFusedThreads / 32][12];
@@ -70,6 +76,7 @@ __global__ void __launch_bounds__(kFusedThreads) hist_fused_kernel(FusedHistArgs
     const float INF = __int_as_float(0x7f800000);
     const float4* xb = a.X + (size_t)p * a.N;
     const float4* yb = a.Y + (size_t)p * a.N;
+    if (a.only_flagged && a.need_global[p] == 0) return;
     if (tid < 2) s_cnt[tid] = 0;
     if (tid == 0) s_bad = 0;
     __syncthreads();
@@ -150,11 +157,14 @@ __global__ void __launch_bounds__(kFusedThreads) hist_fused_kernel(FusedHistArgs
         return;
     }
     if (tid == 0) a.need_global[p] = 0;
-    float4* tile = fsm;                                                      // [kFusedTile]
-    unsigned int* hist = reinterpret_cast<unsigned int*>(fsm + kFusedTile);    // [ncol * lz]
-    float* colmax = reinterpret_cast<float*>(hist + (size_t)a.cap_cols * lz);  // [ncol]
-    float* rowmax = colmax + a.cap_cols;                                       // [ncol]
-    for (int i = tid; i < ncol * lz; i += kFusedThreads) hist[i] = 0u;
+    using cnt_t = typename std::conditional<COUNT16, unsigned short, unsigned int>::type;
+    float4* tile = fsm;                                                          // [kFusedTile]
+    unsigned int* histw = reinterpret_cast<unsigned int*>(fsm + kFusedTile);       // counters as 32-bit words
+    const cnt_t* hist = reinterpret_cast<const cnt_t*>(histw);                     // [ncol * lz]
+    const int hist_words = COUNT16 ? (a.cap_cols * lz + 1) / 2 : a.cap_cols * lz;
+    cnt_t* colmax = reinterpret_cast<cnt_t*>(histw + hist_words);                  // [ncol] max over z
+    cnt_t* rowmax = colmax + a.cap_cols + (a.cap_cols & 1);                        // [ncol] max over the y window
+    for (int i = tid; i < (COUNT16 ? (ncol * lz + 1) / 2 : ncol * lz); i += kFusedThreads) histw[i] = 0u;
     __syncthreads();
 
     // ---- votes (hist_cuda_core.cuh:48-60 restated; shared-memory atomics).
@@ -216,7 +226,14 @@ __global__ void __launch_bounds__(kFusedThreads) hist_fused_kernel(FusedHistArgs
                         if (px < 0 || px >= wx || py < 0 || py >= wy) {
                             s_bad = 1;      // cannot happen (the range is conservative); fall back if it ever does
                         } else {
-                            atomicAdd(&hist[(px * wy + py) * lz + pz], 1u);
+                            const int bin = (px * wy + py) * lz + pz;
+                            if (COUNT16) {
+                                const int sh = (bin & 1) * 16;
+                                const unsigned int was = atomicAdd(&histw[bin >> 1], 1u << sh);
+                                if (((was >> sh) & 0xffffu) == 0xffffu) s_bad = 1;      // this increment wrapped it
+                            } else {
+                                atomicAdd(&histw[bin], 1u);
+                            }
                         }
                     }
                 }
@@ -232,15 +249,16 @@ __global__ void __launch_bounds__(kFusedThreads) hist_fused_kernel(FusedHistArgs
     // ---- 11^3 max-pool (separable; the z extent is always inside the window) + survivors == window max
     for (int c = tid; c < ncol; c += kFusedThreads) {
         unsigned int m = hist[c * lz];
-        for (int z = 1; z < lz; ++z) m = max(m, hist[c * lz + z]);
-        colmax[c] = (float)m;
+        for (int z = 1; z < lz; ++z) m = max(m, (unsigned int)hist[c * lz + z]);
+        colmax[c] = (cnt_t)m;
     }
     __syncthreads();
     for (int c = tid; c < ncol; c += kFusedThreads) {
         const int x = c / wy, y = c - x * wy;
-        float m = colmax[c];
-        for (int d = max(0, y - kFusedNmsHalf); d <= min(wy - 1, y + kFusedNmsHalf); ++d) m = fmaxf(m, colmax[x * wy + d]);
-        rowmax[c] = m;
+        unsigned int m = colmax[c];
+        for (int d = max(0, y - kFusedNmsHalf); d <= min(wy - 1, y + kFusedNmsHalf); ++d)
+            m = max(m, (unsigned int)colmax[x * wy + d]);
+        rowmax[c] = (cnt_t)m;
     }
     __syncthreads();
     unsigned long long top[kFusedTopK];
@@ -248,12 +266,13 @@ __global__ void __launch_bounds__(kFusedThreads) hist_fused_kernel(FusedHistArgs
     for (int k = 0; k < kFusedTopK; ++k) top[k] = 0ull;
     for (int c = tid; c < ncol; c += kFusedThreads) {
         const int x = c / wy, y = c - x * wy;
-        float m = rowmax[c];
-        for (int d = max(0, x - kFusedNmsHalf); d <= min(wx - 1, x + kFusedNmsHalf); ++d) m = fmaxf(m, rowmax[d * wy + y]);
-        if (!(m > 0.f)) continue;
+        unsigned int mi = rowmax[c];
+        for (int d = max(0, x - kFusedNmsHalf); d <= min(wx - 1, x + kFusedNmsHalf); ++d)
+            mi = max(mi, (unsigned int)rowmax[d * wy + y]);
+        if (mi == 0u) continue;
         for (int z = 0; z < lz; ++z) {
             const float v = (float)hist[c * lz + z];
-            if (v == m) {
+            if ((unsigned int)hist[c * lz + z] == mi) {
                 // flat index in the FULL volume: ties rank by it, exactly as on the global path
                 unsigned long long key = fused_peak_key(v, ((x + bx0) * a.len_y + (y + by0)) * lz + z);
 #pragma unroll
@@ -318,14 +337,7 @@ int launch_hist_fused(const float* X, const float* Y, int P, int N, const float*
     if (P == 0) return ICPF_OK;
     const size_t budget = 200 * 1024;
     const size_t fixed = (size_t)kFusedTile * 16;
-    const size_t per_col = (size_t)lens[2] * 4 + 8;
-    int cap_cols = (int)((budget - fixed) / per_col);
-    if (cap_cols > lens[0] * lens[1]) cap_cols = lens[0] * lens[1];
-    const size_t smem = fixed + (size_t)cap_cols * per_col;
     const bool wide = N >= 512;
-#ifndef ICPF_FUSED_WIDE
-#define ICPF_FUSED_WIDE 1024
-#endif
     // Markstein's division needs a divisor whose significand is not all ones and quotients / remainders far from the
     // under- and overflow thresholds (dividends are differences of coordinates, |x| < range)
     bool fastdiv = true;
@@ -336,15 +348,35 @@ int launch_hist_fused(const float* X, const float* Y, int P, int N, const float*
         const int e = (int)((u >> 23) & 0xffu);
         fastdiv = fastdiv && (u & 0x7fffffu) != 0x7fffffu && e > 127 - 40 && e < 127 + 40;
     }
-    auto kernel = wide ? (fastdiv ? hist_fused_kernel<ICPF_FUSED_WIDE, true> : hist_fused_kernel<ICPF_FUSED_WIDE, false>)
-                       : (fastdiv ? hist_fused_kernel<256, true> : hist_fused_kernel<256, false>);
-    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return (int)err;
-    FusedHistArgs a{reinterpret_cast<const float4*>(X), reinterpret_cast<const float4*>(Y), N,
-                    mins[0], mins[1], mins[2], maxs[0], maxs[1], maxs[2], lens[0], lens[1], lens[2],
-                    auto_swap, cap_cols, out_idx, out_votes, need_global};
-    kernel<<<P, wide ? ICPF_FUSED_WIDE : 256, smem, stream>>>(a);
-    return (int)cudaGetLastError();
+#ifndef ICPF_FUSED_WIDE
+#define ICPF_FUSED_WIDE 1024
+#endif
+    // tier 1: u32 counters + u32 max planes (4 lz + 8 bytes per column); tier 2, only for the pairs tier 1 flagged:
+    // u16 (2 lz + 4 bytes per column, twice the columns); whatever is still flagged takes the global-memory kernels
+    for (int tier = 0; tier < 2; ++tier) {
+        const size_t per_col = tier == 0 ? (size_t)lens[2] * 4 + 8 : (size_t)lens[2] * 2 + 4;
+        int cap_cols = (int)((budget - fixed - 16) / per_col);
+        if (cap_cols > lens[0] * lens[1]) cap_cols = lens[0] * lens[1];
+        const size_t smem = fixed + 16 +
+                            (tier == 0 ? (size_t)cap_cols * lens[2] * 4 + (size_t)(cap_cols + (cap_cols & 1)) * 8
+                                       : ((size_t)(cap_cols * lens[2] + 1) / 2) * 4 + (size_t)(cap_cols + (cap_cols & 1)) * 4);
+        void (*kernel)(FusedHistArgs);
+        if (tier == 0)
+            kernel = wide ? (fastdiv ? hist_fused_kernel<ICPF_FUSED_WIDE, true, false> : hist_fused_kernel<ICPF_FUSED_WIDE, false, false>)
+                          : (fastdiv ? hist_fused_kernel<256, true, false> : hist_fused_kernel<256, false, false>);
+        else
+            kernel = wide ? (fastdiv ? hist_fused_kernel<ICPF_FUSED_WIDE, true, true> : hist_fused_kernel<ICPF_FUSED_WIDE, false, true>)
+                          : (fastdiv ? hist_fused_kernel<256, true, true> : hist_fused_kernel<256, false, true>);
+        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return (int)err;
+        FusedHistArgs a{reinterpret_cast<const float4*>(X), reinterpret_cast<const float4*>(Y), N,
+                        mins[0], mins[1], mins[2], maxs[0], maxs[1], maxs[2], lens[0], lens[1], lens[2],
+                        auto_swap, cap_cols, out_idx, out_votes, need_global, tier};
+        kernel<<<P, wide ? ICPF_FUSED_WIDE : 256, smem, stream>>>(a);
+        err = cudaGetLastError();
+        if (err != cudaSuccess) return (int)err;
+    }
+    return ICPF_OK;
 }
 
 }  // namespace icpf
