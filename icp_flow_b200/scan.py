@@ -14,7 +14,6 @@ raise.  PyTorch is used for device memory, streams and the few [K]-sized index m
 """
 from __future__ import annotations
 
-import ctypes
 import weakref
 from typing import Optional, Tuple
 

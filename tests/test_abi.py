@@ -59,6 +59,58 @@ def test_argument_validation_without_gpu():
     assert L.icpf_nn_f32(fake, fake, 2, 8, 8, 2, 3, fake, fake, null) == -3
 
 
+def test_scan_level_argument_validation_without_gpu():
+    """Rows f2 / f3: every scan-level entry point rejects bad arguments before touching the device."""
+    L = _lib.lib()
+    null = ctypes.c_void_p(0)
+    fake = ctypes.c_void_p(4096)
+    odd = ctypes.c_void_p(4100)
+    # cluster index: label range, row stride, NULL outputs, workspace
+    assert L.icpf_cluster_index_workspace_bytes(1000, 0) == 0
+    assert L.icpf_cluster_index_workspace_bytes(150000, 200) >= 200 * 4
+    assert L.icpf_cluster_index_workspace_bytes(150000, 1 << 20) <= (16 << 20) + 256        # bounded counter table
+    ci = L.icpf_cluster_index_f32
+    assert ci(fake, 3, fake, 100, 0, fake, fake, fake, fake, 1 << 20, null) == -2           # n_labels < 1
+    assert ci(fake, 3, fake, 100, (1 << 20) + 1, fake, fake, fake, fake, 1 << 20, null) == -2
+    assert ci(fake, 2, fake, 100, 8, fake, fake, fake, fake, 1 << 20, null) == -3           # rows need x, y, z
+    assert ci(fake, 3, fake, 100, 8, fake, null, fake, fake, 1 << 20, null) == -1
+    assert ci(null, 3, fake, 100, 8, fake, fake, fake, fake, 1 << 20, null) == -1
+    assert ci(fake, 3, fake, 100, 8, fake, fake, fake, null, 0, null) == -5                 # workspace
+    # sanity_check
+    sc = L.icpf_sanity_check_f32
+    assert sc(fake, fake, 0, fake, fake, 8, fake, 4, 20, 2.0, 0.1, fake, fake, fake, null) == -2
+    assert sc(fake, fake, 8, fake, fake, 8, null, 4, 20, 2.0, 0.1, fake, fake, fake, null) == -1
+    assert sc(fake, fake, 8, fake, fake, 8, fake, 4, 20, 2.0, 0.1, fake, fake, null, null) == -1
+    # gather / pad
+    gp = L.icpf_gather_pairs_f32
+    ok_args = [fake, 3, fake, fake, 8, fake, 3, fake, fake, 8, fake, 4, 256, null, null, fake, fake, null]
+    bad = lambda i, v: ok_args[:i] + [v] + ok_args[i + 1:]
+    assert gp(*bad(11, 0)) == 0                                   # no pairs: nothing to do
+    assert gp(*bad(12, 0)) == -2                                  # max_points < 1
+    assert gp(*bad(1, 2)) == -3                                   # src stride
+    assert gp(*bad(15, null)) == -1                               # NULL output
+    assert gp(*bad(15, odd)) == -4                                # outputs are written as 16-byte rows
+    assert gp(*bad(13, fake)) == -1                               # sample_rows without sample_offsets
+    # flow
+    fl = L.icpf_flow_f32
+    assert fl(fake, 3, fake, 0, fake, 10, fake, 4, null, fake, null) == 0
+    assert fl(fake, 3, fake, 100, fake, 10, fake, 70000, null, fake, null) == -2            # pair table is u16-indexed
+    assert fl(fake, 2, fake, 100, fake, 10, fake, 4, null, fake, null) == -3
+    assert fl(fake, 3, fake, 100, null, 10, fake, 4, null, fake, null) == -1
+    assert fl(fake, 3, null, 100, fake, 10, fake, 4, null, fake, null) == -1
+
+
+def test_scan_shims_refuse_cpu_tensors_and_bad_shapes():
+    import icp_flow_b200 as E
+    pts, lab = torch.zeros(10, 3), torch.zeros(10)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        E.ScanIndex(pts, lab)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        E.flow_estimation_torch(None, pts, None, lab, None, torch.zeros(0, 10), torch.zeros(0, 4, 4), None)
+    with pytest.raises(TypeError):
+        E.ScanIndex(pts.numpy(), lab)
+
+
 def test_python_shim_refuses_cpu_tensors():
     x = torch.zeros(2, 8, 4)
     with pytest.raises(RuntimeError, match="no CPU"):
