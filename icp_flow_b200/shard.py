@@ -43,6 +43,41 @@ def gather_transforms(local: torch.Tensor, num_pairs: int, group: Optional[dist.
     return torch.cat(parts, dim=0).view(num_pairs, 4, 4)
 
 
+def batch_stop_from_masks(conv_mask: torch.Tensor, max_iterations: int,
+                          group: Optional[dist.ProcessGroup] = None) -> Tuple[int, bool]:
+    """The reference's batch stop (utils_icp_pytorch3d.py:209) over the pairs of ALL ranks, from the per-pair convergence
+    masks ``icp_batch`` returns (``[p_local, 4]`` int32, bit k <=> relative rmse <= thr at iteration k): the first
+    iteration at which every pair of every rank passes the test.  Returns ``(iterations, converged)`` like
+    ``IcpBatchResult.batch`` -- ``(k* + 1, True)`` or ``(max_iterations, False)``.
+
+    One 16-byte exchange per rank (all-gather of the local AND; NCCL has no bitwise reduction).  This is the building
+    block for a sharded ``hist_icp`` that stops where the unsharded batch would."""
+    words = conv_mask.reshape(-1, 4).to(torch.int32)
+    local = torch.full((4,), -1, dtype=torch.int32, device=words.device)
+    if words.shape[0] > 0:
+        local = _and_rows(words).clone()                            # AND-reduce over the pairs
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world > 1:
+        parts = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(parts, local, group=group)
+        for other in parts:
+            local &= other
+    bits = local.cpu().numpy().astype("uint32")
+    for k in range(min(int(max_iterations), 128)):
+        if (int(bits[k >> 5]) >> (k & 31)) & 1:
+            return k + 1, True
+    return int(max_iterations), False
+
+
+def _and_rows(rows: torch.Tensor) -> torch.Tensor:
+    """Bitwise AND over dim 0 of an int32 ``[n, 4]`` tensor (log-depth halving; torch has no AND reduction)."""
+    while rows.shape[0] > 1:
+        half = rows.shape[0] // 2
+        head = rows[:half] & rows[half:2 * half]
+        rows = torch.cat([head, rows[2 * half:]], dim=0) if rows.shape[0] % 2 else head
+    return rows[0]
+
+
 def hist_icp_sharded(args, src: torch.Tensor, dst: torch.Tensor, group: Optional[dist.ProcessGroup] = None):
     """``hist_icp`` over the pairs of ALL ranks: ``src`` / ``dst`` are this rank's shard (``shard_range``) of the
     global padded batch; returns the transforms of every pair, ``[num_pairs, 4, 4]``, on every rank."""

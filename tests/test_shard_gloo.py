@@ -57,3 +57,49 @@ def test_gather_transforms_world2_gloo(num_pairs):
         p.join(120)
         assert p.exitcode == 0
     assert list(ok) == [1] * world
+
+
+def _mask(bits):
+    w = [0, 0, 0, 0]
+    for k in bits:
+        w[k >> 5] |= 1 << (k & 31)
+    return [x - (1 << 32) if x >= (1 << 31) else x for x in w]
+
+
+def test_batch_stop_from_masks_single_process():
+    """Mirror of icp_resolve_batch_kernel: first iteration at which EVERY pair passes, else (max_iterations, False)."""
+    m = torch.tensor([_mask([3, 7, 40, 41, 100]), _mask([7, 40, 100, 127]), _mask(range(5, 128))], dtype=torch.int32)
+    assert shard.batch_stop_from_masks(m, 100) == (8, True)
+    assert shard.batch_stop_from_masks(m[:, :], 7) == (7, False)              # bit 7 lies beyond max_iterations = 7
+    assert shard.batch_stop_from_masks(m[:1], 100) == (4, True)
+    assert shard.batch_stop_from_masks(torch.zeros(5, 4, dtype=torch.int32), 100) == (100, False)
+    assert shard.batch_stop_from_masks(torch.zeros(0, 4, dtype=torch.int32), 100) == (1, True)   # vacuous .all()
+    odd = torch.tensor([_mask([64 + 31])] * 7, dtype=torch.int32)             # sign bit of a word, odd row count
+    assert shard.batch_stop_from_masks(odd, 128) == (96, True)
+
+
+def _stop_worker(rank, world, port, ok):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # rank 0 passes at {4, 9, 33}, rank 1 at {9, 33, 70}: the batch of both stops at iteration 9
+        mine = [_mask([4, 9, 33]), _mask([2, 4, 9, 33])] if rank == 0 else [_mask([9, 33, 70])]
+        got = shard.batch_stop_from_masks(torch.tensor(mine, dtype=torch.int32), 100)
+        none = shard.batch_stop_from_masks(torch.tensor([_mask([rank + 1])], dtype=torch.int32), 50)
+        ok[rank] = int(got == (10, True) and none == (50, False))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_batch_stop_from_masks_world2_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    ok = ctx.Array("i", [0] * world)
+    port = _free_port()
+    procs = [ctx.Process(target=_stop_worker, args=(r, world, port, ok)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert list(ok) == [1] * world
