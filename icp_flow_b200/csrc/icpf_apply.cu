@@ -162,7 +162,7 @@ int launch_icp_finalize(const float* src, const float* dst, int P, int N, const 
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
     FinalizeArgs a{src, dst, N, init_pose, icp_R, icp_T, auto_swap, tau, out_pose, out_err, out_flags};
-    kernel<<<P, kThreads, smem, stream>>>(a);
+    ICPF_LAUNCH(kernel, P, kThreads, smem, stream)(a);
     return (int)cudaGetLastError();
 }
 

@@ -11,11 +11,54 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// dynamic shared memory of a kernel (see ICPF_LAUNCH in icpf_internal.h)
+#ifdef ICPF_SIMT_EMU
+#define ICPF_DYN_SHARED extern
+#else
+#define ICPF_DYN_SHARED extern __shared__
+#endif
+
 namespace icpf {
 
 constexpr unsigned FULL_MASK = 0xffffffffu;
 
 // ------------------------------------------------------------------------------------------------ TMA / mbarrier
+#ifdef ICPF_SIMT_EMU
+// Emulated mbarrier (tests/simt/): the 64-bit word holds {phase parity, arrival count of a phase, pending arrivals,
+// pending transaction bytes}; a bulk copy is a memcpy that completes its bytes at once.
+struct EmuMbar { uint8_t phase; uint8_t unused; uint8_t count; uint8_t pending; int32_t tx; };
+static_assert(sizeof(EmuMbar) == 8, "an mbarrier is one 64-bit word");
+__device__ __forceinline__ void mbar_settle(EmuMbar* b) {
+    if (b->pending == 0 && b->tx == 0) {      // phase complete: flip the parity, re-arm
+        b->phase ^= 1;
+        b->pending = b->count;
+    }
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrive_count) {
+    EmuMbar* b = reinterpret_cast<EmuMbar*>(bar);
+    b->phase = 0; b->unused = 0; b->count = (uint8_t)arrive_count; b->pending = (uint8_t)arrive_count; b->tx = 0;
+}
+__device__ __forceinline__ void fence_barrier_init() {}
+__device__ __forceinline__ void fence_proxy_async() {}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    EmuMbar* b = reinterpret_cast<EmuMbar*>(bar);
+    b->tx += (int32_t)bytes;
+    b->pending -= 1;
+    mbar_settle(b);
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    return reinterpret_cast<EmuMbar*>(bar)->phase != (parity & 1u);      // true once the phase `parity` has completed
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) simt::yield();
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    EmuMbar* b = reinterpret_cast<EmuMbar*>(bar);
+    memcpy(smem_dst, gmem_src, bytes);
+    b->tx -= (int32_t)bytes;
+    mbar_settle(b);
+}
+#else
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -63,6 +106,8 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                  "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+
+#endif  // ICPF_SIMT_EMU
 
 // ------------------------------------------------------------------------------------------------ reductions
 __device__ __forceinline__ float warp_sum(float v) {

@@ -211,7 +211,7 @@ int launch_match_eval(const float* src, const float* dst, const float* pose, int
     const size_t smem = gridnn ? with_grids : 0;
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
-    kernel<<<P, kThreads, smem, stream>>>(a);
+    ICPF_LAUNCH(kernel, P, kThreads, smem, stream)(a);
     return (int)cudaGetLastError();
 }
 

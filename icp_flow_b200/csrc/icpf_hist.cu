@@ -98,7 +98,7 @@ int launch_hist_votes(const float* X, const float* Y, int B, int NX, int NY, con
     if (err != cudaSuccess) return (int)err;
     const int nmax = auto_swap ? max(NX, NY) : NX;
     dim3 grid((nmax + kVoteThreads - 1) / kVoteThreads, B);
-    hist_votes_kernel<<<grid, kVoteThreads, 0, stream>>>(reinterpret_cast<const float4*>(X),
+    ICPF_LAUNCH(hist_votes_kernel, grid, kVoteThreads, 0, stream)(reinterpret_cast<const float4*>(X),
                                                          reinterpret_cast<const float4*>(Y), NX, NY, gm, bins,
                                                          auto_swap, need);
     return (int)cudaGetLastError();
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(kPeakThreads) hist_peaks_kernel(const float* _
                                                                   float* __restrict__ out_votes,
                                                                   const int* __restrict__ need,
                                                                   float* __restrict__ scratch) {
-    extern __shared__ float sm[];
+    ICPF_DYN_SHARED float sm[];
     __shared__ unsigned long long s_best[kPeakThreads / 32];
     __shared__ unsigned long long s_pick[kTopK];
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -227,7 +227,7 @@ int launch_hist_peaks(const float* bins, int B, int lx, int ly, int lz, int* out
     const size_t smem = global ? 0 : (size_t)lx * ly * 2 * sizeof(float);
     cudaError_t err = cudaFuncSetAttribute(hist_peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
-    hist_peaks_kernel<<<B, kPeakThreads, smem, stream>>>(bins, lx, ly, lz, out_idx, out_votes, need,
+    ICPF_LAUNCH(hist_peaks_kernel, B, kPeakThreads, smem, stream)(bins, lx, ly, lz, out_idx, out_votes, need,
                                                          global ? scratch : nullptr);
     return (int)cudaGetLastError();
 }
@@ -584,7 +584,7 @@ int launch_hist_score(const float* src, const float* dst, int P, int N, const in
     if (err != cudaSuccess) return (int)err;
     ScoreArgs a{src, dst, N, cand_idx, bins_x, bins_y, bins_z, lx, ly, lz, half_bin, tau, auto_swap, out_pose,
                 out_scores, out_which};
-    kernel<<<P, kThreads, smem, stream>>>(a);
+    ICPF_LAUNCH(kernel, P, kThreads, smem, stream)(a);
     return (int)cudaGetLastError();
 }
 

@@ -66,7 +66,7 @@ __device__ __forceinline__ unsigned long long fused_peak_key(float v, int idx) {
 // the exact global-memory path.
 template <int kFusedThreads, bool FASTDIV, bool COUNT16>
 __global__ void __launch_bounds__(kFusedThreads) hist_fused_kernel(FusedHistArgs a) {
-    extern __shared__ __align__(16) float4 fsm[];
+    ICPF_DYN_SHARED __align__(16) float4 fsm[];
     __shared__ float s_red[kFusedThreads / 32][12];
     __shared__ int s_cnt[2];
     __shared__ int s_bad;
@@ -372,7 +372,7 @@ int launch_hist_fused(const float* X, const float* Y, int P, int N, const float*
         FusedHistArgs a{reinterpret_cast<const float4*>(X), reinterpret_cast<const float4*>(Y), N,
                         mins[0], mins[1], mins[2], maxs[0], maxs[1], maxs[2], lens[0], lens[1], lens[2],
                         auto_swap, cap_cols, out_idx, out_votes, need_global, tier};
-        kernel<<<P, wide ? ICPF_FUSED_WIDE : 256, smem, stream>>>(a);
+        ICPF_LAUNCH(kernel, P, wide ? ICPF_FUSED_WIDE : 256, smem, stream)(a);
         err = cudaGetLastError();
         if (err != cudaSuccess) return (int)err;
     }

@@ -284,7 +284,7 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
     int* decided = reinterpret_cast<int*>(ws + icp_ws_off_batch(P)) + 8;
     a.stats = reinterpret_cast<int*>(ws + icp_ws_off_stats(P));
     if (t_prof_start && t_prof_stop) cudaEventRecord(t_prof_start, stream);
-    kernel<<<P, kThreads, smem, stream>>>(a);
+    ICPF_LAUNCH(kernel, P, kThreads, smem, stream)(a);
     err = cudaGetLastError();
     if (t_prof_start && t_prof_stop) {
         cudaEventRecord(t_prof_stop, stream);
@@ -292,15 +292,15 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
     }
     if (err != cudaSuccess) return (int)err;
 
-    icp_resolve_batch_kernel<<<1, 256, 0, stream>>>(conv, P, prm.max_iterations, a.cap, prm.batch_stop, batch,
+    ICPF_LAUNCH(icp_resolve_batch_kernel, 1, 256, 0, stream)(conv, P, prm.max_iterations, a.cap, prm.batch_stop, batch,
                                                     capped ? decided : nullptr);
     err = cudaGetLastError();
     if (err != cudaSuccess) return (int)err;
     if (capped) {
         a.decided = decided;
-        kernel<<<P, kThreads, smem, stream>>>(a);
+        ICPF_LAUNCH(kernel, P, kThreads, smem, stream)(a);
         a.decided = nullptr;
-        icp_resolve_batch_kernel<<<1, 256, 0, stream>>>(conv, P, prm.max_iterations, prm.max_iterations, prm.batch_stop,
+        ICPF_LAUNCH(icp_resolve_batch_kernel, 1, 256, 0, stream)(conv, P, prm.max_iterations, prm.max_iterations, prm.batch_stop,
                                                         batch, decided);
         err = cudaGetLastError();
         if (err != cudaSuccess) return (int)err;
@@ -308,7 +308,7 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
 
     if (prm.batch_stop) {
         a.batch = batch;
-        kernel<<<P, kThreads, smem, stream>>>(a);
+        ICPF_LAUNCH(kernel, P, kThreads, smem, stream)(a);
         err = cudaGetLastError();
         if (err != cudaSuccess) return (int)err;
     }

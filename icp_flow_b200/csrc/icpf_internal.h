@@ -7,6 +7,14 @@
 
 #include "../../include/icpflow_b200.h"
 
+// Kernel launches and dynamic shared memory go through these two macros so that the same sources also compile for the
+// SIMT-on-CPU emulator of the test-suite (tests/simt/, test infrastructure only: the product is the nvcc build).
+#ifdef ICPF_SIMT_EMU
+#define ICPF_LAUNCH(kernel, grid, block, smem, stream) simt::bind(kernel, dim3(grid), dim3(block), (size_t)(smem))
+#else
+#define ICPF_LAUNCH(kernel, grid, block, smem, stream) kernel<<<(grid), (block), (smem), (stream)>>>
+#endif
+
 namespace icpf {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }

@@ -67,7 +67,7 @@ int launch_nn(const float* src, const float* dst, int B, int Ns, int Nd, int src
     if (B == 0 || Ns == 0) return ICPF_OK;
     if (B > 65535) return ICPF_E_SHAPE;
     dim3 grid((Ns + kThreads * kNnQB - 1) / (kThreads * kNnQB), B);
-    nn_all_rows_kernel<<<grid, kThreads, 0, stream>>>(src, dst, Ns, Nd, src_stride, dst_stride, out_idx, out_dist);
+    ICPF_LAUNCH(nn_all_rows_kernel, grid, kThreads, 0, stream)(src, dst, Ns, Nd, src_stride, dst_stride, out_idx, out_dist);
     return (int)cudaGetLastError();
 }
 
@@ -95,7 +95,7 @@ int launch_transform_points(const float* xyz, const float* pose, int B, int N, f
     if (B == 0 || N == 0) return ICPF_OK;
     if (B > 65535) return ICPF_E_SHAPE;
     dim3 grid((N + 255) / 256, B);
-    transform_points_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(xyz), pose, N,
+    ICPF_LAUNCH(transform_points_kernel, grid, 256, 0, stream)(reinterpret_cast<const float4*>(xyz), pose, N,
                                                      reinterpret_cast<float4*>(out));
     return (int)cudaGetLastError();
 }

@@ -43,7 +43,7 @@ enum : int { B_R = 0, B_T = 9, B_RC = 12 /* last step R_k - R_{k-1} */, B_TC = 2
 
 // Dynamic shared memory of every pair kernel.  Tiles are addressed as OFFSETS into this one array so that the
 // compiler always knows the address space (a run-time swap of two pointers degrades every access to a generic LD/ST).
-extern __shared__ __align__(128) float4 g_tile[];
+ICPF_DYN_SHARED __align__(128) float4 g_tile[];
 
 // Shared-memory carve-up for one pair (float4 / 16-byte units unless noted).
 struct PairTiles {

@@ -393,12 +393,12 @@ int launch_cluster_index(const float* points, int stride, const float* labels, i
     if (e != cudaSuccess) return (int)e;
     const int chunk = ((n + B - 1) / B + kScanThreads - 1) / kScanThreads * kScanThreads;
     const int lb = (n_labels + kScanThreads - 1) / kScanThreads;
-    if (n > 0) cluster_count_kernel<<<B, kScanThreads, 0, stream>>>(labels, n, n_labels, chunk, blockhist);
-    cluster_totals_kernel<<<lb, kScanThreads, 0, stream>>>(blockhist, B, n_labels, offsets);
-    cluster_offsets_kernel<<<1, 1024, 0, stream>>>(offsets, n_labels);
-    cluster_bases_kernel<<<lb, kScanThreads, 0, stream>>>(blockhist, B, n_labels, offsets);
-    if (n > 0) cluster_scatter_kernel<<<B, kScanThreads, 0, stream>>>(labels, n, n_labels, chunk, blockhist, order);
-    cluster_stats_kernel<<<n_labels, 128, 0, stream>>>(points, stride, order, offsets, n_labels, stats);
+    if (n > 0) ICPF_LAUNCH(cluster_count_kernel, B, kScanThreads, 0, stream)(labels, n, n_labels, chunk, blockhist);
+    ICPF_LAUNCH(cluster_totals_kernel, lb, kScanThreads, 0, stream)(blockhist, B, n_labels, offsets);
+    ICPF_LAUNCH(cluster_offsets_kernel, 1, 1024, 0, stream)(offsets, n_labels);
+    ICPF_LAUNCH(cluster_bases_kernel, lb, kScanThreads, 0, stream)(blockhist, B, n_labels, offsets);
+    if (n > 0) ICPF_LAUNCH(cluster_scatter_kernel, B, kScanThreads, 0, stream)(labels, n, n_labels, chunk, blockhist, order);
+    ICPF_LAUNCH(cluster_stats_kernel, n_labels, 128, 0, stream)(points, stride, order, offsets, n_labels, stats);
     return (int)cudaGetLastError();
 }
 
@@ -407,7 +407,7 @@ int launch_sanity_check(const int* src_offsets, const float* src_stats, int n_sr
                         float translation_frame, float thres_box, int* out_keep, int64_t* out_pairs, int* out_count,
                         cudaStream_t stream) {
     SanityGates g{min_cluster_size, translation_frame, thres_box};
-    sanity_check_kernel<<<1, 1024, 0, stream>>>(src_offsets, src_stats, n_src, dst_offsets, dst_stats, n_dst,
+    ICPF_LAUNCH(sanity_check_kernel, 1, 1024, 0, stream)(src_offsets, src_stats, n_src, dst_offsets, dst_stats, n_dst,
                                                 reinterpret_cast<const long long*>(pairs), P, g, out_keep,
                                                 reinterpret_cast<long long*>(out_pairs), out_count);
     return (int)cudaGetLastError();
@@ -419,7 +419,7 @@ int launch_gather_pairs(const float* src_points, int src_stride, const int* src_
                         const int64_t* sample_offsets, float* out_src, float* out_dst, cudaStream_t stream) {
     ScanView s{src_points, src_order, src_offsets, src_stride, n_src};
     ScanView d{dst_points, dst_order, dst_offsets, dst_stride, n_dst};
-    gather_pairs_kernel<<<dim3(P, 2), kScanThreads, 0, stream>>>(
+    ICPF_LAUNCH(gather_pairs_kernel, dim3(P, 2), kScanThreads, 0, stream)(
         s, d, reinterpret_cast<const long long*>(pairs), max_points, sample_rows,
         reinterpret_cast<const long long*>(sample_offsets), reinterpret_cast<float4*>(out_src),
         reinterpret_cast<float4*>(out_dst));
@@ -430,7 +430,7 @@ int launch_flow(const float* points, int stride, const float* labels, int n, con
                 const float* transforms, int K, const float* pose, float* flow, cudaStream_t stream) {
     int blocks = (n + kScanThreads - 1) / kScanThreads;
     blocks = blocks > 148 * 4 ? 148 * 4 : blocks;
-    flow_kernel<<<blocks, kScanThreads, 0, stream>>>(points, stride, labels, n, pair_labels, pair_stride, transforms, K,
+    ICPF_LAUNCH(flow_kernel, blocks, kScanThreads, 0, stream)(points, stride, labels, n, pair_labels, pair_stride, transforms, K,
                                                      pose, flow);
     return (int)cudaGetLastError();
 }

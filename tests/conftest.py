@@ -15,6 +15,29 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+@pytest.fixture(params=[pytest.param("cuda", marks=pytest.mark.gpu), "simt"])
+def engine(request):
+    """Every test that uses it runs twice: on the GPU through the product library (marked gpu) and, in the CPU suite,
+    through the SIMT-on-CPU emulator build of the same kernel sources (tests/engines.py)."""
+    import engines
+
+    if request.param == "cuda":
+        e = engines.CudaEngine()
+        engines.activate(e)
+        try:
+            yield e
+        finally:
+            engines.activate(None)
+    else:
+        e = engines.SimtEngine()
+        with e._harness.emulated():
+            engines.activate(e)
+            try:
+                yield e
+            finally:
+                engines.activate(None)
+
+
 @pytest.fixture(scope="session")
 def golden():
     def load(name):

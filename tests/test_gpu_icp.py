@@ -8,17 +8,14 @@ import numpy as np
 import pytest
 import torch
 
+from engines import device, put, sync
 from icp_flow_b200 import ops, synth
 from oracle import icp_oracle as O
 
-pytestmark = pytest.mark.gpu
+# every test runs on the GPU (marked gpu) and through the SIMT-on-CPU emulator build of the kernels (tests/engines.py)
+pytestmark = pytest.mark.usefixtures("engine")
 
 TOL = 1e-4
-
-
-def _dev():
-    assert torch.cuda.is_available()
-    return torch.device("cuda:0")
 
 
 def _moved_err(src, R, T, R_ref, T_ref):
@@ -49,10 +46,9 @@ def _assert_parity(src, R, T, R_ref, T_ref, trace, max_unstable_frac=0.2):
 
 
 def _run(src, dst, **kw):
-    dev = _dev()
     p = ops.make_params(**kw)
-    r = ops.icp_batch(torch.from_numpy(src).to(dev), torch.from_numpy(dst).to(dev), p)
-    torch.cuda.synchronize()
+    r = ops.icp_batch(put(torch.from_numpy(src)), put(torch.from_numpy(dst)), p)
+    sync()
     return r
 
 
@@ -105,13 +101,12 @@ def test_oracle_parity_on_seeded_batch():
 
 
 def test_mirror_api_returns_reference_types():
-    dev = _dev()
     src, dst, _ = synth.make_pairs(8, 64, seed=3, residual_only=True)
-    s, d = torch.from_numpy(src).to(dev), torch.from_numpy(dst).to(dev)
+    s, d = put(torch.from_numpy(src)), put(torch.from_numpy(dst))
     sol = ops.iterative_closest_point(s, d, thres=0.1, max_iterations=100, relative_rmse_thr=1e-6)
     assert isinstance(sol.converged, bool) and sol.RTs.R.shape == (8, 3, 3) and sol.RTs.T.shape == (8, 3)
     assert sol.Xt.shape == (8, 64, 3) and sol.rmse.shape == (8,) and len(sol.t_history) >= 1
-    assert torch.equal(sol.RTs.s, torch.ones(8, device=dev))
+    assert torch.equal(sol.RTs.s, torch.ones(8, device=device()))
     ref = O.icp_loop(torch.from_numpy(src), torch.from_numpy(dst), diagnostics=True)
     assert abs(len(sol.t_history) - ref.iterations) <= 2
     ok = ~O.unstable_pairs(ref)
@@ -123,7 +118,6 @@ def test_mirror_api_returns_reference_types():
 
 def test_c1_demo_icp_stage_vs_reference_golden(golden):
     """BASELINE config C1 (demo.npz clusters): ICP from the reference's own histogram initialisation."""
-    dev = _dev()
     g = golden("c1_demo.npz")
     src, dst = torch.from_numpy(g["src"]), torch.from_numpy(g["dst"])
     swap = torch.from_numpy(g["swapped"])
@@ -132,14 +126,13 @@ def test_c1_demo_icp_stage_vs_reference_golden(golden):
     moved = O.transform_points_batch(a, torch.from_numpy(g["init_pose"]))
     trace = O.icp_loop(moved, c, float(g["thres_dist"]), 100, 1e-6, diagnostics=True)
     assert np.array_equal(trace.R.numpy(), g["icp_R"])
-    r = ops.icp_batch(moved.to(dev), c.to(dev), ops.make_params(thres=float(g["thres_dist"])))
+    r = ops.icp_batch(put(moved), put(c), ops.make_params(thres=float(g["thres_dist"])))
     assert abs(r.batch.tolist()[0] - int(g["icp_iterations"])) <= 2
     _assert_parity(moved.numpy(), r.R.cpu(), r.T.cpu(), g["icp_R"], g["icp_T"], trace, max_unstable_frac=0.35)
 
 
 def test_degenerate_pairs():
     """identity pair (rmse 0 -> NaN relative rmse in the reference), zero-inlier pair, tiny clusters."""
-    dev = _dev()
     rng = np.random.default_rng(0)
     N = 64
     src = np.full((4, N, 4), 1e8, np.float32); src[..., 3] = 0
@@ -149,7 +142,7 @@ def test_degenerate_pairs():
     src[1, :40, :3] = pts; src[1, :40, 3] = 1; dst[1, :40, :3] = pts + 5; dst[1, :40, 3] = 1    # no inliers
     src[2, :3, :3] = pts[:3]; src[2, :3, 3] = 1; dst[2, :3, :3] = pts[:3] + 0.01; dst[2, :3, 3] = 1  # 3 points
     src[3, :40, :3] = pts; src[3, :40, 3] = 1; dst[3, :1, :3] = pts[:1]; dst[3, :1, 3] = 1       # single dst point
-    r = ops.icp_batch(torch.from_numpy(src).to(dev), torch.from_numpy(dst).to(dev),
+    r = ops.icp_batch(put(torch.from_numpy(src)), put(torch.from_numpy(dst)),
                       ops.make_params(max_iterations=100, relative_rmse_thr=1e-6, batch_stop=False))
     R, T = r.R.cpu().numpy(), r.T.cpu().numpy()
     assert np.isfinite(R).all() and np.isfinite(T).all()
@@ -164,28 +157,27 @@ def test_degenerate_pairs():
 
 
 def test_nn_and_transform_seams(golden):
-    dev = _dev()
     g = golden("c1_demo.npz")
     src, dst = torch.from_numpy(g["src"]), torch.from_numpy(g["dst"])
     swap = torch.from_numpy(g["swapped"])
     a, c = src.clone(), dst.clone()
     a[swap] = dst[swap]; c[swap] = src[swap]
-    idx, dist = ops.nearest_neighbor_batch(a.to(dev), c.to(dev))
+    idx, dist = ops.nearest_neighbor_batch(put(a), put(c))
     assert np.array_equal(idx.cpu().numpy(), g["nn_idx"])            # index work: bit exact
     # squared distances use the reference leaf's fp32 op order; the engine's sqrt is IEEE-rounded while torch's
     # CPU sqrt (the golden) is 1 ulp off on ~0.2 % of the values, hence 1 ulp instead of array_equal
     got, want = dist.cpu().numpy(), g["nn_dist"]
     assert np.allclose(got, want, rtol=1.2e-7, atol=0)
     assert (got != want).mean() < 0.01
-    idx3, dist3 = ops.nearest_neighbor_batch(a[:, :, :3].to(dev), c[:, :, :3].to(dev))
+    idx3, dist3 = ops.nearest_neighbor_batch(put(a[:, :, :3]), put(c[:, :, :3]))
     assert torch.equal(idx3, idx) and torch.equal(dist3, dist)
     pose = torch.from_numpy(g["init_pose"])
-    moved = ops.transform_points_batch(a.to(dev), pose.to(dev)).cpu()
+    moved = ops.transform_points_batch(put(a), put(pose)).cpu()
     assert torch.equal(moved, O.transform_points_batch(a, pose))     # translation-only poses: exact
     torch.manual_seed(0)
     q = torch.linalg.qr(torch.randn(len(a), 3, 3))[0]
     pose2 = torch.eye(4).repeat(len(a), 1, 1); pose2[:, :3, :3] = q; pose2[:, :3, 3] = torch.randn(len(a), 3)
-    got = ops.transform_points_batch(a.to(dev), pose2.to(dev)).cpu()
+    got = ops.transform_points_batch(put(a), put(pose2)).cpu()
     want = O.transform_points_batch(a, pose2)
     valid = a[:, :, 3] > 0
     assert (got - want)[valid].abs().max() <= 2e-5
@@ -267,4 +259,10 @@ def test_batch_stop_beyond_the_first_pass_cap():
     ref2 = O.icp_loop(torch.from_numpy(src[1:]), torch.from_numpy(dst[1:]), 0.1, 100, 1e-6, diagnostics=True)
     r2 = _run(src[1:], dst[1:], max_iterations=100, relative_rmse_thr=1e-6, early_exit=True, batch_stop=True)
     assert r2.batch.tolist()[1] == int(ref2.converged) and abs(r2.batch.tolist()[0] - ref2.iterations) <= 2
+    if r2.batch.tolist()[0] != ref2.iterations:
+        # A flip-prone pair whose relative rmse sits at the 1e-6 threshold moves the BATCH stop by an iteration or two,
+        # and with it the state of every pair that is still moving (utils_icp_pytorch3d.py:209 couples the pairs):
+        # compare with the oracle stopped at the same iteration.
+        ref2 = O.icp_loop(torch.from_numpy(src[1:]), torch.from_numpy(dst[1:]), 0.1, r2.batch.tolist()[0], -1.0,
+                          diagnostics=True)
     _assert_parity(src[1:], r2.R.cpu(), r2.T.cpu(), ref2.R, ref2.T, ref2, max_unstable_frac=0.35)
