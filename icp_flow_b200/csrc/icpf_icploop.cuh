@@ -316,7 +316,25 @@ __device__ __forceinline__ IcpResult icp_iterations(const Tiles& tl, const GridI
                 h[4] = fmaf(-sx1, my1, total[11]) * iW; h[5] = fmaf(-sx1, my2, total[12]) * iW;
                 h[6] = fmaf(-sx2, my0, total[13]) * iW; h[7] = fmaf(-sx2, my1, total[14]) * iW;
                 h[8] = fmaf(-sx2, my2, total[15]) * iW;
-                const Rot3 rot = kabsch_rotation(h, reinterpret_cast<KabschState*>(bc + B_KABSCH));
+                // The reference's rotation is a pure function of H (torch.svd, utils_icp_pytorch3d.py:339).  The
+                // warm-started solve below is a function of (H, stored frame), and two frames that are both converged
+                // to working precision can hand over to each other for ever (R flips by an ulp, the rmse by 1e-6 of its
+                // value -- the size of the reference's own stopping threshold).  So when H repeats bit for bit the
+                // previous R stands: same H, same R, as in the reference, and the pair is at its fixed point.
+                KabschState* kst = reinterpret_cast<KabschState*>(bc + B_KABSCH);
+                bool same_h = (it > 0);
+#pragma unroll
+                for (int i = 0; i < 9; ++i) same_h = same_h && (__float_as_uint(h[i]) == __float_as_uint(bc[B_HPREV + i]));
+                Rot3 rot;
+                if (same_h) {
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) rot.r[i] = bc[B_R + i];
+                    kst->changed = false;
+                } else {
+                    rot = kabsch_rotation(h, kst);
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) bc[B_HPREV + i] = h[i];
+                }
                 // centroids: mu = pivot + S / W   (zero-weight iteration: both are the pivots, T = 0 like the reference)
                 const float cx0 = bc[B_PX] + mx0, cx1 = bc[B_PX + 1] + mx1, cx2 = bc[B_PX + 2] + mx2;
                 const float cy0 = bc[B_PY] + my0, cy1 = bc[B_PY + 1] + my1, cy2 = bc[B_PY + 2] + my2;

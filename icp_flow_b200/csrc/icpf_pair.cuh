@@ -34,12 +34,13 @@ constexpr int kSums = 18;                      // 16 moments + rmse numerator + 
 constexpr int kScrPart = 0;                    // [kWarps][kSums]
 constexpr int kScrTotal = kScrPart + kWarps * kSums;
 constexpr int kRedFloats = kScrTotal + 24;
-constexpr int kBcastFloats = 48;
+constexpr int kBcastFloats = 64;
 constexpr int kCellWords = (kGridMaxCells + 2 + 1) / 2 + 2;   // packed u16 entries 0..G (+pad), as u32 words
 
 // broadcast block written by thread 0 once per iteration
 enum : int { B_R = 0, B_T = 9, B_RC = 12 /* last step R_k - R_{k-1} */, B_TC = 21 /* last step T_k - T_{k-1} */, B_PX = 24, B_PY = 27, B_EXIT = 30, B_DEFER = 31 /* int: rows queued for a search */,
-             B_KABSCH = 32 /* KabschState: 9 floats + flag */ };
+             B_KABSCH = 32 /* KabschState: 9 floats + 2 flags */, B_HPREV = 44 /* cross-covariance of the previous solve */ };
+static_assert(B_HPREV + 9 <= kBcastFloats, "broadcast block");
 
 // Dynamic shared memory of every pair kernel.  Tiles are addressed as OFFSETS into this one array so that the
 // compiler always knows the address space (a run-time swap of two pointers degrades every access to a generic LD/ST).
