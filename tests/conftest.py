@@ -21,21 +21,8 @@ def engine(request):
     through the SIMT-on-CPU emulator build of the same kernel sources (tests/engines.py)."""
     import engines
 
-    if request.param == "cuda":
-        e = engines.CudaEngine()
-        engines.activate(e)
-        try:
-            yield e
-        finally:
-            engines.activate(None)
-    else:
-        e = engines.SimtEngine()
-        with e._harness.emulated():
-            engines.activate(e)
-            try:
-                yield e
-            finally:
-                engines.activate(None)
+    with engines.running(request.param) as e:
+        yield e
 
 
 @pytest.fixture(scope="session")

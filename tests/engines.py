@@ -11,6 +11,7 @@ the ``engine`` fixture (conftest.py) selects what they mean.
 """
 from __future__ import annotations
 
+import contextlib
 import os
 import sys
 
@@ -48,6 +49,26 @@ class SimtEngine:
 
     def sync(self):
         pass
+
+
+@contextlib.contextmanager
+def running(name: str):
+    """Activate the engine ``name`` ("cuda" | "simt") for the duration of a test."""
+    if name == "cuda":
+        e = CudaEngine()
+        activate(e)
+        try:
+            yield e
+        finally:
+            activate(None)
+    else:
+        e = SimtEngine()
+        with e._harness.emulated():
+            activate(e)
+            try:
+                yield e
+            finally:
+                activate(None)
 
 
 def activate(engine):

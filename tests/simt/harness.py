@@ -28,6 +28,10 @@ class SimtTensor(torch.Tensor):
     def is_cuda(self):  # noqa: D401
         return True
 
+    def cpu(self, *args, **kwargs):
+        """Back "on the host": a plain tensor over the same memory (what `.cpu()` of a CUDA tensor is to the tests)."""
+        return self.as_subclass(torch.Tensor)
+
 
 def dev_tensor(x) -> torch.Tensor:
     t = torch.as_tensor(x)
@@ -44,7 +48,17 @@ def emulated(extra_flags=(), out=None):
     from icp_flow_b200 import _lib, ops, scan
 
     path = simt_build.build() if out is None else simt_build.build(force=True, extra_flags=extra_flags, out=out)
-    saved = (_lib._LIB, _lib.LIB_PATH, ops._stream_ptr, scan._stream_ptr, torch.cuda.device)
+    saved = (_lib._LIB, _lib.LIB_PATH, ops._stream_ptr, scan._stream_ptr, torch.cuda.device, ops._require_cuda_f32,
+             scan._require_cuda_f32)
+
+    def require_f32(t, name):
+        # outputs of one emulated call (plain CPU tensors the shim allocated "on the device") feed the next one
+        if not torch.is_tensor(t):
+            raise TypeError(f"{name} must be a torch.Tensor")
+        if t.dtype != torch.float32:
+            raise TypeError(f"{name} must be float32 (got {t.dtype})")
+        return t.contiguous()
+
     try:
         _lib._LIB, _lib.LIB_PATH = None, path
         _lib.lib()                                       # binds the argtypes of the same ABI on the emulator library
@@ -52,6 +66,9 @@ def emulated(extra_flags=(), out=None):
         ops._stream_ptr = null_stream
         scan._stream_ptr = null_stream
         torch.cuda.device = lambda *_a, **_k: contextlib.nullcontext()
+        ops._require_cuda_f32 = require_f32
+        scan._require_cuda_f32 = require_f32
         yield _lib._LIB
     finally:
-        _lib._LIB, _lib.LIB_PATH, ops._stream_ptr, scan._stream_ptr, torch.cuda.device = saved
+        (_lib._LIB, _lib.LIB_PATH, ops._stream_ptr, scan._stream_ptr, torch.cuda.device, ops._require_cuda_f32,
+         scan._require_cuda_f32) = saved

@@ -12,17 +12,14 @@ import numpy as np
 import pytest
 import torch
 
+from engines import device, is_simt, put, sync
 from icp_flow_b200 import ops
 from oracle import icp_oracle as O
 from oracle import leaves
 
-pytestmark = pytest.mark.gpu
+# every test runs on the GPU (marked gpu) and through the SIMT-on-CPU emulator build of the kernels (tests/engines.py)
+pytestmark = pytest.mark.usefixtures("engine")
 TOL = 1e-4
-
-
-def _dev():
-    assert torch.cuda.is_available()
-    return torch.device("cuda:0")
 
 
 def _args(g):
@@ -51,10 +48,9 @@ def _pose_err(points, T, T_ref):
 
 def test_hist_votes_known_answer(golden):
     """hist_cuda/test.py:19-56 -> arg-max bin (50,130,7); bit-exact counts against the oracle leaf."""
-    dev = _dev()
     g = golden("hist_test_vector.npz")
     X, Y = torch.from_numpy(g["X"]), torch.from_numpy(g["Y"])
-    h = ops.hist(X.to(dev), Y.to(dev), *g["mins"].tolist(), *g["maxs"].tolist(), *g["lens"].tolist()).cpu()
+    h = ops.hist(put(X), put(Y), *g["mins"].tolist(), *g["maxs"].tolist(), *g["lens"].tolist()).cpu()
     want = leaves.hist_votes(X, Y, g["mins"], g["maxs"], g["lens"])
     assert torch.equal(h, want)
     flat = h.reshape(3, -1).argmax(dim=1)
@@ -66,29 +62,27 @@ def test_hist_votes_known_answer(golden):
 
 
 def test_hist_votes_edges_and_errors():
-    dev = _dev()
     # v == min is counted, v == max is not (half-open range), flags <= 0 never vote, empty batch is fine
     X = torch.tensor([[[0.0, 0.0, 0.0, 1.0], [1.0, 0.0, 0.0, 1.0], [0.5, 0.5, 0.0, 0.0]]])
     Y = torch.tensor([[[1.0, 1.0, 0.0, 1.0], [0.0, 1.0, 0.0, 1.0]]])
-    h = ops.hist(X.to(dev), Y.to(dev), -1.0, -1.0, -0.5, 1.0, 1.0, 0.5, 4, 4, 2).cpu()
+    h = ops.hist(put(X), put(Y), -1.0, -1.0, -0.5, 1.0, 1.0, 0.5, 4, 4, 2).cpu()
     want = leaves.hist_votes(X, Y, (-1.0, -1.0, -0.5), (1.0, 1.0, 0.5), (4, 4, 2))
     assert torch.equal(h, want) and h.sum() == 3     # (0,0)-(1,1) -> v=-1 in; (1,0)-(1,1); (0,0)-(0,1); (1,0)-(0,1) -> vx=1 == max out
-    assert ops.hist(X[:0].to(dev), Y[:0].to(dev), -1.0, -1.0, -0.5, 1.0, 1.0, 0.5, 4, 4, 2).shape == (0, 4, 4, 2)
+    assert ops.hist(put(X[:0]), put(Y[:0]), -1.0, -1.0, -0.5, 1.0, 1.0, 0.5, 4, 4, 2).shape == (0, 4, 4, 2)
     with pytest.raises(RuntimeError, match="dim"):
-        ops.hist(X[:, :, :3].contiguous().to(dev), Y[:, :, :3].contiguous().to(dev), -1, -1, -1, 1, 1, 1, 2, 2, 2)
+        ops.hist(put(X[:, :, :3].contiguous()), put(Y[:, :, :3].contiguous()), -1, -1, -1, 1, 1, 1, 2, 2, 2)
     with pytest.raises(RuntimeError, match="batch"):
-        ops.hist(X.to(dev), Y.repeat(2, 1, 1).to(dev), -1, -1, -1, 1, 1, 1, 2, 2, 2)
+        ops.hist(put(X), put(Y.repeat(2, 1, 1)), -1, -1, -1, 1, 1, 1, 2, 2, 2)
     with pytest.raises(RuntimeError, match="CUDA"):
         ops.hist(X, Y, -1, -1, -1, 1, 1, 1, 2, 2, 2)
 
 
 @pytest.mark.parametrize("name", ["c1_demo.npz", "synth_hist.npz"])
 def test_estimate_init_pose_vs_reference_golden(golden, name):
-    dev = _dev()
     g = golden(name)
     _, _, a, c = _swapped(g)
     args = _args(g)
-    pose, dbg = ops.estimate_init_pose(args, a.to(dev), c.to(dev), return_debug=True)
+    pose, dbg = ops.estimate_init_pose(args, put(a), put(c), return_debug=True)
     p = O.PathParams(thres_dist=args.thres_dist, translation_frame=args.translation_frame, chunk_size=args.chunk_size)
     want, odbg = O.estimate_init_pose(a, c, p, return_debug=True)
     assert np.array_equal(want.numpy(), g["init_pose"])
@@ -124,19 +118,18 @@ def test_estimate_init_pose_vs_reference_golden(golden, name):
             assert abs(float(sc[r, 5]) - float(osc[r, 5])) <= 2e-5 * abs(float(osc[r, 5])) + 1e-7
     assert np.abs(pose.cpu().numpy() - g["init_pose"])[~amb].max() <= 1e-6
     # the same result with the swap decided on the device
-    src, dst = torch.from_numpy(g["src"]).to(dev), torch.from_numpy(g["dst"]).to(dev)
+    src, dst = put(torch.from_numpy(g["src"])), put(torch.from_numpy(g["dst"]))
     pose2 = ops.estimate_init_pose(args, src, dst, auto_swap=True)
     assert torch.equal(pose2, pose)
 
 
 @pytest.mark.parametrize("name", ["c1_demo.npz", "synth_hist.npz"])
 def test_apply_icp_vs_reference_golden(golden, name):
-    dev = _dev()
     g = golden(name)
     _, _, a, c = _swapped(g)
     args = _args(g)
     init = torch.from_numpy(g["init_pose"])
-    out, dbg = ops.apply_icp(args, a.to(dev), c.to(dev), init.to(dev), return_debug=True)
+    out, dbg = ops.apply_icp(args, put(a), put(c), put(init), return_debug=True)
     p = O.PathParams(thres_dist=args.thres_dist, translation_frame=args.translation_frame, chunk_size=args.chunk_size)
     want, odbg = O.apply_icp(a, c, init, p, return_debug=True)
     assert np.array_equal(want.numpy(), g["T_apply_icp"])
@@ -158,11 +151,10 @@ def test_apply_icp_vs_reference_golden(golden, name):
 @pytest.mark.parametrize("name", ["c1_demo.npz", "synth_hist.npz"])
 def test_hist_icp_vs_reference_golden(golden, name):
     """The whole path in one native call (utils_match.hist_icp), including the swap and the final inversion."""
-    dev = _dev()
     g = golden(name)
     src, dst, a, c = _swapped(g)
     args = _args(g)
-    T, dbg = ops.hist_icp(args, src.to(dev), dst.to(dev), return_debug=True)
+    T, dbg = ops.hist_icp(args, put(src), put(dst), return_debug=True)
     p = O.PathParams(thres_dist=args.thres_dist, translation_frame=args.translation_frame, chunk_size=args.chunk_size)
     amb = O.ambiguous_topk_rows(a, c, p).numpy()
     init_ok = np.abs(dbg["init"].cpu().numpy() - g["init_pose"]).reshape(len(amb), -1).max(1) <= 1e-6
@@ -182,10 +174,9 @@ def test_hist_icp_vs_reference_golden(golden, name):
 
 def test_c1_flow_vectors_within_tolerance(golden):
     """final scene-flow vectors of config C1 through the reference's own flow recovery."""
-    dev = _dev()
     g = golden("c1_demo.npz")
     args = _args(g)
-    T = ops.hist_icp(args, torch.from_numpy(g["src"]).to(dev), torch.from_numpy(g["dst"]).to(dev)).cpu()
+    T = ops.hist_icp(args, put(torch.from_numpy(g["src"])), put(torch.from_numpy(g["dst"]))).cpu()
     flow = O.flow_from_transforms(torch.from_numpy(g["flow_points"]), torch.from_numpy(g["flow_labels"]),
                                   torch.from_numpy(g["pair_labels"][:, 0]), T)
     diff = (flow - torch.from_numpy(g["flow"])).abs().amax(dim=1).numpy()
@@ -206,12 +197,11 @@ def test_c1_flow_vectors_within_tolerance(golden):
 
 def test_path_on_ragged_synthetic_batch_vs_oracle():
     from icp_flow_b200 import synth
-    dev = _dev()
     src, dst, _ = synth.make_pairs(40, 192, seed=9, ragged=True, residual_only=False, wrong_frac=0.1)
     args = types.SimpleNamespace(thres_dist=0.1, translation_frame=2.5, chunk_size=50)
     p = O.PathParams(thres_dist=0.1, translation_frame=2.5)
     want, odbg = O.hist_icp(torch.from_numpy(src), torch.from_numpy(dst), p, return_debug=True)
-    T, dbg = ops.hist_icp(args, torch.from_numpy(src).to(dev), torch.from_numpy(dst).to(dev), return_debug=True)
+    T, dbg = ops.hist_icp(args, put(torch.from_numpy(src)), put(torch.from_numpy(dst)), return_debug=True)
     init_ok = (dbg["init"].cpu() - odbg["init"]).abs().amax(dim=(1, 2)).numpy() <= 1e-6
     assert init_ok.mean() >= 0.9          # near-tied candidate scores may pick the other candidate
     sw = odbg["swapped"]
@@ -239,21 +229,20 @@ def test_padding_invariance_and_large_cluster_variant():
     """Padded rows must not change anything, and clusters padded beyond what fits shared memory (max_points up to
     10 000, BASELINE config C4) run the global-memory variant of the same kernels: bit-identical results."""
     from icp_flow_b200 import synth
-    dev = _dev()
     src, dst, _ = synth.make_pairs(12, 384, seed=17, ragged=True, residual_only=False, wrong_frac=0.1)
     args = types.SimpleNamespace(thres_dist=0.1, translation_frame=2.5, chunk_size=50)
-    base, base_dbg = ops.hist_icp(args, torch.from_numpy(src).to(dev), torch.from_numpy(dst).to(dev), return_debug=True)
-    base_icp = ops.icp_batch(torch.from_numpy(src).to(dev), torch.from_numpy(dst).to(dev), ops.make_params())
+    base, base_dbg = ops.hist_icp(args, put(torch.from_numpy(src)), put(torch.from_numpy(dst)), return_debug=True)
+    base_icp = ops.icp_batch(put(torch.from_numpy(src)), put(torch.from_numpy(dst)), ops.make_params())
     # the unbounded NN passes (candidate scores, errors before / after ICP) come from grid searches when the tiles and
     # their NN grids fit shared memory (N = 384, 1024) and from full scans otherwise (5000: shared memory without grids,
     # 10000: global memory): a minimum is a minimum, so the mean distances must agree bit for bit
-    _, base_init = ops.estimate_init_pose(args, torch.from_numpy(src).to(dev), torch.from_numpy(dst).to(dev),
+    _, base_init = ops.estimate_init_pose(args, put(torch.from_numpy(src)), put(torch.from_numpy(dst)),
                                           auto_swap=True, return_debug=True)
-    _, base_apply = ops.apply_icp(args, torch.from_numpy(src).to(dev), torch.from_numpy(dst).to(dev), base_dbg["init"],
+    _, base_apply = ops.apply_icp(args, put(torch.from_numpy(src)), put(torch.from_numpy(dst)), put(base_dbg["init"]),
                                   return_debug=True, auto_swap=True)
     assert torch.isfinite(base_init["scores"]).any(dim=1).all()
     for N in (1024, 5000, 10000):
-        s, d = torch.from_numpy(_repad(src, N)).to(dev), torch.from_numpy(_repad(dst, N)).to(dev)
+        s, d = put(torch.from_numpy(_repad(src, N))), put(torch.from_numpy(_repad(dst, N)))
         T, dbg = ops.hist_icp(args, s, d, return_debug=True)
         assert torch.equal(dbg["init"], base_dbg["init"]), N
         assert torch.equal(T, base), N
@@ -267,18 +256,17 @@ def test_padding_invariance_and_large_cluster_variant():
         r = ops.icp_batch(s, d, ops.make_params())
         assert torch.equal(r.R, base_icp.R) and torch.equal(r.T, base_icp.T) and torch.equal(r.iterations, base_icp.iterations), N
     with pytest.raises(RuntimeError, match="not supported"):
-        ops.icp_batch(torch.from_numpy(_repad(src, 20000)).to(dev), torch.from_numpy(_repad(dst, 20000)).to(dev),
+        ops.icp_batch(put(torch.from_numpy(_repad(src, 20000))), put(torch.from_numpy(_repad(dst, 20000))),
                       ops.make_params())
 
 
 def test_large_clusters_vs_oracle():
     """Clusters of several thousand points (global-memory variant) against the CPU oracle."""
     from icp_flow_b200 import synth
-    dev = _dev()
     src, dst, _ = synth.make_pairs(3, 6000, seed=23, ragged=True, residual_only=True, wrong_frac=0.0, min_points=3000,
                                    keep_density=False)
     ref = O.icp_loop(torch.from_numpy(src), torch.from_numpy(dst), 0.1, 100, 1e-6, diagnostics=True)
-    r = ops.icp_batch(torch.from_numpy(src).to(dev), torch.from_numpy(dst).to(dev), ops.make_params())
+    r = ops.icp_batch(put(torch.from_numpy(src)), put(torch.from_numpy(dst)), ops.make_params())
     pts = torch.from_numpy(src[:, :, :3]).double()
     valid = torch.from_numpy(src[:, :, 3] > 0)
     a = torch.bmm(pts, r.R.cpu().double()) + r.T.cpu().double()[:, None]
@@ -294,7 +282,6 @@ def test_histogram_global_fallback_for_wide_clusters(frame):
     global-memory histogram path; both paths must agree with the oracle (peaks, votes, chosen translation).
     translation_frame 6.666: the whole 135 x 135 window fits the u16 sub-histogram (fused path even for the 16 m patch);
     10.0: 201 x 201 columns do not fit, the wide pair takes the global-memory kernels."""
-    dev = _dev()
     rng = np.random.default_rng(3)
     N = 512
     src = np.full((3, N, 4), 1e8, np.float32); src[..., 3] = 0
@@ -309,7 +296,7 @@ def test_histogram_global_fallback_for_wide_clusters(frame):
         dst[k, :, :3] = moved; dst[k, :, 3] = 1
     args = types.SimpleNamespace(thres_dist=0.1, translation_frame=frame, chunk_size=50)
     p = O.PathParams(thres_dist=0.1, translation_frame=frame)
-    pose, dbg = ops.estimate_init_pose(args, torch.from_numpy(src).to(dev), torch.from_numpy(dst).to(dev), return_debug=True)
+    pose, dbg = ops.estimate_init_pose(args, put(torch.from_numpy(src)), put(torch.from_numpy(dst)), return_debug=True)
     want, odbg = O.estimate_init_pose(torch.from_numpy(src), torch.from_numpy(dst), p, return_debug=True)
     amb = O.ambiguous_topk_rows(torch.from_numpy(src), torch.from_numpy(dst), p).numpy()
     assert torch.equal(dbg["votes"].cpu(), odbg["votes"])

@@ -1,7 +1,8 @@
 """Known-answer tests of the path's semantics (SURVEY.md section 7 lists them; the reference ships none).
 
-Each case is checked on the CPU oracle (always) and, with `-m gpu`, on the engine through the same helper, so the two
-sides are held to the same analytic answers and not only to each other.
+Each case is checked on the CPU oracle, on the engine with `-m gpu`, and on the engine's kernels under the SIMT-on-CPU
+emulator (tests/simt/) through the same helper, so all sides are held to the same analytic answers and not only to
+each other.
 """
 import types
 
@@ -9,6 +10,8 @@ import numpy as np
 import pytest
 import torch
 
+import engines
+from engines import put
 from oracle import icp_oracle as O
 
 TAU = 0.1
@@ -47,9 +50,8 @@ class EngineSide:
     @staticmethod
     def hist_icp(src, dst, F):
         from icp_flow_b200 import ops
-        dev = torch.device("cuda:0")
         args = types.SimpleNamespace(thres_dist=TAU, translation_frame=F, chunk_size=50)
-        s, d = torch.from_numpy(src).to(dev), torch.from_numpy(dst).to(dev)
+        s, d = put(torch.from_numpy(src)), put(torch.from_numpy(dst))
         T, dbg = ops.hist_icp(args, s, d, return_debug=True)
         # roll-back flags through the apply_icp seam on the swapped clouds
         n_s, n_d = (s[:, :, 3] > 0).sum(1), (d[:, :, 3] > 0).sum(1)
@@ -62,16 +64,22 @@ class EngineSide:
     @staticmethod
     def icp(src, dst, iters=100):
         from icp_flow_b200 import ops
-        dev = torch.device("cuda:0")
-        r = ops.icp_batch(torch.from_numpy(src).to(dev), torch.from_numpy(dst).to(dev),
+        r = ops.icp_batch(put(torch.from_numpy(src)), put(torch.from_numpy(dst)),
                           ops.make_params(thres=TAU, max_iterations=iters))
         return r.R.cpu().numpy(), r.T.cpu().numpy()
 
 
-SIDES = [pytest.param(OracleSide, id="oracle"), pytest.param(EngineSide, id="engine", marks=pytest.mark.gpu)]
+@pytest.fixture(params=["oracle", pytest.param("cuda", marks=pytest.mark.gpu), "simt"])
+def side(request):
+    """oracle: the CPU restatement; cuda: the engine on the GPU; simt: the engine's kernels under the SIMT-on-CPU
+    emulator (tests/engines.py)."""
+    if request.param == "oracle":
+        yield OracleSide
+    else:
+        with engines.running(request.param):
+            yield EngineSide
 
 
-@pytest.mark.parametrize("side", SIDES)
 def test_identity_pair_gives_identity(side):
     """Identical clouds: R = I, T = 0 (to fp32), init translation exactly zero."""
     rng = np.random.default_rng(0)
@@ -84,7 +92,6 @@ def test_identity_pair_gives_identity(side):
     assert np.abs(moved - pts).max() < 2e-5
 
 
-@pytest.mark.parametrize("side", SIDES)
 def test_pure_translation_on_the_bin_lattice_is_recovered(side):
     """dst = src + (0.7, -0.4, 0): the histogram peak decodes to that lattice point and ICP keeps it."""
     rng = np.random.default_rng(1)
@@ -98,7 +105,6 @@ def test_pure_translation_on_the_bin_lattice_is_recovered(side):
     assert np.abs(moved - (pts + shift)).max() < 1e-3
 
 
-@pytest.mark.parametrize("side", SIDES)
 def test_zero_inlier_pair_is_identity_icp_and_rolls_back(side):
     """Clouds 5 m apart in z (outside the histogram's z range and the ICP gate): no votes -> zero init translation,
     no inliers -> ICP returns the identity, error does not drop -> roll back to the init pose."""
@@ -113,7 +119,6 @@ def test_zero_inlier_pair_is_identity_icp_and_rolls_back(side):
     assert np.abs(T[0, :3, :3] - np.eye(3)).max() == 0.0
 
 
-@pytest.mark.parametrize("side", SIDES)
 def test_padded_rows_do_not_matter(side):
     """The same clusters padded to 256 and to 640 rows give the same transforms."""
     rng = np.random.default_rng(3)
@@ -129,7 +134,6 @@ def test_padded_rows_do_not_matter(side):
     assert np.abs(moved - b).max() < 5e-3
 
 
-@pytest.mark.parametrize("side", SIDES)
 def test_swap_symmetry(side):
     """n_src > n_dst: the clouds are swapped internally and the result inverted (utils_match.py:139-154), so the
     transform still maps src onto dst."""
@@ -142,7 +146,6 @@ def test_swap_symmetry(side):
     assert np.array_equal(T[0, 3], np.array([0, 0, 0, 1], np.float32))
 
 
-@pytest.mark.parametrize("side", SIDES)
 def test_planar_and_tiny_clusters_stay_finite_rigid(side):
     """Exactly planar cluster (rank-2 cross-covariance) and a 4-point cluster: finite proper rotations."""
     rng = np.random.default_rng(5)

@@ -11,6 +11,7 @@ import numpy as np
 import pytest
 import torch
 
+from engines import put, sync
 from oracle import icp_oracle as O
 
 NAMES = ("errors", "inliers", "ratios", "ious", "translations", "rotations")
@@ -52,10 +53,9 @@ def _near_gate_pairs(src, dst, T, p, margin=1e-6):
 
 def _engine(src, dst, T, thres):
     from icp_flow_b200 import ops
-    dev = torch.device("cuda:0")
     args = types.SimpleNamespace(thres_dist=thres)
-    out = ops.match_eval(args, src.to(dev), dst.to(dev), T.to(dev))
-    torch.cuda.synchronize()
+    out = ops.match_eval(args, put(src), put(dst), put(T))
+    sync()
     return [o.cpu().numpy() for o in out]
 
 
@@ -69,7 +69,7 @@ def _compare(ev, ref, det):
     np.testing.assert_allclose(rots, ref["rotations"], atol=1e-4, equal_nan=True)
 
 
-@pytest.mark.gpu
+@pytest.mark.usefixtures("engine")
 @pytest.mark.parametrize("name", ["c1_demo.npz", "synth_hist.npz"])
 def test_engine_match_eval_vs_reference_golden(golden, name):
     g = golden(name)
@@ -79,7 +79,7 @@ def test_engine_match_eval_vs_reference_golden(golden, name):
     _compare(_engine(src, dst, T, float(g["thres_dist"])), {n: g["eval_" + n] for n in NAMES}, det)
 
 
-@pytest.mark.gpu
+@pytest.mark.usefixtures("engine")
 @pytest.mark.parametrize("P,N", [(64, 512), (3, 9000)])
 def test_engine_match_eval_vs_oracle_ragged_and_large(P, N):
     """Ragged batch incl. an EMPTY src cloud (0/0 -> NaN like the reference) and clusters beyond one staged tile."""
@@ -99,7 +99,7 @@ def test_engine_match_eval_vs_oracle_ragged_and_large(P, N):
     _compare(ev, ref, det)
 
 
-@pytest.mark.gpu
+@pytest.mark.usefixtures("engine")
 def test_engine_match_eval_known_answers():
     """dst = src + shift and T = that translation: zero error, every valid row an inlier, ratio 1, IoU n/(2n-n) = 1,
     translation = shift, angles 0; with T = identity and the shift > gate: no inliers."""
@@ -122,15 +122,14 @@ def test_engine_match_eval_known_answers():
     assert inliers[1].max() < n * 0.2 and np.abs(trans[1]).max() == 0.0
 
 
-@pytest.mark.gpu
+@pytest.mark.usefixtures("engine")
 def test_engine_match_eval_argument_errors():
     from icp_flow_b200 import _lib, ops
-    dev = torch.device("cuda:0")
-    a = torch.zeros(2, 16, 4, device=dev)
+    a = put(torch.zeros(2, 16, 4))
     with pytest.raises(ValueError):
-        ops.match_eval(types.SimpleNamespace(thres_dist=0.1), a, a, torch.eye(4, device=dev).repeat(3, 1, 1))
+        ops.match_eval(types.SimpleNamespace(thres_dist=0.1), a, a, put(torch.eye(4)).repeat(3, 1, 1))
     with pytest.raises(_lib.IcpfError):
-        ops.match_eval(types.SimpleNamespace(thres_dist=0.0), a, a, torch.eye(4, device=dev).repeat(2, 1, 1))
+        ops.match_eval(types.SimpleNamespace(thres_dist=0.0), a, a, put(torch.eye(4)).repeat(2, 1, 1))
 
 
 # ------------------------------------------------------------------------------------------ match_pairs (gates + selection)
@@ -176,7 +175,7 @@ def test_host_match_select_equals_oracle_loop(golden, name):
     assert rows0.shape == (0, 10) and T0.shape == (0, 4, 4)
 
 
-@pytest.mark.gpu
+@pytest.mark.usefixtures("engine")
 @pytest.mark.parametrize("name", ["c1_demo.npz", "synth_match_dyn.npz"])
 def test_engine_check_transformation_flags(golden, name):
     """Fused accept flag == check_transformation on the oracle's metrics (pairs near a gate excluded)."""
@@ -186,10 +185,9 @@ def test_engine_check_transformation_flags(golden, name):
     _, _, dbg = O.match_pairs(*(torch.from_numpy(x) for x in (sp, dp, sl, dl, pairs)), p, gates, return_debug=True)
     ev = dbg["evals"]
     want = np.array([O.check_transformation(ev[4][k], ev[5][k], min(ev[3][k]), p, gates) for k in range(len(pairs))])
-    dev = torch.device("cuda:0")
     args = types.SimpleNamespace(thres_dist=p.thres_dist, translation_frame=p.translation_frame,
                                  thres_iou=gates.thres_iou, thres_rot=gates.thres_rot)
-    out = ops.match_eval(args, dbg["segs_src"].to(dev), dbg["segs_dst"].to(dev), dbg["T"].to(dev), return_accept=True)
+    out = ops.match_eval(args, put(dbg["segs_src"]), put(dbg["segs_dst"]), put(dbg["T"]), return_accept=True)
     got = out[6].cpu().numpy().astype(bool)
     tn = torch.linalg.norm(ev[4], dim=1).numpy()
     near = (np.abs(tn - p.translation_frame) < 1e-4) | (np.abs(ev[3].min(1)[0].numpy() - gates.thres_iou) < 1e-3) | \
@@ -198,7 +196,7 @@ def test_engine_check_transformation_flags(golden, name):
     assert det.mean() > 0.8 and np.array_equal(got[det], want[det])
 
 
-@pytest.mark.gpu
+@pytest.mark.usefixtures("engine")
 @pytest.mark.parametrize("name", ["c1_demo.npz", "synth_match_dyn.npz"])
 def test_engine_match_pairs_vs_reference_golden(golden, name):
     """Whole match_pairs on the engine: same selected (src, dst) label pairs as the reference, metrics within tolerance
@@ -206,12 +204,11 @@ def test_engine_match_pairs_vs_reference_golden(golden, name):
     from icp_flow_b200 import ops
     g, sp, sl, dp, dl, pairs = _mp_inputs(golden, name)
     p, gates = _params(g), _gates(g)
-    dev = torch.device("cuda:0")
     args = types.SimpleNamespace(thres_dist=p.thres_dist, translation_frame=p.translation_frame, chunk_size=p.chunk_size,
                                  max_points=gates.max_points, thres_error=gates.thres_error, thres_iou=gates.thres_iou,
                                  thres_rot=gates.thres_rot)
     import icp_flow_b200
-    rows, T = icp_flow_b200.match_pairs(args, *(torch.from_numpy(x).to(dev) for x in (sp, dp, sl, dl, pairs)))
+    rows, T = icp_flow_b200.match_pairs(args, *(put(torch.from_numpy(x)) for x in (sp, dp, sl, dl, pairs)))
     rows, T = rows.cpu().numpy(), T.cpu().numpy()
     ref_rows, ref_T = g["mp_rows"], g["mp_T"]
     assert rows.shape[1] == 10
