@@ -281,7 +281,7 @@ def main():
     out = None
     outs = [None, None]
     gathered = [torch.empty(n_gpus * P, 4, 4, device=dev, dtype=torch.float32) for _ in range(2)]
-    launches_per_step = 3   # icp_pairs_kernel (first pass) + icp_resolve_batch_kernel + icp_pairs_kernel (re-run pass)
+    launches_per_step = 3   # icp_pairs_kernel + icp_resolve_batch_kernel + icp_select_batch_kernel (state at the batch stop)
     comm_stream = torch.cuda.Stream() if world > 1 else None
     peer = None
     gather_kind = "none"

@@ -104,10 +104,13 @@ __device__ __forceinline__ float moved_sq(const float (&dr)[9], const float (&dt
 //           always uses the exactly recomputed d_best^2, so the results are bit-identical to MODE 1/2.
 //   n_s / n_d : valid-row counts (knn `lengths`); tau2 = fp32(thres^2); pivot0 = any point near the clouds
 //   init_R / init_T (may be NULL) = init_transform of the reference: used for the first correspondence search only.
+//   hist (may be NULL) = this pair's [hist_depth][13] record of (R, T, rmse) after each iteration: when the batch stop
+//           falls on an iteration this pair went beyond, its state there is read back instead of re-running the pair.
 template <int MODE, class Tiles>
 __device__ __forceinline__ IcpResult icp_iterations(const Tiles& tl, const GridInfo& g, int n_s, int n_d, float tau2,
                                            int max_it, float rel_thr, bool early_exit, const float* init_R,
-                                           const float* init_T, float pivx, float pivy, float pivz) {
+                                           const float* init_T, float pivx, float pivy, float pivz,
+                                           float* __restrict__ hist = nullptr, int hist_depth = 0) {
     constexpr bool GRID = MODE >= 2;
     constexpr bool CACHE = MODE == 3;
     using NW = NnWord<Tiles::kPosBits>;
@@ -303,7 +306,10 @@ __device__ __forceinline__ IcpResult icp_iterations(const Tiles& tl, const GridI
             }
             __syncwarp();
             if (lane == 0) {
-                if (it > 0) record_rmse(res, it - 1, sqrtf(__fdiv_rn(total[16], W_prev)), rel_thr);
+                if (it > 0) {
+                    record_rmse(res, it - 1, sqrtf(__fdiv_rn(total[16], W_prev)), rel_thr);
+                    if (hist != nullptr && it - 1 < hist_depth) hist[(it - 1) * 13 + 12] = res.rmse;
+                }
                 const float W = fmaxf(total[0], 1e-9f);
                 const float sx0 = total[1], sx1 = total[2], sx2 = total[3];
                 const float sy0 = total[4], sy1 = total[5], sy2 = total[6];
@@ -382,6 +388,8 @@ __device__ __forceinline__ IcpResult icp_iterations(const Tiles& tl, const GridI
         }
         __syncthreads();
         done = bc[B_EXIT] != 0.f;
+        // (R, T) after this iteration; thread 0 rewrites the broadcast block only behind the next iteration's barriers
+        if (hist != nullptr && it < hist_depth && tid < 12) hist[it * 13 + tid] = bc[B_R + tid];
     }
 
     // ---------------- rmse of the last iteration executed (final transform against its own correspondences)
@@ -411,6 +419,7 @@ __device__ __forceinline__ IcpResult icp_iterations(const Tiles& tl, const GridI
             for (int w = 1; w < kWarps; ++w) s += part[w * kSums + 16];
             const float rmse = sqrtf(__fdiv_rn(s, W_prev));
             record_rmse(res, iters - 1, rmse, rel_thr);
+            if (hist != nullptr && iters - 1 < hist_depth) hist[(iters - 1) * 13 + 12] = rmse;
             if (iters < max_it) {
                 // stopped at a bitwise fixed point: every later iteration repeats this state, so its relative rmse is
                 // (rmse - rmse) / rmse = 0 (NaN when rmse == 0)

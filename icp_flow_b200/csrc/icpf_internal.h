@@ -19,11 +19,17 @@ namespace icpf {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// iters [P] int32 | conv [P,4] uint32 | batch [2] int32 (256 B slot) | stats [P,2] int32 {full searches, cache refreshes}
+// iters [P] int32 | conv [P,4] uint32 | batch [2] int32 + flags (256 B slot) | stats [P,2] int32 {full searches, cache
+// refreshes} | history [P, kIcpHistDepth, kIcpHistFloats] fp32: (R, T, rmse) after each of the first iterations of a pair
+constexpr int kIcpHistDepth = 32;      // = the iteration cap of the first pass (icpf_icp.cu)
+constexpr int kIcpHistFloats = 13;     // R[9] T[3] rmse
 inline size_t icp_ws_off_conv(int P) { return align_up((size_t)P * 4, 256); }
 inline size_t icp_ws_off_batch(int P) { return icp_ws_off_conv(P) + align_up((size_t)P * 16, 256); }
 inline size_t icp_ws_off_stats(int P) { return icp_ws_off_batch(P) + 256; }
-inline size_t icp_workspace_bytes(int P) { return icp_ws_off_stats(P) + align_up((size_t)P * 8, 256); }
+inline size_t icp_ws_off_hist(int P) { return icp_ws_off_stats(P) + align_up((size_t)P * 8, 256); }
+inline size_t icp_workspace_bytes(int P) {
+    return icp_ws_off_hist(P) + align_up((size_t)P * kIcpHistDepth * kIcpHistFloats * 4, 256);
+}
 
 int launch_icp(const float* src, const float* dst, const float* init_R, const float* init_T, const float* init_pose,
                int auto_swap, int P, int N, const icpf_params& prm, float* out_R, float* out_T,

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from engines import device, put, sync
+from engines import device, is_simt, put, sync
 from icp_flow_b200 import ops, synth
 from oracle import icp_oracle as O
 
@@ -266,3 +266,25 @@ def test_batch_stop_beyond_the_first_pass_cap():
         ref2 = O.icp_loop(torch.from_numpy(src[1:]), torch.from_numpy(dst[1:]), 0.1, r2.batch.tolist()[0], -1.0,
                           diagnostics=True)
     _assert_parity(src[1:], r2.R.cpu(), r2.T.cpu(), ref2.R, ref2.T, ref2, max_unstable_frac=0.35)
+
+
+@pytest.mark.parametrize("case", ["stop_inside_the_record", "stop_beyond_the_first_pass"])
+def test_state_at_the_batch_stop_equals_a_forced_run(case):
+    """Whatever way a pair obtains its state at the batch stop k* -- it stopped at its fixed point before, it reads the
+    per-iteration record of the first pass (k* < 32), or it is re-run (k* beyond the capped first pass) -- the result
+    must be, bit for bit, what running every pair for exactly k*+1 iterations gives (utils_icp_pytorch3d.py:209: the
+    reference stops ALL pairs at that iteration)."""
+    if case == "stop_inside_the_record":
+        src, dst, _ = synth.make_pairs(24, 192, seed=5, ragged=True, residual_only=True, wrong_frac=0.0)
+    else:
+        src, dst, _ = synth.make_pairs(96, 1024, seed=5, ragged=False, residual_only=True, wrong_frac=0.0)
+        keep = [0, 1, 2, 3, 37, 73, 87]            # three slow pairs (41-48 iterations) among fast ones
+        src, dst = src[keep], dst[keep]
+    r = _run(src, dst, max_iterations=100, relative_rmse_thr=1e-6, early_exit=True, batch_stop=True)
+    its, conv = r.batch.tolist()
+    assert conv == 1
+    if is_simt():
+        assert (its < 32) if case == "stop_inside_the_record" else (its > 32), its      # the path this case is about
+    assert int(r.iterations.max()) == its and int(r.iterations.min()) < its
+    f = _run(src, dst, max_iterations=its, relative_rmse_thr=-1.0, early_exit=False, batch_stop=False)
+    assert torch.equal(r.R, f.R) and torch.equal(r.T, f.T) and torch.equal(r.rmse, f.rmse) and torch.equal(r.pose, f.pose)
