@@ -145,8 +145,11 @@ __global__ void __launch_bounds__(kThreads) match_eval_kernel(EvalArgs a) {
         eval_direction_grid<false>(m, D, n_d, gS, ts.sorted_p, reinterpret_cast<const unsigned short*>(ts.cells_p), n_s,
                                    a.thr, acc[2], acc[3]);
     } else {
-        eval_direction<true>(m, S, n_s, D, n_d > 0 ? n_d : a.N, a.thr, tile, acc[0], acc[1]);
-        eval_direction<false>(m, D, n_d, S, n_s > 0 ? n_s : a.N, a.thr, tile, acc[2], acc[3]);
+        // (an empty cloud in the grid variant lands here too: its one-row `tile` is a placeholder, the staging area is
+        //  the dynamic shared memory the grids would have used -- 2 (N + 257) rows, a tile holds at most min(kEvTile, N))
+        float4* stage = GRIDNN ? g_tile : tile;
+        eval_direction<true>(m, S, n_s, D, n_d > 0 ? n_d : a.N, a.thr, stage, acc[0], acc[1]);
+        eval_direction<false>(m, D, n_d, S, n_s > 0 ? n_s : a.N, a.thr, stage, acc[2], acc[3]);
     }
     __syncthreads();
     block_allreduce_sum<4, kWarps>(acc, s_scratch);

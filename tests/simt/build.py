@@ -31,16 +31,31 @@ def _deps():
             + glob.glob(os.path.join(HERE, "shim", "*")) + [os.path.join(ROOT, "include", "icpflow_b200.h"), __file__])
 
 
-def stale() -> bool:
-    if not os.path.exists(OUT):
+def stale_against(path: str) -> bool:
+    if not os.path.exists(path):
         return True
-    t = os.path.getmtime(OUT)
+    t = os.path.getmtime(path)
     return any(os.path.getmtime(d) > t for d in _deps())
 
 
+def stale() -> bool:
+    return stale_against(OUT)
+
+
+ASAN_OUT = os.path.join(BUILD, "libicpflow_simt_asan.so")
+# AddressSanitizer variant (tests/simt/memcheck.sh): every "global memory" access of a kernel is checked against the
+# bounds of the host allocation behind it, and the dynamic shared-memory arrays get red zones.  Stack instrumentation is
+# off because the fibers switch stacks behind ASan's back.
+ASAN_FLAGS = ["-fsanitize=address", "--param", "asan-stack=0", "-fno-omit-frame-pointer"]
+
+
 def build(force: bool = False, extra_flags=(), out: str = OUT) -> str:
+    if os.environ.get("ICPF_SIMT_ASAN") == "1" and out == OUT:
+        out, extra_flags, force = ASAN_OUT, tuple(extra_flags) + tuple(ASAN_FLAGS), force or not os.path.exists(ASAN_OUT) or stale_against(ASAN_OUT)
     if not force and out == OUT and not stale():
         return OUT
+    if not force and out != OUT and os.path.exists(out) and not stale_against(out):
+        return out
     os.makedirs(BUILD, exist_ok=True)
     tag = os.path.splitext(os.path.basename(out))[0]
     units = [(s, ["-x", "c++"]) for s in sorted(glob.glob(os.path.join(CSRC, "*.cu")))]
@@ -55,7 +70,7 @@ def build(force: bool = False, extra_flags=(), out: str = OUT) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:
         objs = list(ex.map(compile_one, units))
-    subprocess.check_call([CXX, "-shared", "-o", out] + objs)
+    subprocess.check_call([CXX, "-shared", "-o", out] + [f for f in extra_flags if f.startswith("-fsanitize")] + objs)
     return out
 
 

@@ -169,7 +169,27 @@ const uint64_t* exchange(unsigned mask, uint64_t v, unsigned* members) {
     return w.slot[buf];
 }
 
-void register_dyn_shared(void* base) { g_dyn_shared.push_back(base); }
+void register_dyn_shared(void* base) {
+    memset(base, 0xff, kDynSharedBytes);
+    g_dyn_shared.push_back(base);
+}
+
+namespace {
+// A block may only touch the `smem` bytes it was launched with: everything behind them must still hold the poison.
+void check_dyn_shared_tail(size_t smem) {
+    const size_t lo = smem ? smem : 16, hi = lo + 65536 < kDynSharedBytes ? lo + 65536 : kDynSharedBytes;
+    for (void* base : g_dyn_shared) {
+        const unsigned char* b = static_cast<const unsigned char*>(base);
+        for (size_t i = lo; i < hi; ++i) {
+            if (b[i] != 0xff) {
+                fprintf(stderr, "simt: block (%u,%u,%u) wrote dynamic shared memory at byte %zu, beyond the %zu bytes of its launch\n",
+                        cur.bid.x, cur.bid.y, cur.bid.z, i, smem);
+                abort();
+            }
+        }
+    }
+}
+}  // namespace
 
 void run_grid(dim3 grid, dim3 block, size_t smem, void (*thread_fn)(void*), void* ctx) {
     const int nthreads = (int)(block.x * block.y * block.z);
@@ -183,7 +203,10 @@ void run_grid(dim3 grid, dim3 block, size_t smem, void (*thread_fn)(void*), void
         for (unsigned by = 0; by < grid.y; ++by)
             for (unsigned bx = 0; bx < grid.x; ++bx) {
                 // poison the dynamic shared memory: reading a word no thread of THIS block wrote yields NaN / 0xffff
-                for (void* base : g_dyn_shared) memset(base, 0xff, smem ? smem : 16);
+                {   // (the tail behind `smem` is re-poisoned too: check_dyn_shared_tail looks at it after the block)
+                    const size_t lo = smem ? smem : 16, n = lo + 65536 < kDynSharedBytes ? lo + 65536 : kDynSharedBytes;
+                    for (void* base : g_dyn_shared) memset(base, 0xff, n);
+                }
                 g_blk.nthreads = nthreads;
                 g_blk.live = nthreads;
                 g_blk.bar_arrived = 0;
@@ -211,6 +234,7 @@ void run_grid(dim3 grid, dim3 block, size_t smem, void (*thread_fn)(void*), void
                 g_spins = 0;
                 switch_to(0);      // returns when the last fiber of the block has finished
                 if (g_blk.live != 0) { fprintf(stderr, "simt: block ended with %d live threads\n", g_blk.live); abort(); }
+                check_dyn_shared_tail(smem);
             }
 }
 
