@@ -222,11 +222,13 @@ __device__ __forceinline__ IcpResult icp_iterations(const Tiles& tl, const GridI
                         const float m = fast_sqrt(m2) * 1.0001f;
                         // (a) every other point is provably farther than tau: only the cached candidate can pass
                         bool hit = bound > tau_hi + m;
-                        // (b) the cached candidate is provably still the strict nearest neighbour: (d_best + m) < B
-                        if (pos >= 0) hit = hit || ((d2 + 2.0002f * fast_sqrt(d2 * m2) + m2) * 1.0002f < bound * bound);
+                        // (b) the cached candidate is provably still the strict nearest neighbour: d_best < B - m, tested on
+                        //     the squares (rem > 0), with 1.5e-4 of head-room for the rounding of either side
+                        const float rem = bound - m;
+                        if (pos >= 0) hit = hit || (rem > 0.f && d2 * 1.0003f < rem * rem);
                         if (hit) {
                             // re-anchor: relative to the row's NEW position every other point is >= bound - m away
-                            nnw[q] = NW::pack(pos, bound - m - anchor_slack, (pos >= 0) && (d2 <= tau2) && (x0.w > 0.f));
+                            nnw[q] = NW::pack(pos, rem - anchor_slack, (pos >= 0) && (d2 <= tau2) && (x0.w > 0.f));
                             need = false;
                         }
                     }
