@@ -1,0 +1,57 @@
+"""Kernel variants that must agree bit for bit, compared under the SIMT-on-CPU emulator (tests/simt/): the product
+build of a kernel against a build of the same sources with the simpler algorithm it replaces switched back on.
+
+  ICPF_GRIDNN_FULL_SCAN   far queries of the unbounded NN (csrc/icpf_gridnn.cuh) scan every row, as the reference does,
+                          instead of visiting the grid slab by slab with lower-bound pruning.  The NN distance is a
+                          minimum, so hist_score's scores, apply_icp's errors and match_eval's metrics must not move
+                          by a bit."""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "simt"))
+import build as simt_build  # noqa: E402
+import harness  # noqa: E402
+from icp_flow_b200 import ops, synth  # noqa: E402
+
+
+def _path_outputs(src, dst, args):
+    put = harness.dev_tensor
+    pose, dbg = ops.estimate_init_pose(args, put(src), put(dst), return_debug=True)
+    out, adbg = ops.apply_icp(args, put(src), put(dst), put(pose), return_debug=True, auto_swap=True)
+    ev = ops.match_eval(args, put(src), put(dst), put(out))
+    res = {"pose": pose, "out": out}
+    res.update({"init_" + k: v for k, v in dbg.items() if torch.is_tensor(v)})
+    res.update({"apply_" + k: v for k, v in adbg.items() if torch.is_tensor(v)})
+    res.update({f"eval_{i}": v for i, v in enumerate(ev)})
+    return {k: harness.plain(v).clone() for k, v in res.items()}
+
+
+def test_pruned_far_query_search_equals_the_full_scan():
+    args = types.SimpleNamespace(thres_dist=0.1, translation_frame=6.666, chunk_size=50)
+    batches = []
+    # unrelated clusters (every query far), large motions (most candidate translations are wrong), ragged sizes
+    s, d, _ = synth.make_pairs(12, 256, seed=3, ragged=True, residual_only=False, wrong_frac=0.5)
+    batches.append((s, d))
+    s, d, _ = synth.make_pairs(6, 700, seed=8, ragged=False, residual_only=False, wrong_frac=0.3)
+    d = d.copy()
+    d[0, :, :3] = np.where(d[0, :, 3:4] > 0, d[0, :, :3] + np.float32(40.0), d[0, :, :3])       # tens of metres apart
+    d[1, :, 1] = np.where(d[1, :, 3] > 0, d[1, :, 1] - np.float32(7.5), d[1, :, 1])             # far along y only
+    batches.append((s, d))
+    variant = os.path.join(simt_build.BUILD, "libicpflow_simt_fullscan.so")
+    got, want = [], []
+    with harness.emulated():
+        for s, d in batches:
+            got.append(_path_outputs(s, d, args))
+    with harness.emulated(extra_flags=("-DICPF_GRIDNN_FULL_SCAN",), out=variant):
+        for s, d in batches:
+            want.append(_path_outputs(s, d, args))
+    for g, w in zip(got, want):
+        assert g.keys() == w.keys()
+        for k in g:
+            a, b = g[k], w[k]
+            same = torch.equal(a, b) if not a.is_floating_point() else torch.equal(a.nan_to_num(-7.0), b.nan_to_num(-7.0))
+            assert same, k
