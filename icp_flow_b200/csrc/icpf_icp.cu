@@ -6,9 +6,8 @@
 //   kernel 1  every pair iterates to its bitwise fixed point (or max_iterations) and records, per iteration, whether
 //             its relative-rmse test passed (128-bit mask);
 //   kernel 2  AND-reduces the masks over the batch -> k* = first iteration at which the reference's `.all()` fires;
-//   kernel 3  gives the pairs that were still moving at k* their state at k*: read back from the per-iteration record
-//             (R, T, rmse) the first pass keeps for its first 32 iterations, or -- when k* lies beyond that record --
-//             by re-running those pairs capped at k*+1 iterations.
+//   kernel 3  gives the pairs that were still moving at k* their state at k*, read back from the per-iteration record
+//             (R, T, rmse; 52 B per pair and iteration) kernel 1 keeps -- no pair is run twice for it.
 #include "icpf_internal.h"
 #include <type_traits>
 
@@ -37,9 +36,7 @@ struct IcpArgs {
     int* iters;            // [P] (never NULL inside the library)
     uint32_t* conv;        // [P,4]
     int* stats;            // [P,2] {full searches, cache refreshes} of the first pass
-    const int* batch;      // re-run pass: batch[0] = k*+1 (iterations the reference executed); NULL otherwise
     const int* decided;    // second full pass: runs only while *decided == 0; NULL otherwise
-    const int* skip;       // re-run pass: nothing to do when *skip != 0 (the record answered already); may be NULL
     float* hist;           // [P, kIcpHistDepth, 13] (R, T, rmse) after each iteration, or NULL
     int cap;               // first pass: iteration cap (<= max_it)
     unsigned char* big_ws; // global-memory variant: per-pair workspace (pair_global_ws_bytes(N) each)
@@ -53,14 +50,7 @@ __global__ void __launch_bounds__(kThreads, BIG ? 4 : 7) icp_pairs_kernel(IcpArg
     const int p = blockIdx.x;
     int max_it = a.max_it;
     bool early_exit = a.early_exit != 0;
-    if (a.batch != nullptr) {
-        // re-run pass: only pairs that executed more iterations than the batch did need their state at k*
-        if (a.skip != nullptr && *a.skip != 0) return;
-        const int batch_iters = a.batch[0];
-        if (a.iters[p] <= batch_iters) return;
-        max_it = batch_iters;
-        early_exit = false;
-    } else if (a.decided != nullptr) {
+    if (a.decided != nullptr) {
         if (*a.decided != 0) return;      // the capped first pass already found the batch stop
         if (a.iters[p] < a.cap) {
             // This pair stopped at its bitwise fixed point below the cap: every later iteration repeats that state, so
@@ -139,8 +129,7 @@ __global__ void __launch_bounds__(kThreads, BIG ? 4 : 7) icp_pairs_kernel(IcpArg
     const IcpResult r = icp_iterations<MODE>(tl, g, n_s, n_d, a.tau2, max_it, a.rel_thr, early_exit,
                                        a.init_R ? a.init_R + (size_t)p * 9 : nullptr,
                                        a.init_T ? a.init_T + (size_t)p * 3 : nullptr, piv.x, piv.y, piv.z,
-                                       (a.hist != nullptr && a.batch == nullptr)
-                                           ? a.hist + (size_t)p * kIcpHistDepth * kIcpHistFloats : nullptr,
+                                       a.hist != nullptr ? a.hist + (size_t)p * kIcpHistDepth * kIcpHistFloats : nullptr,
                                        kIcpHistDepth);
 
     // the final (R, T) also sit in the broadcast block (no dynamic register indexing)
@@ -169,25 +158,21 @@ __global__ void __launch_bounds__(kThreads, BIG ? 4 : 7) icp_pairs_kernel(IcpArg
     if (threadIdx.x == 0) {
         if (a.out_rmse) a.out_rmse[p] = r.rmse;
         a.iters[p] = r.iters;
-        if (a.batch == nullptr) {
-            a.stats[(size_t)p * 2 + 0] = (int)r.searches;
-            a.stats[(size_t)p * 2 + 1] = r.refreshes;
-            a.conv[(size_t)p * 4 + 0] = (uint32_t)r.conv_lo;
-            a.conv[(size_t)p * 4 + 1] = (uint32_t)(r.conv_lo >> 32);
-            a.conv[(size_t)p * 4 + 2] = (uint32_t)r.conv_hi;
-            a.conv[(size_t)p * 4 + 3] = (uint32_t)(r.conv_hi >> 32);
-        }
+        a.stats[(size_t)p * 2 + 0] = (int)r.searches;
+        a.stats[(size_t)p * 2 + 1] = r.refreshes;
+        a.conv[(size_t)p * 4 + 0] = (uint32_t)r.conv_lo;
+        a.conv[(size_t)p * 4 + 1] = (uint32_t)(r.conv_lo >> 32);
+        a.conv[(size_t)p * 4 + 2] = (uint32_t)r.conv_hi;
+        a.conv[(size_t)p * 4 + 3] = (uint32_t)(r.conv_hi >> 32);
     }
 }
 
 // AND of the per-pair convergence masks -> first iteration k* where every pair passes (utils_icp_pytorch3d.py:209).
 // batch[0] = iterations the reference loop would have executed, batch[1] = converged flag.
 // `limit` = iterations the masks cover (the cap of the first pass, or max_it); `decided` (may be NULL) is set to 1 when
-// the answer is final and left 0 when the capped pass could not tell (a later full pass decides); `decided_first` (may be
-// NULL) receives the same verdict and is not touched by the resolve that follows the full pass.
+// the answer is final and left 0 when the capped pass could not tell (a later full pass decides).
 __global__ void __launch_bounds__(256) icp_resolve_batch_kernel(const uint32_t* conv, int P, int max_it, int limit,
-                                                                int batch_stop, int* batch, int* decided,
-                                                                int* decided_first) {
+                                                                int batch_stop, int* batch, int* decided) {
     __shared__ uint32_t s_and[4];
     if (decided != nullptr && limit == max_it && *decided != 0) return;     // second resolve, nothing left to do
     if (threadIdx.x < 4) s_and[threadIdx.x] = 0xffffffffu;
@@ -223,17 +208,15 @@ __global__ void __launch_bounds__(256) icp_resolve_batch_kernel(const uint32_t* 
             verdict = 0;
         }
         if (decided) *decided = verdict;
-        if (decided_first) *decided_first = verdict;
     }
 }
 
 // State at the batch stop from the per-iteration record: a pair that executed more iterations than the batch did
-// (batch[0] = k* + 1 <= kIcpHistDepth) takes (R, T, rmse) of iteration k* and reports k* + 1 iterations -- what the re-run
-// pass would compute (same bits: the record holds the very values that run produced).  One thread per pair.
+// (batch[0] = k* + 1 <= kIcpHistDepth) takes (R, T, rmse) of iteration k* and reports k* + 1 iterations -- exactly what
+// running it for k* + 1 iterations gives (the record holds the very values that run produced).  One thread per pair.
 struct IcpSelectArgs {
     const float* hist;
     const int* batch;
-    const int* decided;    // acts only when *decided != 0 (NULL: always)
     int P;
     int* iters;
     float* out_R;
@@ -248,7 +231,6 @@ struct IcpSelectArgs {
 __global__ void __launch_bounds__(128) icp_select_batch_kernel(IcpSelectArgs a) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.P) return;
-    if (a.decided != nullptr && *a.decided == 0) return;
     const int b = a.batch[0];
     if (a.iters[p] <= b || b < 1 || b > kIcpHistDepth) return;
     const float* h = a.hist + ((size_t)p * kIcpHistDepth + (b - 1)) * kIcpHistFloats;
@@ -340,7 +322,7 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
     a.rel_thr = prm.relative_rmse_thr;
     a.early_exit = prm.early_exit;
     a.out_R = out_R; a.out_T = out_T; a.out_rmse = out_rmse; a.out_pose = out_pose;
-    a.iters = iters; a.conv = conv; a.batch = nullptr; a.decided = nullptr; a.skip = nullptr;
+    a.iters = iters; a.conv = conv; a.decided = nullptr;
     // Pairs that never reach a bitwise fixed point (limit cycles of a few ulp, non-convergent clusters) would run all
     // max_iterations in the first pass although the reference's batch stop fires after 10-25: cap the first pass and
     // fall back to a full pass only when the batch stop was not found below the cap.
@@ -351,14 +333,10 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
     a.peer_pose = t_peer_pose; a.peer_world = t_peer_world; a.peer_row0 = t_peer_row0;
     t_peer_pose = nullptr;       // one-shot: applies to this call only
     int* decided = reinterpret_cast<int*>(ws + icp_ws_off_batch(P)) + 8;
-    int* decided_first = decided + 1;
     a.stats = reinterpret_cast<int*>(ws + icp_ws_off_stats(P));
-    // The first pass records (R, T, rmse) after each of its first kIcpHistDepth iterations whenever a batch stop inside
-    // that window is possible; the pairs still moving at the stop then read their state back instead of being re-run.
-    const bool use_hist = prm.batch_stop && a.cap <= kIcpHistDepth;
-    a.hist = use_hist ? reinterpret_cast<float*>(ws + icp_ws_off_hist(P)) : nullptr;
-    const float* hist = a.hist;
-    float* const* peer_pose = a.peer_pose;
+    // With a batch stop every pair records (R, T, rmse) after each iteration; the pairs still moving at the stop read
+    // their state back from that record (icp_select_batch_kernel) instead of being run again.
+    a.hist = prm.batch_stop ? reinterpret_cast<float*>(ws + icp_ws_off_hist(P)) : nullptr;
     if (t_prof_start && t_prof_stop) cudaEventRecord(t_prof_start, stream);
     ICPF_LAUNCH(kernel, P, kThreads, smem, stream)(a);
     err = cudaGetLastError();
@@ -367,36 +345,26 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
         t_prof_start = t_prof_stop = nullptr;
     }
     if (err != cudaSuccess) return (int)err;
-    a.hist = nullptr;
 
     ICPF_LAUNCH(icp_resolve_batch_kernel, 1, 256, 0, stream)(conv, P, prm.max_iterations, a.cap, prm.batch_stop, batch,
-                                                    capped ? decided : nullptr, capped ? decided_first : nullptr);
+                                                    capped ? decided : nullptr);
     err = cudaGetLastError();
     if (err != cudaSuccess) return (int)err;
-    if (use_hist) {
-        IcpSelectArgs sa;
-        sa.hist = hist; sa.batch = batch; sa.decided = capped ? decided_first : nullptr; sa.P = P; sa.iters = iters;
-        sa.out_R = out_R; sa.out_T = out_T; sa.out_rmse = out_rmse; sa.out_pose = out_pose;
-        sa.peer_pose = peer_pose; sa.peer_world = a.peer_world; sa.peer_row0 = a.peer_row0;
-        ICPF_LAUNCH(icp_select_batch_kernel, (P + 127) / 128, 128, 0, stream)(sa);
-        err = cudaGetLastError();
-        if (err != cudaSuccess) return (int)err;
-    }
     if (capped) {
         a.decided = decided;
         ICPF_LAUNCH(kernel, P, kThreads, smem, stream)(a);
         a.decided = nullptr;
         ICPF_LAUNCH(icp_resolve_batch_kernel, 1, 256, 0, stream)(conv, P, prm.max_iterations, prm.max_iterations, prm.batch_stop,
-                                                        batch, decided, nullptr);
+                                                        batch, decided);
         err = cudaGetLastError();
         if (err != cudaSuccess) return (int)err;
     }
-
-    // re-run pass: only when the record could not answer (batch stop beyond the first pass, or no record at all)
-    if (prm.batch_stop && (capped || !use_hist)) {
-        a.batch = batch;
-        a.skip = capped ? decided_first : nullptr;
-        ICPF_LAUNCH(kernel, P, kThreads, smem, stream)(a);
+    if (prm.batch_stop) {
+        IcpSelectArgs sa;
+        sa.hist = a.hist; sa.batch = batch; sa.P = P; sa.iters = iters;
+        sa.out_R = out_R; sa.out_T = out_T; sa.out_rmse = out_rmse; sa.out_pose = out_pose;
+        sa.peer_pose = a.peer_pose; sa.peer_world = a.peer_world; sa.peer_row0 = a.peer_row0;
+        ICPF_LAUNCH(icp_select_batch_kernel, (P + 127) / 128, 128, 0, stream)(sa);
         err = cudaGetLastError();
         if (err != cudaSuccess) return (int)err;
     }

@@ -20,8 +20,8 @@ namespace icpf {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // iters [P] int32 | conv [P,4] uint32 | batch [2] int32 + flags (256 B slot) | stats [P,2] int32 {full searches, cache
-// refreshes} | history [P, kIcpHistDepth, kIcpHistFloats] fp32: (R, T, rmse) after each of the first iterations of a pair
-constexpr int kIcpHistDepth = 32;      // = the iteration cap of the first pass (icpf_icp.cu)
+// refreshes} | history [P, kIcpHistDepth, kIcpHistFloats] fp32: (R, T, rmse) after each of the first 128 iterations of a pair
+constexpr int kIcpHistDepth = 128;     // = the iterations the 128-bit convergence masks cover: a batch stop lies inside
 constexpr int kIcpHistFloats = 13;     // R[9] T[3] rmse
 inline size_t icp_ws_off_conv(int P) { return align_up((size_t)P * 4, 256); }
 inline size_t icp_ws_off_batch(int P) { return icp_ws_off_conv(P) + align_up((size_t)P * 16, 256); }
