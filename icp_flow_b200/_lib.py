@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("ICPF_LIB_PATH") or os.path.join(_HERE, "libicpflow_b2
 EXPORTS = (
     "icpf_version", "icpf_error_string", "icpf_default_params", "icpf_workspace_bytes",
     "icpf_icp_f32", "icpf_nn_f32", "icpf_transform_points_f32", "icpf_host_kabsch", "icpf_profile_next_icp",
-    "icpf_host_kabsch_sequence", "icpf_peer_gather_next_icp", "icpf_hist_votes_f32", "icpf_hist_init_f32", "icpf_apply_icp_f32", "icpf_hist_icp_f32",
+    "icpf_host_kabsch_sequence", "icpf_peer_gather_next_icp", "icpf_hist_votes_f32", "icpf_hist_init_f32", "icpf_apply_icp_f32", "icpf_apply_icp_phase_f32", "icpf_hist_icp_f32",
     "icpf_match_eval_f32",
     "icpf_cluster_index_workspace_bytes", "icpf_cluster_index_f32", "icpf_sanity_check_f32", "icpf_gather_pairs_f32",
     "icpf_flow_f32",
@@ -105,6 +105,9 @@ def lib() -> ctypes.CDLL:
     L.icpf_apply_icp_f32.restype = ctypes.c_int
     L.icpf_apply_icp_f32.argtypes = [vp, vp, vp, i32, i32, ctypes.POINTER(IcpfParams), i32, vp, vp, vp, vp, vp,
                                      ctypes.c_size_t, vp]
+    L.icpf_apply_icp_phase_f32.restype = ctypes.c_int
+    L.icpf_apply_icp_phase_f32.argtypes = [vp, vp, vp, i32, i32, ctypes.POINTER(IcpfParams), i32, i32, i32, i32, vp, vp, vp,
+                                           vp, vp, vp, ctypes.c_size_t, vp]
     L.icpf_hist_icp_f32.restype = ctypes.c_int
     L.icpf_hist_icp_f32.argtypes = [vp, vp, i32, i32, ctypes.POINTER(IcpfHistBins), ctypes.POINTER(IcpfParams), vp, vp,
                                     vp, vp, ctypes.c_size_t, vp]

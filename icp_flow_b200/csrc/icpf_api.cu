@@ -150,6 +150,25 @@ int icpf_apply_icp_f32(const float* src, const float* dst, const float* init_pos
                             workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
+int icpf_apply_icp_phase_f32(const float* src, const float* dst, const float* init_pose, int32_t P, int32_t N,
+                             const icpf_params* params, int32_t auto_swap, int32_t phase, int32_t batch_iterations,
+                             int32_t batch_converged, uint32_t* out_and, float* out_pose, float* out_err,
+                             int32_t* out_flags, int32_t* out_batch, void* workspace, size_t workspace_bytes,
+                             void* stream) {
+    const int rc = check_params(params);
+    if (rc != ICPF_OK) return rc;
+    if (P < 0 || N <= 0) return ICPF_E_SHAPE;
+    if (phase < 0 || phase > 2 || !params->batch_stop) return ICPF_E_PARAM;
+    if (phase == 2 && (batch_iterations < 1 || batch_iterations > params->max_iterations)) return ICPF_E_PARAM;
+    if (P == 0) return ICPF_OK;
+    if (!src || !dst || !init_pose) return ICPF_E_NULL;
+    if (phase < 2 ? !out_and : !out_pose) return ICPF_E_NULL;
+    if (!aligned16(src) || !aligned16(dst)) return ICPF_E_ALIGN;
+    IcpPhase ph{phase, batch_iterations, batch_converged != 0 ? 1 : 0, out_and};
+    return launch_apply_icp(src, dst, init_pose, P, N, *params, auto_swap, out_pose, out_err, out_flags, out_batch,
+                            workspace, workspace_bytes, static_cast<cudaStream_t>(stream), &ph);
+}
+
 int icpf_hist_icp_f32(const float* src, const float* dst, int32_t P, int32_t N, const icpf_hist_bins* bins,
                       const icpf_params* params, float* out_pose, float* out_init, int32_t* out_batch,
                       void* workspace, size_t workspace_bytes, void* stream) {

@@ -245,13 +245,16 @@ int launch_hist_init(const float* src, const float* dst, int P, int N, const icp
 
 int launch_apply_icp(const float* src, const float* dst, const float* init_pose, int P, int N, const icpf_params& prm,
                      int auto_swap, float* out_pose, float* out_err, int* out_flags, int* out_batch, void* workspace,
-                     size_t workspace_bytes, cudaStream_t stream) {
+                     size_t workspace_bytes, cudaStream_t stream, const IcpPhase* phase) {
     if (P == 0) return ICPF_OK;
     if (workspace == nullptr || workspace_bytes < path_workspace_bytes(P, N, 0, 0, 0)) return ICPF_E_WORKSPACE;
     PathWs w = carve_ws(workspace, P, N);
+    // (a phased call keeps iterations and masks in the workspace between its phases: out_iters / out_conv stay NULL)
     int rc = launch_icp(src, dst, nullptr, nullptr, init_pose, auto_swap, P, N, prm, w.R, w.T, nullptr, nullptr,
-                        nullptr, nullptr, out_batch, w.icp, icp_workspace_bytes(P) + icp_big_workspace_bytes(P, N), stream);
+                        nullptr, nullptr, out_batch, w.icp, icp_workspace_bytes(P) + icp_big_workspace_bytes(P, N), stream,
+                        phase);
     if (rc != ICPF_OK) return rc;
+    if (phase != nullptr && phase->phase < 2) return ICPF_OK;
     return launch_icp_finalize(src, dst, P, N, init_pose, w.R, w.T, auto_swap, (float)prm.thres_dist, out_pose, out_err,
                                out_flags, stream);
 }

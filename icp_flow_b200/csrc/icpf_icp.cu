@@ -170,9 +170,11 @@ __global__ void __launch_bounds__(kThreads, BIG ? 4 : 7) icp_pairs_kernel(IcpArg
 // AND of the per-pair convergence masks -> first iteration k* where every pair passes (utils_icp_pytorch3d.py:209).
 // batch[0] = iterations the reference loop would have executed, batch[1] = converged flag.
 // `limit` = iterations the masks cover (the cap of the first pass, or max_it); `decided` (may be NULL) is set to 1 when
-// the answer is final and left 0 when the capped pass could not tell (a later full pass decides).
+// the answer is final and left 0 when the capped pass could not tell (a later full pass decides); `and_out` (may be NULL)
+// receives the AND of the masks -- what a caller with several shards exchanges (IcpPhase, icpf_internal.h).
 __global__ void __launch_bounds__(256) icp_resolve_batch_kernel(const uint32_t* conv, int P, int max_it, int limit,
-                                                                int batch_stop, int* batch, int* decided) {
+                                                                int batch_stop, int* batch, int* decided,
+                                                                uint32_t* and_out) {
     __shared__ uint32_t s_and[4];
     if (decided != nullptr && limit == max_it && *decided != 0) return;     // second resolve, nothing left to do
     if (threadIdx.x < 4) s_and[threadIdx.x] = 0xffffffffu;
@@ -188,6 +190,7 @@ __global__ void __launch_bounds__(256) icp_resolve_batch_kernel(const uint32_t* 
         if ((threadIdx.x & 31) == 0) atomicAnd(&s_and[i], m[i]);
     }
     __syncthreads();
+    if (and_out != nullptr && threadIdx.x < 4) and_out[threadIdx.x] = s_and[threadIdx.x];
     if (threadIdx.x == 0) {
         int kstar = -1;
         if (batch_stop) {
@@ -209,6 +212,12 @@ __global__ void __launch_bounds__(256) icp_resolve_batch_kernel(const uint32_t* 
         }
         if (decided) *decided = verdict;
     }
+}
+
+// phase 2 of a phased call: the batch stop found over ALL shards, as given by the caller
+__global__ void icp_set_batch_kernel(int* batch, int iters, int converged) {
+    batch[0] = iters;
+    batch[1] = converged;
 }
 
 // State at the batch stop from the per-iteration record: a pair that executed more iterations than the batch did
@@ -289,7 +298,7 @@ void set_profile_events(cudaEvent_t start, cudaEvent_t stop) {
 int launch_icp(const float* src, const float* dst, const float* init_R, const float* init_T, const float* init_pose,
                int auto_swap, int P, int N, const icpf_params& prm, float* out_R, float* out_T,
                float* out_rmse, float* out_pose, int* out_iters, uint32_t* out_conv, int* out_batch, void* workspace,
-               size_t workspace_bytes, cudaStream_t stream) {
+               size_t workspace_bytes, cudaStream_t stream, const IcpPhase* phase) {
     if (P == 0) return ICPF_OK;
     // nn_mode: 0 auto (grid + cache whenever the tiles fit in shared memory), 1 brute force, 2 grid, 3 grid + cache
     if (N > kMaxRows) return ICPF_E_UNSUPPORTED;
@@ -337,25 +346,40 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
     // With a batch stop every pair records (R, T, rmse) after each iteration; the pairs still moving at the stop read
     // their state back from that record (icp_select_batch_kernel) instead of being run again.
     a.hist = prm.batch_stop ? reinterpret_cast<float*>(ws + icp_ws_off_hist(P)) : nullptr;
-    if (t_prof_start && t_prof_stop) cudaEventRecord(t_prof_start, stream);
-    ICPF_LAUNCH(kernel, P, kThreads, smem, stream)(a);
-    err = cudaGetLastError();
-    if (t_prof_start && t_prof_stop) {
-        cudaEventRecord(t_prof_stop, stream);
-        t_prof_start = t_prof_stop = nullptr;
+    const int ph = phase ? phase->phase : -1;          // -1: the whole call at once (one device holds the batch)
+    uint32_t* and_out = phase ? phase->and_out : nullptr;
+    if (ph <= 0) {
+        if (t_prof_start && t_prof_stop) cudaEventRecord(t_prof_start, stream);
+        ICPF_LAUNCH(kernel, P, kThreads, smem, stream)(a);
+        err = cudaGetLastError();
+        if (t_prof_start && t_prof_stop) {
+            cudaEventRecord(t_prof_stop, stream);
+            t_prof_start = t_prof_stop = nullptr;
+        }
+        if (err != cudaSuccess) return (int)err;
+        ICPF_LAUNCH(icp_resolve_batch_kernel, 1, 256, 0, stream)(conv, P, prm.max_iterations, a.cap, prm.batch_stop, batch,
+                                                        capped ? decided : nullptr, and_out);
+        err = cudaGetLastError();
+        if (err != cudaSuccess) return (int)err;
+        if (ph == 0) return ICPF_OK;
     }
-    if (err != cudaSuccess) return (int)err;
-
-    ICPF_LAUNCH(icp_resolve_batch_kernel, 1, 256, 0, stream)(conv, P, prm.max_iterations, a.cap, prm.batch_stop, batch,
-                                                    capped ? decided : nullptr);
-    err = cudaGetLastError();
-    if (err != cudaSuccess) return (int)err;
-    if (capped) {
+    if (ph == 1 || (ph < 0 && capped)) {
+        if (ph == 1) {
+            // the shards decided together that the stop lies beyond the capped pass
+            err = cudaMemsetAsync(decided, 0, sizeof(int), stream);
+            if (err != cudaSuccess) return (int)err;
+        }
         a.decided = decided;
         ICPF_LAUNCH(kernel, P, kThreads, smem, stream)(a);
         a.decided = nullptr;
         ICPF_LAUNCH(icp_resolve_batch_kernel, 1, 256, 0, stream)(conv, P, prm.max_iterations, prm.max_iterations, prm.batch_stop,
-                                                        batch, decided);
+                                                        batch, decided, and_out);
+        err = cudaGetLastError();
+        if (err != cudaSuccess) return (int)err;
+        if (ph == 1) return ICPF_OK;
+    }
+    if (ph == 2) {
+        ICPF_LAUNCH(icp_set_batch_kernel, 1, 1, 0, stream)(batch, phase->batch_iters, phase->converged);
         err = cudaGetLastError();
         if (err != cudaSuccess) return (int)err;
     }

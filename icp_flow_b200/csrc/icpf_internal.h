@@ -31,10 +31,23 @@ inline size_t icp_workspace_bytes(int P) {
     return icp_ws_off_hist(P) + align_up((size_t)P * kIcpHistDepth * kIcpHistFloats * 4, 256);
 }
 
+// The ICP call split at the two points where the reference's batch stop couples the pairs (utils_icp_pytorch3d.py:209),
+// for callers whose batch is spread over several devices (icp_flow_b200/shard.py): between the phases the caller ANDs
+// the convergence masks of all shards and hands the stop it found to the last phase.
+//   phase 0  first pass (capped at 32 iterations when early exit applies); and_out[4] = AND of this shard's masks
+//   phase 1  full pass for the pairs still moving at the cap (only when phase 0 could not decide); and_out likewise
+//   phase 2  batch = {batch_iters, converged} as given; pairs beyond it read their state back; outputs are final
+struct IcpPhase {
+    int phase;
+    int batch_iters;
+    int converged;
+    uint32_t* and_out;     // device [4], phases 0 and 1
+};
+
 int launch_icp(const float* src, const float* dst, const float* init_R, const float* init_T, const float* init_pose,
                int auto_swap, int P, int N, const icpf_params& prm, float* out_R, float* out_T,
                float* out_rmse, float* out_pose, int* out_iters, uint32_t* out_conv, int* out_batch, void* workspace,
-               size_t workspace_bytes, cudaStream_t stream);
+               size_t workspace_bytes, cudaStream_t stream, const IcpPhase* phase = nullptr);
 
 void set_profile_events(cudaEvent_t start, cudaEvent_t stop);
 void set_peer_gather(float* const* peer_pose_dev, int world, int row0);
@@ -62,7 +75,7 @@ int launch_hist_init(const float* src, const float* dst, int P, int N, const icp
                      void* workspace, size_t workspace_bytes, cudaStream_t stream);
 int launch_apply_icp(const float* src, const float* dst, const float* init_pose, int P, int N, const icpf_params& prm,
                      int auto_swap, float* out_pose, float* out_err, int* out_flags, int* out_batch, void* workspace,
-                     size_t workspace_bytes, cudaStream_t stream);
+                     size_t workspace_bytes, cudaStream_t stream, const IcpPhase* phase = nullptr);
 int launch_hist_icp(const float* src, const float* dst, int P, int N, const icpf_hist_bins& hb, const icpf_params& prm,
                     float* out_pose, float* out_init, int* out_batch, void* workspace, size_t workspace_bytes,
                     cudaStream_t stream);

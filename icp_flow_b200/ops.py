@@ -357,6 +357,57 @@ def apply_icp(args, src, dst, init_poses, return_debug: bool = False, auto_swap:
     return out
 
 
+class ApplyIcpPhases:
+    """``apply_icp`` split at the two points where the reference's batch stop couples the pairs of a call
+    (utils_icp_pytorch3d.py:209), for a batch that is spread over several devices (``shard.hist_icp_sharded``):
+
+        ph = ApplyIcpPhases(args, src, dst, init_poses, auto_swap=True)
+        words = ph.first_pass()              # [4] int32: AND of this shard's convergence masks
+        ... AND the words of all shards; lowest set bit below ph.cap = the batch stop ...
+        words = ph.full_pass()               # only if no stop below the cap and ph.cap < ph.max_iterations
+        T = ph.finish(iterations, converged)
+
+    With one shard the result is exactly ``apply_icp``'s.  A shard without pairs makes no native call and reports
+    all-ones words."""
+
+    def __init__(self, args, src, dst, init_poses, auto_swap: bool = False):
+        self.src, self.dst = _check_pair_batch(src, dst)
+        self.init = _require_cuda_f32(init_poses, "init_poses")
+        self.P, self.N, _ = self.src.shape
+        assert self.init.shape == (self.P, 4, 4)
+        self.dev = self.src.device
+        self.params = _path_params(args)
+        self.auto_swap = int(auto_swap)
+        self.max_iterations = int(self.params.max_iterations)
+        self.cap = min(32, self.max_iterations) if self.params.early_exit else self.max_iterations
+        self.ws = _workspace(self.P, self.N, (0, 0, 0), self.dev)
+        self.words = torch.full((4,), -1, device=self.dev, dtype=torch.int32)
+        self.out = torch.empty(self.P, 4, 4, device=self.dev, dtype=torch.float32)
+        self.batch = torch.empty(2, device=self.dev, dtype=torch.int32)
+
+    def _call(self, phase: int, iterations: int = 0, converged: int = 0):
+        if self.P == 0:
+            return
+        with torch.cuda.device(self.dev):
+            code = _lib.lib().icpf_apply_icp_phase_f32(
+                _ptr(self.src), _ptr(self.dst), _ptr(self.init), self.P, self.N, ctypes.byref(self.params),
+                self.auto_swap, phase, int(iterations), int(converged), _ptr(self.words), _ptr(self.out), None, None,
+                _ptr(self.batch), _ptr(self.ws), self.ws.numel(), _stream_ptr())
+        _lib.check(code, "icpf_apply_icp_phase_f32")
+
+    def first_pass(self) -> torch.Tensor:
+        self._call(0)
+        return self.words
+
+    def full_pass(self) -> torch.Tensor:
+        self._call(1)
+        return self.words
+
+    def finish(self, iterations: int, converged: bool) -> torch.Tensor:
+        self._call(2, iterations, int(bool(converged)))
+        return self.out
+
+
 def pytorch3d_icp(args, src, dst):
     """Drop-in for ``utils_icp.pytorch3d_icp(args, src, dst) -> [P,4,4]`` (utils_icp.py:50-73)."""
     src, dst = _check_pair_batch(src, dst)

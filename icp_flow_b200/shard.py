@@ -78,14 +78,36 @@ def _and_rows(rows: torch.Tensor) -> torch.Tensor:
     return rows[0]
 
 
-def hist_icp_sharded(args, src: torch.Tensor, dst: torch.Tensor, group: Optional[dist.ProcessGroup] = None):
+def _stop_from_words(words: torch.Tensor, limit: int, group) -> Tuple[int, bool]:
+    """Lowest bit below ``limit`` that is set in the AND of every rank's four mask words -> (k* + 1, True)."""
+    return batch_stop_from_masks(words.reshape(1, 4), limit, group)
+
+
+def hist_icp_sharded(args, src: torch.Tensor, dst: torch.Tensor, group: Optional[dist.ProcessGroup] = None,
+                     exact_stop: bool = True):
     """``hist_icp`` over the pairs of ALL ranks: ``src`` / ``dst`` are this rank's shard (``shard_range``) of the
-    global padded batch; returns the transforms of every pair, ``[num_pairs, 4, 4]``, on every rank."""
+    global padded batch; returns the transforms of every pair, ``[num_pairs, 4, 4]``, on every rank.
+
+    ``exact_stop`` (default): the reference's batch stop looks at all pairs of the call, so the shards exchange the AND
+    of their convergence masks (16 bytes, once or twice) and stop where the unsharded batch would -- the result is the
+    unsharded ``hist_icp`` bit for bit.  ``exact_stop=False`` applies the stop per shard (no exchange, no host sync):
+    pairs still moving when their shard's stop fires may end a few iterations earlier or later."""
     from . import ops
 
     counts = torch.tensor([src.shape[0]], device=src.device, dtype=torch.int64)
     dist.all_reduce(counts, group=group)
-    local = ops.hist_icp(args, src, dst)
+    if not exact_stop:
+        local = ops.hist_icp(args, src, dst)
+        return gather_transforms(local, int(counts.item()), group)
+    # the histogram initialisation is per pair; utils_match.hist_icp registers the smaller cloud onto the larger one
+    init = ops.estimate_init_pose(args, src, dst, auto_swap=True) if src.shape[0] > 0 else src.new_empty(0, 4, 4)
+    ph = ops.ApplyIcpPhases(args, src, dst, init, auto_swap=True)
+    iterations, converged = _stop_from_words(ph.first_pass(), ph.cap, group)
+    if not converged and ph.cap < ph.max_iterations:
+        iterations, converged = _stop_from_words(ph.full_pass(), ph.max_iterations, group)
+    if not converged:
+        iterations = ph.max_iterations
+    local = ph.finish(iterations, converged)
     return gather_transforms(local, int(counts.item()), group)
 
 

@@ -168,6 +168,25 @@ int icpf_apply_icp_f32(const float* src, const float* dst, const float* init_pos
                        int32_t* out_flags, int32_t* out_batch, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * apply_icp in phases, for a batch whose pairs are spread over several devices (one process per GPU): the reference's
+ * batch stop (utils_icp_pytorch3d.py:209, `.all()` over the pairs of the call) is the only coupling between pairs, so a
+ * sharded caller that wants the transforms of the unsharded batch bit for bit exchanges 16 bytes between the phases:
+ *   phase 0  first ICP pass; out_and[4] (device uint32) = AND of the shard's 128-bit convergence masks.  The caller ANDs
+ *            the words of all shards: the lowest set bit k* < min(32, max_iterations) is the batch stop.
+ *   phase 1  only when phase 0 found none and max_iterations > 32: full pass for the pairs still moving; out_and again.
+ *   phase 2  batch_iterations / batch_converged = the stop found over all shards ((k*+1, 1) or (max_iterations, 0)):
+ *            pairs that went beyond it read their state at the stop back, roll-back / un-swap as in icpf_apply_icp_f32;
+ *            out_pose, out_err, out_flags, out_batch are written by this phase only.
+ * Same arguments and the SAME workspace (untouched in between) in every phase; a shard of P = 0 pairs skips the calls
+ * and contributes all-ones words.  With one shard the three phases give exactly icpf_apply_icp_f32.
+ */
+int icpf_apply_icp_phase_f32(const float* src, const float* dst, const float* init_pose, int32_t P, int32_t N,
+                             const icpf_params* params, int32_t auto_swap, int32_t phase, int32_t batch_iterations,
+                             int32_t batch_converged, uint32_t* out_and, float* out_pose, float* out_err,
+                             int32_t* out_flags, int32_t* out_batch, void* workspace, size_t workspace_bytes,
+                             void* stream);
+
+/*
  * The whole per-cluster-pair path -- replaces utils_match.hist_icp (utils_match.py:138-157).
  *   src, dst [P,N,4] -> out_pose [P,16] column-convention 4x4 transforms  p' = T[:3,:3] p + T[:3,3]
  *   out_init [P,16] (may be NULL) the histogram initialisation in the swapped frame; out_batch [2] (may be NULL)

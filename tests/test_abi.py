@@ -59,6 +59,25 @@ def test_argument_validation_without_gpu():
     assert L.icpf_nn_f32(fake, fake, 2, 8, 8, 2, 3, fake, fake, null) == -3
 
 
+def test_phased_apply_icp_argument_validation_without_gpu():
+    """icpf_apply_icp_phase_f32: phase range, a stop inside [1, max_iterations], the outputs each phase needs."""
+    L = _lib.lib()
+    p = _lib.default_params()
+    null = ctypes.c_void_p(0)
+    fake = ctypes.c_void_p(4096)
+    f = L.icpf_apply_icp_phase_f32
+    base = lambda phase, its, and_out, out_pose, P=4: f(fake, fake, fake, P, 8, ctypes.byref(p), 1, phase, its, 1, and_out,
+                                                        out_pose, null, null, null, fake, 0, null)
+    assert base(0, 0, fake, null, P=0) == 0                      # an empty shard: nothing to do in any phase
+    assert base(3, 0, fake, fake) == -3 and base(-1, 0, fake, fake) == -3
+    assert base(2, 0, null, fake) == -3 and base(2, 101, null, fake) == -3      # stop outside [1, max_iterations]
+    assert base(0, 0, null, fake) == -1                          # phases 0 / 1 report the AND of the masks
+    assert base(2, 10, null, null) == -1                         # phase 2 writes the transforms
+    assert base(0, 0, fake, null) == -5                          # workspace (checked before any launch)
+    p.batch_stop = 0
+    assert base(0, 0, fake, fake) == -3                          # without a batch stop there is nothing to exchange
+
+
 def test_scan_level_argument_validation_without_gpu():
     """Rows f2 / f3: every scan-level entry point rejects bad arguments before touching the device."""
     L = _lib.lib()

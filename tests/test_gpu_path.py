@@ -13,7 +13,7 @@ import pytest
 import torch
 
 from engines import device, is_simt, put, sync
-from icp_flow_b200 import ops
+from icp_flow_b200 import ops, synth
 from oracle import icp_oracle as O
 from oracle import leaves
 
@@ -306,3 +306,66 @@ def test_histogram_global_fallback_for_wide_clusters(frame):
             assert sorted(dbg["flat_idx"].cpu().long()[r][pos].tolist()) == sorted(odbg["flat_idx"][r][pos].tolist()), r
     assert np.abs(pose.cpu().numpy() - want.numpy())[~amb].max() <= 1e-6
     assert np.abs(pose.cpu().numpy()[:, :3, 3] - np.array([1.3, -0.7, 0.0])).max() < 0.11
+
+
+def _first_set_bit(words, limit):
+    w = words.cpu().numpy().astype(np.uint32)
+    for k in range(min(limit, 128)):
+        if (int(w[k >> 5]) >> (k & 31)) & 1:
+            return k
+    return None
+
+
+@pytest.mark.parametrize("case", ["stop_below_the_cap", "stop_beyond_the_cap"])
+def test_apply_icp_in_phases_equals_the_single_call(case):
+    """icpf_apply_icp_phase_f32 (the seam a sharded caller uses to exchange the batch stop, include/icpflow_b200.h) with
+    one shard: the three phases give exactly apply_icp -- and a stop imposed from outside (what another shard's slower
+    pair would cause) gives exactly the state a forced run to that iteration has."""
+    args = types.SimpleNamespace(thres_dist=0.1, translation_frame=2.0, chunk_size=50)
+    if case == "stop_below_the_cap":
+        src, dst, _ = synth.make_pairs(24, 192, seed=5, ragged=True, residual_only=True, wrong_frac=0.1)
+    else:
+        src, dst, _ = synth.make_pairs(96, 1024, seed=5, ragged=False, residual_only=True, wrong_frac=0.0)
+        keep = [0, 1, 2, 3, 37, 73, 87]
+        src, dst = src[keep], dst[keep]
+    s, d = put(src), put(dst)
+    init = ops.estimate_init_pose(args, s, d, auto_swap=True)
+    want, dbg = ops.apply_icp(args, s, d, put(init), return_debug=True, auto_swap=True)
+    its, conv = dbg["batch"].tolist()
+    ph = ops.ApplyIcpPhases(args, s, d, put(init), auto_swap=True)
+    k = _first_set_bit(ph.first_pass(), ph.cap)
+    if k is None:
+        k = _first_set_bit(ph.full_pass(), ph.max_iterations)
+    assert (k is not None) == bool(conv) and (k + 1 if k is not None else ph.max_iterations) == its
+    if is_simt():
+        assert (its <= 32) == (case == "stop_below_the_cap"), its
+    got = ph.finish(its, conv)
+    assert torch.equal(got, want) and ph.batch.tolist() == [its, conv]
+    # a later stop than this shard's own (imposed by the pairs of another shard): nothing moves past its fixed point,
+    # the pairs that were still moving take their state at the imposed iteration
+    if case == "stop_below_the_cap":
+        later = its + 3
+        ph2 = ops.ApplyIcpPhases(args, s, d, put(init), auto_swap=True)
+        ph2.first_pass()
+        got2 = ph2.finish(later, True)
+        ref_icp = ops.icp_batch(put(ops.transform_points_batch(put(_swap_smaller_first(src, dst)[0]), put(init))),
+                                put(_swap_smaller_first(src, dst)[1]),
+                                ops.make_params(max_iterations=later, relative_rmse_thr=-1.0, early_exit=False,
+                                                batch_stop=False))
+        # compare through the un-finalised ICP transforms: finish() composes, rolls back and un-swaps, so check the
+        # property on the pairs that were not rolled back and not swapped
+        n_s, n_d = (src[:, :, 3] > 0).sum(1), (dst[:, :, 3] > 0).sum(1)
+        plain_pairs = np.nonzero(n_s <= n_d)[0]
+        comp = torch.bmm(ref_icp.pose.cpu(), init.cpu())
+        _, dbg2 = ops.apply_icp(args, s, d, put(init), return_debug=True, auto_swap=True)
+        kept = [int(p) for p in plain_pairs if not (int(dbg2["flags"][p]) & 1)]
+        assert len(kept) >= 4
+        assert (got2.cpu()[kept] - comp[kept]).abs().max() <= 1e-5
+
+
+def _swap_smaller_first(src, dst):
+    n_s, n_d = (src[:, :, 3] > 0).sum(1), (dst[:, :, 3] > 0).sum(1)
+    sw = n_s > n_d
+    a, c = src.copy(), dst.copy()
+    a[sw], c[sw] = dst[sw], src[sw]
+    return a, c
