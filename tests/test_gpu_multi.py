@@ -1,5 +1,6 @@
 """GPU, >= 2 devices: the fused peer-store all-gather of the transforms (kernel epilogue writing into every rank's
-buffer through NVLink peer pointers) must equal an NCCL all_gather.  Skipped on single-GPU boxes."""
+buffer through NVLink peer pointers) must equal an NCCL all_gather, and the sharded hist_icp with the exchanged batch stop
+must equal the unsharded call bit for bit.  Skipped on single-GPU boxes."""
 import os
 import subprocess
 import sys
@@ -19,3 +20,4 @@ def test_fused_peer_gather_matches_nccl():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert out.stdout.count("fused peer gather == NCCL all_gather: True") == 2
+    assert out.stdout.count("sharded hist_icp == unsharded: True") == 2

@@ -19,4 +19,15 @@ torch.cuda.synchronize()
 ok = torch.equal(full, want) and torch.equal(full[rank * P:(rank + 1) * P], r.pose)
 print(f"rank {rank}: fused peer gather == NCCL all_gather: {ok}", flush=True)
 assert ok
+# the sharded hist_icp with the exchanged batch stop == the unsharded call on the whole batch, bit for bit
+import types
+args = types.SimpleNamespace(thres_dist=0.1, translation_frame=2.0, chunk_size=50)
+gs, gd, _ = synth.make_pairs(11, 160, seed=14, ragged=True, residual_only=False, wrong_frac=0.2)
+whole = ops.hist_icp(args, torch.from_numpy(gs).to(dev), torch.from_numpy(gd).to(dev))
+lo, hi = shard.shard_range(len(gs), rank, world)
+got = shard.hist_icp_sharded(args, torch.from_numpy(gs[lo:hi]).to(dev), torch.from_numpy(gd[lo:hi]).to(dev))
+torch.cuda.synchronize()
+ok2 = torch.equal(got, whole)
+print(f"rank {rank}: sharded hist_icp == unsharded: {ok2}", flush=True)
+assert ok2
 dist.barrier(); dist.destroy_process_group()
