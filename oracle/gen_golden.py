@@ -211,6 +211,20 @@ def gen_synth_hist(ref):
     print("synth_hist: icp iterations", int(out["icp_iterations"]), "swapped", int(out["swapped"].sum()))
 
 
+def gen_synth_hist_default(ref):
+    """The reference's argparse defaults (main.py: translation_frame 6.666 -> 135 x 135 x 3 bins, the setting of BASELINE
+    config C3) on 512-row clusters moved by up to 2 m."""
+    src, dst, meta = synth.make_pairs(12, 512, seed=78, ragged=True, residual_only=False, wrong_frac=0.1)
+    args = _args(translation_frame=6.666)
+    out = _run_path(ref, args, src, dst)
+    np.savez_compressed(os.path.join(GOLDEN, "synth_hist_default.npz"), src=src, dst=dst,
+                        thres_dist=np.float64(args.thres_dist), translation_frame=np.float64(args.translation_frame),
+                        chunk_size=np.int64(args.chunk_size), gt_translation=meta["translation"], gt_yaw=meta["yaw"],
+                        wrong=meta["wrong"], **out)
+    print("synth_hist_default: icp iterations", int(out["icp_iterations"]), "swapped", int(out["swapped"].sum()),
+          "nonzero init", int((np.abs(out["init_pose"][:, :3, 3]).sum(1) > 0).sum()))
+
+
 def gen_synth_icp20(ref):
     src, dst, meta = synth.make_pairs(32, 256, seed=1234, ragged=False, residual_only=True)
     src_r, dst_r, _ = synth.make_pairs(16, 256, seed=4321, ragged=True, residual_only=True)
@@ -298,6 +312,7 @@ def main():
     gen_hist_test_vector(ref)
     gen_synth_icp20(ref)
     gen_synth_hist(ref)
+    gen_synth_hist_default(ref)
     gen_match_dyn(ref)
     gen_c1_demo(ref)
     gen_frame_demo(ref)

@@ -39,7 +39,7 @@ def test_hist_known_answer(golden):
     assert (g["total"] <= nx * ny).all()
 
 
-@pytest.mark.parametrize("name", ["c1_demo.npz", "synth_hist.npz"])
+@pytest.mark.parametrize("name", ["c1_demo.npz", "synth_hist.npz", "synth_hist_default.npz"])
 def test_full_path_bitwise(golden, name):
     g = golden(name)
     p = _params(g)
