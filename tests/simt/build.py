@@ -50,6 +50,20 @@ ASAN_FLAGS = ["-fsanitize=address", "--param", "asan-stack=0", "-fno-omit-frame-
 
 
 def build(force: bool = False, extra_flags=(), out: str = OUT) -> str:
+    """Build (or reuse) the emulator library.  Serialised across processes with a file lock: the gloo tests start two
+    ranks that both ask for it."""
+    import fcntl
+
+    os.makedirs(BUILD, exist_ok=True)
+    with open(os.path.join(BUILD, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, extra_flags, out)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, extra_flags, out: str) -> str:
     if os.environ.get("ICPF_SIMT_ASAN") == "1" and out == OUT:
         out, extra_flags, force = ASAN_OUT, tuple(extra_flags) + tuple(ASAN_FLAGS), force or not os.path.exists(ASAN_OUT) or stale_against(ASAN_OUT)
     if not force and out == OUT and not stale():
