@@ -15,6 +15,8 @@
 
 namespace icpf {
 
+static_assert(kIcpStateWords == kIcpStateFloats, "state record");
+
 struct IcpArgs {
     const float* src;
     const float* dst;
@@ -38,6 +40,7 @@ struct IcpArgs {
     int* stats;            // [P,2] {full searches, cache refreshes} of the first pass
     const int* decided;    // second full pass: runs only while *decided == 0; NULL otherwise
     float* hist;           // [P, kIcpHistDepth, 13] (R, T, rmse) after each iteration, or NULL
+    float* state;          // [P, kIcpStateWords] loop state of the pairs the capped first pass paused, or NULL
     int cap;               // first pass: iteration cap (<= max_it)
     unsigned char* big_ws; // global-memory variant: per-pair workspace (pair_global_ws_bytes(N) each)
     float* const* peer_pose;   // fused all-gather: DEVICE array of `peer_world` base pointers (peer-mapped [*,16]) or NULL
@@ -45,17 +48,24 @@ struct IcpArgs {
     int peer_row0;             // first row of this rank's block in the gathered buffer
 };
 
-template <int MODE, bool BIG>
+// FULLPASS = the pass after a capped first pass: only the pairs still moving at the cap run, continuing from where the
+// first pass paused them (a separate instantiation, so that the kernel of the first pass -- the one every call pays for --
+// carries no continuation logic in its loop).
+template <int MODE, bool BIG, bool FULLPASS>
 __global__ void __launch_bounds__(kThreads, BIG ? 4 : 7) icp_pairs_kernel(IcpArgs a) {
     const int p = blockIdx.x;
     int max_it = a.max_it;
     bool early_exit = a.early_exit != 0;
-    if (a.decided != nullptr) {
+    int resume_it = 0;
+    if (FULLPASS) {
         if (*a.decided != 0) return;      // the capped first pass already found the batch stop
-        if (a.iters[p] < a.cap) {
-            // This pair stopped at its bitwise fixed point below the cap: every later iteration repeats that state, so
+        // the capped pass left the loop state of every pair behind: bit 3 of its flags = stopped at its fixed point
+        const bool stopped = a.state != nullptr &&
+                             (__float_as_uint(a.state[(size_t)p * kIcpStateWords + S_FLAGS]) & 8u) != 0u;
+        if (a.iters[p] < a.cap || stopped) {
+            // This pair stopped at its bitwise fixed point within the cap: every later iteration repeats that state, so
             // its transform stands and its convergence history continues the way the tail of the capped pass went
-            // (icpf_icploop.cuh, tail rule) -- only the pairs still moving at the cap are run again.
+            // (icpf_icploop.cuh, tail rule) -- only the pairs still moving at the cap go on, from where they paused.
             if (threadIdx.x == 0 && a.cap >= 1) {
                 uint32_t* c = a.conv + (size_t)p * 4;
                 const int last = a.cap - 1;
@@ -65,6 +75,7 @@ __global__ void __launch_bounds__(kThreads, BIG ? 4 : 7) icp_pairs_kernel(IcpArg
             }
             return;
         }
+        if (a.state != nullptr && a.hist != nullptr) resume_it = a.cap;
     } else {
         max_it = min(max_it, a.cap);
     }
@@ -126,11 +137,13 @@ __global__ void __launch_bounds__(kThreads, BIG ? 4 : 7) icp_pairs_kernel(IcpArg
 
     GridInfo g;
     if (GRID && n_s > 0 && n_d > 0) g = build_grid(tl, n_d, a.tau, a.cell_factor);
-    const IcpResult r = icp_iterations<MODE>(tl, g, n_s, n_d, a.tau2, max_it, a.rel_thr, early_exit,
+    const IcpResult r = icp_iterations<MODE, FULLPASS>(tl, g, n_s, n_d, a.tau2, max_it, a.rel_thr, early_exit,
                                        a.init_R ? a.init_R + (size_t)p * 9 : nullptr,
                                        a.init_T ? a.init_T + (size_t)p * 3 : nullptr, piv.x, piv.y, piv.z,
                                        a.hist != nullptr ? a.hist + (size_t)p * kIcpHistDepth * kIcpHistFloats : nullptr,
-                                       kIcpHistDepth);
+                                       kIcpHistDepth,
+                                       (FULLPASS && a.state != nullptr) ? a.state + (size_t)p * kIcpStateWords : nullptr,
+                                       resume_it);
 
     // the final (R, T) also sit in the broadcast block (no dynamic register indexing)
     if (threadIdx.x < 9) a.out_R[(size_t)p * 9 + threadIdx.x] = tl.bcast()[B_R + threadIdx.x];
@@ -154,6 +167,9 @@ __global__ void __launch_bounds__(kThreads, BIG ? 4 : 7) icp_pairs_kernel(IcpArg
         else if (col == 3) v = tl.bcast()[B_T + row];
         else v = tl.bcast()[B_R + col * 3 + row];
         for (int w = 0; w < a.peer_world; ++w) a.peer_pose[w][(size_t)(a.peer_row0 + p) * 16 + threadIdx.x] = v;
+    }
+    if (!FULLPASS && a.state != nullptr && threadIdx.x == 0) {
+        save_icp_state(r, tl.bcast(), a.state + (size_t)p * kIcpStateWords);       // a capped pass: the full pass may go on
     }
     if (threadIdx.x == 0) {
         if (a.out_rmse) a.out_rmse[p] = r.rmse;
@@ -314,11 +330,17 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
     uint32_t* conv = out_conv ? out_conv : reinterpret_cast<uint32_t*>(ws + icp_ws_off_conv(P));
     int* batch = out_batch ? out_batch : reinterpret_cast<int*>(ws + icp_ws_off_batch(P));
 
-    auto kernel = big ? (!grid ? icp_pairs_kernel<1, true>
-                               : (prm.nn_mode == 2 ? icp_pairs_kernel<2, true> : icp_pairs_kernel<3, true>))
-                      : (!grid ? icp_pairs_kernel<1, false>
-                               : (prm.nn_mode == 2 ? icp_pairs_kernel<2, false> : icp_pairs_kernel<3, false>));
+    auto kernel = big ? (!grid ? icp_pairs_kernel<1, true, false>
+                               : (prm.nn_mode == 2 ? icp_pairs_kernel<2, true, false> : icp_pairs_kernel<3, true, false>))
+                      : (!grid ? icp_pairs_kernel<1, false, false>
+                               : (prm.nn_mode == 2 ? icp_pairs_kernel<2, false, false> : icp_pairs_kernel<3, false, false>));
+    auto kernel_full = big ? (!grid ? icp_pairs_kernel<1, true, true>
+                                    : (prm.nn_mode == 2 ? icp_pairs_kernel<2, true, true> : icp_pairs_kernel<3, true, true>))
+                           : (!grid ? icp_pairs_kernel<1, false, true>
+                                    : (prm.nn_mode == 2 ? icp_pairs_kernel<2, false, true> : icp_pairs_kernel<3, false, true>));
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return (int)err;
+    err = cudaFuncSetAttribute(kernel_full, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
 
     IcpArgs a;
@@ -346,6 +368,9 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
     // With a batch stop every pair records (R, T, rmse) after each iteration; the pairs still moving at the stop read
     // their state back from that record (icp_select_batch_kernel) instead of being run again.
     a.hist = prm.batch_stop ? reinterpret_cast<float*>(ws + icp_ws_off_hist(P)) : nullptr;
+    // ... and a capped first pass leaves its loop state, so that the full pass continues the pairs still moving at the
+    // cap instead of starting them over
+    a.state = capped ? reinterpret_cast<float*>(ws + icp_ws_off_state(P)) : nullptr;
     const int ph = phase ? phase->phase : -1;          // -1: the whole call at once (one device holds the batch)
     uint32_t* and_out = phase ? phase->and_out : nullptr;
     if (ph <= 0) {
@@ -370,7 +395,7 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
             if (err != cudaSuccess) return (int)err;
         }
         a.decided = decided;
-        ICPF_LAUNCH(kernel, P, kThreads, smem, stream)(a);
+        ICPF_LAUNCH(kernel_full, P, kThreads, smem, stream)(a);
         a.decided = nullptr;
         ICPF_LAUNCH(icp_resolve_batch_kernel, 1, 256, 0, stream)(conv, P, prm.max_iterations, prm.max_iterations, prm.batch_stop,
                                                         batch, decided, and_out);

@@ -25,6 +25,10 @@
 
 namespace icpf {
 
+// layout of the per-pair loop state a paused run leaves behind (floats; see icp_iterations)
+enum : int { S_PIV = 0, S_FRAME = 6, S_FLAGS = 15, S_HPREV = 16, S_WPREV = 25, S_RMSE = 26, S_CONV = 27, S_STATS = 31,
+             kIcpStateFloats = 36 };
+
 struct IcpResult {
     float r[9];                   // valid in every thread
     float t[3];                   // valid in every thread
@@ -37,6 +41,8 @@ struct IcpResult {
     int refreshes;
     float prev_rmse;
     bool have_prev;
+    float w_prev;                 // clamp(sum of weights) of the last iteration executed
+    bool stopped;                 // left the loop at its bitwise fixed point (not at max_it)
 };
 
 __device__ __forceinline__ void set_conv_bit(IcpResult& r, int k) {
@@ -106,11 +112,17 @@ __device__ __forceinline__ float moved_sq(const float (&dr)[9], const float (&dt
 //   init_R / init_T (may be NULL) = init_transform of the reference: used for the first correspondence search only.
 //   hist (may be NULL) = this pair's [hist_depth][13] record of (R, T, rmse) after each iteration: when the batch stop
 //           falls on an iteration this pair went beyond, its state there is read back instead of re-running the pair.
-template <int MODE, class Tiles>
+//   state (may be NULL) = this pair's kIcpStateFloats words of loop state (pivots, warm-start frame, previous H, rmse
+//           bookkeeping) as save_icp_state() left them.  RESUME and resume_it >= 2: the loop CONTINUES at iteration
+//           resume_it from that state and the record -- the correspondences of iteration resume_it - 1 are searched
+//           again under its recorded transform (a search is a function of the transform alone), everything else is
+//           restored, so the continued run is the uninterrupted one bit for bit.
+template <int MODE, bool RESUME, class Tiles>
 __device__ __forceinline__ IcpResult icp_iterations(const Tiles& tl, const GridInfo& g, int n_s, int n_d, float tau2,
                                            int max_it, float rel_thr, bool early_exit, const float* init_R,
                                            const float* init_T, float pivx, float pivy, float pivz,
-                                           float* __restrict__ hist = nullptr, int hist_depth = 0) {
+                                           float* __restrict__ hist = nullptr, int hist_depth = 0,
+                                           float* __restrict__ state = nullptr, int resume_it = 0) {
     constexpr bool GRID = MODE >= 2;
     constexpr bool CACHE = MODE == 3;
     using NW = NnWord<Tiles::kPosBits>;
@@ -146,17 +158,57 @@ __device__ __forceinline__ IcpResult icp_iterations(const Tiles& tl, const GridI
     __syncthreads();
     float W_prev = 1.f;                                 // thread 0: clamp(sum of weights) of the previous iteration
     bool done = (n_s <= 0 || n_d <= 0 || max_it <= 0);  // engine-defined: nothing to align -> identity
+    // (RESUME is a template parameter so that the kernel of the first pass carries none of this in its loop)
+    const bool resume = RESUME && (state != nullptr) && (hist != nullptr) && (resume_it >= 2) && (resume_it <= hist_depth) && !done;
+    const int first_it = resume ? resume_it - 1 : 0;    // resumed: iteration resume_it - 1 only repeats its search
+    if (resume) {
+        if (tid < 12) bc[B_R + tid] = hist[(resume_it - 1) * 13 + tid];                                   // (R, T) now
+        if (tid < 12) bc[B_RC + tid] = hist[(resume_it - 1) * 13 + tid] - hist[(resume_it - 2) * 13 + tid];  // last step
+        if (tid == 0) {
+            KabschState* kst = reinterpret_cast<KabschState*>(bc + B_KABSCH);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) bc[B_PX + i] = state[S_PIV + i];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) kst->v[i] = state[S_FRAME + i];
+            const unsigned int fl = __float_as_uint(state[S_FLAGS]);
+            kst->warm = (fl & 1u) != 0u;
+            kst->changed = (fl & 2u) != 0u;
+            res.have_prev = (fl & 4u) != 0u;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) bc[B_HPREV + i] = state[S_HPREV + i];
+            W_prev = state[S_WPREV];
+            res.prev_rmse = res.rmse = state[S_RMSE];
+            res.conv_lo = (unsigned long long)__float_as_uint(state[S_CONV]) |
+                          ((unsigned long long)__float_as_uint(state[S_CONV + 1]) << 32);
+            res.conv_hi = (unsigned long long)__float_as_uint(state[S_CONV + 2]) |
+                          ((unsigned long long)__float_as_uint(state[S_CONV + 3]) << 32);
+            res.searches = state[S_STATS];
+            res.refreshes = (int)state[S_STATS + 1];
+            res.iters = resume_it;
+        }
+        __syncthreads();
+    }
 
-    for (int it = 0; !done && it < max_it; ++it) {
+    for (int it = first_it; !done && it < max_it; ++it) {
+        // the first iteration of a resumed run only rebuilds the correspondences of iteration resume_it - 1, under the
+        // transform that iteration searched with (on record); its solve is on record too
+        const bool presearch = resume && (it == first_it);
         float R[9], T[3];
+        if (presearch) {
 #pragma unroll
-        for (int i = 0; i < 9; ++i) R[i] = bc[B_R + i];
+            for (int i = 0; i < 9; ++i) R[i] = hist[(resume_it - 2) * 13 + i];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) T[i] = bc[B_T + i];
+            for (int i = 0; i < 3; ++i) T[i] = hist[(resume_it - 2) * 13 + 9 + i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) R[i] = bc[B_R + i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) T[i] = bc[B_T + i];
+        }
         // The cache is re-anchored every iteration: bounds are kept relative to the row's position in the previous
         // iteration, so the motion that counts is the step (R_k - R_{k-1}, T_k - T_{k-1}) thread 0 left in the
         // broadcast block; a row is searched again only when its own bound is used up.
-        const bool refresh = !CACHE || (it == 0);      // dense search of every row (always, without the cache)
+        const bool refresh = !CACHE || (it == first_it);      // dense search of every row (always, without the cache)
         float dr[9], dt[3];
         if (CACHE && !refresh) {
 #pragma unroll
@@ -186,7 +238,7 @@ __device__ __forceinline__ IcpResult icp_iterations(const Tiles& tl, const GridI
                     const bool valid = q < n_s;
                     x0[k] = valid ? tl.src()[q] : make_float4(0.f, 0.f, 0.f, 0.f);
                     apply_rt(R, T, x0[k].x, x0[k].y, x0[k].z, qx[k], qy[k], qz[k]);
-                    const unsigned int wold = (it > 0 && valid) ? nnw[q] : (kNnMasked | kNnNone);
+                    const unsigned int wold = (it > first_it && valid) ? nnw[q] : (kNnMasked | kNnNone);
                     if (!(wold & kNnMasked)) {
                         const float4 c = cand[wold & kNnPosMask];
                         sq += sqdist(qx[k], qy[k], qz[k], c.x, c.y, c.z);
@@ -206,7 +258,7 @@ __device__ __forceinline__ IcpResult icp_iterations(const Tiles& tl, const GridI
                 const float4 x0 = valid ? tl.src()[q] : make_float4(0.f, 0.f, 0.f, 0.f);
                 float qx, qy, qz;
                 apply_rt(R, T, x0.x, x0.y, x0.z, qx, qy, qz);
-                const unsigned int wold = (it > 0 && valid) ? nnw[q] : (kNnMasked | kNnNone);
+                const unsigned int wold = (it > first_it && valid) ? nnw[q] : (kNnMasked | kNnNone);
                 int pos = (wold & kNnPosMask) == kNnNone ? -1 : (int)(wold & kNnPosMask);
                 float d2 = INF;
                 if (pos >= 0 && (!(wold & kNnMasked) || (CACHE && !refresh))) {
@@ -266,6 +318,11 @@ __device__ __forceinline__ IcpResult icp_iterations(const Tiles& tl, const GridI
             }
         }
 
+        if (presearch) {
+            __syncthreads();          // the correspondence words are complete before the next iteration reads them
+            continue;
+        }
+
         // ---------------- pass B: raw moments about the pivots (same code and order in every mode)
         float mom[16];
 #pragma unroll
@@ -308,7 +365,7 @@ __device__ __forceinline__ IcpResult icp_iterations(const Tiles& tl, const GridI
             }
             __syncwarp();
             if (lane == 0) {
-                if (it > 0) {
+                if (it > (resume ? resume_it : 0)) {        // (a resumed run recorded iteration resume_it - 1 before it paused)
                     record_rmse(res, it - 1, sqrtf(__fdiv_rn(total[16], W_prev)), rel_thr);
                     if (hist != nullptr && it - 1 < hist_depth) hist[(it - 1) * 13 + 12] = res.rmse;
                 }
@@ -432,7 +489,33 @@ __device__ __forceinline__ IcpResult icp_iterations(const Tiles& tl, const GridI
             }
         }
     }
+    if (tid == 0) {
+        res.w_prev = W_prev;
+        res.stopped = done;
+    }
     return res;
+}
+
+// Thread 0: leave the loop state of a finished (or paused) run in `state` for a later continuation (icp_iterations,
+// `state` / `resume_it`); S_FLAGS bit 3 = stopped at its fixed point.  `bc` is the pair's broadcast block.
+__device__ __forceinline__ void save_icp_state(const IcpResult& res, const float* bc, float* __restrict__ state) {
+    const KabschState* kst = reinterpret_cast<const KabschState*>(bc + B_KABSCH);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) state[S_PIV + i] = bc[B_PX + i];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) state[S_FRAME + i] = kst->v[i];
+    state[S_FLAGS] = __uint_as_float((kst->warm ? 1u : 0u) | (kst->changed ? 2u : 0u) | (res.have_prev ? 4u : 0u) |
+                                     (res.stopped ? 8u : 0u));
+#pragma unroll
+    for (int i = 0; i < 9; ++i) state[S_HPREV + i] = bc[B_HPREV + i];
+    state[S_WPREV] = res.w_prev;
+    state[S_RMSE] = res.prev_rmse;
+    state[S_CONV] = __uint_as_float((unsigned int)res.conv_lo);
+    state[S_CONV + 1] = __uint_as_float((unsigned int)(res.conv_lo >> 32));
+    state[S_CONV + 2] = __uint_as_float((unsigned int)res.conv_hi);
+    state[S_CONV + 3] = __uint_as_float((unsigned int)(res.conv_hi >> 32));
+    state[S_STATS] = res.searches;
+    state[S_STATS + 1] = (float)res.refreshes;
 }
 
 }  // namespace icpf

@@ -21,15 +21,16 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // iters [P] int32 | conv [P,4] uint32 | batch [2] int32 + flags (256 B slot) | stats [P,2] int32 {full searches, cache
 // refreshes} | history [P, kIcpHistDepth, kIcpHistFloats] fp32: (R, T, rmse) after each of the first 128 iterations of a pair
+// | state [P, kIcpStateWords]: the loop state of a pair paused at the cap of the first pass
 constexpr int kIcpHistDepth = 128;     // = the iterations the 128-bit convergence masks cover: a batch stop lies inside
 constexpr int kIcpHistFloats = 13;     // R[9] T[3] rmse
 inline size_t icp_ws_off_conv(int P) { return align_up((size_t)P * 4, 256); }
 inline size_t icp_ws_off_batch(int P) { return icp_ws_off_conv(P) + align_up((size_t)P * 16, 256); }
 inline size_t icp_ws_off_stats(int P) { return icp_ws_off_batch(P) + 256; }
 inline size_t icp_ws_off_hist(int P) { return icp_ws_off_stats(P) + align_up((size_t)P * 8, 256); }
-inline size_t icp_workspace_bytes(int P) {
-    return icp_ws_off_hist(P) + align_up((size_t)P * kIcpHistDepth * kIcpHistFloats * 4, 256);
-}
+constexpr int kIcpStateWords = 36;     // loop state a pair leaves behind when the capped first pass pauses it (icpf_icploop.cuh)
+inline size_t icp_ws_off_state(int P) { return icp_ws_off_hist(P) + align_up((size_t)P * kIcpHistDepth * kIcpHistFloats * 4, 256); }
+inline size_t icp_workspace_bytes(int P) { return icp_ws_off_state(P) + align_up((size_t)P * kIcpStateWords * 4, 256); }
 
 // The ICP call split at the two points where the reference's batch stop couples the pairs (utils_icp_pytorch3d.py:209),
 // for callers whose batch is spread over several devices (icp_flow_b200/shard.py): between the phases the caller ANDs
