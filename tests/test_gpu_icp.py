@@ -288,3 +288,23 @@ def test_state_at_the_batch_stop_equals_a_forced_run(case):
     assert int(r.iterations.max()) == its and int(r.iterations.min()) < its
     f = _run(src, dst, max_iterations=its, relative_rmse_thr=-1.0, early_exit=False, batch_stop=False)
     assert torch.equal(r.R, f.R) and torch.equal(r.T, f.T) and torch.equal(r.rmse, f.rmse) and torch.equal(r.pose, f.pose)
+
+
+def test_paused_and_continued_pairs_equal_the_uninterrupted_run():
+    """With early exit the first pass is capped at 32 iterations and the pairs still moving there are CONTINUED by the
+    full pass (loop state + per-iteration record).  Without early exit nothing is capped or paused: both runs must give
+    the same batch stop, the same transforms and the same convergence history up to the stop, bit for bit."""
+    src, dst, _ = synth.make_pairs(96, 1024, seed=5, ragged=False, residual_only=True, wrong_frac=0.0)
+    keep = [0, 1, 2, 3, 37, 73, 87, 45, 60]
+    src, dst = src[keep], dst[keep]
+    for mode in (3, 1):
+        a = _run(src, dst, max_iterations=100, relative_rmse_thr=1e-6, early_exit=True, batch_stop=True, nn_mode=mode)
+        b = _run(src, dst, max_iterations=100, relative_rmse_thr=1e-6, early_exit=False, batch_stop=True, nn_mode=mode)
+        its = a.batch.tolist()[0]
+        assert a.batch.tolist() == b.batch.tolist()
+        if is_simt():
+            assert its > 32
+        assert torch.equal(a.R, b.R) and torch.equal(a.T, b.T) and torch.equal(a.rmse, b.rmse), mode
+        ca, cb = a.conv_mask.cpu().numpy().astype(np.uint32), b.conv_mask.cpu().numpy().astype(np.uint32)
+        for k in range(min(its, 128)):
+            assert np.array_equal((ca[:, k >> 5] >> (k & 31)) & 1, (cb[:, k >> 5] >> (k & 31)) & 1), (mode, k)
