@@ -75,7 +75,9 @@ __global__ void __launch_bounds__(kThreads, BIG ? 4 : 7) icp_pairs_kernel(IcpArg
             }
             return;
         }
+#ifndef ICPF_NO_RESUME         // A/B switch (tools/ab_kernel.py): the full pass starts the pairs over
         if (a.state != nullptr && a.hist != nullptr) resume_it = a.cap;
+#endif
     } else {
         max_it = min(max_it, a.cap);
     }

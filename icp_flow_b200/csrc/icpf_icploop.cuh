@@ -387,7 +387,11 @@ __device__ __forceinline__ IcpResult icp_iterations(const Tiles& tl, const GridI
                 // value -- the size of the reference's own stopping threshold).  So when H repeats bit for bit the
                 // previous R stands: same H, same R, as in the reference, and the pair is at its fixed point.
                 KabschState* kst = reinterpret_cast<KabschState*>(bc + B_KABSCH);
+#ifdef ICPF_NO_SAME_H       // A/B switch (tools/ab_kernel.py): always solve
+                bool same_h = false;
+#else
                 bool same_h = (it > 0);
+#endif
 #pragma unroll
                 for (int i = 0; i < 9; ++i) same_h = same_h && (__float_as_uint(h[i]) == __float_as_uint(bc[B_HPREV + i]));
                 Rot3 rot;

@@ -55,3 +55,25 @@ def test_pruned_far_query_search_equals_the_full_scan():
             a, b = g[k], w[k]
             same = torch.equal(a, b) if not a.is_floating_point() else torch.equal(a.nan_to_num(-7.0), b.nan_to_num(-7.0))
             assert same, k
+
+
+def test_continued_full_pass_equals_the_restarted_one():
+    """ICPF_NO_RESUME: the full pass starts the pairs still moving at the cap over (the behaviour before the loop state was
+    kept).  Continuing them must not move a bit: transforms, rmse, iterations, batch stop, convergence masks."""
+    src, dst, _ = synth.make_pairs(96, 1024, seed=5, ragged=False, residual_only=True, wrong_frac=0.0)
+    keep = [0, 1, 2, 3, 37, 73, 87, 45, 60]            # stop at iteration 48: beyond the cap of the first pass
+    src, dst = src[keep], dst[keep]
+
+    def run():
+        out = []
+        for mode in (3, 2, 1):
+            r = ops.icp_batch(harness.dev_tensor(src), harness.dev_tensor(dst), ops.make_params(nn_mode=mode))
+            out += [harness.plain(x).clone() for x in (r.R, r.T, r.rmse, r.iterations, r.batch, r.conv_mask, r.pose)]
+        return out
+
+    with harness.emulated():
+        got = run()
+    with harness.emulated(extra_flags=("-DICPF_NO_RESUME",), out=os.path.join(simt_build.BUILD, "libicpflow_simt_noresume.so")):
+        want = run()
+    assert got[4].tolist()[0] > 32
+    assert all(torch.equal(a, b) for a, b in zip(got, want))
