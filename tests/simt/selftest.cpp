@@ -85,5 +85,11 @@ extern "C" int simt_selftest() {
     int ds[2] = {0, 0};
     simt::bind(dyn_shared_kernel, dim3(2), dim3(96), 100 * sizeof(float) + 64)(ds, (const float*)src, 100);
     if (ds[0] != 1 || ds[1] != 9900) { ++g_fail; fprintf(stderr, "selftest: dynamic shared memory %d %d\n", ds[0], ds[1]); }
+    // an empty grid / oversized block is rejected like the runtime does (the launch does not happen, the error is fetched once)
+    int untouched[2] = {7, 7};
+    simt::bind(partial_warp_kernel, dim3(0), dim3(40), 0)(untouched);
+    if (cudaGetLastError() != 9 || cudaGetLastError() != 0 || untouched[0] != 7) { ++g_fail; fprintf(stderr, "selftest: empty grid\n"); }
+    simt::bind(partial_warp_kernel, dim3(1), dim3(2048), 0)(untouched);
+    if (cudaGetLastError() != 9 || untouched[0] != 7) { ++g_fail; fprintf(stderr, "selftest: oversized block\n"); }
     return g_fail;
 }

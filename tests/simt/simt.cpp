@@ -28,6 +28,7 @@ asm(".text\n"
 namespace simt {
 
 Ids cur;
+int last_error = 0;
 
 namespace {
 
@@ -193,8 +194,13 @@ void check_dyn_shared_tail(size_t smem) {
 
 void run_grid(dim3 grid, dim3 block, size_t smem, void (*thread_fn)(void*), void* ctx) {
     const int nthreads = (int)(block.x * block.y * block.z);
-    if (nthreads <= 0 || nthreads > kMaxThreads) { fprintf(stderr, "simt: bad block size %d\n", nthreads); abort(); }
-    if (smem > kDynSharedBytes) { fprintf(stderr, "simt: %zu bytes of dynamic shared memory requested\n", smem); abort(); }
+    // what the CUDA runtime rejects with cudaErrorInvalidConfiguration: the launch does not happen, the error is sticky
+    // until cudaGetLastError() fetches it
+    if (nthreads <= 0 || nthreads > kMaxThreads || smem > kDynSharedBytes || grid.x == 0 || grid.y == 0 || grid.z == 0 ||
+        grid.y > 65535 || grid.z > 65535) {
+        last_error = 9;
+        return;
+    }
     if (g_running >= 0) { fprintf(stderr, "simt: nested launch\n"); abort(); }
     if ((int)g_fibers.size() < nthreads) g_fibers.resize(nthreads);
     g_thread_fn = thread_fn;

@@ -55,8 +55,11 @@ typedef void* cudaStream_t;
 typedef void* cudaEvent_t;
 enum { cudaSuccess = 0 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
-inline cudaError_t cudaGetLastError() { return cudaSuccess; }
-inline const char* cudaGetErrorString(cudaError_t) { return "simt emulator: no CUDA runtime"; }
+namespace simt { extern int last_error; }
+// like the runtime: returns and clears the error of the last launch (9 = cudaErrorInvalidConfiguration: empty grid,
+// empty or oversized block, too much dynamic shared memory)
+inline cudaError_t cudaGetLastError() { const int e = simt::last_error; simt::last_error = 0; return e; }
+inline const char* cudaGetErrorString(cudaError_t e) { return e == 9 ? "invalid configuration argument (simt emulator)" : "simt emulator: no CUDA runtime"; }
 template <class K> inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
 inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
