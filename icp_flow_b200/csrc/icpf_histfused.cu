@@ -196,43 +196,60 @@ __global__ void __launch_bounds__(kFusedThreads) hist_fused_kernel(FusedHistArgs
                     __syncthreads();
                 }
             }
-            for (int i = tid; i < a.N; i += kFusedThreads) {
-                const float4 xi = xb[i];
-                if (!(xi.w > 0.f)) continue;
-                // first j with  fl(z_i - z_j) <  max_z   (predicate false..false true..true as z_j grows)
-                int lo_j = 0, hi_j = n;
-                while (lo_j < hi_j) {
-                    const int mid = (lo_j + hi_j) >> 1;
-                    if (__fsub_rn(xi.z, tile[mid].z) < a.max_z) hi_j = mid; else lo_j = mid + 1;
+            // Each warp takes 32 consecutive X rows: every lane finds the run of ITS row (two binary searches, the same
+            // trip count in every lane), then the rows are served one after the other with the run of the row dealt to
+            // the 32 lanes -- runs differ a lot in length, and a lane that iterated over its own run alone left the warp
+            // at 19 of 32 active lanes (profiles/hist_fused_r1_by_line.txt); consecutive lanes now also read consecutive
+            // tile rows (no bank conflicts).  Votes are integer atomics: the counts do not depend on the order.
+            for (int i0 = warp * 32; i0 < a.N; i0 += kFusedThreads) {
+                const int i = i0 + lane;
+                const float4 xi = (i < a.N) ? xb[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                int j0 = 0, j1 = 0;
+                if (xi.w > 0.f) {
+                    // first j with  fl(z_i - z_j) <  max_z   (predicate false..false true..true as z_j grows)
+                    int lo_j = 0, hi_j = n;
+                    while (lo_j < hi_j) {
+                        const int mid = (lo_j + hi_j) >> 1;
+                        if (__fsub_rn(xi.z, tile[mid].z) < a.max_z) hi_j = mid; else lo_j = mid + 1;
+                    }
+                    j0 = lo_j;
+                    // first j with  fl(z_i - z_j) >= min_z  false  (true..true false..false)
+                    hi_j = n;
+                    while (lo_j < hi_j) {
+                        const int mid = (lo_j + hi_j) >> 1;
+                        if (__fsub_rn(xi.z, tile[mid].z) >= a.min_z) lo_j = mid + 1; else hi_j = mid;
+                    }
+                    j1 = lo_j;
                 }
-                const int j0 = lo_j;
-                // first j with  fl(z_i - z_j) >= min_z  false  (true..true false..false)
-                hi_j = n;
-                while (lo_j < hi_j) {
-                    const int mid = (lo_j + hi_j) >> 1;
-                    if (__fsub_rn(xi.z, tile[mid].z) >= a.min_z) lo_j = mid + 1; else hi_j = mid;
-                }
-                for (int j = j0; j < lo_j; ++j) {
-                    const float4 yj = tile[j];
-                    const float vz = __fsub_rn(xi.z, yj.z);
-                    const float vx = __fsub_rn(xi.x, yj.x), vy = __fsub_rn(xi.y, yj.y);
-                    if (vx >= a.min_x && vx < a.max_x && vy >= a.min_y && vy < a.max_y && vz >= a.min_z && vz < a.max_z) {
-                        const int px = (FASTDIV ? vote_bin_fast(vx, a.min_x, rx, irx, flx, a.len_x)
-                                                : vote_bin(vx, a.min_x, rx, flx, a.len_x)) - bx0;
-                        const int py = (FASTDIV ? vote_bin_fast(vy, a.min_y, ry, iry, fly, a.len_y)
-                                                : vote_bin(vy, a.min_y, ry, fly, a.len_y)) - by0;
-                        const int pz = FASTDIV ? vote_bin_fast(vz, a.min_z, rz, irz, flz, a.len_z)
-                                               : vote_bin(vz, a.min_z, rz, flz, a.len_z);
-                        if (px < 0 || px >= wx || py < 0 || py >= wy) {
-                            s_bad = 1;      // cannot happen (the range is conservative); fall back if it ever does
-                        } else {
-                            const int bin = (px * wy + py) * lz + pz;
-                            if (COUNT16) {
-                                const int sh = (bin & 1) * 16;
-                                const unsigned int was = atomicAdd(&histw[bin >> 1], 1u << sh);
-                                if (((was >> sh) & 0xffffu) == 0xffffu) s_bad = 1;      // this increment wrapped it
+                unsigned int live = __ballot_sync(FULL_MASK, j1 > j0);
+                while (live != 0u) {
+                    const int r = __ffs((int)live) - 1;
+                    live &= live - 1u;
+                    const float xix = __shfl_sync(FULL_MASK, xi.x, r), xiy = __shfl_sync(FULL_MASK, xi.y, r),
+                                xiz = __shfl_sync(FULL_MASK, xi.z, r);
+                    const int rs = __shfl_sync(FULL_MASK, j0, r), re = __shfl_sync(FULL_MASK, j1, r);
+                    for (int j = rs + lane; j < re; j += 32) {
+                        const float4 yj = tile[j];
+                        const float vz = __fsub_rn(xiz, yj.z);
+                        const float vx = __fsub_rn(xix, yj.x), vy = __fsub_rn(xiy, yj.y);
+                        if (vx >= a.min_x && vx < a.max_x && vy >= a.min_y && vy < a.max_y && vz >= a.min_z && vz < a.max_z) {
+                            const int px = (FASTDIV ? vote_bin_fast(vx, a.min_x, rx, irx, flx, a.len_x)
+                                                    : vote_bin(vx, a.min_x, rx, flx, a.len_x)) - bx0;
+                            const int py = (FASTDIV ? vote_bin_fast(vy, a.min_y, ry, iry, fly, a.len_y)
+                                                    : vote_bin(vy, a.min_y, ry, fly, a.len_y)) - by0;
+                            const int pz = FASTDIV ? vote_bin_fast(vz, a.min_z, rz, irz, flz, a.len_z)
+                                                   : vote_bin(vz, a.min_z, rz, flz, a.len_z);
+                            if (px < 0 || px >= wx || py < 0 || py >= wy) {
+                                s_bad = 1;      // cannot happen (the range is conservative); fall back if it ever does
                             } else {
-                                atomicAdd(&histw[bin], 1u);
+                                const int bin = (px * wy + py) * lz + pz;
+                                if (COUNT16) {
+                                    const int sh = (bin & 1) * 16;
+                                    const unsigned int was = atomicAdd(&histw[bin >> 1], 1u << sh);
+                                    if (((was >> sh) & 0xffffu) == 0xffffu) s_bad = 1;      // this increment wrapped it
+                                } else {
+                                    atomicAdd(&histw[bin], 1u);
+                                }
                             }
                         }
                     }
