@@ -11,6 +11,8 @@ mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 {
   echo "== pytest -m gpu"; timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -15
+  echo "== non-finite inputs on the GPU (first run: under its own timeout)"
+  ICPF_RUN_NONFINITE_ON_GPU=1 timeout 120 python -m pytest tests/test_edge_fuzz.py -q -m gpu -k non_finite 2>&1 | tail -5
   echo "== bench (N=1)"; timeout 600 python bench.py 2>&1 | tail -2
   echo "== A/B (product + variants: C2 step, stop / big-cluster / init / hist_icp timings, output hashes)"
   timeout 600 python tools/ab_kernel.py run
