@@ -8,5 +8,7 @@ cd "$(dirname "$0")/../.."
 export ICPF_SIMT_ASAN=1
 export ASAN_OPTIONS=detect_leaks=0:halt_on_error=1
 export LD_PRELOAD="$(/usr/bin/gcc -print-file-name=libasan.so)"
-if [ $# -eq 0 ]; then set -- tests/ -k simt; fi
-exec python -m pytest -q -x -m "not gpu" "$@"
+if [ $# -eq 0 ]; then set -- tests/ -k "simt or fuzz or variants"; fi
+python -m pytest -q -x -m "not gpu" "$@"
+# ... and once more with the fibers of every block handed over in reverse order: same results = no order-dependent reads
+SIMT_ORDER=reverse python -m pytest -q -x -m "not gpu" "$@"

@@ -4,6 +4,7 @@
 #include "simt.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 
 #define ICPF_DYN_SHARED extern
 namespace icpf { ICPF_DYN_SHARED __align__(128) float4 g_tile[]; }
@@ -72,6 +73,18 @@ __global__ void dyn_shared_kernel(int* out, const float* src, int n) {
     if (threadIdx.x == blockDim.x - 1) out[1] = (int)s;
 }
 
+// a deliberate race: thread t reads what thread t + 1 writes, with no barrier in between.  The deterministic schedule
+// makes the outcome a function of the hand-over order -- forward: the neighbour has not run yet (stale value); reverse:
+// it has.  This is what running the suite under SIMT_ORDER=reverse relies on to expose missing barriers.
+__global__ void race_kernel(int* out) {
+    __shared__ int cell[64];
+    const int t = threadIdx.x;
+    cell[t] = -1;
+    __syncthreads();
+    cell[t] = t;
+    out[t] = cell[(t + 1) % 64];
+}
+
 extern "C" int simt_selftest() {
     g_fail = 0;
     int out[4] = {0, 0, 0, 0};
@@ -85,6 +98,18 @@ extern "C" int simt_selftest() {
     int ds[2] = {0, 0};
     simt::bind(dyn_shared_kernel, dim3(2), dim3(96), 100 * sizeof(float) + 64)(ds, (const float*)src, 100);
     if (ds[0] != 1 || ds[1] != 9900) { ++g_fail; fprintf(stderr, "selftest: dynamic shared memory %d %d\n", ds[0], ds[1]); }
+    {
+        int seen[64];
+        simt::bind(race_kernel, dim3(1), dim3(64), 0)(seen);
+        const char* ord = getenv("SIMT_ORDER");
+        const bool reverse = ord && ord[0] == 'r';
+        // (the thread that completes the barrier goes on first, then the others in hand-over order)
+        // forward: thread t runs before t + 1 -> stale -1, except thread 62 whose neighbour 63 completed the barrier;
+        // reverse: thread t runs after t + 1 -> fresh value, except thread 0 which completed the barrier itself
+        const bool ok = reverse ? (seen[5] == 6 && seen[63] == 0 && seen[0] == -1)
+                                : (seen[5] == -1 && seen[62] == 63 && seen[0] == -1);
+        if (!ok) { ++g_fail; fprintf(stderr, "selftest: race kernel saw %d %d %d %d\n", seen[0], seen[5], seen[62], seen[63]); }
+    }
     // an empty grid / oversized block is rejected like the runtime does (the launch does not happen, the error is fetched once)
     int untouched[2] = {7, 7};
     simt::bind(partial_warp_kernel, dim3(0), dim3(40), 0)(untouched);

@@ -79,10 +79,15 @@ void switch_to(int next) {
     simt_switch(save, to);
 }
 
+// Hand-over order.  The schedule is deterministic, so a missing barrier only shows when the reader happens to run before
+// the writer: SIMT_ORDER=reverse runs the fibers of a block from the last thread to the first (tests/simt/memcheck.sh
+// runs the suite both ways) -- results that differ between the two orders point at a race.
+const int g_step = (getenv("SIMT_ORDER") && getenv("SIMT_ORDER")[0] == 'r') ? -1 : 1;
+
 int next_live(int from) {
     const int n = g_blk.nthreads;
     for (int k = 1; k <= n; ++k) {
-        const int j = (from + k) % n;
+        const int j = ((from + g_step * k) % n + n) % n;
         if (g_fibers[j].live) return j;
     }
     return -1;
@@ -238,7 +243,7 @@ void run_grid(dim3 grid, dim3 block, size_t smem, void (*thread_fn)(void*), void
                     f.ids.warp = t >> 5;
                 }
                 g_spins = 0;
-                switch_to(0);      // returns when the last fiber of the block has finished
+                switch_to(g_step > 0 ? 0 : nthreads - 1);      // returns when the last fiber of the block has finished
                 if (g_blk.live != 0) { fprintf(stderr, "simt: block ended with %d live threads\n", g_blk.live); abort(); }
                 check_dyn_shared_tail(smem);
             }

@@ -17,6 +17,8 @@ def test_emulator_known_answers():
     flags = [f for f in simt_build.CXXFLAGS if f != "-include" and not f.endswith("simt.h")]
     subprocess.check_call([simt_build.CXX] + flags + ["-shared", "-o", out, os.path.join(SIMT, "selftest.cpp"),
                                                      os.path.join(SIMT, "simt.cpp"), os.path.join(SIMT, "dynshared.cpp")])
-    lib = ctypes.CDLL(out)
-    lib.simt_selftest.restype = ctypes.c_int
-    assert lib.simt_selftest() == 0
+    # both hand-over orders, each in a fresh process (the order is read when the library is loaded)
+    for order in ("forward", "reverse"):
+        code = f"import ctypes; L = ctypes.CDLL({out!r}); L.simt_selftest.restype = ctypes.c_int; raise SystemExit(L.simt_selftest())"
+        env = dict(os.environ, SIMT_ORDER=order)
+        assert subprocess.run([sys.executable, "-c", code], env=env).returncode == 0, order
