@@ -304,6 +304,23 @@ __device__ __forceinline__ IcpResult icp_iterations(const Tiles& tl, const GridI
                 // ---------------- deferred searches: dense lanes over the warp's compacted list
                 __syncthreads();
                 ndefer = *dcount;
+#ifdef ICPF_COOP_SEARCH
+                // A/B variant: four lanes per deferred row, one run each (grid_search_coop4) -- 32 rows per pass of the CTA
+                for (int i0 = 0; i0 < ndefer; i0 += kThreads / 4) {
+                    const int i = i0 + (tid >> 2);
+                    const bool active = i < ndefer;
+                    const int q = active ? dlist[i] : 0;
+                    const float4 x0 = active ? tl.src()[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float qx, qy, qz, d2, d2nd, box;
+                    int pos;
+                    apply_rt(R, T, x0.x, x0.y, x0.z, qx, qy, qz);
+                    grid_search_coop4(g, cand, cell_runs, active, tid & 3, qx, qy, qz, d2, pos, d2nd, box);
+                    if (active && (tid & 3) == 0) {
+                        const float bound = fminf(sqrtf(d2nd), box) * 0.9999f - g.pad;
+                        nnw[q] = NW::pack(pos, bound, (pos >= 0) && (d2 <= tau2) && (x0.w > 0.f));
+                    }
+                }
+#else
                 for (int i = tid; i < ndefer; i += kThreads) {
                     const int q = dlist[i];
                     const float4 x0 = tl.src()[q];
@@ -314,6 +331,7 @@ __device__ __forceinline__ IcpResult icp_iterations(const Tiles& tl, const GridI
                     const float bound = fminf(sqrtf(d2nd), box) * 0.9999f - g.pad;      // fresh, at the current position
                     nnw[q] = NW::pack(pos, bound, (pos >= 0) && (d2 <= tau2) && (x0.w > 0.f));
                 }
+#endif
                 __syncthreads();
             }
         }

@@ -399,6 +399,65 @@ __device__ __forceinline__ void grid_search(const GridInfo& g, const float4* __r
     pos = (key == kNone) ? -1 : (int)((unsigned int)key & 0xffffu);
 }
 
+// The same search by FOUR lanes (opt-in A/B variant ICPF_COOP_SEARCH, tools/ab_kernel.py): a query inspects at most 2 x 2
+// runs, lane `sub` (0..3) of the group scans run (ix0 + sub / 2, iy0 + sub % 2) and the four partial results are merged
+// with two xor-shuffles -- the winner is the minimum of the 64-bit keys and the runner-up distance the second smallest of
+// the multiset of distances, both independent of how the candidates were split, so every output equals grid_search's
+// bit for bit.  All 32 lanes of the warp must call it (shuffles); `active` = this lane's group has a query.
+__device__ __forceinline__ void grid_search_coop4(const GridInfo& g, const float4* __restrict__ sorted,
+                                                  const unsigned short* __restrict__ a, bool active, int sub, float qx,
+                                                  float qy, float qz, float& d2, int& pos, float& d2nd, float& box) {
+    const float INF = __int_as_float(0x7f800000);
+    const unsigned long long kNone = (0x7f800000ull << 32) | 0xffffffffull;
+    unsigned long long key = kNone;
+    d2nd = INF;
+    box = 0.f;
+    if (active) {
+        const float fx = (qx - g.ox) * g.inv_c, fy = (qy - g.oy) * g.inv_c, fz = (qz - g.oz) * g.inv_c;
+        const float x0 = floorf(fx - g.r), x1 = floorf(fx + g.r);
+        const float y0 = floorf(fy - g.r), y1 = floorf(fy + g.r);
+        const float z0 = floorf(fz - g.r), z1 = floorf(fz + g.r);
+        const float hx = (float)(g.gx - 1), hy = (float)(g.gy - 1), hz = (float)(g.gz - 1);
+        if (!(x1 >= 0.f && y1 >= 0.f && z1 >= 0.f && x0 <= hx && y0 <= hy && z0 <= hz)) {
+            const float gapx = fmaxf(-fx, fx - (hx + 1.f)), gapy = fmaxf(-fy, fy - (hy + 1.f)),
+                        gapz = fmaxf(-fz, fz - (hz + 1.f));
+            box = fmaxf(fmaxf(gapx, fmaxf(gapy, gapz)) * g.c - g.pad, 0.f);
+        } else {
+            const float bx = fminf(x0 < 0.f ? INF : fx - x0, x1 > hx ? INF : x1 + 1.f - fx);
+            const float by = fminf(y0 < 0.f ? INF : fy - y0, y1 > hy ? INF : y1 + 1.f - fy);
+            const float bz = fminf(z0 < 0.f ? INF : fz - z0, z1 > hz ? INF : z1 + 1.f - fz);
+            box = fmaxf(fminf(bx, fminf(by, bz)) * g.c - g.pad, 0.f);
+            const int ix0 = max(0, (int)x0), ix1 = min(g.gx - 1, (int)x1);
+            const int iy0 = max(0, (int)y0), iy1 = min(g.gy - 1, (int)y1);
+            const int iz0 = max(0, (int)z0), iz1 = min(g.gz - 1, (int)z1);
+            const int ix = ix0 + (sub >> 1), iy = iy0 + (sub & 1);
+            if (ix <= ix1 && iy <= iy1) {
+                const int base = (ix * g.gy + iy) * g.gz;
+                const int s = a[base + iz0], e = a[base + iz1 + 1];
+                for (int j = s; j < e; ++j) {
+                    const float4 c = sorted[j];
+                    const float d = sqdist(qx, qy, qz, c.x, c.y, c.z);
+                    const unsigned long long k = ((unsigned long long)__float_as_uint(d) << 32) | __float_as_uint(c.w);
+                    const bool better = k < key;
+                    d2nd = fminf(d2nd, better ? __uint_as_float((unsigned int)(key >> 32)) : d);
+                    key = better ? k : key;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+        const unsigned long long ok = __shfl_xor_sync(FULL_MASK, key, o);
+        const float od2nd = __shfl_xor_sync(FULL_MASK, d2nd, o);
+        // runner-up of the union: the smaller of the two runner-ups and the LOSING best
+        const unsigned long long lose = ok < key ? key : ok;
+        d2nd = fminf(fminf(d2nd, od2nd), __uint_as_float((unsigned int)(lose >> 32)));
+        key = ok < key ? ok : key;
+    }
+    d2 = __uint_as_float((unsigned int)(key >> 32));
+    pos = (key == kNone) ? -1 : (int)((unsigned int)key & 0xffffu);
+}
+
 // correspondence word kept per src row (PB = position bits: 13 for the shared-memory tiles, 14 for the large-cluster
 // variant): bits [0,PB) sorted position of the best candidate (all ones = none), bit PB "masked out", the remaining
 // high bits a lower bound on the distance of every OTHER dst point (the top bits of the fp32 pattern without its sign:

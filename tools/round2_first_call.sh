@@ -2,7 +2,8 @@
 # The first GPU call of the next round, in one command: everything this round changed after its last GPU measurement
 #  gets its parity run, its timing and its ncu evidence.  Run HERE first (builds the variants):
 #
-#     python tools/ab_kernel.py build nosameh=-DICPF_NO_SAME_H fullscan=-DICPF_GRIDNN_FULL_SCAN noresume=-DICPF_NO_RESUME
+#     python tools/ab_kernel.py build nosameh=-DICPF_NO_SAME_H fullscan=-DICPF_GRIDNN_FULL_SCAN noresume=-DICPF_NO_RESUME \
+#                                    coop=-DICPF_COOP_SEARCH
 #     gpurun --timeout 1500 -- 'bash tools/round2_first_call.sh'
 #
 # Outputs land in gpurun_out/ (copy what is to be judged into profiles/).
