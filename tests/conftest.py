@@ -13,6 +13,15 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "order_last: run after every other test (tests whose cuda variant has not had a GPU "
+                                       "run yet: a surprise in one of them must not hide the established ones under -x)")
+
+
+def pytest_collection_modifyitems(config, items):
+    last = [it for it in items if it.get_closest_marker("order_last") is not None]
+    if last:
+        first = [it for it in items if it.get_closest_marker("order_last") is None]
+        items[:] = first + last
 
 
 @pytest.fixture(params=[pytest.param("cuda", marks=pytest.mark.gpu), "simt"])

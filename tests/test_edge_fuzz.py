@@ -13,7 +13,7 @@ import torch
 from engines import is_simt, put
 from icp_flow_b200 import ops
 
-pytestmark = pytest.mark.usefixtures("engine")
+pytestmark = [pytest.mark.usefixtures("engine"), pytest.mark.order_last]
 
 
 def _batch(rng, P, N, kind):

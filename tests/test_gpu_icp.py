@@ -268,6 +268,7 @@ def test_batch_stop_beyond_the_first_pass_cap():
     _assert_parity(src[1:], r2.R.cpu(), r2.T.cpu(), ref2.R, ref2.T, ref2, max_unstable_frac=0.35)
 
 
+@pytest.mark.order_last
 @pytest.mark.parametrize("case", ["stop_inside_the_record", "stop_beyond_the_first_pass"])
 def test_state_at_the_batch_stop_equals_a_forced_run(case):
     """Whatever way a pair obtains its state at the batch stop k* -- it stopped at its fixed point before, it reads the
@@ -290,6 +291,7 @@ def test_state_at_the_batch_stop_equals_a_forced_run(case):
     assert torch.equal(r.R, f.R) and torch.equal(r.T, f.T) and torch.equal(r.rmse, f.rmse) and torch.equal(r.pose, f.pose)
 
 
+@pytest.mark.order_last
 def test_paused_and_continued_pairs_equal_the_uninterrupted_run():
     """With early exit the first pass is capped at 32 iterations and the pairs still moving there are CONTINUED by the
     full pass (loop state + per-iteration record).  Without early exit nothing is capped or paused: both runs must give

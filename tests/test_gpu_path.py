@@ -316,6 +316,7 @@ def _first_set_bit(words, limit):
     return None
 
 
+@pytest.mark.order_last
 @pytest.mark.parametrize("case", ["stop_below_the_cap", "stop_beyond_the_cap"])
 def test_apply_icp_in_phases_equals_the_single_call(case):
     """icpf_apply_icp_phase_f32 (the seam a sharded caller uses to exchange the batch stop, include/icpflow_b200.h) with
