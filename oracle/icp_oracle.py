@@ -271,15 +271,19 @@ def icp_loop(X: torch.Tensor, Y: torch.Tensor, thres: float = 0.1, max_iteration
 
 
 def unstable_pairs(trace: IcpTrace, margin_m: float = 3e-5, min_inliers: int = 6, sigma_ratio: float = 1e-3,
-                   last: int = 3):
+                   last: int = 3, early_margin_m: float = 1e-6):
     """Pairs whose reference result is not numerically determined to 1e-4: during the last `last` iterations a
     correspondence sat within `margin_m` of the gate (a differently-rounded but equally valid fp32 evaluation of
-    x R + T -- 1 ulp at 50 m is 4e-6 m -- flips it and moves the fixed point), or the Kabsch system was (nearly)
-    rank deficient (fewer than `min_inliers` correspondences / second singular value below `sigma_ratio` of the
-    first: the reference returns whatever LAPACK picks, SURVEY.md section 7 "3x3 SVD")."""
+    x R + T -- 1 ulp at 50 m is 4e-6 m -- flips it and moves the fixed point), or at ANY iteration one sat within
+    `early_margin_m` of it (half an ulp of a coordinate at 16-32 m: which side it falls on is decided by the last bit of
+    R, and a poorly constrained registration need not find its way back to the same fixed point), or the Kabsch system
+    was (nearly) rank deficient (fewer than `min_inliers` correspondences / second singular value below `sigma_ratio` of
+    the first: the reference returns whatever LAPACK picks, SURVEY.md section 7 "3x3 SVD")."""
     assert trace.min_gate_margin is not None, "run icp_loop(..., diagnostics=True)"
     tail = trace.min_gate_margin[-last:].amin(dim=0)
-    return (tail < margin_m) | (trace.min_inliers < min_inliers) | (trace.min_sigma_ratio < sigma_ratio)
+    anywhere = trace.min_gate_margin.amin(dim=0)
+    return ((tail < margin_m) | (anywhere < early_margin_m) | (trace.min_inliers < min_inliers) |
+            (trace.min_sigma_ratio < sigma_ratio))
 
 
 def pack_rt(R: torch.Tensor, T: torch.Tensor) -> torch.Tensor:
