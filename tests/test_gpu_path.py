@@ -77,7 +77,7 @@ def test_hist_votes_edges_and_errors():
         ops.hist(X, Y, -1, -1, -1, 1, 1, 1, 2, 2, 2)
 
 
-@pytest.mark.parametrize("name", ["c1_demo.npz", "synth_hist.npz", "synth_hist_default.npz"])
+@pytest.mark.parametrize("name", ["c1_demo.npz", "synth_hist.npz", pytest.param("synth_hist_default.npz", marks=pytest.mark.order_last)])
 def test_estimate_init_pose_vs_reference_golden(golden, name):
     g = golden(name)
     _, _, a, c = _swapped(g)
@@ -123,7 +123,7 @@ def test_estimate_init_pose_vs_reference_golden(golden, name):
     assert torch.equal(pose2, pose)
 
 
-@pytest.mark.parametrize("name", ["c1_demo.npz", "synth_hist.npz", "synth_hist_default.npz"])
+@pytest.mark.parametrize("name", ["c1_demo.npz", "synth_hist.npz", pytest.param("synth_hist_default.npz", marks=pytest.mark.order_last)])
 def test_apply_icp_vs_reference_golden(golden, name):
     g = golden(name)
     _, _, a, c = _swapped(g)
@@ -148,7 +148,7 @@ def test_apply_icp_vs_reference_golden(golden, name):
     assert abs(dbg["batch"].tolist()[0] - int(g["icp_iterations"])) <= 2
 
 
-@pytest.mark.parametrize("name", ["c1_demo.npz", "synth_hist.npz", "synth_hist_default.npz"])
+@pytest.mark.parametrize("name", ["c1_demo.npz", "synth_hist.npz", pytest.param("synth_hist_default.npz", marks=pytest.mark.order_last)])
 def test_hist_icp_vs_reference_golden(golden, name):
     """The whole path in one native call (utils_match.hist_icp), including the swap and the final inversion."""
     g = golden(name)

@@ -21,7 +21,7 @@ def _params(g):
     return O.PathParams(thres_dist=float(g["thres_dist"]), translation_frame=float(g["translation_frame"]))
 
 
-@pytest.mark.parametrize("name", ["c1_demo.npz", "synth_hist.npz", "synth_hist_default.npz"])
+@pytest.mark.parametrize("name", ["c1_demo.npz", "synth_hist.npz", pytest.param("synth_hist_default.npz", marks=pytest.mark.order_last)])
 def test_oracle_match_eval_bitwise(golden, name):
     g = golden(name)
     ev = O.match_eval(torch.from_numpy(g["src"]), torch.from_numpy(g["dst"]), torch.from_numpy(g["T_hist_icp"]), _params(g))
@@ -70,7 +70,7 @@ def _compare(ev, ref, det):
 
 
 @pytest.mark.usefixtures("engine")
-@pytest.mark.parametrize("name", ["c1_demo.npz", "synth_hist.npz", "synth_hist_default.npz"])
+@pytest.mark.parametrize("name", ["c1_demo.npz", "synth_hist.npz", pytest.param("synth_hist_default.npz", marks=pytest.mark.order_last)])
 def test_engine_match_eval_vs_reference_golden(golden, name):
     g = golden(name)
     src, dst, T = torch.from_numpy(g["src"]), torch.from_numpy(g["dst"]), torch.from_numpy(g["T_hist_icp"])
