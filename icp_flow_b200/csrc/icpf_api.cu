@@ -10,7 +10,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 extern "C" {
 
-int icpf_version(void) { return 100; }
+int icpf_version(void) { return 101; }   // 101: icpf_apply_icp_phase_f32, larger icpf_workspace_bytes (per-iteration record)
 
 const char* icpf_error_string(int code) {
     switch (code) {
