@@ -97,8 +97,10 @@ __device__ __forceinline__ void grid_pruned_min(const GridInfo& g, const float4*
     bool xlo_open = true, xhi_open = xhi < g.gx;
     while (xlo_open || xhi_open) {
         // gap (cells) between the position and the next slab of either side; the nearer side goes first
-        const float gl = xlo_open ? fmaxf(fx - (float)(xlo + 1), 0.f) : INF;
-        const float gh = xhi_open ? fmaxf((float)xhi - fx, 0.f) : INF;
+        // (distance from fx to the slab's interval [i, i + 1]; the query's own slab is clamped into the grid, so a
+        //  position outside the grid is at a positive distance from it too)
+        const float gl = xlo_open ? fmaxf(fmaxf(fx - (float)(xlo + 1), (float)xlo - fx), 0.f) : INF;
+        const float gh = xhi_open ? fmaxf(fmaxf((float)xhi - fx, fx - (float)(xhi + 1)), 0.f) : INF;
         const bool lo_side = gl <= gh;
         const float lbx = fmaxf((lo_side ? gl : gh) * g.c - g.pad, 0.f);
         if (lbx >= best) {                       // every slab further out on this side is at least as far
@@ -111,8 +113,8 @@ __device__ __forceinline__ void grid_pruned_min(const GridInfo& g, const float4*
         int ylo = sy0, yhi = sy0 + 1;
         bool ylo_open = true, yhi_open = yhi < g.gy;
         while (ylo_open || yhi_open) {
-            const float hl = ylo_open ? fmaxf(fy - (float)(ylo + 1), 0.f) : INF;
-            const float hh = yhi_open ? fmaxf((float)yhi - fy, 0.f) : INF;
+            const float hl = ylo_open ? fmaxf(fmaxf(fy - (float)(ylo + 1), (float)ylo - fy), 0.f) : INF;
+            const float hh = yhi_open ? fmaxf(fmaxf((float)yhi - fy, fy - (float)(yhi + 1)), 0.f) : INF;
             const bool ylo_side = hl <= hh;
             const float lby = fmaxf((ylo_side ? hl : hh) * g.c - g.pad, 0.f);
             if (fmaf(lby, lby, lbx2) >= best2) {
