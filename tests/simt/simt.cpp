@@ -82,10 +82,24 @@ void switch_to(int next) {
 // Hand-over order.  The schedule is deterministic, so a missing barrier only shows when the reader happens to run before
 // the writer: SIMT_ORDER=reverse runs the fibers of a block from the last thread to the first (tests/simt/memcheck.sh
 // runs the suite both ways) -- results that differ between the two orders point at a race.
-const int g_step = (getenv("SIMT_ORDER") && getenv("SIMT_ORDER")[0] == 'r') ? -1 : 1;
+// SIMT_ORDER=shuffle[:seed] picks the next fiber at random at every hand-over (any interleaving of the threads between
+// their synchronisation points is a legal CUDA execution); slower -- a barrier completes only once every fiber has been
+// drawn -- so it is meant for a subset of the tests.
+const char* const g_order = getenv("SIMT_ORDER") ? getenv("SIMT_ORDER") : "forward";
+const int g_step = (g_order[0] == 'r') ? -1 : 1;
+const bool g_shuffle = (g_order[0] == 's');
+unsigned long long g_rng = []() {
+    const char* c = strchr(g_order, ':');
+    return 0x9e3779b97f4a7c15ull ^ (c ? strtoull(c + 1, nullptr, 10) * 0xbf58476d1ce4e5b9ull : 0ull);
+}();
 
 int next_live(int from) {
     const int n = g_blk.nthreads;
+    if (g_shuffle) {
+        g_rng ^= g_rng << 13; g_rng ^= g_rng >> 7; g_rng ^= g_rng << 17;          // xorshift64
+        from = (int)(g_rng % (unsigned long long)n);
+        if (g_fibers[from].live) return from;
+    }
     for (int k = 1; k <= n; ++k) {
         const int j = ((from + g_step * k) % n + n) % n;
         if (g_fibers[j].live) return j;
