@@ -22,6 +22,13 @@
 #pragma once
 
 #include "icpf_pair.cuh"
+#ifdef ICPF_PHASE_CLOCKS
+#include <cstdio>
+#endif
+#if defined(ICPF_ITER_STATS) && defined(ICPF_SIMT_EMU)
+// emulator-only instrumentation (tools/iter_stats_simt.py): per iteration {rows re-validated, rows searched, warps that summed again, pairs}
+extern "C" { long long icpf_dbg_iter_stats[128][4]; }
+#endif
 
 namespace icpf {
 
@@ -93,14 +100,6 @@ __device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
     return v[0];
 }
 
-// Squared distance a row moved since the cache reference transform: | x0 (R - Rc) + (T - Tc) |^2, inflated.
-__device__ __forceinline__ float moved_sq(const float (&dr)[9], const float (&dt)[3], const float4& x0) {
-    const float mx = fmaf(x0.z, dr[6], fmaf(x0.y, dr[3], x0.x * dr[0])) + dt[0];
-    const float my = fmaf(x0.z, dr[7], fmaf(x0.y, dr[4], x0.x * dr[1])) + dt[1];
-    const float mz = fmaf(x0.z, dr[8], fmaf(x0.y, dr[5], x0.x * dr[2])) + dt[2];
-    return fmaf(mz, mz, fmaf(my, my, mx * mx)) * 1.001f + 1e-12f;
-}
-
 // The ICP loop for the pair held in `tl`.
 //   MODE 1: candidates = tl.dst(), brute force.  MODE 2: candidates = tl.sorted() + grid `g` (build_grid must have run).
 //   MODE 3: grid + correspondence cache.  A row whose cached best candidate is provably still its strict nearest
@@ -152,7 +151,11 @@ __device__ __forceinline__ IcpResult icp_iterations(const Tiles& tl, const GridI
         bc[B_PX] = pivx; bc[B_PX + 1] = pivy; bc[B_PX + 2] = pivz;
         bc[B_PY] = pivx; bc[B_PY + 1] = pivy; bc[B_PY + 2] = pivz;
         bc[B_EXIT] = 0.f;
-        *reinterpret_cast<int*>(bc + B_DEFER) = 0;
+        bc[B_ZEROSTEP] = 0.f;
+        *reinterpret_cast<int*>(bc + B_SEARCH) = 0;
+        bc[B_PIVMOVED] = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) reinterpret_cast<int*>(bc + B_DIRTY)[w] = 0;
         reinterpret_cast<KabschState*>(bc + B_KABSCH)->warm = false;     // first solve of this pair starts cold
     }
     __syncthreads();
@@ -189,6 +192,15 @@ __device__ __forceinline__ IcpResult icp_iterations(const Tiles& tl, const GridI
         __syncthreads();
     }
 
+#ifdef ICPF_PHASE_CLOCKS
+    long long pc[6] = {0, 0, 0, 0, 0, 0}, pt0 = clock64();
+#define ICPF_PC(i) { const long long now_ = clock64(); pc[i] += now_ - pt0; pt0 = now_; }
+#else
+#define ICPF_PC(i)
+#endif
+    // The moment sums of a warp's rows are a pure function of (correspondences, gate flags, pivots): a warp whose rows
+    // kept all three since it last summed them finds its 16 partial sums still in the scratch, bit for bit.
+    bool have_partials = false;
     for (int it = first_it; !done && it < max_it; ++it) {
         // the first iteration of a resumed run only rebuilds the correspondences of iteration resume_it - 1, under the
         // transform that iteration searched with (on record); its solve is on record too
@@ -206,24 +218,12 @@ __device__ __forceinline__ IcpResult icp_iterations(const Tiles& tl, const GridI
             for (int i = 0; i < 3; ++i) T[i] = bc[B_T + i];
         }
         // The cache is re-anchored every iteration: bounds are kept relative to the row's position in the previous
-        // iteration, so the motion that counts is the step (R_k - R_{k-1}, T_k - T_{k-1}) thread 0 left in the
-        // broadcast block; a row is searched again only when its own bound is used up.
+        // iteration, so the motion that counts is the last step; a row is searched again only when its own bound is used up.
         const bool refresh = !CACHE || (it == first_it);      // dense search of every row (always, without the cache)
-        float dr[9], dt[3];
-        if (CACHE && !refresh) {
-#pragma unroll
-            for (int i = 0; i < 9; ++i) dr[i] = bc[B_RC + i];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) dt[i] = bc[B_TC + i];
-        }
-        const float anchor_slack = 0.1f * g.pad;      // fp32 rounding of the two positions whose distance is m
         float sq = 0.f;
-        int ndefer = 0;
-        // rows whose cached neighbour failed are appended to ONE list per CTA (warp-aggregated atomic), so that the
-        // searches afterwards run with dense lanes: a few failing rows per warp would otherwise cost every warp a
-        // whole divergent search
+        int nsearch = 0;
+        bool chg = !(CACHE && !refresh) || !have_partials || (bc[B_PIVMOVED] != 0.f);     // this lane saw a reason to sum again
         unsigned short* dlist = GRID ? tl.defer() : nullptr;
-        int* dcount = reinterpret_cast<int*>(bc + B_DEFER);
 
         // ---------------- pass A: rmse numerator of the previous iteration + correspondence search of this one
         if (MODE == 1) {
@@ -252,87 +252,108 @@ __device__ __forceinline__ IcpResult icp_iterations(const Tiles& tl, const GridI
                 }
             }
         } else {
-            for (int b = 0; b < nbatch; ++b) {
-                const int q = b * kThreads + tid;
-                const bool valid = q < n_s;
-                const float4 x0 = valid ? tl.src()[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-                float qx, qy, qz;
-                apply_rt(R, T, x0.x, x0.y, x0.z, qx, qy, qz);
-                const unsigned int wold = (it > first_it && valid) ? nnw[q] : (kNnMasked | kNnNone);
-                int pos = (wold & kNnPosMask) == kNnNone ? -1 : (int)(wold & kNnPosMask);
-                float d2 = INF;
-                if (pos >= 0 && (!(wold & kNnMasked) || (CACHE && !refresh))) {
-                    const float4 c = cand[pos];
-                    d2 = sqdist(qx, qy, qz, c.x, c.y, c.z);
-                    if (!(wold & kNnMasked)) sq += d2;
+            if (CACHE && !refresh && bc[B_ZEROSTEP] != 0.f) {
+                // The transform is the previous iteration's bit for bit: every row sits where it sat, so every cached
+                // correspondence, gate flag and bound stands as it is; only the rmse numerator is due.
+                for (int b = 0; b < nbatch; ++b) {
+                    const int q = b * kThreads + tid;
+                    if (q >= n_s) continue;
+                    const unsigned int wold = nnw[q];
+                    if (wold & kNnMasked) continue;
+                    const float4 x0 = tl.src()[q];
+                    const float4 c = cand[wold & kNnPosMask];
+                    float qx, qy, qz;
+                    apply_rt(R, T, x0.x, x0.y, x0.z, qx, qy, qz);
+                    sq += sqdist(qx, qy, qz, c.x, c.y, c.z);
                 }
-                bool need = valid;
-                if (CACHE && !refresh) {
-                    if (valid) {
-                        const float bound = NW::bound(wold);
-                        const float m2 = moved_sq(dr, dt, x0);
-                        const float m = fast_sqrt(m2) * 1.0001f;
-                        // (a) every other point is provably farther than tau: only the cached candidate can pass
-                        bool hit = bound > tau_hi + m;
-                        // (b) the cached candidate is provably still the strict nearest neighbour: d_best < B - m, tested on
-                        //     the squares (rem > 0), with 1.5e-4 of head-room for the rounding of either side
-                        const float rem = bound - m;
-                        if (pos >= 0) hit = hit || (rem > 0.f && d2 * 1.0003f < rem * rem);
-                        if (hit) {
-                            // re-anchor: relative to the row's NEW position every other point is >= bound - m away
-                            nnw[q] = NW::pack(pos, rem - anchor_slack, (pos >= 0) && (d2 <= tau2) && (x0.w > 0.f));
-                            need = false;
-                        }
+            } else if (CACHE && !refresh) {
+                // the step (R_k - R_{k-1}, T_k - T_{k-1}) thread 0 left in the broadcast block: bounds are kept relative to
+                // the row's position in the previous iteration and re-anchored every iteration
+                float dr[9], dt[3];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) dr[i] = bc[B_RC + i];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) dt[i] = bc[B_TC + i];
+                const float anchor_slack = 0.1f * g.pad;      // fp32 rounding of the two positions whose distance is m
+                const unsigned int lt = (1u << lane) - 1u;
+                int* dcount = reinterpret_cast<int*>(bc + B_SEARCH);
+                for (int b = 0; b < nbatch; ++b) {
+                    const int q = b * kThreads + tid;
+                    const bool valid = q < n_s;
+                    const float4 x0 = valid ? tl.src()[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const unsigned int wold = valid ? nnw[q] : (kNnMasked | kNnNone);
+                    float qx, qy, qz;
+                    apply_rt(R, T, x0.x, x0.y, x0.z, qx, qy, qz);
+                    const unsigned int pos = wold & kNnPosMask;
+                    const bool has = pos != kNnNone;
+                    const float4 c = cand[has ? pos : 0u];
+                    const float d2 = has ? sqdist(qx, qy, qz, c.x, c.y, c.z) : INF;
+                    if (!(wold & kNnMasked)) sq += d2;          // rmse numerator: new transform, old correspondence
+                    // distance the row moved in this step (inflated), and what is left of its bound
+                    const float mx = fmaf(x0.z, dr[6], fmaf(x0.y, dr[3], x0.x * dr[0])) + dt[0];
+                    const float my = fmaf(x0.z, dr[7], fmaf(x0.y, dr[4], x0.x * dr[1])) + dt[1];
+                    const float mz = fmaf(x0.z, dr[8], fmaf(x0.y, dr[5], x0.x * dr[2])) + dt[2];
+                    const float rem = NW::bound(wold) - (sqrtf(fmaf(mz, mz, fmaf(my, my, mx * mx))) * 1.0002f + anchor_slack);
+                    // (a) every other point is provably beyond the gate: only the cached candidate can pass it;
+                    // (b) the cached candidate is provably still the strict nearest neighbour: d_best < rem, tested on
+                    //     the squares with 1.5e-4 of head-room for the rounding of either side
+                    const bool hit = (rem > tau_hi) || (rem > 0.f && d2 * 1.0003f < rem * rem);
+                    const bool masked = !((d2 <= tau2) && (x0.w > 0.f));           // (no candidate: d2 = inf)
+                    if (hit) {
+                        nnw[q] = NW::pack(has ? (int)pos : -1, rem, !masked);       // re-anchored at the new position
+                        chg = chg || (masked != ((wold & kNnMasked) != 0u));      // the gate flag changed
                     }
+                    const bool need = valid && !hit;
                     const unsigned int vote = __ballot_sync(FULL_MASK, need);
                     if (vote != 0u) {
+                        // rows whose cached neighbour failed go to ONE list per CTA (warp-aggregated atomic), so that
+                        // the searches afterwards run with dense lanes
                         int base = 0;
                         if (lane == 0) base = atomicAdd(dcount, __popc(vote));
                         base = __shfl_sync(FULL_MASK, base, 0);
-                        if (need) dlist[base + __popc(vote & ((1u << lane) - 1u))] = (unsigned short)q;
+                        if (need) dlist[base + __popc(vote & lt)] = (unsigned short)q;
                     }
-                } else if (need) {
-                    float d2nd, box;
-                    grid_search(g, cand, cell_runs, qx, qy, qz, d2, pos, d2nd, box);
+                }
+                __syncthreads();
+                ICPF_PC(0)
+                nsearch = *dcount;
+                if (nsearch > 0) {
+                    // ---------------- searches of the rows whose cached neighbour could not be proven
+                    for (int i = tid; i < nsearch; i += kThreads) {
+                        const int q = dlist[i];
+                        const float4 x0 = tl.src()[q];
+                        float qx, qy, qz;
+                        apply_rt(R, T, x0.x, x0.y, x0.z, qx, qy, qz);
+                        const NnTop2 nn = grid_search(g, cand, cell_runs, qx, qy, qz);
+                        const unsigned int wnew = NW::pack(nn.pos1, fminf(sqrtf(nn.d2), nn.box) * 0.9999f - g.pad, (nn.d1 <= tau2) && (x0.w > 0.f));
+                        if (((wnew ^ nnw[q]) & (kNnPosMask | kNnMasked)) != 0u) reinterpret_cast<int*>(bc + B_DIRTY)[(q >> 5) & (kWarps - 1)] = 1;
+                        nnw[q] = wnew;
+                    }
+                    __syncthreads();
+                    if (reinterpret_cast<int*>(bc + B_DIRTY)[warp] != 0) chg = true;
+                    __syncwarp();
+                    if (lane == 0) reinterpret_cast<int*>(bc + B_DIRTY)[warp] = 0;
+                }
+                ICPF_PC(1)
+            } else {
+                for (int b = 0; b < nbatch; ++b) {
+                    const int q = b * kThreads + tid;
+                    if (q >= n_s) continue;
+                    const float4 x0 = tl.src()[q];
+                    float qx, qy, qz;
+                    apply_rt(R, T, x0.x, x0.y, x0.z, qx, qy, qz);
+                    if (it > first_it) {
+                        const unsigned int wold = nnw[q];
+                        if (!(wold & kNnMasked)) {
+                            const float4 c = cand[wold & kNnPosMask];
+                            sq += sqdist(qx, qy, qz, c.x, c.y, c.z);
+                        }
+                    }
                     // g.pad (>= 1e-4 m, >= 16 ulp of the largest coordinate) covers the fp32 rounding of the
                     // transformed positions whose separation m is bounded analytically
-                    const float bound = fminf(sqrtf(d2nd), box) * 0.9999f - g.pad;
-                    nnw[q] = NW::pack(pos, bound, (pos >= 0) && (d2 <= tau2) && (x0.w > 0.f));
+                    const NnTop2 nn = grid_search(g, cand, cell_runs, qx, qy, qz);
+                    nnw[q] = NW::pack(nn.pos1, CACHE ? fminf(sqrtf(nn.d2), nn.box) * 0.9999f - g.pad : 0.f, (nn.d1 <= tau2) && (x0.w > 0.f));
                 }
-            }
-            if (CACHE && !refresh) {
-                // ---------------- deferred searches: dense lanes over the warp's compacted list
-                __syncthreads();
-                ndefer = *dcount;
-#ifdef ICPF_COOP_SEARCH
-                // A/B variant: four lanes per deferred row, one run each (grid_search_coop4) -- 32 rows per pass of the CTA
-                for (int i0 = 0; i0 < ndefer; i0 += kThreads / 4) {
-                    const int i = i0 + (tid >> 2);
-                    const bool active = i < ndefer;
-                    const int q = active ? dlist[i] : 0;
-                    const float4 x0 = active ? tl.src()[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    float qx, qy, qz, d2, d2nd, box;
-                    int pos;
-                    apply_rt(R, T, x0.x, x0.y, x0.z, qx, qy, qz);
-                    grid_search_coop4(g, cand, cell_runs, active, tid & 3, qx, qy, qz, d2, pos, d2nd, box);
-                    if (active && (tid & 3) == 0) {
-                        const float bound = fminf(sqrtf(d2nd), box) * 0.9999f - g.pad;
-                        nnw[q] = NW::pack(pos, bound, (pos >= 0) && (d2 <= tau2) && (x0.w > 0.f));
-                    }
-                }
-#else
-                for (int i = tid; i < ndefer; i += kThreads) {
-                    const int q = dlist[i];
-                    const float4 x0 = tl.src()[q];
-                    float qx, qy, qz, d2, d2nd, box;
-                    int pos;
-                    apply_rt(R, T, x0.x, x0.y, x0.z, qx, qy, qz);
-                    grid_search(g, cand, cell_runs, qx, qy, qz, d2, pos, d2nd, box);
-                    const float bound = fminf(sqrtf(d2nd), box) * 0.9999f - g.pad;      // fresh, at the current position
-                    nnw[q] = NW::pack(pos, bound, (pos >= 0) && (d2 <= tau2) && (x0.w > 0.f));
-                }
-#endif
-                __syncthreads();
             }
         }
 
@@ -342,10 +363,19 @@ __device__ __forceinline__ IcpResult icp_iterations(const Tiles& tl, const GridI
         }
 
         // ---------------- pass B: raw moments about the pivots (same code and order in every mode)
-        float mom[16];
+        const bool sum_again = __any_sync(FULL_MASK, chg) != 0;
+#if defined(ICPF_ITER_STATS) && defined(ICPF_SIMT_EMU)
+        if (lane == 0 && it < 128) {
+            icpf_dbg_iter_stats[it][0] += (bc[B_ZEROSTEP] != 0.f && warp == 0) ? 1 : 0;
+            icpf_dbg_iter_stats[it][1] += (warp == 0) ? nsearch : 0;
+            icpf_dbg_iter_stats[it][2] += sum_again ? 1 : 0;
+            icpf_dbg_iter_stats[it][3] += (warp == 0) ? 1 : 0;
+        }
+#endif
+        if (sum_again) {
+            float mom[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) mom[i] = 0.f;
-        {
+            for (int i = 0; i < 16; ++i) mom[i] = 0.f;
             const float px = bc[B_PX], py = bc[B_PX + 1], pz = bc[B_PX + 2];
             const float ux = bc[B_PY], uy = bc[B_PY + 1], uz = bc[B_PY + 2];
             for (int b = 0; b < nbatch; ++b) {
@@ -363,15 +393,17 @@ __device__ __forceinline__ IcpResult icp_iterations(const Tiles& tl, const GridI
                 mom[10] = fmaf(ay, bx, mom[10]); mom[11] = fmaf(ay, by, mom[11]); mom[12] = fmaf(ay, bz, mom[12]);
                 mom[13] = fmaf(az, bx, mom[13]); mom[14] = fmaf(az, by, mom[14]); mom[15] = fmaf(az, bz, mom[15]);
             }
+            const float msum = warp_reduce16(mom, lane);
+            if ((lane & 1) == 0) part[warp * kSums + reduce16_slot(lane)] = msum;
+            have_partials = true;
         }
-        const float msum = warp_reduce16(mom, lane);
         sq = warp_sum(sq);
-        if ((lane & 1) == 0) part[warp * kSums + reduce16_slot(lane)] = msum;
         if (lane == 0) {
             part[warp * kSums + 16] = sq;
-            part[warp * kSums + 17] = (warp == 0) ? (float)ndefer : 0.f;
+            part[warp * kSums + 17] = (warp == 0) ? (float)nsearch : 0.f;      // (the CTA's count)
         }
         __syncthreads();
+        ICPF_PC(2)
 
         // ---------------- one warp folds the partials, one thread solves the 3x3 problem
         if (warp == 0) {
@@ -444,6 +476,7 @@ __device__ __forceinline__ IcpResult icp_iterations(const Tiles& tl, const GridI
                 for (int i = 0; i < 9; ++i) same = same && (__float_as_uint(rot.r[i]) == __float_as_uint(bc[B_R + i]));
 #pragma unroll
                 for (int i = 0; i < 3; ++i) same = same && (__float_as_uint(t[i]) == __float_as_uint(bc[B_T + i]));
+                bc[B_PIVMOVED] = move_pivot ? 1.f : 0.f;
                 if (move_pivot) {
                     bc[B_PX] = cx0; bc[B_PX + 1] = cx1; bc[B_PX + 2] = cx2;
                     bc[B_PY] = cy0; bc[B_PY + 1] = cy1; bc[B_PY + 2] = cy2;
@@ -454,25 +487,40 @@ __device__ __forceinline__ IcpResult icp_iterations(const Tiles& tl, const GridI
                     res.searches += refresh ? (float)n_s : total[17];
                     res.refreshes += refresh ? 1 : 0;
                     // the step the rows take between this search and the next one
+                    bool zero = true;
 #pragma unroll
-                    for (int i = 0; i < 9; ++i) bc[B_RC + i] = rot.r[i] - bc[B_R + i];
+                    for (int i = 0; i < 9; ++i) {
+                        const float d = rot.r[i] - bc[B_R + i];
+                        bc[B_RC + i] = d;
+                        zero = zero && (d == 0.f);
+                    }
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) bc[B_TC + i] = t[i] - bc[B_T + i];
+                    for (int i = 0; i < 3; ++i) {
+                        const float d = t[i] - bc[B_T + i];
+                        bc[B_TC + i] = d;
+                        zero = zero && (d == 0.f);
+                    }
+                    bc[B_ZEROSTEP] = zero ? 1.f : 0.f;
                 }
 #pragma unroll
                 for (int i = 0; i < 9; ++i) bc[B_R + i] = rot.r[i];
 #pragma unroll
                 for (int i = 0; i < 3; ++i) bc[B_T + i] = t[i];
-                *reinterpret_cast<int*>(bc + B_DEFER) = 0;
+                *reinterpret_cast<int*>(bc + B_SEARCH) = 0;
                 bc[B_EXIT] = (early_exit && same) ? 1.f : 0.f;
             }
         }
         __syncthreads();
+        ICPF_PC(3)
         done = bc[B_EXIT] != 0.f;
         // (R, T) after this iteration; thread 0 rewrites the broadcast block only behind the next iteration's barriers
         if (hist != nullptr && it < hist_depth && tid < 12) hist[it * 13 + tid] = bc[B_R + tid];
     }
 
+#ifdef ICPF_PHASE_CLOCKS
+    if (tid == 0 && (blockIdx.x % 251) == 0)
+        printf("PC block %d: A %lld D %lld B %lld S %lld (cycles over all iterations)\n", (int)blockIdx.x, pc[0], pc[1], pc[2], pc[3]);
+#endif
     // ---------------- rmse of the last iteration executed (final transform against its own correspondences)
 #pragma unroll
     for (int i = 0; i < 9; ++i) res.r[i] = bc[B_R + i];

@@ -30,7 +30,7 @@ constexpr float kCellFactor = 2.2f;  // grid cell size in units of the padded ga
 constexpr int kGridMaxCells = 2048;    // uniform-grid cells per pair (u16 offsets: 4 KB of shared memory)
 
 // reduction scratch (floats): per-warp partials of the 18 per-iteration sums, their totals; the grid build reuses it
-constexpr int kSums = 18;                      // 16 moments + rmse numerator + deferred-search count
+constexpr int kSums = 18;                      // 16 moments + rmse numerator + rows searched
 constexpr int kScrPart = 0;                    // [kWarps][kSums]
 constexpr int kScrTotal = kScrPart + kWarps * kSums;
 constexpr int kRedFloats = kScrTotal + 24;
@@ -38,9 +38,12 @@ constexpr int kBcastFloats = 64;
 constexpr int kCellWords = (kGridMaxCells + 2 + 1) / 2 + 2;   // packed u16 entries 0..G (+pad), as u32 words
 
 // broadcast block written by thread 0 once per iteration
-enum : int { B_R = 0, B_T = 9, B_RC = 12 /* last step R_k - R_{k-1} */, B_TC = 21 /* last step T_k - T_{k-1} */, B_PX = 24, B_PY = 27, B_EXIT = 30, B_DEFER = 31 /* int: rows queued for a search */,
-             B_KABSCH = 32 /* KabschState: 9 floats + 2 flags */, B_HPREV = 44 /* cross-covariance of the previous solve */ };
-static_assert(B_HPREV + 9 <= kBcastFloats, "broadcast block");
+enum : int { B_R = 0, B_T = 9, B_RC = 12 /* last step R_k - R_{k-1} */, B_TC = 21 /* last step T_k - T_{k-1} */, B_PX = 24, B_PY = 27, B_EXIT = 30,
+             B_SEARCH = 31 /* int: rows queued for a search */, B_KABSCH = 32 /* KabschState: 9 floats + 2 flags */,
+             B_HPREV = 44 /* cross-covariance of the previous solve */,
+             B_DIRTY = 53 /* int[kWarps]: a search changed a correspondence of this warp's rows */, B_PIVMOVED = 57 /* the pivots moved */,
+             B_ZEROSTEP = 58 /* the last step was exactly zero */ };
+static_assert(B_ZEROSTEP < kBcastFloats && B_HPREV + 9 <= B_DIRTY, "broadcast block");
 
 // Dynamic shared memory of every pair kernel.  Tiles are addressed as OFFSETS into this one array so that the
 // compiler always knows the address space (a run-time swap of two pointers degrades every access to a generic LD/ST).
@@ -52,7 +55,7 @@ struct PairTiles {
     int dst_off;      // [N] float4 (x,y,z,flag) -- the fixed cloud as stored (TMA landing zone)
     int sorted_off;   // [N] float4 grid mode: dst rows in cell order, .w = (original row << 16 | sorted position)
     int cells_off;    // [kCellWords] u32 grid mode: packed u16 run boundaries; run of cell i = [a[i], a[i+1])
-    int nn_off;       // [N] u32 correspondence word of each src row (see pack_nn)
+    int nn_off;       // [N] u32 correspondence word of each src row (NnWord); grid mode: inside the dead raw dst rows
     int defer_off;    // [kWarps * defer_cap >= N] u16 grid mode: rows whose cached neighbour could not be proven
     int defer_cap;
     int red_off;      // [kRedFloats] float reduction scratch
@@ -344,118 +347,74 @@ __device__ __forceinline__ GridInfo build_grid(const Tiles& tl, int n_d, float t
     return build_grid_rows(tl, n_d, tau, cell_factor, [rows](int j) { return rows[j]; });
 }
 
-// Radius-bounded NN: best candidate among the cells overlapping the padded tau-box of q, ranked by the 64-bit key
-// (d^2 bits, original row, sorted position) -- i.e. (squared distance, row index), the reference's tie rule.
-//   pos     sorted position of the winner, -1 when no candidate was inspected (the true NN is then farther than tau)
-//   d2      its squared distance (+inf when none)
-//   d2nd    second smallest squared distance among the inspected candidates (+inf when fewer than two)
-//   box     distance (m) from q to the nearest face of the inspected block that has un-inspected space behind it:
-//           every point that was NOT inspected is farther than `box` from q
-__device__ __forceinline__ void grid_search(const GridInfo& g, const float4* __restrict__ sorted,
-                                            const unsigned short* __restrict__ a, float qx, float qy, float qz,
-                                            float& d2, int& pos, float& d2nd, float& box) {
+// Radius-bounded NN: the best candidate among the cells overlapping the box q +- g.r cells (the padded gate
+// radius), ranked by the 64-bit key (d^2 bits, original row, sorted position) -- i.e. (squared distance, row
+// index), the reference's tie rule.
+//   pos1/d1   sorted position / squared distance of the winner (-1 / +inf when no candidate was inspected: the true NN
+//             is then farther than tau)
+//   d2        second smallest squared distance among the inspected candidates (+inf when fewer than two)
+//   box       distance (m) from q to the nearest face of the inspected block that has un-inspected space behind it:
+//             every point that was NOT inspected is farther than `box` from q
+struct NnTop2 {
+    float d1, d2, box;
+    int pos1;
+};
+
+__device__ __forceinline__ NnTop2 grid_search(const GridInfo& g, const float4* __restrict__ sorted,
+                                              const unsigned short* __restrict__ a, float qx, float qy, float qz) {
     const float INF = __int_as_float(0x7f800000);
     const unsigned long long kNone = (0x7f800000ull << 32) | 0xffffffffull;
-    unsigned long long key = kNone;
-    d2nd = INF;
+    unsigned long long key1 = kNone;
+    NnTop2 o;
+    o.d2 = INF;
+    const float r = g.r;
     const float fx = (qx - g.ox) * g.inv_c, fy = (qy - g.oy) * g.inv_c, fz = (qz - g.oz) * g.inv_c;
-    const float x0 = floorf(fx - g.r), x1 = floorf(fx + g.r);
-    const float y0 = floorf(fy - g.r), y1 = floorf(fy + g.r);
-    const float z0 = floorf(fz - g.r), z1 = floorf(fz + g.r);
+    const float x0 = floorf(fx - r), x1 = floorf(fx + r);
+    const float y0 = floorf(fy - r), y1 = floorf(fy + r);
+    const float z0 = floorf(fz - r), z1 = floorf(fz + r);
     const float hx = (float)(g.gx - 1), hy = (float)(g.gy - 1), hz = (float)(g.gz - 1);
     // (NaN coordinates fail every comparison below and fall through to "no candidate")
     if (!(x1 >= 0.f && y1 >= 0.f && z1 >= 0.f && x0 <= hx && y0 <= hy && z0 <= hz)) {
-        // the tau-box misses the grid: all points lie inside [0, g]^3 cell coordinates
+        // the box misses the grid: all points lie inside [0, g]^3 cell coordinates
         const float gapx = fmaxf(-fx, fx - (hx + 1.f)), gapy = fmaxf(-fy, fy - (hy + 1.f)),
                     gapz = fmaxf(-fz, fz - (hz + 1.f));
-        box = fmaxf(fmaxf(gapx, fmaxf(gapy, gapz)) * g.c - g.pad, 0.f);
-        d2 = INF;
-        pos = -1;
-        return;
+        o.box = fmaxf(fmaxf(gapx, fmaxf(gapy, gapz)) * g.c - g.pad, 0.f);
+        o.d1 = INF;
+        o.pos1 = -1;
+        return o;
     }
     // faces clamped by the grid boundary have no points behind them
     const float bx = fminf(x0 < 0.f ? INF : fx - x0, x1 > hx ? INF : x1 + 1.f - fx);
     const float by = fminf(y0 < 0.f ? INF : fy - y0, y1 > hy ? INF : y1 + 1.f - fy);
     const float bz = fminf(z0 < 0.f ? INF : fz - z0, z1 > hz ? INF : z1 + 1.f - fz);
-    box = fmaxf(fminf(bx, fminf(by, bz)) * g.c - g.pad, 0.f);
+    o.box = fmaxf(fminf(bx, fminf(by, bz)) * g.c - g.pad, 0.f);
     const int ix0 = max(0, (int)x0), ix1 = min(g.gx - 1, (int)x1);
     const int iy0 = max(0, (int)y0), iy1 = min(g.gy - 1, (int)y1);
     const int iz0 = max(0, (int)z0), iz1 = min(g.gz - 1, (int)z1);
-    for (int ix = ix0; ix <= ix1; ++ix) {
-        for (int iy = iy0; iy <= iy1; ++iy) {
-            const int base = (ix * g.gy + iy) * g.gz;
-            const int s = a[base + iz0], e = a[base + iz1 + 1];
-            for (int j = s; j < e; ++j) {
-                const float4 c = sorted[j];
-                const float d = sqdist(qx, qy, qz, c.x, c.y, c.z);
-                const unsigned long long k = ((unsigned long long)__float_as_uint(d) << 32) | __float_as_uint(c.w);
-                const bool better = k < key;
-                d2nd = fminf(d2nd, better ? __uint_as_float((unsigned int)(key >> 32)) : d);
-                key = better ? k : key;
-            }
-        }
+    // r < 0.5 cells: the block is at most 2 x 2 columns, and the cells a column contributes are one contiguous run of the
+    // sorted rows (z runs fastest).  The <= 4 runs are walked as ONE flat candidate sequence t = 0 .. total-1, so that the
+    // lanes of a warp never wait for each other's runs: a lane's trip count is its own number of candidates.
+    const bool two_x = ix1 > ix0, two_y = iy1 > iy0;
+    const int b00 = (ix0 * g.gy + iy0) * g.gz, b01 = b00 + g.gz, b10 = b00 + g.gy * g.gz, b11 = b10 + g.gz;
+    const int s0 = a[b00 + iz0], e0 = a[b00 + iz1 + 1];
+    int s1 = 0, e1 = 0, s2 = 0, e2 = 0, s3 = 0, e3 = 0;
+    if (two_y) { s1 = a[b01 + iz0]; e1 = a[b01 + iz1 + 1]; }
+    if (two_x) { s2 = a[b10 + iz0]; e2 = a[b10 + iz1 + 1]; }
+    if (two_x && two_y) { s3 = a[b11 + iz0]; e3 = a[b11 + iz1 + 1]; }
+    const int c1 = e0 - s0, c2 = c1 + (e1 - s1), c3 = c2 + (e2 - s2), total = c3 + (e3 - s3);
+    const int o0 = s0, o1 = s1 - c1, o2 = s2 - c2, o3 = s3 - c3;       // sorted position = t + offset of t's run
+    for (int t = 0; t < total; ++t) {
+        const int off = t < c2 ? (t < c1 ? o0 : o1) : (t < c3 ? o2 : o3);
+        const float4 c = sorted[t + off];
+        const float d = sqdist(qx, qy, qz, c.x, c.y, c.z);
+        const unsigned long long k = ((unsigned long long)__float_as_uint(d) << 32) | __float_as_uint(c.w);
+        const bool better = k < key1;
+        o.d2 = fminf(o.d2, better ? __uint_as_float((unsigned int)(key1 >> 32)) : d);
+        key1 = better ? k : key1;
     }
-    d2 = __uint_as_float((unsigned int)(key >> 32));
-    pos = (key == kNone) ? -1 : (int)((unsigned int)key & 0xffffu);
-}
-
-// The same search by FOUR lanes (opt-in A/B variant ICPF_COOP_SEARCH, tools/ab_kernel.py): a query inspects at most 2 x 2
-// runs, lane `sub` (0..3) of the group scans run (ix0 + sub / 2, iy0 + sub % 2) and the four partial results are merged
-// with two xor-shuffles -- the winner is the minimum of the 64-bit keys and the runner-up distance the second smallest of
-// the multiset of distances, both independent of how the candidates were split, so every output equals grid_search's
-// bit for bit.  All 32 lanes of the warp must call it (shuffles); `active` = this lane's group has a query.
-__device__ __forceinline__ void grid_search_coop4(const GridInfo& g, const float4* __restrict__ sorted,
-                                                  const unsigned short* __restrict__ a, bool active, int sub, float qx,
-                                                  float qy, float qz, float& d2, int& pos, float& d2nd, float& box) {
-    const float INF = __int_as_float(0x7f800000);
-    const unsigned long long kNone = (0x7f800000ull << 32) | 0xffffffffull;
-    unsigned long long key = kNone;
-    d2nd = INF;
-    box = 0.f;
-    if (active) {
-        const float fx = (qx - g.ox) * g.inv_c, fy = (qy - g.oy) * g.inv_c, fz = (qz - g.oz) * g.inv_c;
-        const float x0 = floorf(fx - g.r), x1 = floorf(fx + g.r);
-        const float y0 = floorf(fy - g.r), y1 = floorf(fy + g.r);
-        const float z0 = floorf(fz - g.r), z1 = floorf(fz + g.r);
-        const float hx = (float)(g.gx - 1), hy = (float)(g.gy - 1), hz = (float)(g.gz - 1);
-        if (!(x1 >= 0.f && y1 >= 0.f && z1 >= 0.f && x0 <= hx && y0 <= hy && z0 <= hz)) {
-            const float gapx = fmaxf(-fx, fx - (hx + 1.f)), gapy = fmaxf(-fy, fy - (hy + 1.f)),
-                        gapz = fmaxf(-fz, fz - (hz + 1.f));
-            box = fmaxf(fmaxf(gapx, fmaxf(gapy, gapz)) * g.c - g.pad, 0.f);
-        } else {
-            const float bx = fminf(x0 < 0.f ? INF : fx - x0, x1 > hx ? INF : x1 + 1.f - fx);
-            const float by = fminf(y0 < 0.f ? INF : fy - y0, y1 > hy ? INF : y1 + 1.f - fy);
-            const float bz = fminf(z0 < 0.f ? INF : fz - z0, z1 > hz ? INF : z1 + 1.f - fz);
-            box = fmaxf(fminf(bx, fminf(by, bz)) * g.c - g.pad, 0.f);
-            const int ix0 = max(0, (int)x0), ix1 = min(g.gx - 1, (int)x1);
-            const int iy0 = max(0, (int)y0), iy1 = min(g.gy - 1, (int)y1);
-            const int iz0 = max(0, (int)z0), iz1 = min(g.gz - 1, (int)z1);
-            const int ix = ix0 + (sub >> 1), iy = iy0 + (sub & 1);
-            if (ix <= ix1 && iy <= iy1) {
-                const int base = (ix * g.gy + iy) * g.gz;
-                const int s = a[base + iz0], e = a[base + iz1 + 1];
-                for (int j = s; j < e; ++j) {
-                    const float4 c = sorted[j];
-                    const float d = sqdist(qx, qy, qz, c.x, c.y, c.z);
-                    const unsigned long long k = ((unsigned long long)__float_as_uint(d) << 32) | __float_as_uint(c.w);
-                    const bool better = k < key;
-                    d2nd = fminf(d2nd, better ? __uint_as_float((unsigned int)(key >> 32)) : d);
-                    key = better ? k : key;
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int o = 1; o <= 2; o <<= 1) {
-        const unsigned long long ok = __shfl_xor_sync(FULL_MASK, key, o);
-        const float od2nd = __shfl_xor_sync(FULL_MASK, d2nd, o);
-        // runner-up of the union: the smaller of the two runner-ups and the LOSING best
-        const unsigned long long lose = ok < key ? key : ok;
-        d2nd = fminf(fminf(d2nd, od2nd), __uint_as_float((unsigned int)(lose >> 32)));
-        key = ok < key ? ok : key;
-    }
-    d2 = __uint_as_float((unsigned int)(key >> 32));
-    pos = (key == kNone) ? -1 : (int)((unsigned int)key & 0xffffu);
+    o.d1 = __uint_as_float((unsigned int)(key1 >> 32));
+    o.pos1 = (key1 == kNone) ? -1 : (int)((unsigned int)key1 & 0xffffu);
+    return o;
 }
 
 // correspondence word kept per src row (PB = position bits: 13 for the shared-memory tiles, 14 for the large-cluster
@@ -475,10 +434,5 @@ template <int PB> struct NnWord {
     __device__ __forceinline__ static float bound(unsigned int w) { return __uint_as_float((w & kBoundMask) >> 1); }
 };
 constexpr int kMaxRows = NnWord<14>::kMaxRows;      // rows per cloud the engine accepts
-
-__device__ __forceinline__ float fast_sqrt(float x) {      // ~2 ulp, callers keep slack; x >= 0
-    const float y = fmaxf(x, 1e-30f);
-    return y * rsqrtf(y);
-}
 
 }  // namespace icpf

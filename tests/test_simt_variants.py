@@ -77,25 +77,3 @@ def test_continued_full_pass_equals_the_restarted_one():
         want = run()
     assert got[4].tolist()[0] > 32
     assert all(torch.equal(a, b) for a, b in zip(got, want))
-
-
-def test_four_lane_cooperative_search_equals_the_single_lane_one():
-    """ICPF_COOP_SEARCH (an A/B variant for the next GPU session, not the product build): deferred correspondence
-    searches by four lanes per row.  Winner and runner-up distance are minima over the same multiset of candidates, so
-    transforms, rmse, iteration counts, masks and the search statistics must not move by a bit."""
-    src, dst, _ = synth.make_pairs(40, 384, seed=31, ragged=True, residual_only=True, wrong_frac=0.1)
-    dst[:, 7, :3] = dst[:, 3, :3]                        # exact distance ties: the row index decides
-
-    def run():
-        out = []
-        for kw in (dict(max_iterations=20, relative_rmse_thr=-1.0, early_exit=False), dict()):
-            r = ops.icp_batch(harness.dev_tensor(src), harness.dev_tensor(dst), ops.make_params(nn_mode=3, **kw))
-            out += [harness.plain(x).clone() for x in (r.R, r.T, r.rmse, r.iterations, r.batch, r.conv_mask)]
-        return out
-
-    with harness.emulated():
-        want = run()
-    with harness.emulated(extra_flags=("-DICPF_COOP_SEARCH",), out=os.path.join(simt_build.BUILD, "libicpflow_simt_coop.so")):
-        got = run()
-    assert all(torch.equal(a.nan_to_num(-7.0) if a.is_floating_point() else a,
-                           b.nan_to_num(-7.0) if b.is_floating_point() else b) for a, b in zip(got, want))
