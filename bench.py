@@ -43,8 +43,9 @@ def algorithmic_bytes_per_pair_iter(n_s: int, n_d: int) -> int:
 
 
 def load_ncu_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
-    path = os.path.join(ROOT, "profiles", "ncu_r1_metrics.json")
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of the same workload
+    (profiles/ncu_r2_metrics.json, written by tools/ncu_metrics.py from `ncu --set full`), or None."""
+    path = os.path.join(ROOT, "profiles", "ncu_r2_metrics.json")
     try:
         with open(path) as f:
             m = json.load(f)
@@ -142,7 +143,8 @@ def time_cpu_oracle(target_seconds: float = 12.0, max_pairs: int = PAIRS_PER_GPU
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU implementation of the path (restated oracle) on the host cores."""
+    """--impl reference: the reference's CPU implementation of the path (restated oracle) on the host cores.  One step =
+    the engine arm's step: the full batch of PAIRS_PER_GPU pairs x ICP_ITERS iterations (same `config`)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -152,22 +154,30 @@ def run_reference_arm(args):
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample_pairs = 128
-    src, dst, _ = synth.make_pairs(sample_pairs, POINTS, seed=1234, residual_only=True)
+    src, dst, _ = synth.make_pairs(PAIRS_PER_GPU, POINTS, seed=1234, residual_only=True)
     a, c = torch.from_numpy(src), torch.from_numpy(dst)
     run = lambda: O.icp_loop(a, c, thres=THRES, max_iterations=ICP_ITERS, relative_rmse_thr=-1.0)
-    for _ in range(args.warmup):
+    budget_s = 200.0                 # the whole run has to end within a few minutes on any host
+    t_w = time.perf_counter()
+    warm = 0
+    for _ in range(max(1, args.warmup)):
         run()
+        warm += 1
+        if time.perf_counter() - t_w > 0.2 * budget_s:
+            break
+    per_step = (time.perf_counter() - t_w) / warm
+    steps = max(1, min(args.steps, int(budget_s / max(per_step, 1e-9))))
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         run()
     dt = time.perf_counter() - t0
-    value = sample_pairs * ICP_ITERS * args.steps / dt
-    sample = (f"each step = {sample_pairs} of the {PAIRS_PER_GPU} pairs x {POINTS} pts x {ICP_ITERS} iterations; "
+    value = PAIRS_PER_GPU * ICP_ITERS * steps / dt
+    sample = (f"each step = the full batch: {PAIRS_PER_GPU} pairs x {POINTS} pts x {ICP_ITERS} iterations; {steps} timed steps "
+              f"of the {args.steps} requested (CPU time budget {budget_s:.0f} s), {warm} warm-up; "
               "oracle/icp_oracle.py icp_loop (torch CPU fp32 + OpenMP C knn leaf)")
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -186,29 +196,118 @@ def workload_config(n_gpus: int):
 
 
 # ---------------------------------------------------------------------------------------------- secondary configs
-def time_secondary(dev):
-    """Not the headline metric: the two other single-GPU BASELINE configs, timed with CUDA events / wall clock so that
-    they are measured in the same run.  C3 at a quarter of its pair count (1024 of 4096 pairs x 1024 points, full
-    hist_icp with the 135 x 135 x 3 histogram) and C4 (Waymo-shape frame pair through match_pcds + flow)."""
-    import types
+def _events_ms(fn, reps, sync):
     import torch
-    import icp_flow_b200 as E
-    from icp_flow_b200 import scan, synth
-    out = {}
-    s, d, _ = synth.make_pairs(1024, 1024, seed=99, ragged=False, residual_only=False)
-    s, d = torch.from_numpy(s).to(dev), torch.from_numpy(d).to(dev)
-    args = types.SimpleNamespace(thres_dist=THRES, translation_frame=6.666, chunk_size=50)
-    for _ in range(2):
-        E.hist_icp(args, s, d)
+    fn()
+    sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
     e0.record()
-    for _ in range(5):
-        E.hist_icp(args, s, d)
+    for _ in range(reps):
+        fn()
+    e1.record()
+    sync()
+    return e0.elapsed_time(e1) / reps
+
+
+def time_c5_shard(dev, pairs=4096, steps=20, ext_fn=None, after_step=None):
+    """One GPU's share of C5 (32768 pairs x 512 points over 8 GPUs = 4096 pairs per GPU, 20 forced iterations): four
+    waves of CTAs instead of the single wave of the C2 batch.  Rotating pool of 5 batches (336 MB > 2x L2)."""
+    import torch
+    from icp_flow_b200 import _lib, ops, synth
+    rank = int(os.environ.get("RANK", "0"))
+    pool = []
+    for i in range(5):
+        s, d, _ = synth.make_pairs(pairs, POINTS, seed=4321 + rank + 1000 * i, residual_only=True)
+        pool.append((torch.from_numpy(s).to(dev), torch.from_numpy(d).to(dev)))
+    prm = ops.make_params(thres=THRES, max_iterations=ICP_ITERS, relative_rmse_thr=-1.0, early_exit=False, batch_stop=True)
+    ws = torch.empty(_lib.lib().icpf_workspace_bytes(pairs, POINTS, 0, 0, 0), device=dev, dtype=torch.uint8)
+    out = [None]
+
+    def one(i):
+        out[0] = ops.icp_batch(*pool[i % 5], prm, out=out[0], workspace=ws, ext=ext_fn(i) if ext_fn else None)
+        if after_step:
+            after_step(i, out[0])
+
+    for i in range(3):
+        one(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        one(3 + i)
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 5
-    out["c3_hist_icp"] = {"pairs": 1024, "points": 1024, "bins": [135, 135, 3], "ms": ms, "pairs_per_s": 1024 / ms * 1e3}
+    ms = e0.elapsed_time(e1) / steps
+    assert int(out[0].iterations.sum().item()) == pairs * ICP_ITERS
+    return ms, out[0]
+
+
+def time_secondary(dev):
+    """Not the headline metric: the other single-GPU BASELINE configs measured in the same run.  C1 (the demo-frame
+    plumbing case), C3 at its full size (4096 pairs x 1024 points, full hist_icp, 135 x 135 x 3 histogram) with per-stage
+    times, its own roofline accounting and a CPU hist_icp baseline on a stated subsample, C4 (Waymo-shape frame pair through
+    match_pcds + flow) and one GPU's share of C5 (4096 pairs x 512 points)."""
+    import types
+    import numpy as np
+    import torch
+    import icp_flow_b200 as E
+    from icp_flow_b200 import ops, scan, synth
+    from oracle import icp_oracle as O
+    out = {}
+    peak, _ = load_peaks()
+    sync = torch.cuda.synchronize
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+
+    # ---- C1: demo.npz frame pair, the 32 cluster pairs <= 256 points of tests/golden/c1_demo.npz (F = 2.0, demo.sh)
+    try:
+        g = dict(np.load(os.path.join(ROOT, "tests", "golden", "c1_demo.npz")))
+        s1, d1 = torch.from_numpy(g["src"]).to(dev), torch.from_numpy(g["dst"]).to(dev)
+        a1 = types.SimpleNamespace(thres_dist=THRES, translation_frame=2.0, chunk_size=50)
+        ms = _events_ms(lambda: E.hist_icp(a1, s1, d1), 20, sync)
+        t0 = time.perf_counter()
+        O.hist_icp(torch.from_numpy(g["src"]), torch.from_numpy(g["dst"]), O.PathParams(thres_dist=THRES, translation_frame=2.0))
+        cpu_s = time.perf_counter() - t0
+        out["c1_demo"] = {"pairs": int(s1.shape[0]), "points": int(s1.shape[1]), "hist_icp_ms": ms,
+                          "pairs_per_s": s1.shape[0] / ms * 1e3,
+                          "cpu_baseline": {"ms": cpu_s * 1e3, "cores": cores, "kind": "port",
+                                           "sample": "the same 32 pairs in full, oracle/icp_oracle.py hist_icp"}}
+    except Exception as exc:
+        out["c1_demo"] = {"error": f"{type(exc).__name__}: {exc}"}
+
+    # ---- C3 at size
+    P3, N3, F3 = 4096, 1024, 6.666
+    s_np, d_np, _ = synth.make_pairs(P3, N3, seed=99, ragged=False, residual_only=False)
+    s, d = torch.from_numpy(s_np).to(dev), torch.from_numpy(d_np).to(dev)
+    args = types.SimpleNamespace(thres_dist=THRES, translation_frame=F3, chunk_size=50)
+    init = ops.estimate_init_pose(args, s, d, auto_swap=True)
+    ms_init = _events_ms(lambda: ops.estimate_init_pose(args, s, d, auto_swap=True), 3, sync)
+    ms_apply = _events_ms(lambda: ops.apply_icp(args, s, d, init, auto_swap=True), 3, sync)
+    ms_all = _events_ms(lambda: E.hist_icp(args, s, d), 3, sync)
+    _, dbg = ops.hist_icp(args, s, d, return_debug=True)
+    batch_iters = int(dbg["batch"].tolist()[0])
+    b_hist = P3 * (16 * (N3 + N3) + 16)                      # SURVEY 8d: one read of both clouds + one translation per pair
+    tests = float(P3) * N3 * N3                                # range tests (candidate votes) of the vote stage
+    cpu_pairs = 128
+    t0 = time.perf_counter()
+    O.hist_icp(torch.from_numpy(s_np[:cpu_pairs]), torch.from_numpy(d_np[:cpu_pairs]), O.PathParams(thres_dist=THRES, translation_frame=F3))
+    cpu_s = time.perf_counter() - t0
+    out["c3_hist_icp"] = {
+        "pairs": P3, "points": N3, "bins": [135, 135, 3], "ms": ms_all, "pairs_per_s": P3 / ms_all * 1e3,
+        "stages_ms": {"estimate_init_pose": ms_init, "apply_icp": ms_apply}, "batch_iterations": batch_iters,
+        "roofline": {"bound": "hbm", "stage": "estimate_init_pose (hist_fused + hist_score kernels)",
+                     "achieved": b_hist / (ms_init * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": b_hist / (ms_init * 1e-3) / 1e9 / peak, "algorithmic_bytes": b_hist,
+                     "real_bound": "shared-memory atomics / instruction issue, not HBM: the vote stage is n_s*n_d range tests per pair",
+                     "range_tests_per_s": tests / (ms_init * 1e-3),
+                     "issue_ceiling_range_tests_per_s": 148 * 128 * 1.965e9 / 8.0,
+                     "ceiling_note": "fp32 lane-op issue peak (148 SMs x 128 lanes x 1.965 GHz) / ~8 lane-ops per range test (SURVEY 8d)"},
+        "cpu_baseline": {"pairs_per_s": cpu_pairs / cpu_s, "cores": cores, "kind": "port",
+                         "sample": f"the first {cpu_pairs} of the {P3} pairs, full hist_icp, {cpu_s:.1f} s, oracle/icp_oracle.py"},
+    }
+    del s, d, init
+
+    # ---- C4: Waymo-shape frame pair
     sp, sl, dp, dl, _ = synth.make_scene()
     t = [torch.from_numpy(x).to(dev) for x in (sp, dp, sl, dl)]
     fargs = types.SimpleNamespace(thres_dist=THRES, translation_frame=3.34, chunk_size=50, min_cluster_size=30,
@@ -225,7 +324,27 @@ def time_secondary(dev):
         best, matched = min(best, time.perf_counter() - t0), len(rows)
     out["c4_frame"] = {"points": [len(sp), len(dp)], "clusters": 200, "max_points": 10000, "matched_pairs": matched,
                        "ms": best * 1e3, "what": "cluster index + match_pcds (both stages) + flow, wall clock"}
+
+    # ---- C5, one GPU's share (the 8-GPU line carries the sharded run itself)
+    ms5, _ = time_c5_shard(dev)
+    out["c5_one_gpu_share"] = {"pairs": 4096, "points": POINTS, "icp_iterations": ICP_ITERS, "ms": ms5,
+                               "pair_iters_per_s": 4096 * ICP_ITERS / ms5 * 1e3,
+                               "roofline_frac": 4096 * ICP_ITERS * algorithmic_bytes_per_pair_iter(POINTS, POINTS) / (ms5 * 1e-3) / 1e9 / peak}
     return out
+
+
+def bind_to_gpu_cpus(index: int):
+    """Pin this rank to the CPUs NVML names as local to its GPU (same NUMA node / PCIe root), so that the pinned staging
+    buffers are first-touched there and the H2D streams of the ranks do not all pull through one node."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        cpus = sorted(os.sched_getaffinity(0))
+        return f"{len(cpus)} cpus [{cpus[0]}..{cpus[-1]}]"
+    except Exception as exc:
+        return f"unbound ({type(exc).__name__})"
 
 
 # ---------------------------------------------------------------------------------------------- engine arm
@@ -257,6 +376,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU (the engine has no CPU path)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    affinity = bind_to_gpu_cpus(local_rank)      # before any pinned allocation: first touch lands on the GPU's NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
@@ -269,8 +389,9 @@ def main():
     for i in range(pool_n):
         s, d, _ = synth.make_pairs(P, N, seed=1234 + rank + 1000 * i, residual_only=True)
         if i == 0:
-            host_src = torch.from_numpy(s).pin_memory()
-            host_dst = torch.from_numpy(d).pin_memory()
+            # the host side of the e2e path ships the compact format: xyz of the valid rows + CSR offsets (12 B per row)
+            host_src = [t.pin_memory() for t in ops.compact_rows(torch.from_numpy(s))]
+            host_dst = [t.pin_memory() for t in ops.compact_rows(torch.from_numpy(d))]
         src_pool.append(torch.from_numpy(s).to(dev))
         dst_pool.append(torch.from_numpy(d).to(dev))
     params = ops.make_params(thres=THRES, max_iterations=ICP_ITERS, relative_rmse_thr=-1.0, early_exit=False,
@@ -311,20 +432,20 @@ def main():
         s = i & 1
         if world > 1 and i >= 2:
             torch.cuda.current_stream().wait_event(gathered_ev[s])
-        if prof is not None:
-            L.icpf_profile_next_icp(ctypes.c_void_p(prof[0].cuda_event), ctypes.c_void_p(prof[1].cuda_event))
+        ev = (prof[0].cuda_event, prof[1].cuda_event) if prof is not None else (0, 0)
         if peer is not None:
             # fused: the kernel epilogue stores the transforms into every rank's gathered buffer (NVLink peer memory);
             # the cross-rank barrier that publishes them runs on the side stream, under the next batch's kernels
-            peer.arm(s)
-            outs[s] = out = ops.icp_batch(src_pool[i % pool_n], dst_pool[i % pool_n], params, out=outs[s], workspace=ws)
+            outs[s] = out = ops.icp_batch(src_pool[i % pool_n], dst_pool[i % pool_n], params, out=outs[s], workspace=ws,
+                                          ext=peer.ext(s, *ev))
             computed[s].record()
             with torch.cuda.stream(comm_stream):
                 comm_stream.wait_event(computed[s])
                 peer.finish(s)
                 gathered_ev[s].record(comm_stream)
             return out
-        outs[s] = out = ops.icp_batch(src_pool[i % pool_n], dst_pool[i % pool_n], params, out=outs[s], workspace=ws)
+        outs[s] = out = ops.icp_batch(src_pool[i % pool_n], dst_pool[i % pool_n], params, out=outs[s], workspace=ws,
+                                      ext=ops.icp_ext(start_event=ev[0], stop_event=ev[1]) if prof is not None else None)
         if world > 1:
             computed[s].record()
             with torch.cuda.stream(comm_stream):
@@ -381,9 +502,8 @@ def main():
         # the public host-buffer call: H2D of this step's inputs, kernels, D2H of its transforms (double-buffered)
         nonlocal e2e_i
         s = e2e_i & 1
-        if peer is not None:
-            peer.arm(s)
-        o = pipe.submit(host_src, host_dst, h_pose[s])
+        o = pipe.submit_compact(host_src[0], host_src[1], host_dst[0], host_dst[1], h_pose[s],
+                                ext=peer.ext(s) if peer is not None else None)
         if peer is not None:
             with torch.cuda.stream(pipe.compute_stream):
                 peer.finish(s)
@@ -413,6 +533,52 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = pair_iters_per_step * e2e_steps / (float(t.item()) * 1e-3)
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host_src + host_dst)
+
+    # ---- the gathered rows really are every rank's transforms: compare the peer-written buffer with one NCCL all_gather
+    gather_verified = None
+    c5 = None
+    if world > 1:
+        s_last = (e2e_i - 1) & 1
+        ref = torch.empty(n_gpus * P, 16, device=dev, dtype=torch.float32)
+        dist.all_gather_into_tensor(ref, pipe.outs[s_last].pose.view(P, 16).contiguous())
+        got = peer.slots[s_last][0] if peer is not None else gathered[s_last].view(n_gpus * P, 16)
+        torch.cuda.synchronize()
+        okv = torch.tensor([1 if torch.equal(got.view(-1, 16), ref) else 0], device=dev)
+        dist.all_reduce(okv, op=dist.ReduceOp.MIN)
+        gather_verified = bool(int(okv.item()))
+        # ---- C5 as named: 4096 pairs per GPU (32768 pairs over 8 GPUs), 20 forced iterations, gather of the transforms
+        try:
+            P5 = 4096
+            peer5 = None
+            if peer is not None:
+                from icp_flow_b200.shard import PeerGather
+                peer5 = PeerGather(P5, dev, slots=2)
+            g5 = [torch.empty(n_gpus * P5, 16, device=dev, dtype=torch.float32) for _ in range(2)]
+
+            def after(i, o):
+                if peer5 is not None:
+                    peer5.finish(i & 1)
+                else:
+                    dist.all_gather_into_tensor(g5[i & 1], o.pose.view(P5, 16))
+
+            dist.barrier()
+            ms5, o5 = time_c5_shard(dev, P5, steps=20, ext_fn=(lambda i: peer5.ext(i & 1)) if peer5 is not None else None,
+                                    after_step=after)
+            t5 = torch.tensor([ms5], device=dev, dtype=torch.float64)
+            dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+            ref5 = torch.empty(n_gpus * P5, 16, device=dev, dtype=torch.float32)
+            dist.all_gather_into_tensor(ref5, o5.pose.view(P5, 16).contiguous())
+            got5 = peer5.slots[(3 + 20 - 1) & 1][0] if peer5 is not None else g5[(3 + 20 - 1) & 1]
+            torch.cuda.synchronize()
+            ok5 = torch.tensor([1 if torch.equal(got5.view(-1, 16), ref5) else 0], device=dev)
+            dist.all_reduce(ok5, op=dist.ReduceOp.MIN)
+            c5 = {"pairs_total": n_gpus * P5, "pairs_per_gpu": P5, "points": POINTS, "icp_iterations": ICP_ITERS,
+                  "ms_per_step": float(t5.item()), "pair_iters_per_s": n_gpus * P5 * ICP_ITERS / (float(t5.item()) * 1e-3),
+                  "gather": gather_kind, "gather_verified": bool(int(ok5.item())),
+                  "what": "resident inputs, rotating pool of 5 batches per GPU, max over ranks of the CUDA-event time"}
+        except Exception as exc:
+            c5 = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank == 0:
         peak, peak_kind = load_peaks()
@@ -423,20 +589,24 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(n_gpus), l2=f"rotating pool of {pool_n} input batches "
-                           f"({pool_n * batch_bytes / 2**20:.0f} MiB > 2x 126 MiB L2): every step reads its inputs from HBM",
-                           nn_mode=args.nn_mode, gather=gather_kind),
+            "config": workload_config(n_gpus),
+            "run": {"l2": f"rotating pool of {pool_n} input batches ({pool_n * batch_bytes / 2**20:.0f} MiB > 2x 126 MiB L2): "
+                          "every step reads its inputs from HBM", "nn_mode": args.nn_mode, "gather": gather_kind,
+                    "gather_verified": gather_verified, "host_affinity": affinity},
             "clocks": sampler.summary(),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": batch_bytes, "d2h_bytes_per_step": P * 64,
-                    "steps": e2e_steps},
-            "gpu_launches": launches_per_step * args.steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": P * 64,
+                    "steps": e2e_steps, "host_format": "compact: xyz of the valid rows (12 B/row) + CSR offsets, expanded to the "
+                    "padded [P,N,4] batch by icpf_expand_rows_f32 on the device; the padded format would ship "
+                    f"{batch_bytes} B per step", "h2d_gbs": h2d_bytes * e2e_steps / (float(t.item()) * 1e-3) / 1e9},
+            "gpu_launches": launches_per_step * args.steps + (launches_per_step + 2) * e2e_steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": load_ncu_traffic(), "peak_kind": peak_kind, "kernel": "icp_pairs_kernel",
                          "kernel_ms": k_ms, "kernel_share_of_step": k_ms / (ms_total / args.steps),
                          "algorithmic_bytes_per_launch": alg_bytes},
-            "nn_search": {"full_search_fraction": stats[0] / float(P * ICP_ITERS * N),
-                          "cache_refreshes_per_pair": stats[1] / float(P)},
+            "nn_search": {"full_search_fraction": stats[0] / float(P * ICP_ITERS * N)},
         }
+        if c5 is not None:
+            line["secondary"] = {"c5_sharded": c5}
         if n_gpus == 1 and not args.no_secondary:
             try:
                 line["secondary"] = time_secondary(dev)

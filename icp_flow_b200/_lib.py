@@ -15,8 +15,8 @@ LIB_PATH = os.environ.get("ICPF_LIB_PATH") or os.path.join(_HERE, "libicpflow_b2
 # every symbol include/icpflow_b200.h declares (checked by tests/test_abi.py against the header text)
 EXPORTS = (
     "icpf_version", "icpf_error_string", "icpf_default_params", "icpf_workspace_bytes",
-    "icpf_icp_f32", "icpf_nn_f32", "icpf_transform_points_f32", "icpf_host_kabsch", "icpf_profile_next_icp",
-    "icpf_host_kabsch_sequence", "icpf_peer_gather_next_icp", "icpf_hist_votes_f32", "icpf_hist_init_f32", "icpf_apply_icp_f32", "icpf_apply_icp_phase_f32", "icpf_hist_icp_f32",
+    "icpf_icp_f32", "icpf_icp_ex_f32", "icpf_nn_f32", "icpf_transform_points_f32", "icpf_host_kabsch",
+    "icpf_host_kabsch_sequence", "icpf_peer_push_f32", "icpf_expand_rows_f32", "icpf_hist_votes_f32", "icpf_hist_init_f32", "icpf_apply_icp_f32", "icpf_apply_icp_phase_f32", "icpf_hist_icp_f32",
     "icpf_match_eval_f32",
     "icpf_cluster_index_workspace_bytes", "icpf_cluster_index_f32", "icpf_sanity_check_f32", "icpf_gather_pairs_f32",
     "icpf_flow_f32",
@@ -55,6 +55,13 @@ class IcpfMatchGates(ctypes.Structure):
     """Mirror of ``struct icpf_match_gates``."""
 
     _fields_ = [("translation_frame", ctypes.c_double), ("thres_iou", ctypes.c_double), ("thres_rot", ctypes.c_double)]
+
+
+class IcpfIcpExt(ctypes.Structure):
+    """Mirror of ``struct icpf_icp_ext`` (per-call extensions of the ICP loop: fused peer gather, timing events)."""
+
+    _fields_ = [("peer_pose_dev", ctypes.c_void_p), ("peer_world", ctypes.c_int32), ("peer_row0", ctypes.c_int32),
+                ("start_event", ctypes.c_void_p), ("stop_event", ctypes.c_void_p)]
 
 
 class IcpfError(RuntimeError):
@@ -111,10 +118,12 @@ def lib() -> ctypes.CDLL:
     L.icpf_hist_icp_f32.restype = ctypes.c_int
     L.icpf_hist_icp_f32.argtypes = [vp, vp, i32, i32, ctypes.POINTER(IcpfHistBins), ctypes.POINTER(IcpfParams), vp, vp,
                                     vp, vp, ctypes.c_size_t, vp]
-    L.icpf_peer_gather_next_icp.restype = ctypes.c_int
-    L.icpf_peer_gather_next_icp.argtypes = [vp, i32, i32]
-    L.icpf_profile_next_icp.restype = None
-    L.icpf_profile_next_icp.argtypes = [vp, vp]
+    L.icpf_icp_ex_f32.restype = ctypes.c_int
+    L.icpf_icp_ex_f32.argtypes = L.icpf_icp_f32.argtypes + [ctypes.POINTER(IcpfIcpExt)]
+    L.icpf_peer_push_f32.restype = ctypes.c_int
+    L.icpf_peer_push_f32.argtypes = [vp, vp, i32, i32, i32, vp]
+    L.icpf_expand_rows_f32.restype = ctypes.c_int
+    L.icpf_expand_rows_f32.argtypes = [vp, vp, i32, i32, vp, vp]
     L.icpf_host_kabsch.restype = None
     L.icpf_host_kabsch.argtypes = [vp, i32, vp]
     L.icpf_host_kabsch_sequence.restype = None

@@ -10,7 +10,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 extern "C" {
 
-int icpf_version(void) { return 101; }   // 101: icpf_apply_icp_phase_f32, larger icpf_workspace_bytes (per-iteration record)
+int icpf_version(void) { return 102; }   // 102: icpf_icp_ex_f32 (explicit per-call extensions), icpf_peer_push_f32, icpf_expand_rows_f32
 
 const char* icpf_error_string(int code) {
     switch (code) {
@@ -47,7 +47,20 @@ int icpf_icp_f32(const float* src, const float* dst, const float* init_R, const 
                  const icpf_params* params, float* out_R,
                  float* out_T, float* out_rmse, float* out_pose, int32_t* out_iters, uint32_t* out_conv,
                  int32_t* out_batch, void* workspace, size_t workspace_bytes, void* stream) {
+    return icpf_icp_ex_f32(src, dst, init_R, init_T, P, N, params, out_R, out_T, out_rmse, out_pose, out_iters, out_conv,
+                           out_batch, workspace, workspace_bytes, stream, nullptr);
+}
+
+int icpf_icp_ex_f32(const float* src, const float* dst, const float* init_R, const float* init_T, int32_t P, int32_t N,
+                    const icpf_params* params, float* out_R, float* out_T, float* out_rmse, float* out_pose,
+                    int32_t* out_iters, uint32_t* out_conv, int32_t* out_batch, void* workspace, size_t workspace_bytes,
+                    void* stream, const icpf_icp_ext* ext) {
     if (!params) return ICPF_E_NULL;
+    if (ext != nullptr) {
+        if (ext->peer_world < 0 || ext->peer_row0 < 0 || ext->peer_world > 64) return ICPF_E_PARAM;
+        if (ext->peer_world > 0 && ext->peer_pose_dev == nullptr) return ICPF_E_NULL;
+        if ((ext->start_event == nullptr) != (ext->stop_event == nullptr)) return ICPF_E_NULL;
+    }
     if (P < 0 || N <= 0) return ICPF_E_SHAPE;
     if (P == 0) return ICPF_OK;
     if (!src || !dst || !out_R || !out_T) return ICPF_E_NULL;
@@ -56,7 +69,7 @@ int icpf_icp_f32(const float* src, const float* dst, const float* init_R, const 
     if (!(params->thres_dist > 0.0)) return ICPF_E_PARAM;
     if ((init_R == nullptr) != (init_T == nullptr)) return ICPF_E_NULL;
     return launch_icp(src, dst, init_R, init_T, nullptr, 0, P, N, *params, out_R, out_T, out_rmse, out_pose, out_iters, out_conv, out_batch, workspace,
-                      workspace_bytes, static_cast<cudaStream_t>(stream));
+                      workspace_bytes, static_cast<cudaStream_t>(stream), nullptr, ext);
 }
 
 int icpf_nn_f32(const float* src, const float* dst, int32_t B, int32_t Ns, int32_t Nd, int32_t src_stride,
@@ -243,15 +256,22 @@ int icpf_flow_f32(const float* points, int32_t point_stride, const float* labels
                        static_cast<cudaStream_t>(stream));
 }
 
-int icpf_peer_gather_next_icp(void* const* peer_pose_dev, int32_t world, int32_t row0) {
-    if (world < 0 || row0 < 0 || world > 64) return ICPF_E_PARAM;
-    if (world > 0 && peer_pose_dev == nullptr) return ICPF_E_NULL;
-    set_peer_gather(world > 0 ? reinterpret_cast<float* const*>(peer_pose_dev) : nullptr, world, row0);
-    return ICPF_OK;
+int icpf_peer_push_f32(const float* local_pose, void* const* peer_pose_dev, int32_t world, int32_t row0, int32_t P,
+                       void* stream) {
+    if (world < 0 || row0 < 0 || world > 64 || P < 0) return ICPF_E_PARAM;
+    if (P == 0 || world == 0) return ICPF_OK;
+    if (!local_pose || !peer_pose_dev) return ICPF_E_NULL;
+    if (!aligned16(local_pose)) return ICPF_E_ALIGN;
+    return launch_peer_push(local_pose, reinterpret_cast<float* const*>(peer_pose_dev), world, row0, P,
+                            static_cast<cudaStream_t>(stream));
 }
 
-void icpf_profile_next_icp(void* start_event, void* stop_event) {
-    set_profile_events(static_cast<cudaEvent_t>(start_event), static_cast<cudaEvent_t>(stop_event));
+int icpf_expand_rows_f32(const float* rows, const int32_t* offsets, int32_t B, int32_t N, float* out, void* stream) {
+    if (B < 0 || N <= 0) return ICPF_E_SHAPE;
+    if (B == 0) return ICPF_OK;
+    if (!rows || !offsets || !out) return ICPF_E_NULL;
+    if (!aligned16(out)) return ICPF_E_ALIGN;
+    return launch_expand_rows(rows, offsets, B, N, out, static_cast<cudaStream_t>(stream));
 }
 
 void icpf_host_kabsch_sequence(const float* H, int32_t n, float* R) {

@@ -298,25 +298,43 @@ size_t icp_big_workspace_bytes(int P, int N) {
     return pair_needs_global(N) ? (size_t)P * pair_global_ws_bytes(N) : 0;
 }
 
-static thread_local cudaEvent_t t_prof_start = nullptr, t_prof_stop = nullptr;
-static thread_local float* const* t_peer_pose = nullptr;
-static thread_local int t_peer_world = 0, t_peer_row0 = 0;
-
-void set_peer_gather(float* const* peer_pose_dev, int world, int row0) {
-    t_peer_pose = peer_pose_dev;
-    t_peer_world = world;
-    t_peer_row0 = row0;
+// One CTA per (destination rank, 256-row slice): 16-byte stores of this rank's contiguous block into the peer buffer.
+__global__ void __launch_bounds__(256) peer_push_kernel(const float4* __restrict__ local, float* const* peer_pose, int row0,
+                                                        int n_vec) {
+    float4* dst = reinterpret_cast<float4*>(peer_pose[blockIdx.y]) + (size_t)row0 * 4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += gridDim.x * blockDim.x) dst[i] = local[i];
 }
 
-void set_profile_events(cudaEvent_t start, cudaEvent_t stop) {
-    t_prof_start = start;
-    t_prof_stop = stop;
+int launch_peer_push(const float* local_pose, float* const* peer_pose_dev, int world, int row0, int P, cudaStream_t stream) {
+    if (P == 0 || world == 0) return ICPF_OK;
+    const int n_vec = P * 4;
+    const int gx = max(1, min(8, (n_vec + 255) / 256));
+    ICPF_LAUNCH(peer_push_kernel, dim3(gx, world), 256, 0, stream)(reinterpret_cast<const float4*>(local_pose), peer_pose_dev, row0, n_vec);
+    return (int)cudaGetLastError();
+}
+
+// Compact rows (xyz of the valid rows, CSR offsets) -> the reference's padded [B,N,4] layout (pad_segment).
+__global__ void __launch_bounds__(256) expand_rows_kernel(const float* __restrict__ rows, const int* __restrict__ offsets, int N,
+                                                          float4* __restrict__ out) {
+    const int b = blockIdx.x;
+    const int lo = offsets[b], n = min(max(offsets[b + 1] - lo, 0), N);
+    const float* r = rows + (size_t)lo * 3;
+    float4* o = out + (size_t)b * N;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        o[i] = (i < n) ? make_float4(r[3 * i], r[3 * i + 1], r[3 * i + 2], 1.0f) : make_float4(1e8f, 1e8f, 1e8f, 0.0f);
+    }
+}
+
+int launch_expand_rows(const float* rows, const int32_t* offsets, int B, int N, float* out, cudaStream_t stream) {
+    if (B == 0) return ICPF_OK;
+    ICPF_LAUNCH(expand_rows_kernel, B, 256, 0, stream)(rows, offsets, N, reinterpret_cast<float4*>(out));
+    return (int)cudaGetLastError();
 }
 
 int launch_icp(const float* src, const float* dst, const float* init_R, const float* init_T, const float* init_pose,
                int auto_swap, int P, int N, const icpf_params& prm, float* out_R, float* out_T,
                float* out_rmse, float* out_pose, int* out_iters, uint32_t* out_conv, int* out_batch, void* workspace,
-               size_t workspace_bytes, cudaStream_t stream, const IcpPhase* phase) {
+               size_t workspace_bytes, cudaStream_t stream, const IcpPhase* phase, const icpf_icp_ext* ext) {
     if (P == 0) return ICPF_OK;
     // nn_mode: 0 auto (grid + cache whenever the tiles fit in shared memory), 1 brute force, 2 grid, 3 grid + cache
     if (N > kMaxRows) return ICPF_E_UNSUPPORTED;
@@ -363,8 +381,12 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
     const bool capped = prm.batch_stop && prm.early_exit && prm.max_iterations > kFirstPassCap;
     a.cap = capped ? kFirstPassCap : prm.max_iterations;
     a.big_ws = big ? ws + icp_workspace_bytes(P) : nullptr;
-    a.peer_pose = t_peer_pose; a.peer_world = t_peer_world; a.peer_row0 = t_peer_row0;
-    t_peer_pose = nullptr;       // one-shot: applies to this call only
+    const bool peer = ext != nullptr && ext->peer_pose_dev != nullptr && ext->peer_world > 0;
+    a.peer_pose = peer ? reinterpret_cast<float* const*>(ext->peer_pose_dev) : nullptr;
+    a.peer_world = peer ? ext->peer_world : 0;
+    a.peer_row0 = peer ? ext->peer_row0 : 0;
+    cudaEvent_t prof_start = ext ? static_cast<cudaEvent_t>(ext->start_event) : nullptr;
+    cudaEvent_t prof_stop = ext ? static_cast<cudaEvent_t>(ext->stop_event) : nullptr;
     int* decided = reinterpret_cast<int*>(ws + icp_ws_off_batch(P)) + 8;
     a.stats = reinterpret_cast<int*>(ws + icp_ws_off_stats(P));
     // With a batch stop every pair records (R, T, rmse) after each iteration; the pairs still moving at the stop read
@@ -376,13 +398,10 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
     const int ph = phase ? phase->phase : -1;          // -1: the whole call at once (one device holds the batch)
     uint32_t* and_out = phase ? phase->and_out : nullptr;
     if (ph <= 0) {
-        if (t_prof_start && t_prof_stop) cudaEventRecord(t_prof_start, stream);
+        if (prof_start && prof_stop) cudaEventRecord(prof_start, stream);
         ICPF_LAUNCH(kernel, P, kThreads, smem, stream)(a);
         err = cudaGetLastError();
-        if (t_prof_start && t_prof_stop) {
-            cudaEventRecord(t_prof_stop, stream);
-            t_prof_start = t_prof_stop = nullptr;
-        }
+        if (prof_start && prof_stop) cudaEventRecord(prof_stop, stream);
         if (err != cudaSuccess) return (int)err;
         ICPF_LAUNCH(icp_resolve_batch_kernel, 1, 256, 0, stream)(conv, P, prm.max_iterations, a.cap, prm.batch_stop, batch,
                                                         capped ? decided : nullptr, and_out);

@@ -48,10 +48,10 @@ struct IcpPhase {
 int launch_icp(const float* src, const float* dst, const float* init_R, const float* init_T, const float* init_pose,
                int auto_swap, int P, int N, const icpf_params& prm, float* out_R, float* out_T,
                float* out_rmse, float* out_pose, int* out_iters, uint32_t* out_conv, int* out_batch, void* workspace,
-               size_t workspace_bytes, cudaStream_t stream, const IcpPhase* phase = nullptr);
-
-void set_profile_events(cudaEvent_t start, cudaEvent_t stop);
-void set_peer_gather(float* const* peer_pose_dev, int world, int row0);
+               size_t workspace_bytes, cudaStream_t stream, const IcpPhase* phase = nullptr,
+               const icpf_icp_ext* ext = nullptr);
+int launch_peer_push(const float* local_pose, float* const* peer_pose_dev, int world, int row0, int P, cudaStream_t stream);
+int launch_expand_rows(const float* rows, const int32_t* offsets, int B, int N, float* out, cudaStream_t stream);
 
 size_t icp_big_workspace_bytes(int P, int N);     // 0 unless the clusters need the global-memory variant
 int hist_chunk_pairs(int P, int lx, int ly, int lz);

@@ -75,9 +75,20 @@ def make_params(thres: float = 0.1, max_iterations: int = 100, relative_rmse_thr
     return p
 
 
+def icp_ext(peer_pose_dev: int = 0, peer_world: int = 0, peer_row0: int = 0, start_event: int = 0,
+            stop_event: int = 0) -> _lib.IcpfIcpExt:
+    """Per-call extensions of ``icp_batch`` (``struct icpf_icp_ext``): the fused peer all-gather of the transforms and /
+    or a pair of CUDA events recorded around the dominant kernel.  Plain values: the library keeps no state."""
+    e = _lib.IcpfIcpExt()
+    e.peer_pose_dev, e.peer_world, e.peer_row0 = peer_pose_dev or None, int(peer_world), int(peer_row0)
+    e.start_event, e.stop_event = start_event or None, stop_event or None
+    return e
+
+
 def icp_batch(src: torch.Tensor, dst: torch.Tensor, params: _lib.IcpfParams,
               init_R: Optional[torch.Tensor] = None, init_T: Optional[torch.Tensor] = None,
-              out: Optional[IcpBatchResult] = None, workspace: Optional[torch.Tensor] = None) -> IcpBatchResult:
+              out: Optional[IcpBatchResult] = None, workspace: Optional[torch.Tensor] = None,
+              ext: Optional[_lib.IcpfIcpExt] = None) -> IcpBatchResult:
     """Stream-ordered batched ICP on padded ``[P,N,4]`` CUDA tensors; no host synchronisation."""
     src = _require_cuda_f32(src, "src")
     dst = _require_cuda_f32(dst, "dst")
@@ -107,11 +118,12 @@ def icp_batch(src: torch.Tensor, dst: torch.Tensor, params: _lib.IcpfParams,
         init_R = _require_cuda_f32(init_R, "init_R")
         init_T = _require_cuda_f32(init_T, "init_T")
     with torch.cuda.device(dev):
-        code = L.icpf_icp_f32(_ptr(src), _ptr(dst), _ptr(init_R), _ptr(init_T), P, N, ctypes.byref(params),
-                              _ptr(out.R), _ptr(out.T), _ptr(out.rmse), _ptr(out.pose), _ptr(out.iterations),
-                              _ptr(out.conv_mask),
-                              _ptr(out.batch), _ptr(workspace), workspace.numel(), _stream_ptr())
-    _lib.check(code, "icpf_icp_f32")
+        code = L.icpf_icp_ex_f32(_ptr(src), _ptr(dst), _ptr(init_R), _ptr(init_T), P, N, ctypes.byref(params),
+                                 _ptr(out.R), _ptr(out.T), _ptr(out.rmse), _ptr(out.pose), _ptr(out.iterations),
+                                 _ptr(out.conv_mask),
+                                 _ptr(out.batch), _ptr(workspace), workspace.numel(), _stream_ptr(),
+                                 ctypes.byref(ext) if ext is not None else None)
+    _lib.check(code, "icpf_icp_ex_f32")
     return out
 
 
@@ -490,12 +502,43 @@ def match_select(args, pairs, src_labels_unq, dst_labels_unq, evals, accept, tra
     return rows, m_T[rows_i, cols_i]
 
 
+def expand_rows(rows: torch.Tensor, offsets: torch.Tensor, max_points: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Compact clusters -> the reference's padded batch (``pad_segment``, utils_helper.py:185-196) on the device.
+
+    ``rows`` ``[total,3]`` fp32 xyz of the valid rows, cluster after cluster; ``offsets`` ``[B+1]`` int32 (CSR).  Returns
+    ``[B, max_points, 4]``: ``(x,y,z,1)`` rows then ``(1e8,1e8,1e8,0)`` padding."""
+    rows = _require_cuda_f32(rows, "rows")
+    if offsets.dtype != torch.int32 or not offsets.is_cuda:
+        raise TypeError("offsets must be a CUDA int32 tensor [B+1]")
+    B = offsets.numel() - 1
+    if out is None:
+        out = torch.empty(B, int(max_points), 4, device=rows.device, dtype=torch.float32)
+    with torch.cuda.device(rows.device):
+        code = _lib.lib().icpf_expand_rows_f32(_ptr(rows), _ptr(offsets.contiguous()), B, int(max_points), _ptr(out), _stream_ptr())
+    _lib.check(code, "icpf_expand_rows_f32")
+    return out
+
+
+def compact_rows(padded: torch.Tensor):
+    """Host-side inverse of ``expand_rows`` for a padded ``[B,N,4]`` CPU tensor: (rows ``[total,3]``, offsets ``[B+1]`` int32).
+    What a caller that builds its clusters on the host ships instead of the padded batch (12 B per valid row)."""
+    flags = padded[:, :, 3] > 0
+    counts = flags.sum(dim=1).to(torch.int32)
+    offsets = torch.zeros(padded.shape[0] + 1, dtype=torch.int32)
+    offsets[1:] = torch.cumsum(counts, dim=0)
+    return padded[:, :, :3][flags].contiguous(), offsets
+
+
 class IcpHostPipeline:
     """Host-buffer front end of the ICP stage: pinned host inputs -> H2D -> kernels -> D2H of the 4x4 transforms.
 
     Steps are double-buffered: the H2D copy of step k+1 (copy stream) overlaps the kernels of step k (compute stream),
     so a sequence of batches runs at max(PCIe, kernel) instead of their sum.  ``submit`` never blocks the host; call
     ``synchronize`` (or wait on the returned event) before reading the output buffer.
+
+    Two host formats: the reference's padded ``[P,N,4]`` batches (``submit``), or the compact one (``submit_compact``:
+    xyz of the valid rows + CSR offsets, 12 bytes per valid row instead of 16 per padded row -- the path is PCIe-bound,
+    so the bytes are the time), expanded to the padded layout by one small kernel on the device.
     """
 
     def __init__(self, num_pairs: int, max_points: int, params: _lib.IcpfParams, device=None):
@@ -506,6 +549,8 @@ class IcpHostPipeline:
             self.compute_stream = torch.cuda.Stream()
             self.d_src = [torch.empty(self.P, self.N, 4, device=self.dev) for _ in range(2)]
             self.d_dst = [torch.empty(self.P, self.N, 4, device=self.dev) for _ in range(2)]
+            self.c_rows = [[None, None], [None, None]]       # compact staging (allocated on first use)
+            self.c_offs = [[torch.empty(self.P + 1, device=self.dev, dtype=torch.int32) for _ in range(2)] for _ in range(2)]
             self.copied = [torch.cuda.Event() for _ in range(2)]
             self.consumed = [torch.cuda.Event() for _ in range(2)]
             self.outs = [None, None]
@@ -513,7 +558,7 @@ class IcpHostPipeline:
                                   dtype=torch.uint8)
         self.k = 0
 
-    def submit(self, host_src: torch.Tensor, host_dst: torch.Tensor, host_pose_out: torch.Tensor):
+    def submit(self, host_src: torch.Tensor, host_dst: torch.Tensor, host_pose_out: torch.Tensor, ext=None):
         """host_src / host_dst: pinned ``[P,N,4]`` fp32; host_pose_out: pinned ``[P,4,4]`` fp32 (written async)."""
         s = self.k & 1
         with torch.cuda.device(self.dev):
@@ -525,7 +570,32 @@ class IcpHostPipeline:
                 self.copied[s].record(self.copy_stream)
             with torch.cuda.stream(self.compute_stream):
                 self.compute_stream.wait_event(self.copied[s])
-                self.outs[s] = icp_batch(self.d_src[s], self.d_dst[s], self.params, out=self.outs[s], workspace=self.ws)
+                self.outs[s] = icp_batch(self.d_src[s], self.d_dst[s], self.params, out=self.outs[s], workspace=self.ws, ext=ext)
+                self.consumed[s].record(self.compute_stream)
+                host_pose_out.copy_(self.outs[s].pose, non_blocking=True)
+        self.k += 1
+        return self.outs[s]
+
+    def submit_compact(self, host_src_rows: torch.Tensor, host_src_offsets: torch.Tensor, host_dst_rows: torch.Tensor,
+                       host_dst_offsets: torch.Tensor, host_pose_out: torch.Tensor, ext=None):
+        """Compact host format (``compact_rows``): pinned ``[total,3]`` fp32 rows + ``[P+1]`` int32 offsets per cloud."""
+        s = self.k & 1
+        with torch.cuda.device(self.dev):
+            with torch.cuda.stream(self.copy_stream):
+                if self.k >= 2:
+                    self.copy_stream.wait_event(self.consumed[s])
+                for side, (rows, offs) in enumerate(((host_src_rows, host_src_offsets), (host_dst_rows, host_dst_offsets))):
+                    buf = self.c_rows[s][side]
+                    if buf is None or buf.shape[0] < rows.shape[0]:
+                        buf = self.c_rows[s][side] = torch.empty(max(rows.shape[0], 1), 3, device=self.dev)
+                    buf[:rows.shape[0]].copy_(rows, non_blocking=True)
+                    self.c_offs[s][side].copy_(offs, non_blocking=True)
+                self.copied[s].record(self.copy_stream)
+            with torch.cuda.stream(self.compute_stream):
+                self.compute_stream.wait_event(self.copied[s])
+                expand_rows(self.c_rows[s][0], self.c_offs[s][0], self.N, out=self.d_src[s])
+                expand_rows(self.c_rows[s][1], self.c_offs[s][1], self.N, out=self.d_dst[s])
+                self.outs[s] = icp_batch(self.d_src[s], self.d_dst[s], self.params, out=self.outs[s], workspace=self.ws, ext=ext)
                 self.consumed[s].record(self.compute_stream)
                 host_pose_out.copy_(self.outs[s].pose, non_blocking=True)
         self.k += 1

@@ -133,16 +133,26 @@ class PeerGather:
             hdl = symm.rendezvous(buf, self.group)
             self.slots.append((buf, hdl))
 
-    def arm(self, slot: int = 0):
-        """Route the next ``icp_batch`` call's transforms into slot ``slot`` of every rank."""
-        import ctypes
-        from . import _lib
+    def ext(self, slot: int = 0, start_event: int = 0, stop_event: int = 0):
+        """The ``icp_batch(..., ext=...)`` argument that routes that call's transforms into slot ``slot`` of every rank
+        (fused: stored by the ICP kernel's epilogue)."""
+        from . import ops
 
-        buf, hdl = self.slots[slot]
-        code = _lib.lib().icpf_peer_gather_next_icp(ctypes.c_void_p(hdl.buffer_ptrs_dev), self.world,
-                                                     self.rank * self.pairs)
-        _lib.check(code, "icpf_peer_gather_next_icp")
-        return buf
+        _buf, hdl = self.slots[slot]
+        return ops.icp_ext(hdl.buffer_ptrs_dev, self.world, self.rank * self.pairs, start_event, stop_event)
+
+    def push(self, local_pose: torch.Tensor, slot: int = 0):
+        """Un-fused variant for transforms that are final only after a later kernel (``hist_icp``): one small launch
+        copies this rank's ``[pairs,4,4]`` block into slot ``slot`` of every rank with 16-byte peer stores."""
+        import ctypes
+        from . import _lib, ops
+
+        _buf, hdl = self.slots[slot]
+        lp = local_pose.contiguous()
+        with torch.cuda.device(lp.device):
+            code = _lib.lib().icpf_peer_push_f32(ctypes.c_void_p(lp.data_ptr()), ctypes.c_void_p(hdl.buffer_ptrs_dev),
+                                                 self.world, self.rank * self.pairs, lp.shape[0], ops._stream_ptr())
+        _lib.check(code, "icpf_peer_push_f32")
 
     def finish(self, slot: int = 0) -> torch.Tensor:
         """Stream-ordered cross-rank barrier; afterwards the slot holds the transforms of every rank's pairs."""

@@ -259,19 +259,49 @@ int icpf_flow_f32(const float* points, int32_t point_stride, const float* labels
                   float* out_flow, void* stream);
 
 /*
- * Fused all-gather of the transforms (multi-GPU): the next icpf_icp_f32 call on this host thread also stores every
- * pair's 4x4 (64 B) directly into the gathered buffers of ALL ranks through peer-mapped pointers -- row (row0 + p) of
- * each `[world * P, 16]` buffer -- from the kernel epilogue, instead of a separate NCCL all-gather.
- *   peer_pose_dev  DEVICE array of `world` base pointers (e.g. torch symmetric memory `buffer_ptrs_dev`)
- * The caller runs a cross-rank barrier on the stream afterwards (rows are visible once every rank's kernel has ended).
- * One-shot: the setting applies to the next call only.
+ * Per-call extensions of the ICP loop.  Everything a call needs is an explicit argument: the library keeps NO state
+ * between calls (no globals, no thread-locals), so calls from any number of host threads / streams are independent.
+ *   peer_pose_dev / peer_world / peer_row0   fused all-gather of the transforms (multi-GPU, one process per GPU): the
+ *       kernel epilogue also stores every pair's 4x4 (64 B) into row (peer_row0 + p) of the `[world * P, 16]` buffers of
+ *       ALL ranks through peer-mapped pointers (DEVICE array of `peer_world` base pointers, e.g. torch symmetric memory
+ *       `buffer_ptrs_dev`) instead of a separate NCCL all-gather; the caller runs a cross-rank barrier on the stream
+ *       afterwards (rows are visible once every rank's kernel has ended).  NULL / 0 = off.
+ *   start_event / stop_event   measurement hook (bench.py): cudaEvent_t handles recorded on `stream` immediately around
+ *       the launch of the dominant kernel (icp_pairs_kernel, first pass).  NULL = off.  No effect on results.
  */
-int icpf_peer_gather_next_icp(void* const* peer_pose_dev, int32_t world, int32_t row0);
+typedef struct icpf_icp_ext {
+    void* const* peer_pose_dev;
+    int32_t peer_world;
+    int32_t peer_row0;
+    void* start_event;
+    void* stop_event;
+} icpf_icp_ext;
 
-/* Measurement hook (bench.py): when both handles are non-NULL the next icpf_icp_f32 call on this host thread records
- * `start_event` / `stop_event` (cudaEvent_t) on its stream immediately around the launch of the dominant kernel
- * (icp_pairs_kernel, first pass), then the hook clears itself.  No effect on results. */
-void icpf_profile_next_icp(void* start_event, void* stop_event);
+/* icpf_icp_f32 with the extensions above (`ext` may be NULL: then exactly icpf_icp_f32). */
+int icpf_icp_ex_f32(const float* src, const float* dst, const float* init_R, const float* init_T, int32_t P, int32_t N,
+                    const icpf_params* params, float* out_R, float* out_T, float* out_rmse, float* out_pose,
+                    int32_t* out_iters, uint32_t* out_conv, int32_t* out_batch, void* workspace, size_t workspace_bytes,
+                    void* stream, const icpf_icp_ext* ext);
+
+/*
+ * The all-gather of the transforms as ONE small launch (multi-GPU): copies this rank's contiguous block local_pose
+ * [P,16] into rows [row0, row0 + P) of the `[world * P, 16]` buffer of every rank (peer-mapped pointers as above) with
+ * 16-byte stores.  The alternative to the fused epilogue stores for callers whose transforms are final only after a later
+ * kernel (apply_icp / hist_icp).  The caller runs the cross-rank barrier afterwards.
+ */
+int icpf_peer_push_f32(const float* local_pose, void* const* peer_pose_dev, int32_t world, int32_t row0, int32_t P,
+                       void* stream);
+
+/*
+ * Compact input format -> the padded layout.  The reference's padded batch ships 16 bytes per row for 12 bytes of
+ * information and pads every cluster to max_points (utils_helper.py:185-196); a host that feeds the engine over PCIe can
+ * send the valid rows only:
+ *   rows     [total, 3] fp32 xyz, the valid rows of cluster 0, then of cluster 1, ... (DEVICE, after the H2D copy)
+ *   offsets  [B + 1] int32, rows of cluster b = rows[offsets[b] .. offsets[b+1])   (at most N rows each)
+ *   out      [B, N, 4] fp32: (x, y, z, 1) for the valid rows, then (1e8, 1e8, 1e8, 0) -- bit for bit what pad_segment
+ *            builds from the same rows.
+ */
+int icpf_expand_rows_f32(const float* rows, const int32_t* offsets, int32_t B, int32_t N, float* out, void* stream);
 
 /* CPU-callable test hook: the closed-form 3x3 Kabsch rotation used inside the kernels, evaluated on the host
  * for `n` row-major cross-covariance matrices H (n*9 floats) -> R (n*9 floats).  Not part of the data path. */

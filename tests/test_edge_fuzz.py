@@ -141,3 +141,17 @@ def test_non_finite_points_do_not_spread_or_hang():
     assert T.shape == (6, 4, 4) and bool(torch.isfinite(T[2:]).all())
     ev = ops.match_eval(args, put(bad_s), put(bad_d), put(T))
     assert bool(torch.isfinite(ev[0][2:]).all())
+
+
+def test_expand_rows_rebuilds_the_padded_batch_bit_for_bit():
+    """The compact host format (valid xyz rows + CSR offsets, `ops.compact_rows`) expanded on the device is the padded
+    batch pad_segment builds (utils_helper.py:185-196): same rows, flag 1, then (1e8, 1e8, 1e8, 0)."""
+    rng = np.random.default_rng(11)
+    for P, N in [(1, 1), (3, 5), (4, 64), (7, 129), (2, 512)]:
+        src, _ = _batch(rng, P, N, "ragged")
+        rows, offsets = ops.compact_rows(torch.from_numpy(src))
+        assert rows.shape[0] == int((src[..., 3] > 0).sum()) and offsets[-1] == rows.shape[0]
+        if rows.shape[0] == 0:
+            rows = torch.zeros(1, 3)
+        got = ops.expand_rows(put(rows), put(offsets), N).cpu().numpy()
+        assert got.tobytes() == src.tobytes(), (P, N)

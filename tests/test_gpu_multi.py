@@ -20,4 +20,5 @@ def test_fused_peer_gather_matches_nccl():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert out.stdout.count("fused peer gather == NCCL all_gather: True") == 2
+    assert out.stdout.count("peer push == NCCL all_gather: True") == 2
     assert out.stdout.count("sharded hist_icp == unsharded: True") == 2

@@ -11,13 +11,21 @@ src, dst, _ = synth.make_pairs(P, 256, seed=100 + rank, ragged=True, residual_on
 s, d = torch.from_numpy(src).to(dev), torch.from_numpy(dst).to(dev)
 peer = shard.PeerGather(P, dev, slots=1)
 prm = ops.make_params()
-peer.arm(0)
-r = ops.icp_batch(s, d, prm)
-full = peer.finish(0)
+r = ops.icp_batch(s, d, prm, ext=peer.ext(0))
+full = peer.finish(0).clone()
 want = shard.gather_transforms(r.pose, world * P)
 torch.cuda.synchronize()
 ok = torch.equal(full, want) and torch.equal(full[rank * P:(rank + 1) * P], r.pose)
 print(f"rank {rank}: fused peer gather == NCCL all_gather: {ok}", flush=True)
+assert ok
+# the un-fused variant: one small launch pushes the rank's block to every peer
+peer.slots[0][0].zero_()
+dist.barrier()
+peer.push(r.pose, 0)
+full = peer.finish(0)
+torch.cuda.synchronize()
+ok = torch.equal(full, want)
+print(f"rank {rank}: peer push == NCCL all_gather: {ok}", flush=True)
 assert ok
 # the sharded hist_icp with the exchanged batch stop == the unsharded call on the whole batch, bit for bit
 import types
