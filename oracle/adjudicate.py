@@ -1,0 +1,186 @@
+"""oracle/adjudicate.py -- TEST INFRASTRUCTURE (CPU checker), never imported by the product path.
+
+Verdicts for the pairs of a parity comparison that are NOT within the tolerance of the fp32 oracle.
+
+The reference path is full of discrete decisions taken on fp32 values -- a correspondence within a few ulp of the gate
+``d^2 <= thres^2`` (utils_icp_pytorch3d.py:160), the nearest-neighbour tie rule, a histogram bin edge, the order of
+tied ``topk`` peaks (utils_hist.py:27), the roll-back comparison ``error_icp >= error_init`` (utils_icp.py:34) -- so on
+some inputs two equally valid fp32 evaluations of the reference (another summation order inside ``bmm``, another BLAS)
+already disagree by more than 1e-4.  A differently-ordered fp32 engine cannot be held to ONE of those outcomes; it has
+to be held to the SET of outcomes the reference admits.  This module constructs that set explicitly, per pair:
+
+  * the reference algorithm re-run in fp64 (what the reference computes when rounding is taken out of the decisions),
+  * the reference algorithm re-run in fp32 on inputs whose coordinates are moved by one / a few fp32 ulps
+    (``x * (1 + k * 2^-23)``): every rounding-level decision of the run gets the chance to fall the other way,
+  * for the ICP loop: both at the batch iteration count of the oracle and at the engine's (the batch stop itself is a
+    threshold decision on a relative rmse of 1e-6),
+  * for the histogram initialisation: the other orders `torch.topk` may return EQUAL vote counts in (lowest / highest
+    bin index first; CPU partial sort and CUDA radix select differ, utils_hist.py:27) -- a tie at the k-th place changes
+    the candidate SET and with it the initial translation.
+
+A pair outside the tolerance of the plain fp32 oracle is EXPLAINED when the engine's transform agrees with one member of
+that set to the same tolerance -- the reference itself does not determine the pair -- and UNEXPLAINED otherwise.  The
+parity tests fail on any unexplained pair and bound the fraction of explained ones by what was observed.
+
+One class of pairs has no admitted SET at all: a Kabsch system with fewer than three independent correspondences
+(unrelated clusters that touch in one or two points).  Its cross-covariance has rank <= 1, the rotation about the
+remaining axis is not determined by the data, and the reference returns whatever LAPACK's SVD picks for a singular matrix
+("3x3 SVD") -- every member of the set above then lands somewhere else (metres apart).  Such a pair
+gets the verdict "rank-deficient" when (a) the oracle's own diagnostics show the rank deficiency (fewer than 4 gated
+correspondences or sigma_2 / sigma_1 < 1e-3 at some iteration) AND (b) the admitted outcomes scatter by more than the
+tolerance among themselves; the engine's result is then only required to be a finite rigid transform.
+
+Cites: utils_icp_pytorch3d.py:153-214 (loop, gate, stop), utils_hist.py:21-29,101-106 (top-k, candidate arg-min),
+utils_icp.py:27-35 (roll-back).
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import icp_oracle as O
+
+ULP = 2.0 ** -23
+
+
+def moved_err(src: torch.Tensor, T_a: torch.Tensor, T_b: torch.Tensor) -> np.ndarray:
+    """max over the valid rows of |T_a p - T_b p|_inf per pair (column-convention 4x4) -- the flow-vector difference."""
+    pts = src[:, :, :3].double()
+    valid = src[:, :, 3] > 0
+    a = torch.einsum("pij,pnj->pni", T_a[:, :3, :3].double(), pts) + T_a[:, None, :3, 3].double()
+    b = torch.einsum("pij,pnj->pni", T_b[:, :3, :3].double(), pts) + T_b[:, None, :3, 3].double()
+    return ((a - b).abs().amax(dim=2) * valid).amax(dim=1).numpy()
+
+
+def jitter(x: torch.Tensor, seed: int, ulps: int) -> torch.Tensor:
+    """The padded cloud with every valid coordinate moved by -ulps .. +ulps fp32 ulps (flag column and padding kept)."""
+    g = torch.Generator().manual_seed(seed)
+    k = torch.randint(-ulps, ulps + 1, x[:, :, :3].shape, generator=g).to(torch.float32)
+    out = x.clone()
+    valid = (x[:, :, 3:4] > 0)
+    out[:, :, :3] = torch.where(valid, x[:, :, :3] * (1.0 + k * ULP), x[:, :, :3])
+    return out
+
+
+@dataclasses.dataclass
+class Verdicts:
+    err: np.ndarray                 # error against the plain fp32 oracle, per pair
+    verdict: List[str]              # "ok" | "fp64@its" | "ulp<k>#<seed>@its" | "rank-deficient" | "unexplained"
+    tol: float
+
+    @property
+    def explained(self) -> np.ndarray:
+        return np.array([v not in ("ok", "unexplained") for v in self.verdict])
+
+    @property
+    def unexplained(self) -> np.ndarray:
+        return np.array([v == "unexplained" for v in self.verdict])
+
+    def summary(self) -> str:
+        n = len(self.verdict)
+        ex, un = int(self.explained.sum()), int(self.unexplained.sum())
+        ok = np.array([v == "ok" for v in self.verdict])
+        kinds = sorted({v.split("#")[0].split("@")[0] for v in self.verdict if v not in ("ok", "unexplained")})
+        return (f"{n} pairs: {int(ok.sum())} within {self.tol:g} of the fp32 oracle (max {self.err[ok].max() if ok.any() else 0:.2e} m), "
+                f"{ex} explained by an admitted outcome {kinds} (max err vs the plain oracle {self.err[self.explained].max() if ex else 0:.2e} m), "
+                f"{un} unexplained")
+
+
+def _adjudicate(src_for_err: torch.Tensor, T_eng: torch.Tensor, T_ref: torch.Tensor, tol: float,
+                variants: Sequence, run_variant: Callable, rank_deficient: Optional[np.ndarray] = None) -> Verdicts:
+    """variants: labels; run_variant(label, idx) -> [len(idx),4,4] transforms of the pairs `idx` under that variant.
+    rank_deficient: per pair, the oracle's diagnostics show a Kabsch system of rank <= 1 (see the module docstring)."""
+    err = moved_err(src_for_err, T_eng, T_ref)
+    verdict = ["ok" if e <= tol else "" for e in err]
+    todo = np.nonzero(err > tol)[0]
+    scatter = np.zeros(len(err))                 # largest distance of an admitted outcome from the plain oracle
+    for label in variants:
+        if len(todo) == 0:
+            break
+        T_var = run_variant(label, todo)
+        e = moved_err(src_for_err[todo], T_eng[todo], T_var)
+        scatter[todo] = np.maximum(scatter[todo], moved_err(src_for_err[todo], T_ref[todo], T_var))
+        hit = e <= tol
+        for i in todo[hit]:
+            verdict[i] = label
+        todo = todo[~hit]
+    for i in todo:
+        degenerate = rank_deficient is not None and bool(rank_deficient[i]) and scatter[i] > tol
+        verdict[i] = "rank-deficient" if degenerate else "unexplained"
+    return Verdicts(err, verdict, tol)
+
+
+def rank_deficient_pairs(trace: O.IcpTrace, min_inliers: int = 4, sigma_ratio: float = 1e-3) -> np.ndarray:
+    """Pairs whose Kabsch system had rank <= 1 at some iteration of the oracle run (`icp_loop(..., diagnostics=True)`)."""
+    assert trace.min_inliers is not None, "run icp_loop(..., diagnostics=True)"
+    return ((trace.min_inliers < min_inliers) | (trace.min_sigma_ratio < sigma_ratio)).numpy()
+
+
+def adjudicate_icp(src: torch.Tensor, dst: torch.Tensor, R_eng: torch.Tensor, T_eng: torch.Tensor, R_ref: torch.Tensor,
+                   T_ref: torch.Tensor, its_ref: int, its_eng: Optional[int] = None, thres: float = 0.1,
+                   tol: float = 1e-4, seeds: int = 6, rank_deficient: Optional[np.ndarray] = None) -> Verdicts:
+    """ICP loop (utils_icp_pytorch3d.py:153-214).  `its_ref` / `its_eng`: batch iterations the oracle / the engine
+    executed; the admitted outcomes are evaluated at exactly those iteration counts (relative_rmse_thr = -1), so that the
+    sub-batch re-runs do not depend on the other pairs."""
+    its = sorted({int(its_ref)} | ({int(its_eng)} if its_eng is not None else set()))
+    labels = [f"fp64@{k}" for k in its]
+    for u in (1, 4):
+        labels += [f"ulp{u}#{s}@{k}" for s in range(seeds // 2) for k in its]
+
+    def run(label, idx):
+        kind, k = label.split("@")
+        a, c = src[idx], dst[idx]
+        if kind == "fp64":
+            tr = O.icp_loop(a.double(), c.double(), thres, int(k), -1.0)
+        else:
+            u, s = kind[3:].split("#")
+            tr = O.icp_loop(jitter(a, 100 + int(s), int(u)), jitter(c, 200 + int(s), int(u)), thres, int(k), -1.0)
+        return O.pack_rt(tr.R.float(), tr.T.float())
+
+    return _adjudicate(src, O.pack_rt(torch.as_tensor(R_eng).float(), torch.as_tensor(T_eng).float()),
+                       O.pack_rt(torch.as_tensor(R_ref).float(), torch.as_tensor(T_ref).float()), tol, labels, run,
+                       rank_deficient)
+
+
+def adjudicate_path(src: torch.Tensor, dst: torch.Tensor, T_eng: torch.Tensor, T_ref: torch.Tensor, p: O.PathParams,
+                    its_ref: int, its_eng: Optional[int] = None, stage: str = "hist_icp",
+                    init: Optional[torch.Tensor] = None, tol: float = 1e-4, seeds: int = 6,
+                    rank_deficient: Optional[np.ndarray] = None) -> Verdicts:
+    """`hist_icp` (utils_match.py:138-157) or, with `stage="apply_icp"` and `init`, `apply_icp` (utils_icp.py:20-48).
+    The batch stop couples the pairs of a call, so the sub-batch re-runs force the ICP iteration count to the oracle's /
+    the engine's (max_iterations = k, relative_rmse_thr = -1: utils_icp_pytorch3d.py:209 never fires before k)."""
+    its = sorted({int(its_ref)} | ({int(its_eng)} if its_eng is not None else set()))
+    labels = [f"fp64@{k}" for k in its]
+    if stage == "hist_icp":
+        labels += [f"topk-{t}@{k}" for t in ("low", "high") for k in its]
+    for u in (1, 4):
+        labels += [f"ulp{u}#{s}@{k}" for s in range(seeds // 2) for k in its]
+
+    def run(label, idx):
+        kind, k = label.split("@")
+        q = dataclasses.replace(p, max_iterations=int(k), relative_rmse_thr=-1.0)
+        a, c = src[idx], dst[idx]
+        i0 = init[idx] if init is not None else None
+        if kind == "fp64":
+            a, c = a.double(), c.double()
+            i0 = i0.double() if i0 is not None else None
+        elif kind.startswith("topk-"):
+            q = dataclasses.replace(q, topk_ties=kind[5:])
+        else:
+            u, s = kind[3:].split("#")
+            a, c = jitter(a, 100 + int(s), int(u)), jitter(c, 200 + int(s), int(u))
+        # (the reference builds its bins / identities with torch.arange / torch.eye in the DEFAULT dtype: the fp64 run
+        # switches it like SURVEY.md section 8c describes)
+        saved = torch.get_default_dtype()
+        torch.set_default_dtype(torch.float64 if kind == "fp64" else torch.float32)
+        try:
+            if stage == "apply_icp":
+                return O.apply_icp(a, c, i0, q).float()
+            return O.hist_icp(a, c, q).float()
+        finally:
+            torch.set_default_dtype(saved)
+
+    return _adjudicate(src, torch.as_tensor(T_eng).float(), torch.as_tensor(T_ref).float(), tol, labels, run, rank_deficient)

@@ -54,6 +54,11 @@ class PathParams:
     relative_rmse_thr: float = 1e-6
     topk: int = 5
     nms_kernel: int = 11
+    # NOT a reference parameter: which of several EQUAL vote counts `torch.topk` returns first is implementation-defined
+    # (CPU partial sort vs CUDA radix select, utils_hist.py:27).  "torch" = whatever this torch build does (the pinned
+    # goldens); "low" / "high" = lowest / highest flat bin index first -- the other outcomes the reference admits, used by
+    # oracle/adjudicate.py only.
+    topk_ties: str = "torch"
 
 
 class IcpTrace(NamedTuple):
@@ -125,13 +130,23 @@ def vote_histogram(src: torch.Tensor, dst: torch.Tensor, p: PathParams):
     return h, (bx, by, bz)
 
 
-def topk_nms(x: torch.Tensor, k: int = 5, kernel_size: int = 11):
-    """utils_hist.py:21-29 -- keep bins equal to their 11^3 window max, then top-k of the flattened volume."""
+def topk_nms(x: torch.Tensor, k: int = 5, kernel_size: int = 11, ties: str = "torch"):
+    """utils_hist.py:21-29 -- keep bins equal to their 11^3 window max, then top-k of the flattened volume.
+    `ties` (see PathParams.topk_ties): the order among equal vote counts; "torch" is the reference call itself."""
     b = x.shape[0]
     x5 = x.unsqueeze(1)
     pooled = torch.nn.functional.max_pool3d(x5, kernel_size=kernel_size, stride=1, padding=(kernel_size - 1) // 2)
     keep = (x5 == pooled).float().clamp(min=0.0)
-    votes, idxs = torch.topk((x5 * keep).view(b, -1), dim=1, k=k)
+    flat = (x5 * keep).view(b, -1)
+    if ties == "torch":
+        votes, idxs = torch.topk(flat, dim=1, k=k)
+        return votes, idxs.long()
+    if ties == "high":
+        flat = flat.flip(1)
+    votes, idxs = torch.sort(flat, dim=1, descending=True, stable=True)      # stable: equal counts keep index order
+    votes, idxs = votes[:, :k], idxs[:, :k]
+    if ties == "high":
+        idxs = flat.shape[1] - 1 - idxs
     return votes, idxs.long()
 
 
@@ -170,7 +185,7 @@ def _estimate_init_pose_chunk(src, dst, p: PathParams):
     valid_s, valid_d = src[:, :, -1] > 0.0, dst[:, :, -1] > 0.0
     hist, (bx, by, bz) = vote_histogram(src, dst, p)
     b, h, w, d = hist.shape
-    votes, flat = topk_nms(hist, k=p.topk, kernel_size=p.nms_kernel)
+    votes, flat = topk_nms(hist, k=p.topk, kernel_size=p.nms_kernel, ties=p.topk_ties)
     cand = torch.stack([bx[flat // d // w % h], by[flat // d % w], bz[flat % d]], dim=-1) + p.thres_dist // 2
     n = xyz_s.shape[1]
     cand = torch.cat([cand, cand.new_zeros(b, 1, 3)], dim=1)         # + the zero translation, last

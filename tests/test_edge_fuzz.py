@@ -117,11 +117,7 @@ def test_scan_level_entry_points_on_empty_and_tiny_inputs():
 def test_non_finite_points_do_not_spread_or_hang():
     """NaN / inf coordinates in a valid row (a LiDAR return gone wrong): no crash, no hang, no out-of-bounds access, and
     the OTHER pairs of the batch get exactly the result they get without the poisoned pair next to them (the batch
-    stop aside: compared with a fixed iteration count).  Emulator engine only for now: this case was written after the
-    round's last GPU run, and a non-terminating kernel is not something to find out about in the round-end run -- its
-    first GPU execution belongs under a timeout (tools/round2_first_call.sh runs the whole gpu suite that way)."""
-    if not is_simt() and os.environ.get("ICPF_RUN_NONFINITE_ON_GPU") != "1":
-        pytest.skip("first GPU run pending (set ICPF_RUN_NONFINITE_ON_GPU=1)")
+    stop aside: compared with a fixed iteration count)."""
     rng = np.random.default_rng(42)
     src, dst = _batch(rng, 6, 96, "full")
     clean = [ops.icp_batch(put(src[2:]), put(dst[2:]), ops.make_params(max_iterations=25, relative_rmse_thr=-1.0,

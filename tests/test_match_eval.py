@@ -213,19 +213,13 @@ def test_engine_match_pairs_vs_reference_golden(golden, name):
     ref_rows, ref_T = g["mp_rows"], g["mp_T"]
     assert rows.shape[1] == 10
     assert np.array_equal(rows[:, :2], ref_rows[:, :2]), (rows[:, :2], ref_rows[:, :2])
-    # determined = the reference's ICP on that pair is not at a discrete flip (see test_gpu_path)
+    # every selected pair within 1e-4 m of the reference's transform, or adjudicated (tests/parity.py, oracle/adjudicate.py)
+    from parity import selected_pairs_parity
     _, _, dbg = O.match_pairs(*(torch.from_numpy(x) for x in (sp, dp, sl, dl, pairs)), p, gates, return_debug=True)
-    unstable = O.undetermined_pairs(dbg["segs_src"], dbg["segs_dst"], p).numpy()
-    key = {(float(a), float(b)): k for k, (a, b) in enumerate(pairs)}
-    sel = np.array([key[(float(a), float(b))] for a, b in ref_rows[:, :2]], dtype=np.int64)
-    det = ~unstable[sel]
-    assert det.mean() > 0.8
+    flagged = selected_pairs_parity([(dbg["segs_src"], dbg["segs_dst"], pairs)], p, ref_rows, T, ref_T, max_explained=0.1,
+                                    what=name)
+    det = ~flagged
     np.testing.assert_allclose(rows[det, 2:4], ref_rows[det, 2:4], atol=2e-5)        # mean NN errors (m)
-    for k in np.nonzero(det)[0]:
-        pts = sp[sl == ref_rows[k, 0]].astype(np.float64)
-        a = pts @ T[k, :3, :3].T.astype(np.float64) + T[k, :3, 3]
-        b = pts @ ref_T[k, :3, :3].T.astype(np.float64) + ref_T[k, :3, 3]
-        assert np.abs(a - b).max() < 1e-4
     exact = det & (np.abs(rows[:, 4:6] - ref_rows[:, 4:6]).max(1) == 0)
     assert exact.sum() >= 0.8 * det.sum()                                             # inlier counts: integer work
     np.testing.assert_allclose(rows[exact, 6:10], ref_rows[exact, 6:10], rtol=1e-6)
