@@ -305,6 +305,31 @@ def time_secondary(dev):
         "cpu_baseline": {"pairs_per_s": cpu_pairs / cpu_s, "cores": cores, "kind": "port",
                          "sample": f"the first {cpu_pairs} of the {P3} pairs, full hist_icp, {cpu_s:.1f} s, oracle/icp_oracle.py"},
     }
+    # the reference's own CUDA vote kernel (hist_cuda_core.cuh, built unmodified for sm_100a into oracle/_ref/) as the
+    # kernel-to-beat of the vote stage, on the first 512 pairs (its dense [B,135,135,3] fp32 output is 219 KB per pair)
+    try:
+        from oracle import ref_hist
+        if ref_hist.available():
+            nb = 512
+            hb = ops._hist_bins(THRES, F3, dev)
+            sb, db = s[:nb].contiguous(), d[:nb].contiguous()
+            buf = torch.empty(nb, *hb.lens, device=dev, dtype=torch.float32)
+            ms_ref = _events_ms(lambda: ref_hist.hist(db, sb, list(hb.c.min), list(hb.c.max), hb.lens, out=buf), 3, sync)
+            ref_counts = buf.clone()
+            ms_seam = _events_ms(lambda: ops.hist(db, sb, *hb.c.min, *hb.c.max, *hb.lens), 3, sync)
+            same = bool(torch.equal(ops.hist(db, sb, *hb.c.min, *hb.c.max, *hb.lens), ref_counts))
+            ms_fused = _events_ms(lambda: ops.estimate_init_pose(args, sb, db, auto_swap=True), 3, sync)
+            out["c3_hist_icp"]["vote_stage_vs_reference_kernel"] = {
+                "pairs": nb, "reference_hist_cuda_kernel_ms": ms_ref, "icpf_hist_votes_f32_ms": ms_seam,
+                "counts_bit_identical": same,
+                "whole_estimate_init_pose_ms": ms_fused,
+                "what": "reference: hist_cuda_kernel (one thread per (pair, i, j), global fp32 atomics, 64 launches of 8 pairs) "
+                        "+ the zero-fill of its dense output; icpf_hist_votes_f32: the bit-compatible public seam (same dense "
+                        "output); whole_estimate_init_pose: votes + NMS + top-5 + candidate scoring of the fused path, which "
+                        "never materialises the dense histogram"}
+            del buf, ref_counts
+    except Exception as exc:
+        out["c3_hist_icp"]["vote_stage_vs_reference_kernel"] = {"error": f"{type(exc).__name__}: {exc}"}
     del s, d, init
 
     # ---- C4: Waymo-shape frame pair

@@ -179,3 +179,24 @@ def test_histogram_bin_edges_oracle():
     assert h[0, 0].sum() == 1 and h[0, len(bx) - 1].sum() == 1      # (v - min) / (max - min) * len == len -> clamped
     assert (mx - mn) / len(bx) < 0.1                      # kernel bin width < thres_dist
     assert 0.1 // 2 == 0.0                                # the "+ thres_dist // 2" of utils_hist.py:78 adds nothing
+
+
+@pytest.mark.gpu
+def test_vote_kernel_counts_equal_the_reference_cuda_kernel():
+    """The reference's own `hist_cuda_kernel` (hist_cuda_core.cuh:23-64, built unmodified for sm_100a into oracle/_ref/ by
+    oracle/Makefile) against icpf_hist_votes_f32 on the same inputs: every count of every bin identical."""
+    import torch
+    from icp_flow_b200 import ops, synth
+    from oracle import ref_hist
+    if not ref_hist.available():
+        pytest.skip("oracle/_ref/libref_hist.so not built (needs /root/reference at build time)")
+    dev = torch.device("cuda:0")
+    for (P, N, F, seed) in [(9, 160, 2.0, 1), (20, 512, 6.666, 2), (5, 1024, 3.333, 3)]:
+        src, dst, _ = synth.make_pairs(P, N, seed=seed, ragged=True, residual_only=False, wrong_frac=0.2)
+        s, d = torch.from_numpy(src).to(dev), torch.from_numpy(dst).to(dev)
+        hb = ops._hist_bins(0.1, F, dev)
+        mine = ops.hist(d, s, *hb.c.min, *hb.c.max, *hb.lens)
+        ref = ref_hist.hist(d, s, list(hb.c.min), list(hb.c.max), hb.lens)
+        torch.cuda.synchronize()
+        assert torch.equal(mine, ref), (P, N, F, int((mine != ref).sum()))
+        assert float(ref.sum()) > 0
