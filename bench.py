@@ -427,7 +427,7 @@ def main():
     out = None
     outs = [None, None]
     gathered = [torch.empty(n_gpus * P, 4, 4, device=dev, dtype=torch.float32) for _ in range(2)]
-    launches_per_step = 3   # icp_pairs_kernel + icp_resolve_batch_kernel + icp_select_batch_kernel (state at the batch stop)
+    launches_per_step = 1   # icp_pairs_kernel (the batch stop is resolved by its last CTA; + one 20-byte memset node)
     comm_stream = torch.cuda.Stream() if world > 1 else None
     peer = None
     gather_kind = "none"
@@ -623,6 +623,7 @@ def main():
                     "steps": e2e_steps, "host_format": "compact: xyz of the valid rows (12 B/row) + CSR offsets, expanded to the "
                     "padded [P,N,4] batch by icpf_expand_rows_f32 on the device; the padded format would ship "
                     f"{batch_bytes} B per step", "h2d_gbs": h2d_bytes * e2e_steps / (float(t.item()) * 1e-3) / 1e9},
+            # (+ the two expand_rows kernels of the compact host format in the e2e steps)
             "gpu_launches": launches_per_step * args.steps + (launches_per_step + 2) * e2e_steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": load_ncu_traffic(), "peak_kind": peak_kind, "kernel": "icp_pairs_kernel",

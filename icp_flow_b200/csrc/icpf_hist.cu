@@ -89,13 +89,25 @@ __global__ void __launch_bounds__(kVoteThreads) hist_votes_kernel(const float4* 
     }
 }
 
+__global__ void __launch_bounds__(256) hist_zero_flagged_kernel(float* __restrict__ bins, size_t per_pair, const int* __restrict__ need) {
+    if (need[blockIdx.x] == 0) return;
+    float* h = bins + (size_t)blockIdx.x * per_pair;
+    for (size_t i = threadIdx.x; i < per_pair; i += blockDim.x) h[i] = 0.f;
+}
+
 int launch_hist_votes(const float* X, const float* Y, int B, int NX, int NY, const float* mins, const float* maxs,
                       const int* lens, float* bins, int auto_swap, const int* need, cudaStream_t stream) {
     if (B == 0) return ICPF_OK;
     HistGeom gm{mins[0], mins[1], mins[2], maxs[0], maxs[1], maxs[2], lens[0], lens[1], lens[2]};
-    const size_t bytes = (size_t)B * lens[0] * lens[1] * lens[2] * sizeof(float);
-    cudaError_t err = cudaMemsetAsync(bins, 0, bytes, stream);    // at::zeros of hist_cuda.cu:59
-    if (err != cudaSuccess) return (int)err;
+    const size_t per_pair = (size_t)lens[0] * lens[1] * lens[2];
+    if (need == nullptr) {
+        cudaError_t err = cudaMemsetAsync(bins, 0, (size_t)B * per_pair * sizeof(float), stream);    // at::zeros of hist_cuda.cu:59
+        if (err != cudaSuccess) return (int)err;
+    } else {
+        // fall-back after the fused kernel: only the flagged pairs vote here, so only their histograms are zero-filled
+        // (a chunk is up to 64 MB; on a batch the fused kernel handled completely this is B CTAs that return at once)
+        ICPF_LAUNCH(hist_zero_flagged_kernel, B, 256, 0, stream)(bins, per_pair, need);
+    }
     const int nmax = auto_swap ? max(NX, NY) : NX;
     dim3 grid((nmax + kVoteThreads - 1) / kVoteThreads, B);
     ICPF_LAUNCH(hist_votes_kernel, grid, kVoteThreads, 0, stream)(reinterpret_cast<const float4*>(X),

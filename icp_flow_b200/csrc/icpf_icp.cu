@@ -46,13 +46,19 @@ struct IcpArgs {
     float* const* peer_pose;   // fused all-gather: DEVICE array of `peer_world` base pointers (peer-mapped [*,16]) or NULL
     int peer_world;
     int peer_row0;             // first row of this rank's block in the gathered buffer
+    // fused tail (whole-call mode): the last CTA to finish resolves the batch stop and, when `tail_select`, hands the pairs
+    // that went beyond it their state at the stop -- instead of two more launches
+    unsigned int* tail;        // [5] {tickets, OR of the complemented convergence words x 4}, zero before the launch; or NULL
+    int tail_limit;            // iterations the masks of this pass cover (the cap, or max_it)
+    int tail_select;
+    int batch_stop;
+    int* batch;                // [2]
+    int* decided_out;          // capped passes: 1 when the batch stop is final (may be NULL)
 };
 
-// FULLPASS = the pass after a capped first pass: only the pairs still moving at the cap run, continuing from where the
-// first pass paused them (a separate instantiation, so that the kernel of the first pass -- the one every call pays for --
-// carries no continuation logic in its loop).
+// One pair, from its row blocks to its transform.  cw[4] (thread 0) = the pair's convergence words as this pass leaves them.
 template <int MODE, bool BIG, bool FULLPASS>
-__global__ void __launch_bounds__(kThreads, BIG ? 4 : 7) icp_pairs_kernel(IcpArgs a) {
+__device__ __forceinline__ void icp_pair_body(const IcpArgs& a, uint32_t (&cw)[4]) {
     const int p = blockIdx.x;
     int max_it = a.max_it;
     bool early_exit = a.early_exit != 0;
@@ -60,18 +66,23 @@ __global__ void __launch_bounds__(kThreads, BIG ? 4 : 7) icp_pairs_kernel(IcpArg
     if (FULLPASS) {
         if (*a.decided != 0) return;      // the capped first pass already found the batch stop
         // the capped pass left the loop state of every pair behind: bit 3 of its flags = stopped at its fixed point
-        const bool stopped = a.state != nullptr &&
-                             (__float_as_uint(a.state[(size_t)p * kIcpStateWords + S_FLAGS]) & 8u) != 0u;
+        const unsigned int flags = a.state != nullptr ? __float_as_uint(a.state[(size_t)p * kIcpStateWords + S_FLAGS]) : 0u;
+        const bool stopped = (flags & 8u) != 0u;
         if (a.iters[p] < a.cap || stopped) {
             // This pair stopped at its bitwise fixed point within the cap: every later iteration repeats that state, so
-            // its transform stands and its convergence history continues the way the tail of the capped pass went
-            // (icpf_icploop.cuh, tail rule) -- only the pairs still moving at the cap go on, from where they paused.
+            // its transform stands and its convergence history continues by the tail rule (icpf_icploop.cuh; the capped
+            // pass recorded whether the rule holds -- bit cap-1 is NOT a stand-in for it when the pair stopped exactly at
+            // iteration cap-1: that bit is then the real test of that iteration) -- only the pairs still moving at the cap
+            // go on, from where they paused.
             if (threadIdx.x == 0 && a.cap >= 1) {
                 uint32_t* c = a.conv + (size_t)p * 4;
                 const int last = a.cap - 1;
-                if ((c[last >> 5] >> (last & 31)) & 1u) {
+                const bool tail_ok = a.state != nullptr ? (flags & 16u) != 0u : (((c[last >> 5] >> (last & 31)) & 1u) != 0u);
+                if (tail_ok) {
                     for (int k = a.cap; k < max_it && k < 128; ++k) c[k >> 5] |= 1u << (k & 31);
                 }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) cw[i] = c[i];
             }
             return;
         }
@@ -178,18 +189,44 @@ __global__ void __launch_bounds__(kThreads, BIG ? 4 : 7) icp_pairs_kernel(IcpArg
         a.iters[p] = r.iters;
         a.stats[(size_t)p * 2 + 0] = (int)r.searches;
         a.stats[(size_t)p * 2 + 1] = r.refreshes;
-        a.conv[(size_t)p * 4 + 0] = (uint32_t)r.conv_lo;
-        a.conv[(size_t)p * 4 + 1] = (uint32_t)(r.conv_lo >> 32);
-        a.conv[(size_t)p * 4 + 2] = (uint32_t)r.conv_hi;
-        a.conv[(size_t)p * 4 + 3] = (uint32_t)(r.conv_hi >> 32);
+        cw[0] = (uint32_t)r.conv_lo;
+        cw[1] = (uint32_t)(r.conv_lo >> 32);
+        cw[2] = (uint32_t)r.conv_hi;
+        cw[3] = (uint32_t)(r.conv_hi >> 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a.conv[(size_t)p * 4 + i] = cw[i];
     }
 }
 
-// AND of the per-pair convergence masks -> first iteration k* where every pair passes (utils_icp_pytorch3d.py:209).
-// batch[0] = iterations the reference loop would have executed, batch[1] = converged flag.
+// First iteration k* at which every pair passes the relative-rmse test (utils_icp_pytorch3d.py:209), from the AND of the
+// per-pair convergence masks.  batch[0] = iterations the reference loop would have executed, batch[1] = converged flag.
 // `limit` = iterations the masks cover (the cap of the first pass, or max_it); `decided` (may be NULL) is set to 1 when
-// the answer is final and left 0 when the capped pass could not tell (a later full pass decides); `and_out` (may be NULL)
-// receives the AND of the masks -- what a caller with several shards exchanges (IcpPhase, icpf_internal.h).
+// the answer is final and left 0 when the capped pass could not tell (a later full pass decides).  One thread.
+__device__ __forceinline__ void resolve_from_and(const uint32_t (&all)[4], int max_it, int limit, int batch_stop, int* batch,
+                                                 int* decided) {
+    int kstar = -1;
+    if (batch_stop) {
+        for (int i = 0; i < 4 && kstar < 0; ++i) {
+            if (all[i]) kstar = i * 32 + (__ffs(all[i]) - 1);
+        }
+    }
+    int verdict = 1;
+    if (kstar >= 0 && kstar < limit) {
+        batch[0] = kstar + 1;
+        batch[1] = 1;
+    } else if (limit >= max_it) {
+        batch[0] = max_it;
+        batch[1] = 0;
+    } else {
+        batch[0] = limit;          // provisional: no pair is re-run, the full pass follows
+        batch[1] = 0;
+        verdict = 0;
+    }
+    if (decided) *decided = verdict;
+}
+
+// `and_out` (may be NULL) receives the AND of the masks -- what a caller with several shards exchanges (IcpPhase,
+// icpf_internal.h).  The phased entry points use this kernel; a whole call resolves in the tail of icp_pairs_kernel.
 __global__ void __launch_bounds__(256) icp_resolve_batch_kernel(const uint32_t* conv, int P, int max_it, int limit,
                                                                 int batch_stop, int* batch, int* decided,
                                                                 uint32_t* and_out) {
@@ -210,25 +247,8 @@ __global__ void __launch_bounds__(256) icp_resolve_batch_kernel(const uint32_t* 
     __syncthreads();
     if (and_out != nullptr && threadIdx.x < 4) and_out[threadIdx.x] = s_and[threadIdx.x];
     if (threadIdx.x == 0) {
-        int kstar = -1;
-        if (batch_stop) {
-            for (int i = 0; i < 4 && kstar < 0; ++i) {
-                if (s_and[i]) kstar = i * 32 + (__ffs(s_and[i]) - 1);
-            }
-        }
-        int verdict = 1;
-        if (kstar >= 0 && kstar < limit) {
-            batch[0] = kstar + 1;
-            batch[1] = 1;
-        } else if (limit >= max_it) {
-            batch[0] = max_it;
-            batch[1] = 0;
-        } else {
-            batch[0] = limit;          // provisional: no pair is re-run, the full pass follows
-            batch[1] = 0;
-            verdict = 0;
-        }
-        if (decided) *decided = verdict;
+        const uint32_t all[4] = {s_and[0], s_and[1], s_and[2], s_and[3]};
+        resolve_from_and(all, max_it, limit, batch_stop, batch, decided);
     }
 }
 
@@ -255,22 +275,20 @@ struct IcpSelectArgs {
     int peer_row0;
 };
 
-__global__ void __launch_bounds__(128) icp_select_batch_kernel(IcpSelectArgs a) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= a.P) return;
-    const int b = a.batch[0];
-    if (a.iters[p] <= b || b < 1 || b > kIcpHistDepth) return;
+// (reads of what OTHER CTAs of the same launch wrote go through L2: __ldcg)
+__device__ __forceinline__ void select_pair(const IcpSelectArgs& a, int p, int b) {
+    if (__ldcg(a.iters + p) <= b || b < 1 || b > kIcpHistDepth) return;
     const float* h = a.hist + ((size_t)p * kIcpHistDepth + (b - 1)) * kIcpHistFloats;
     float r[9], t[3];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) r[i] = h[i];
+    for (int i = 0; i < 9; ++i) r[i] = __ldcg(h + i);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) t[i] = h[9 + i];
+    for (int i = 0; i < 3; ++i) t[i] = __ldcg(h + 9 + i);
 #pragma unroll
     for (int i = 0; i < 9; ++i) a.out_R[(size_t)p * 9 + i] = r[i];
 #pragma unroll
     for (int i = 0; i < 3; ++i) a.out_T[(size_t)p * 3 + i] = t[i];
-    if (a.out_rmse) a.out_rmse[p] = h[12];
+    if (a.out_rmse) a.out_rmse[p] = __ldcg(h + 12);
     a.iters[p] = b;
     // column-convention 4x4 [[R^T, T],[0,1]]  (utils_icp.py:60-65)
     float m[16];
@@ -291,6 +309,57 @@ __global__ void __launch_bounds__(128) icp_select_batch_kernel(IcpSelectArgs a) 
 #pragma unroll
             for (int i = 0; i < 16; ++i) a.peer_pose[w][(size_t)(a.peer_row0 + p) * 16 + i] = m[i];
         }
+    }
+}
+
+__global__ void __launch_bounds__(128) icp_select_batch_kernel(IcpSelectArgs a) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.P) return;
+    select_pair(a, p, a.batch[0]);
+}
+
+// FULLPASS = the pass after a capped first pass: only the pairs still moving at the cap run, continuing from where the
+// first pass paused them (a separate instantiation, so that the kernel of the first pass -- the one every call pays for --
+// carries no continuation logic in its loop).
+template <int MODE, bool BIG, bool FULLPASS>
+__global__ void __launch_bounds__(kThreads, BIG ? 4 : 7) icp_pairs_kernel(IcpArgs a) {
+    uint32_t cw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+    const bool settled = FULLPASS && (*a.decided != 0);       // (uniform over the grid: only the tail below writes it)
+    icp_pair_body<MODE, BIG, FULLPASS>(a, cw);
+    if (a.tail == nullptr) return;
+    // ---- fused tail: every CTA folds its convergence words into the launch-wide accumulator and takes a ticket; the last
+    // one holds the AND of all masks, resolves the batch stop and reads the state at the stop back for the pairs beyond it
+    __shared__ int s_last;
+    __syncthreads();                                  // this CTA's global writes are issued
+    if (threadIdx.x == 0) {
+        if (!settled) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (~cw[i] != 0u) atomicOr(a.tail + 1 + i, ~cw[i]);
+            }
+        }
+        __threadfence();
+        s_last = (atomicAdd(a.tail, 1u) == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) {
+        if (!settled) {
+            const uint32_t all[4] = {~__ldcg(a.tail + 1), ~__ldcg(a.tail + 2), ~__ldcg(a.tail + 3), ~__ldcg(a.tail + 4)};
+            resolve_from_and(all, a.max_it, a.tail_limit, a.batch_stop, a.batch, a.decided_out);
+        }
+#pragma unroll
+        for (int i = 0; i < 5; ++i) a.tail[i] = 0u;        // ready for the next pass of this call
+    }
+    __syncthreads();
+    if (a.tail_select) {
+        IcpSelectArgs sa;
+        sa.hist = a.hist; sa.batch = a.batch; sa.P = a.P; sa.iters = a.iters;
+        sa.out_R = a.out_R; sa.out_T = a.out_T; sa.out_rmse = a.out_rmse; sa.out_pose = a.out_pose;
+        sa.peer_pose = a.peer_pose; sa.peer_world = a.peer_world; sa.peer_row0 = a.peer_row0;
+        const int b = a.batch[0];
+        for (int p = threadIdx.x; p < a.P; p += kThreads) select_pair(sa, p, b);
     }
 }
 
@@ -397,7 +466,34 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
     a.state = capped ? reinterpret_cast<float*>(ws + icp_ws_off_state(P)) : nullptr;
     const int ph = phase ? phase->phase : -1;          // -1: the whole call at once (one device holds the batch)
     uint32_t* and_out = phase ? phase->and_out : nullptr;
-    if (ph <= 0) {
+    a.tail = nullptr; a.tail_limit = 0; a.tail_select = 0; a.batch_stop = prm.batch_stop; a.batch = batch; a.decided_out = nullptr;
+    if (ph < 0) {
+        // The whole call at once: the batch stop is resolved (and the state at the stop read back) by the LAST CTA of the
+        // pass itself -- every CTA ORs its complemented convergence words into five words of the workspace and takes a
+        // ticket -- instead of two more launches per pass.  The words must be zero when the first pass starts.
+        unsigned int* tail = reinterpret_cast<unsigned int*>(ws + icp_ws_off_batch(P)) + 16;
+        err = cudaMemsetAsync(tail, 0, 5 * sizeof(unsigned int), stream);
+        if (err != cudaSuccess) return (int)err;
+        a.tail = tail;
+        a.tail_limit = a.cap;
+        a.tail_select = (!capped && prm.batch_stop) ? 1 : 0;
+        a.decided_out = capped ? decided : nullptr;
+        if (prof_start && prof_stop) cudaEventRecord(prof_start, stream);
+        ICPF_LAUNCH(kernel, P, kThreads, smem, stream)(a);
+        err = cudaGetLastError();
+        if (prof_start && prof_stop) cudaEventRecord(prof_stop, stream);
+        if (err != cudaSuccess) return (int)err;
+        if (capped) {
+            a.decided = decided;
+            a.tail_limit = prm.max_iterations;
+            a.tail_select = prm.batch_stop ? 1 : 0;
+            ICPF_LAUNCH(kernel_full, P, kThreads, smem, stream)(a);
+            err = cudaGetLastError();
+            if (err != cudaSuccess) return (int)err;
+        }
+        return ICPF_OK;
+    }
+    if (ph == 0) {
         if (prof_start && prof_stop) cudaEventRecord(prof_start, stream);
         ICPF_LAUNCH(kernel, P, kThreads, smem, stream)(a);
         err = cudaGetLastError();
@@ -407,14 +503,12 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
                                                         capped ? decided : nullptr, and_out);
         err = cudaGetLastError();
         if (err != cudaSuccess) return (int)err;
-        if (ph == 0) return ICPF_OK;
+        return ICPF_OK;
     }
-    if (ph == 1 || (ph < 0 && capped)) {
-        if (ph == 1) {
-            // the shards decided together that the stop lies beyond the capped pass
-            err = cudaMemsetAsync(decided, 0, sizeof(int), stream);
-            if (err != cudaSuccess) return (int)err;
-        }
+    if (ph == 1) {
+        // the shards decided together that the stop lies beyond the capped pass
+        err = cudaMemsetAsync(decided, 0, sizeof(int), stream);
+        if (err != cudaSuccess) return (int)err;
         a.decided = decided;
         ICPF_LAUNCH(kernel_full, P, kThreads, smem, stream)(a);
         a.decided = nullptr;
@@ -422,7 +516,7 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
                                                         batch, decided, and_out);
         err = cudaGetLastError();
         if (err != cudaSuccess) return (int)err;
-        if (ph == 1) return ICPF_OK;
+        return ICPF_OK;
     }
     if (ph == 2) {
         ICPF_LAUNCH(icp_set_batch_kernel, 1, 1, 0, stream)(batch, phase->batch_iters, phase->converged);

@@ -50,6 +50,7 @@ struct IcpResult {
     bool have_prev;
     float w_prev;                 // clamp(sum of weights) of the last iteration executed
     bool stopped;                 // left the loop at its bitwise fixed point (not at max_it)
+    bool tail_ok;                 // ... and every later iteration passes the relative-rmse test (0 <= thr, rmse > 0, finite)
 };
 
 __device__ __forceinline__ void set_conv_bit(IcpResult& r, int k) {
@@ -145,6 +146,7 @@ __device__ __forceinline__ IcpResult icp_iterations(const Tiles& tl, const GridI
     res.refreshes = 0;
     res.prev_rmse = 0.f;
     res.have_prev = false;
+    res.tail_ok = false;
     if (tid < 9) bc[B_R + tid] = init_R ? init_R[tid] : ((tid % 4 == 0) ? 1.f : 0.f);
     if (tid < 3) bc[B_T + tid] = init_T ? init_T[tid] : 0.f;
     if (tid == 0) {
@@ -549,25 +551,24 @@ __device__ __forceinline__ IcpResult icp_iterations(const Tiles& tl, const GridI
             const float rmse = sqrtf(__fdiv_rn(s, W_prev));
             record_rmse(res, iters - 1, rmse, rel_thr);
             if (hist != nullptr && iters - 1 < hist_depth) hist[(iters - 1) * 13 + 12] = rmse;
-            if (iters < max_it) {
-                // stopped at a bitwise fixed point: every later iteration repeats this state, so its relative rmse is
-                // (rmse - rmse) / rmse = 0 (NaN when rmse == 0)
-                const bool tail_ok = (rmse > 0.f) && (0.0f <= rel_thr) && (rmse < INF);
-                if (tail_ok) {
-                    for (int k = iters; k < max_it && k < 128; ++k) set_conv_bit(res, k);
-                }
+            // stopped at a bitwise fixed point: every later iteration repeats this state, so its relative rmse is
+            // (rmse - rmse) / rmse = 0 (NaN when rmse == 0)
+            res.tail_ok = (rmse > 0.f) && (0.0f <= rel_thr) && (rmse < INF);
+            if (iters < max_it && res.tail_ok) {
+                for (int k = iters; k < max_it && k < 128; ++k) set_conv_bit(res, k);
             }
         }
     }
     if (tid == 0) {
         res.w_prev = W_prev;
         res.stopped = done;
+        res.tail_ok = res.tail_ok && done;
     }
     return res;
 }
 
 // Thread 0: leave the loop state of a finished (or paused) run in `state` for a later continuation (icp_iterations,
-// `state` / `resume_it`); S_FLAGS bit 3 = stopped at its fixed point.  `bc` is the pair's broadcast block.
+// `state` / `resume_it`); S_FLAGS bit 3 = stopped at its fixed point, bit 4 = its later iterations pass the stop test.  `bc` is the pair's broadcast block.
 __device__ __forceinline__ void save_icp_state(const IcpResult& res, const float* bc, float* __restrict__ state) {
     const KabschState* kst = reinterpret_cast<const KabschState*>(bc + B_KABSCH);
 #pragma unroll
@@ -575,7 +576,7 @@ __device__ __forceinline__ void save_icp_state(const IcpResult& res, const float
 #pragma unroll
     for (int i = 0; i < 9; ++i) state[S_FRAME + i] = kst->v[i];
     state[S_FLAGS] = __uint_as_float((kst->warm ? 1u : 0u) | (kst->changed ? 2u : 0u) | (res.have_prev ? 4u : 0u) |
-                                     (res.stopped ? 8u : 0u));
+                                     (res.stopped ? 8u : 0u) | (res.tail_ok ? 16u : 0u));
 #pragma unroll
     for (int i = 0; i < 9; ++i) state[S_HPREV + i] = bc[B_HPREV + i];
     state[S_WPREV] = res.w_prev;

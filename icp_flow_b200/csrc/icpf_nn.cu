@@ -65,9 +65,14 @@ __global__ void __launch_bounds__(kThreads) nn_all_rows_kernel(const float* __re
 int launch_nn(const float* src, const float* dst, int B, int Ns, int Nd, int src_stride, int dst_stride,
               int64_t* out_idx, float* out_dist, cudaStream_t stream) {
     if (B == 0 || Ns == 0) return ICPF_OK;
-    if (B > 65535) return ICPF_E_SHAPE;
-    dim3 grid((Ns + kThreads * kNnQB - 1) / (kThreads * kNnQB), B);
-    ICPF_LAUNCH(nn_all_rows_kernel, grid, kThreads, 0, stream)(src, dst, Ns, Nd, src_stride, dst_stride, out_idx, out_dist);
+    // the batch runs on grid.y (<= 65535): larger batches go in slices
+    for (int b0 = 0; b0 < B; b0 += 65535) {
+        const int nb = (B - b0 < 65535) ? (B - b0) : 65535;
+        dim3 grid((Ns + kThreads * kNnQB - 1) / (kThreads * kNnQB), nb);
+        ICPF_LAUNCH(nn_all_rows_kernel, grid, kThreads, 0, stream)(src + (size_t)b0 * Ns * src_stride, dst + (size_t)b0 * Nd * dst_stride,
+                                                          Ns, Nd, src_stride, dst_stride, out_idx + (size_t)b0 * Ns,
+                                                          out_dist + (size_t)b0 * Ns);
+    }
     return (int)cudaGetLastError();
 }
 
@@ -93,10 +98,12 @@ __global__ void __launch_bounds__(256) transform_points_kernel(const float4* __r
 
 int launch_transform_points(const float* xyz, const float* pose, int B, int N, float* out, cudaStream_t stream) {
     if (B == 0 || N == 0) return ICPF_OK;
-    if (B > 65535) return ICPF_E_SHAPE;
-    dim3 grid((N + 255) / 256, B);
-    ICPF_LAUNCH(transform_points_kernel, grid, 256, 0, stream)(reinterpret_cast<const float4*>(xyz), pose, N,
-                                                     reinterpret_cast<float4*>(out));
+    for (int b0 = 0; b0 < B; b0 += 65535) {        // the batch runs on grid.y (<= 65535)
+        const int nb = (B - b0 < 65535) ? (B - b0) : 65535;
+        dim3 grid((N + 255) / 256, nb);
+        ICPF_LAUNCH(transform_points_kernel, grid, 256, 0, stream)(reinterpret_cast<const float4*>(xyz) + (size_t)b0 * N,
+                                                         pose + (size_t)b0 * 16, N, reinterpret_cast<float4*>(out) + (size_t)b0 * N);
+    }
     return (int)cudaGetLastError();
 }
 

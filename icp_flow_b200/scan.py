@@ -89,6 +89,11 @@ _CACHE_SIZE = 4
 
 
 def scan_index(points: torch.Tensor, labels: torch.Tensor) -> ScanIndex:
+    """The cluster index of a scan, cached per (points tensor, labels tensor) OBJECT and their autograd versions: the same
+    scan is addressed several times per frame pair (sanity_check, both stages of match_pcds, flow).  Cache contract: an
+    in-place edit that bumps ``_version`` (every torch in-place op) invalidates the entry; writes that do NOT bump it --
+    through ``.data``, a numpy view, another tensor aliasing the same storage, or a kernel writing the raw pointer -- are
+    invisible here: call ``clear_cache()`` after such a write (or pass fresh tensors)."""
     for ent in _CACHE:
         rp, rl, vp, vl, idx = ent
         if rp() is points and rl() is labels and vp == points._version and vl == labels._version:

@@ -205,6 +205,8 @@ inline unsigned __float_as_uint(float v) { return (unsigned)simt::to_bits(v); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
+inline void __threadfence() {}
+template <class T> inline T __ldcg(const T* p) { return *p; }
 inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
 
 inline int min(int a, int b) { return a < b ? a : b; }
