@@ -427,7 +427,7 @@ def main():
     out = None
     outs = [None, None]
     gathered = [torch.empty(n_gpus * P, 4, 4, device=dev, dtype=torch.float32) for _ in range(2)]
-    launches_per_step = 1   # icp_pairs_kernel (the batch stop is resolved by its last CTA; + one 20-byte memset node)
+    launches_per_step = 2   # icp_pairs_kernel + icp_resolve_batch_kernel (batch stop + state at the stop, one launch)
     comm_stream = torch.cuda.Stream() if world > 1 else None
     peer = None
     gather_kind = "none"

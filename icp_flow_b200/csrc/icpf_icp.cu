@@ -46,19 +46,13 @@ struct IcpArgs {
     float* const* peer_pose;   // fused all-gather: DEVICE array of `peer_world` base pointers (peer-mapped [*,16]) or NULL
     int peer_world;
     int peer_row0;             // first row of this rank's block in the gathered buffer
-    // fused tail (whole-call mode): the last CTA to finish resolves the batch stop and, when `tail_select`, hands the pairs
-    // that went beyond it their state at the stop -- instead of two more launches
-    unsigned int* tail;        // [5] {tickets, OR of the complemented convergence words x 4}, zero before the launch; or NULL
-    int tail_limit;            // iterations the masks of this pass cover (the cap, or max_it)
-    int tail_select;
-    int batch_stop;
-    int* batch;                // [2]
-    int* decided_out;          // capped passes: 1 when the batch stop is final (may be NULL)
 };
 
-// One pair, from its row blocks to its transform.  cw[4] (thread 0) = the pair's convergence words as this pass leaves them.
+// FULLPASS = the pass after a capped first pass: only the pairs still moving at the cap run, continuing from where the
+// first pass paused them (a separate instantiation, so that the kernel of the first pass -- the one every call pays for --
+// carries no continuation logic in its loop).
 template <int MODE, bool BIG, bool FULLPASS>
-__device__ __forceinline__ void icp_pair_body(const IcpArgs& a, uint32_t (&cw)[4]) {
+__global__ void __launch_bounds__(kThreads, BIG ? 4 : 7) icp_pairs_kernel(IcpArgs a) {
     const int p = blockIdx.x;
     int max_it = a.max_it;
     bool early_exit = a.early_exit != 0;
@@ -81,8 +75,6 @@ __device__ __forceinline__ void icp_pair_body(const IcpArgs& a, uint32_t (&cw)[4
                 if (tail_ok) {
                     for (int k = a.cap; k < max_it && k < 128; ++k) c[k >> 5] |= 1u << (k & 31);
                 }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) cw[i] = c[i];
             }
             return;
         }
@@ -189,73 +181,11 @@ __device__ __forceinline__ void icp_pair_body(const IcpArgs& a, uint32_t (&cw)[4
         a.iters[p] = r.iters;
         a.stats[(size_t)p * 2 + 0] = (int)r.searches;
         a.stats[(size_t)p * 2 + 1] = r.refreshes;
-        cw[0] = (uint32_t)r.conv_lo;
-        cw[1] = (uint32_t)(r.conv_lo >> 32);
-        cw[2] = (uint32_t)r.conv_hi;
-        cw[3] = (uint32_t)(r.conv_hi >> 32);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a.conv[(size_t)p * 4 + i] = cw[i];
+        a.conv[(size_t)p * 4 + 0] = (uint32_t)r.conv_lo;
+        a.conv[(size_t)p * 4 + 1] = (uint32_t)(r.conv_lo >> 32);
+        a.conv[(size_t)p * 4 + 2] = (uint32_t)r.conv_hi;
+        a.conv[(size_t)p * 4 + 3] = (uint32_t)(r.conv_hi >> 32);
     }
-}
-
-// First iteration k* at which every pair passes the relative-rmse test (utils_icp_pytorch3d.py:209), from the AND of the
-// per-pair convergence masks.  batch[0] = iterations the reference loop would have executed, batch[1] = converged flag.
-// `limit` = iterations the masks cover (the cap of the first pass, or max_it); `decided` (may be NULL) is set to 1 when
-// the answer is final and left 0 when the capped pass could not tell (a later full pass decides).  One thread.
-__device__ __forceinline__ void resolve_from_and(const uint32_t (&all)[4], int max_it, int limit, int batch_stop, int* batch,
-                                                 int* decided) {
-    int kstar = -1;
-    if (batch_stop) {
-        for (int i = 0; i < 4 && kstar < 0; ++i) {
-            if (all[i]) kstar = i * 32 + (__ffs(all[i]) - 1);
-        }
-    }
-    int verdict = 1;
-    if (kstar >= 0 && kstar < limit) {
-        batch[0] = kstar + 1;
-        batch[1] = 1;
-    } else if (limit >= max_it) {
-        batch[0] = max_it;
-        batch[1] = 0;
-    } else {
-        batch[0] = limit;          // provisional: no pair is re-run, the full pass follows
-        batch[1] = 0;
-        verdict = 0;
-    }
-    if (decided) *decided = verdict;
-}
-
-// `and_out` (may be NULL) receives the AND of the masks -- what a caller with several shards exchanges (IcpPhase,
-// icpf_internal.h).  The phased entry points use this kernel; a whole call resolves in the tail of icp_pairs_kernel.
-__global__ void __launch_bounds__(256) icp_resolve_batch_kernel(const uint32_t* conv, int P, int max_it, int limit,
-                                                                int batch_stop, int* batch, int* decided,
-                                                                uint32_t* and_out) {
-    __shared__ uint32_t s_and[4];
-    if (decided != nullptr && limit == max_it && *decided != 0) return;     // second resolve, nothing left to do
-    if (threadIdx.x < 4) s_and[threadIdx.x] = 0xffffffffu;
-    __syncthreads();
-    uint32_t m[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-    for (int p = threadIdx.x; p < P; p += blockDim.x) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) m[i] &= conv[(size_t)p * 4 + i];
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        for (int o = 16; o > 0; o >>= 1) m[i] &= __shfl_xor_sync(FULL_MASK, m[i], o);
-        if ((threadIdx.x & 31) == 0) atomicAnd(&s_and[i], m[i]);
-    }
-    __syncthreads();
-    if (and_out != nullptr && threadIdx.x < 4) and_out[threadIdx.x] = s_and[threadIdx.x];
-    if (threadIdx.x == 0) {
-        const uint32_t all[4] = {s_and[0], s_and[1], s_and[2], s_and[3]};
-        resolve_from_and(all, max_it, limit, batch_stop, batch, decided);
-    }
-}
-
-// phase 2 of a phased call: the batch stop found over ALL shards, as given by the caller
-__global__ void icp_set_batch_kernel(int* batch, int iters, int converged) {
-    batch[0] = iters;
-    batch[1] = converged;
 }
 
 // State at the batch stop from the per-iteration record: a pair that executed more iterations than the batch did
@@ -275,20 +205,19 @@ struct IcpSelectArgs {
     int peer_row0;
 };
 
-// (reads of what OTHER CTAs of the same launch wrote go through L2: __ldcg)
 __device__ __forceinline__ void select_pair(const IcpSelectArgs& a, int p, int b) {
-    if (__ldcg(a.iters + p) <= b || b < 1 || b > kIcpHistDepth) return;
+    if (a.iters[p] <= b || b < 1 || b > kIcpHistDepth) return;
     const float* h = a.hist + ((size_t)p * kIcpHistDepth + (b - 1)) * kIcpHistFloats;
     float r[9], t[3];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) r[i] = __ldcg(h + i);
+    for (int i = 0; i < 9; ++i) r[i] = h[i];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) t[i] = __ldcg(h + 9 + i);
+    for (int i = 0; i < 3; ++i) t[i] = h[9 + i];
 #pragma unroll
     for (int i = 0; i < 9; ++i) a.out_R[(size_t)p * 9 + i] = r[i];
 #pragma unroll
     for (int i = 0; i < 3; ++i) a.out_T[(size_t)p * 3 + i] = t[i];
-    if (a.out_rmse) a.out_rmse[p] = __ldcg(h + 12);
+    if (a.out_rmse) a.out_rmse[p] = h[12];
     a.iters[p] = b;
     // column-convention 4x4 [[R^T, T],[0,1]]  (utils_icp.py:60-65)
     float m[16];
@@ -314,53 +243,74 @@ __device__ __forceinline__ void select_pair(const IcpSelectArgs& a, int p, int b
 
 __global__ void __launch_bounds__(128) icp_select_batch_kernel(IcpSelectArgs a) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= a.P) return;
-    select_pair(a, p, a.batch[0]);
+    if (p < a.P) select_pair(a, p, a.batch[0]);
 }
 
-// FULLPASS = the pass after a capped first pass: only the pairs still moving at the cap run, continuing from where the
-// first pass paused them (a separate instantiation, so that the kernel of the first pass -- the one every call pays for --
-// carries no continuation logic in its loop).
-template <int MODE, bool BIG, bool FULLPASS>
-__global__ void __launch_bounds__(kThreads, BIG ? 4 : 7) icp_pairs_kernel(IcpArgs a) {
-    uint32_t cw[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
-    const bool settled = FULLPASS && (*a.decided != 0);       // (uniform over the grid: only the tail below writes it)
-    icp_pair_body<MODE, BIG, FULLPASS>(a, cw);
-    if (a.tail == nullptr) return;
-    // ---- fused tail: every CTA folds its convergence words into the launch-wide accumulator and takes a ticket; the last
-    // one holds the AND of all masks, resolves the batch stop and reads the state at the stop back for the pairs beyond it
-    __shared__ int s_last;
-    __syncthreads();                                  // this CTA's global writes are issued
-    if (threadIdx.x == 0) {
-        if (!settled) {
+// AND of the per-pair convergence masks -> first iteration k* where every pair passes (utils_icp_pytorch3d.py:209).
+// batch[0] = iterations the reference loop would have executed, batch[1] = converged flag.
+// `limit` = iterations the masks cover (the cap of the first pass, or max_it); `decided` (may be NULL) is set to 1 when
+// the answer is final and left 0 when the capped pass could not tell (a later full pass decides); `and_out` (may be NULL)
+// receives the AND of the masks -- what a caller with several shards exchanges (IcpPhase, icpf_internal.h).
+// `sel.hist != NULL`: once the stop is final, the same launch hands the pairs that went beyond it their state at the stop
+// (select_pair) -- the call ends with one launch instead of two.
+__global__ void __launch_bounds__(256) icp_resolve_batch_kernel(const uint32_t* conv, int P, int max_it, int limit,
+                                                                int batch_stop, int* batch, int* decided,
+                                                                uint32_t* and_out, IcpSelectArgs sel) {
+    __shared__ uint32_t s_and[4];
+    const bool settled = decided != nullptr && limit == max_it && *decided != 0;     // second resolve, nothing left to do
+    if (settled) {
+        if (sel.hist != nullptr) {
+            const int b = batch[0];
+            for (int p = threadIdx.x; p < P; p += blockDim.x) select_pair(sel, p, b);
+        }
+        return;
+    }
+    if (threadIdx.x < 4) s_and[threadIdx.x] = 0xffffffffu;
+    __syncthreads();
+    uint32_t m[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+    for (int p = threadIdx.x; p < P; p += blockDim.x) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (~cw[i] != 0u) atomicOr(a.tail + 1 + i, ~cw[i]);
+        for (int i = 0; i < 4; ++i) m[i] &= conv[(size_t)p * 4 + i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        for (int o = 16; o > 0; o >>= 1) m[i] &= __shfl_xor_sync(FULL_MASK, m[i], o);
+        if ((threadIdx.x & 31) == 0) atomicAnd(&s_and[i], m[i]);
+    }
+    __syncthreads();
+    if (and_out != nullptr && threadIdx.x < 4) and_out[threadIdx.x] = s_and[threadIdx.x];
+    if (threadIdx.x == 0) {
+        int kstar = -1;
+        if (batch_stop) {
+            for (int i = 0; i < 4 && kstar < 0; ++i) {
+                if (s_and[i]) kstar = i * 32 + (__ffs(s_and[i]) - 1);
             }
         }
-        __threadfence();
-        s_last = (atomicAdd(a.tail, 1u) == gridDim.x - 1) ? 1 : 0;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    if (threadIdx.x == 0) {
-        if (!settled) {
-            const uint32_t all[4] = {~__ldcg(a.tail + 1), ~__ldcg(a.tail + 2), ~__ldcg(a.tail + 3), ~__ldcg(a.tail + 4)};
-            resolve_from_and(all, a.max_it, a.tail_limit, a.batch_stop, a.batch, a.decided_out);
+        int verdict = 1;
+        if (kstar >= 0 && kstar < limit) {
+            batch[0] = kstar + 1;
+            batch[1] = 1;
+        } else if (limit >= max_it) {
+            batch[0] = max_it;
+            batch[1] = 0;
+        } else {
+            batch[0] = limit;          // provisional: no pair is re-run, the full pass follows
+            batch[1] = 0;
+            verdict = 0;
         }
-#pragma unroll
-        for (int i = 0; i < 5; ++i) a.tail[i] = 0u;        // ready for the next pass of this call
+        if (decided) *decided = verdict;
     }
-    __syncthreads();
-    if (a.tail_select) {
-        IcpSelectArgs sa;
-        sa.hist = a.hist; sa.batch = a.batch; sa.P = a.P; sa.iters = a.iters;
-        sa.out_R = a.out_R; sa.out_T = a.out_T; sa.out_rmse = a.out_rmse; sa.out_pose = a.out_pose;
-        sa.peer_pose = a.peer_pose; sa.peer_world = a.peer_world; sa.peer_row0 = a.peer_row0;
-        const int b = a.batch[0];
-        for (int p = threadIdx.x; p < a.P; p += kThreads) select_pair(sa, p, b);
+    if (sel.hist != nullptr) {
+        __syncthreads();
+        const int b = batch[0];
+        for (int p = threadIdx.x; p < P; p += blockDim.x) select_pair(sel, p, b);
     }
+}
+
+// phase 2 of a phased call: the batch stop found over ALL shards, as given by the caller
+__global__ void icp_set_batch_kernel(int* batch, int iters, int converged) {
+    batch[0] = iters;
+    batch[1] = converged;
 }
 
 size_t icp_big_workspace_bytes(int P, int N) {
@@ -466,68 +416,49 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
     a.state = capped ? reinterpret_cast<float*>(ws + icp_ws_off_state(P)) : nullptr;
     const int ph = phase ? phase->phase : -1;          // -1: the whole call at once (one device holds the batch)
     uint32_t* and_out = phase ? phase->and_out : nullptr;
-    a.tail = nullptr; a.tail_limit = 0; a.tail_select = 0; a.batch_stop = prm.batch_stop; a.batch = batch; a.decided_out = nullptr;
-    if (ph < 0) {
-        // The whole call at once: the batch stop is resolved (and the state at the stop read back) by the LAST CTA of the
-        // pass itself -- every CTA ORs its complemented convergence words into five words of the workspace and takes a
-        // ticket -- instead of two more launches per pass.  The words must be zero when the first pass starts.
-        unsigned int* tail = reinterpret_cast<unsigned int*>(ws + icp_ws_off_batch(P)) + 16;
-        err = cudaMemsetAsync(tail, 0, 5 * sizeof(unsigned int), stream);
-        if (err != cudaSuccess) return (int)err;
-        a.tail = tail;
-        a.tail_limit = a.cap;
-        a.tail_select = (!capped && prm.batch_stop) ? 1 : 0;
-        a.decided_out = capped ? decided : nullptr;
-        if (prof_start && prof_stop) cudaEventRecord(prof_start, stream);
-        ICPF_LAUNCH(kernel, P, kThreads, smem, stream)(a);
-        err = cudaGetLastError();
-        if (prof_start && prof_stop) cudaEventRecord(prof_stop, stream);
-        if (err != cudaSuccess) return (int)err;
-        if (capped) {
-            a.decided = decided;
-            a.tail_limit = prm.max_iterations;
-            a.tail_select = prm.batch_stop ? 1 : 0;
-            ICPF_LAUNCH(kernel_full, P, kThreads, smem, stream)(a);
-            err = cudaGetLastError();
-            if (err != cudaSuccess) return (int)err;
-        }
-        return ICPF_OK;
-    }
-    if (ph == 0) {
+    // state at the batch stop for the pairs that went beyond it (read back from the record): the last stage of the call
+    IcpSelectArgs sa;
+    sa.hist = a.hist; sa.batch = batch; sa.P = P; sa.iters = iters;
+    sa.out_R = out_R; sa.out_T = out_T; sa.out_rmse = out_rmse; sa.out_pose = out_pose;
+    sa.peer_pose = a.peer_pose; sa.peer_world = a.peer_world; sa.peer_row0 = a.peer_row0;
+    IcpSelectArgs no_sel = sa;
+    no_sel.hist = nullptr;
+    // a whole call resolves the stop and reads the state back in ONE launch after its last pass
+    const bool fuse_sel = (ph < 0) && prm.batch_stop;
+    if (ph <= 0) {
         if (prof_start && prof_stop) cudaEventRecord(prof_start, stream);
         ICPF_LAUNCH(kernel, P, kThreads, smem, stream)(a);
         err = cudaGetLastError();
         if (prof_start && prof_stop) cudaEventRecord(prof_stop, stream);
         if (err != cudaSuccess) return (int)err;
         ICPF_LAUNCH(icp_resolve_batch_kernel, 1, 256, 0, stream)(conv, P, prm.max_iterations, a.cap, prm.batch_stop, batch,
-                                                        capped ? decided : nullptr, and_out);
+                                                        capped ? decided : nullptr, and_out,
+                                                        (fuse_sel && !capped) ? sa : no_sel);
         err = cudaGetLastError();
         if (err != cudaSuccess) return (int)err;
-        return ICPF_OK;
+        if (ph == 0) return ICPF_OK;
     }
-    if (ph == 1) {
-        // the shards decided together that the stop lies beyond the capped pass
-        err = cudaMemsetAsync(decided, 0, sizeof(int), stream);
-        if (err != cudaSuccess) return (int)err;
+    if (ph == 1 || (ph < 0 && capped)) {
+        if (ph == 1) {
+            // the shards decided together that the stop lies beyond the capped pass
+            err = cudaMemsetAsync(decided, 0, sizeof(int), stream);
+            if (err != cudaSuccess) return (int)err;
+        }
         a.decided = decided;
         ICPF_LAUNCH(kernel_full, P, kThreads, smem, stream)(a);
         a.decided = nullptr;
         ICPF_LAUNCH(icp_resolve_batch_kernel, 1, 256, 0, stream)(conv, P, prm.max_iterations, prm.max_iterations, prm.batch_stop,
-                                                        batch, decided, and_out);
+                                                        batch, decided, and_out, fuse_sel ? sa : no_sel);
         err = cudaGetLastError();
         if (err != cudaSuccess) return (int)err;
-        return ICPF_OK;
+        if (ph == 1) return ICPF_OK;
     }
     if (ph == 2) {
         ICPF_LAUNCH(icp_set_batch_kernel, 1, 1, 0, stream)(batch, phase->batch_iters, phase->converged);
         err = cudaGetLastError();
         if (err != cudaSuccess) return (int)err;
     }
-    if (prm.batch_stop) {
-        IcpSelectArgs sa;
-        sa.hist = a.hist; sa.batch = batch; sa.P = P; sa.iters = iters;
-        sa.out_R = out_R; sa.out_T = out_T; sa.out_rmse = out_rmse; sa.out_pose = out_pose;
-        sa.peer_pose = a.peer_pose; sa.peer_world = a.peer_world; sa.peer_row0 = a.peer_row0;
+    if (prm.batch_stop && !fuse_sel) {
         ICPF_LAUNCH(icp_select_batch_kernel, (P + 127) / 128, 128, 0, stream)(sa);
         err = cudaGetLastError();
         if (err != cudaSuccess) return (int)err;
