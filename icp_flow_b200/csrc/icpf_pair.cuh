@@ -24,7 +24,10 @@
 
 namespace icpf {
 
-constexpr int kThreads = 128;          // threads per pair CTA
+#ifndef ICPF_PAIR_THREADS
+#define ICPF_PAIR_THREADS 128
+#endif
+constexpr int kThreads = ICPF_PAIR_THREADS;          // threads per pair CTA
 constexpr int kWarps = kThreads / 32;
 constexpr float kCellFactor = 2.2f;  // grid cell size in units of the padded gate radius (>= 2.002)
 constexpr int kGridMaxCells = 2048;    // uniform-grid cells per pair (u16 offsets: 4 KB of shared memory)
