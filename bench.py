@@ -350,6 +350,22 @@ def time_secondary(dev):
     out["c4_frame"] = {"points": [len(sp), len(dp)], "clusters": 200, "max_points": 10000, "matched_pairs": matched,
                        "ms": best * 1e3, "what": "cluster index + match_pcds (both stages) + flow, wall clock"}
 
+    # ---- row f4: DBSCAN clustering of the C4 source scan (the reference: Open3D / sklearn on the CPU)
+    try:
+        from icp_flow_b200 import cluster
+        from oracle import cluster_oracle as CO
+        nonground = torch.from_numpy(sp[sl > -1e7]).to(dev)
+        ms_db = _events_ms(lambda: cluster.dbscan_labels(nonground, 0.25, 30), 5, sync)
+        t0 = time.perf_counter()
+        want = CO.dbscan_labels(nonground.cpu().numpy(), 0.25, 30)
+        cpu_s = time.perf_counter() - t0
+        got = cluster.dbscan_labels(nonground, 0.25, 30).cpu().numpy()
+        out["c4_dbscan"] = {"points": int(nonground.shape[0]), "eps": 0.25, "min_points": 30, "ms": ms_db,
+                            "clusters": int(want.max() + 1), "labels_equal_sklearn": bool((got == want).all()),
+                            "cpu_baseline": {"ms": cpu_s * 1e3, "kind": "port", "sample": "sklearn.cluster.DBSCAN (kd_tree) on the same points, one run"}}
+    except Exception as exc:
+        out["c4_dbscan"] = {"error": f"{type(exc).__name__}: {exc}"}
+
     # ---- C5, one GPU's share (the 8-GPU line carries the sharded run itself)
     ms5, _ = time_c5_shard(dev)
     out["c5_one_gpu_share"] = {"pairs": 4096, "points": POINTS, "icp_iterations": ICP_ITERS, "ms": ms5,

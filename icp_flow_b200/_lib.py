@@ -19,7 +19,7 @@ EXPORTS = (
     "icpf_host_kabsch_sequence", "icpf_peer_push_f32", "icpf_expand_rows_f32", "icpf_hist_votes_f32", "icpf_hist_init_f32", "icpf_apply_icp_f32", "icpf_apply_icp_phase_f32", "icpf_hist_icp_f32",
     "icpf_match_eval_f32",
     "icpf_cluster_index_workspace_bytes", "icpf_cluster_index_f32", "icpf_sanity_check_f32", "icpf_gather_pairs_f32",
-    "icpf_flow_f32",
+    "icpf_flow_f32", "icpf_dbscan_workspace_bytes", "icpf_dbscan_f32",
 )
 
 
@@ -139,6 +139,10 @@ def lib() -> ctypes.CDLL:
     L.icpf_gather_pairs_f32.argtypes = [vp, i32, vp, vp, i32, vp, i32, vp, vp, i32, vp, i32, i32, vp, vp, vp, vp, vp]
     L.icpf_flow_f32.restype = ctypes.c_int
     L.icpf_flow_f32.argtypes = [vp, i32, vp, i32, vp, i32, vp, i32, vp, vp, vp]
+    L.icpf_dbscan_workspace_bytes.restype = ctypes.c_size_t
+    L.icpf_dbscan_workspace_bytes.argtypes = [i32]
+    L.icpf_dbscan_f32.restype = ctypes.c_int
+    L.icpf_dbscan_f32.argtypes = [vp, i32, i32, ctypes.c_double, i32, vp, vp, vp, ctypes.c_size_t, vp]
     _LIB = L
     return L
 

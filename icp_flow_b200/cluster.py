@@ -1,0 +1,86 @@
+"""Clustering of a scan on the GPU -- SURVEY.md section 8, row f4: the labels the per-pair path consumes.
+
+Mirror of the reference's ``utils_cluster`` (``/root/reference/utils_cluster.py``) for its default clusterer
+(``--if_hdbscan`` off): ``cluster_dbscan(args, points)`` = Open3D ``cluster_dbscan(eps=args.epsilon,
+min_points=args.min_cluster_size)`` followed by "keep the ``args.num_clusters`` largest clusters", and
+``cluster_pcd(args, points, idxs_nonground)``; plus the z-threshold ground removal of ``utils_ground.segment_ground_thres``
+(``utils_ground.py:27-34``).  DBSCAN runs in ``icpf_dbscan_f32`` (``csrc/icpf_cluster.cu``): a parallel formulation whose
+labels are the sequential algorithm's on the same points.  HDBSCAN (``--if_hdbscan``) and Patchwork++ ground removal are
+third-party CPU libraries in the reference and stay there.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .ops import _ptr
+
+
+def dbscan_labels(points: torch.Tensor, eps: float, min_points: int, return_count: bool = False):
+    """Raw DBSCAN labels of a CUDA fp32 ``[n, >=3]`` scan: ``[n]`` int32 on the device, -1 = noise, clusters numbered by
+    their lowest core-point index.  Stream-ordered, no host synchronisation."""
+    if not torch.is_tensor(points) or not points.is_cuda:
+        raise RuntimeError("points must be a CUDA tensor: icp_flow_b200 has no CPU implementation")
+    if points.dim() != 2 or points.shape[1] < 3:
+        raise ValueError("points must be [n, >=3] (x, y, z, ...)")
+    pts = points.float()
+    if pts.stride(1) != 1:
+        pts = pts.contiguous()
+    n = pts.shape[0]
+    labels = torch.empty(n, device=pts.device, dtype=torch.int32)
+    count = torch.zeros(1, device=pts.device, dtype=torch.int32)
+    L = _lib.lib()
+    ws = torch.empty(max(int(L.icpf_dbscan_workspace_bytes(n)), 1), device=pts.device, dtype=torch.uint8)
+    with torch.cuda.device(pts.device):
+        code = L.icpf_dbscan_f32(_ptr(pts), pts.stride(0) if n > 0 else 3, n, float(eps), int(min_points), _ptr(labels),
+                                 _ptr(count), _ptr(ws), ws.numel(), ops._stream_ptr())
+    _lib.check(code, "icpf_dbscan_f32")
+    return (labels, count) if return_count else labels
+
+
+def keep_largest(labels: np.ndarray, num_clusters: int) -> np.ndarray:
+    """utils_cluster.py:40-46 restated on the label array: clusters outside the ``num_clusters`` largest become -1.
+    (Host logic on a few hundred counts; the order among equally large clusters is numpy's argsort, as in the reference.)"""
+    labels = np.array(labels)
+    lbls, counts = np.unique(labels, return_counts=True)
+    # (the reference drops the first unique label assuming it is the noise label -1, utils_cluster.py:42)
+    cluster_info = np.array(list(zip(lbls[1:], counts[1:])))
+    if len(cluster_info) == 0:          # no cluster at all: the reference would raise on the empty array; everything is noise
+        labels[:] = -1
+        return labels
+    cluster_info = cluster_info[cluster_info[:, 1].argsort()]
+    clusters_labels = cluster_info[::-1][:num_clusters, 0]
+    labels[np.isin(labels, clusters_labels, invert=True)] = -1      # unclustered point
+    return labels
+
+
+def cluster_dbscan(args, points) -> np.ndarray:
+    """Drop-in for ``utils_cluster.cluster_dbscan(args, points)`` (reads ``args.epsilon``, ``args.min_cluster_size``,
+    ``args.num_clusters``); ``points`` numpy or tensor ``[n, >=3]``; returns numpy int labels like the reference."""
+    dev = points.device if torch.is_tensor(points) and points.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    pts = torch.as_tensor(np.ascontiguousarray(points[:, :3], dtype=np.float32)) if not torch.is_tensor(points) else points[:, :3]
+    raw = dbscan_labels(pts.to(dev).float().contiguous(), args.epsilon, args.min_cluster_size)
+    return keep_largest(raw.cpu().numpy().astype(np.int64), args.num_clusters)
+
+
+def cluster_pcd(args, points, idxs_nonground) -> np.ndarray:
+    """Drop-in for ``utils_cluster.cluster_pcd`` (utils_cluster.py:50-63): ground points -1e8, the rest DBSCAN labels."""
+    if getattr(args, "if_hdbscan", False):
+        raise NotImplementedError("HDBSCAN stays the reference's CPU library (hdbscan); the engine clusters with DBSCAN")
+    pts = points.cpu().numpy() if torch.is_tensor(points) else np.asarray(points)
+    idx = idxs_nonground.cpu().numpy() if torch.is_tensor(idxs_nonground) else np.asarray(idxs_nonground)
+    labels_nonground = cluster_dbscan(args, pts[idx])
+    labels = np.zeros((len(pts))) - 1e8
+    labels[idx] = labels_nonground
+    return labels
+
+
+def segment_ground_thres(args, points) -> np.ndarray:
+    """utils_ground.segment_ground_thres (utils_ground.py:27-34): True = non-ground, z above range_z + ground_slack."""
+    z = points[:, 2].cpu().numpy() if torch.is_tensor(points) else np.asarray(points)[:, 2]
+    labels = np.ones((len(z))).astype(bool)
+    labels[z <= args.range_z + args.ground_slack] = False
+    return labels

@@ -10,7 +10,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 extern "C" {
 
-int icpf_version(void) { return 102; }   // 102: icpf_icp_ex_f32 (explicit per-call extensions), icpf_peer_push_f32, icpf_expand_rows_f32
+int icpf_version(void) { return 103; }   // 102: icpf_icp_ex_f32, icpf_peer_push_f32, icpf_expand_rows_f32; 103: icpf_dbscan_f32
 
 const char* icpf_error_string(int code) {
     switch (code) {
@@ -272,6 +272,17 @@ int icpf_expand_rows_f32(const float* rows, const int32_t* offsets, int32_t B, i
     if (!rows || !offsets || !out) return ICPF_E_NULL;
     if (!aligned16(out)) return ICPF_E_ALIGN;
     return launch_expand_rows(rows, offsets, B, N, out, static_cast<cudaStream_t>(stream));
+}
+
+size_t icpf_dbscan_workspace_bytes(int32_t n_points) { return n_points < 0 ? 0 : dbscan_workspace_bytes(n_points); }
+
+int icpf_dbscan_f32(const float* points, int32_t point_stride, int32_t n_points, double eps, int32_t min_points,
+                    int32_t* out_labels, int32_t* out_num_clusters, void* workspace, size_t workspace_bytes, void* stream) {
+    if (n_points < 0) return ICPF_E_SHAPE;
+    if (point_stride < 3 || !(eps > 0.0) || min_points < 1) return ICPF_E_PARAM;
+    if (n_points > 0 && (!points || !out_labels)) return ICPF_E_NULL;
+    return launch_dbscan(points, point_stride, n_points, eps, min_points, out_labels, out_num_clusters, workspace,
+                         workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 void icpf_host_kabsch_sequence(const float* H, int32_t n, float* R) {

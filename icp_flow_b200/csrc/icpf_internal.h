@@ -105,4 +105,9 @@ int launch_gather_pairs(const float* src_points, int src_stride, const int* src_
 int launch_flow(const float* points, int stride, const float* labels, int n, const float* pair_labels, int pair_stride,
                 const float* transforms, int K, const float* pose, float* flow, cudaStream_t stream);
 
+// clustering (icpf_cluster.cu)
+size_t dbscan_workspace_bytes(int n);
+int launch_dbscan(const float* points, int stride, int n, double eps, int min_points, int* out_labels, int* out_num_clusters,
+                  void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 }  // namespace icpf

@@ -16,6 +16,8 @@ only the hot-path entry points are rebound, exactly at the seams SURVEY.md secti
     utils_helper.nearest_neighbor_batch / transform_points_batch (and the names re-imported by utils_match / utils_icp /
     utils_hist) <- the engine's, used by match_eval on CUDA tensors
 
+    utils_cluster.cluster_dbscan / cluster_pcd <- icp_flow_b200.cluster_dbscan / cluster_pcd   (opt-in: patch_clustering=True)
+
 ``uninstall()`` restores the originals.  The reference modules must already be importable (``sys.path``).
 """
 from __future__ import annotations
@@ -23,7 +25,7 @@ from __future__ import annotations
 import importlib
 import sys
 
-from . import ops, scan
+from . import cluster, ops, scan
 
 _SAVED = {}
 
@@ -50,6 +52,18 @@ _LOADED_ONLY = (
     ("demo", "flow_estimation_torch", scan.flow_estimation_torch),
 )
 
+# the reference's default clusterer (Open3D DBSCAN) -- opt-in, `install(patch_clustering=True)`:
+# HDBSCAN (--if_hdbscan) is not replaced and raises through cluster_pcd
+_CLUSTERING = (
+    ("utils_cluster", "cluster_dbscan", cluster.cluster_dbscan),
+    ("utils_cluster", "cluster_pcd", cluster.cluster_pcd),
+)
+_CLUSTERING_LOADED_ONLY = (
+    ("demo", "cluster_pcd", cluster.cluster_pcd),
+    ("dataset_pca", "cluster_pcd", cluster.cluster_pcd),
+    ("dataset_argo", "cluster_pcd", cluster.cluster_pcd),
+)
+
 _HELPERS = (
     ("utils_helper", "nearest_neighbor_batch", ops.nearest_neighbor_batch),
     ("utils_helper", "transform_points_batch", ops.transform_points_batch),
@@ -58,16 +72,17 @@ _HELPERS = (
 )
 
 
-def install(patch_helpers: bool = False):
+def install(patch_helpers: bool = False, patch_clustering: bool = False):
     """Rebind the reference's hot-path callables.  ``patch_helpers`` also routes the NN / transform helpers that
-    ``match_eval`` calls (they require CUDA tensors)."""
-    todo = _BINDINGS + (_HELPERS if patch_helpers else ())
+    ``match_eval`` calls (they require CUDA tensors); ``patch_clustering`` routes ``utils_cluster.cluster_dbscan`` /
+    ``cluster_pcd`` (the reference's default, non-HDBSCAN clusterer) to the GPU DBSCAN."""
+    todo = _BINDINGS + (_HELPERS if patch_helpers else ()) + (_CLUSTERING if patch_clustering else ())
     for mod_name, attr, fn in todo:
         mod = sys.modules.get(mod_name) or importlib.import_module(mod_name)
         if hasattr(mod, attr):
             _SAVED.setdefault((mod_name, attr), getattr(mod, attr))
             setattr(mod, attr, fn)
-    for mod_name, attr, fn in _LOADED_ONLY:
+    for mod_name, attr, fn in _LOADED_ONLY + (_CLUSTERING_LOADED_ONLY if patch_clustering else ()):
         mod = sys.modules.get(mod_name)
         if mod is not None and hasattr(mod, attr):
             _SAVED.setdefault((mod_name, attr), getattr(mod, attr))

@@ -303,6 +303,23 @@ int icpf_peer_push_f32(const float* local_pose, void* const* peer_pose_dev, int3
  */
 int icpf_expand_rows_f32(const float* rows, const int32_t* offsets, int32_t B, int32_t N, float* out, void* stream);
 
+/*
+ * Clustering of one scan -- replaces utils_cluster.cluster_dbscan's call into Open3D (utils_cluster.py:32-38:
+ * `pcd.cluster_dbscan(eps=args.epsilon, min_points=args.min_cluster_size)`), SURVEY.md section 8 row f4.
+ *   points [n, stride >= 3] fp32 (x, y, z, ...) DEVICE; rows with a non-finite coordinate are noise
+ *   out_labels [n] int32: -1 noise, else the cluster number.  A core point has >= min_points points (itself included)
+ *   within eps (fp64 distance of the fp32 coordinates, dx*dx + dy*dy + dz*dz <= eps*eps); clusters are the connected
+ *   components of the core points, numbered by their lowest core-point index (the order the sequential algorithm meets
+ *   them); a border point joins the lowest-numbered cluster that has a core point within eps.  The labels are therefore
+ *   the sequential algorithm's (sklearn.cluster.DBSCAN / Open3D) on the same points.
+ *   out_num_clusters [1] int32 (may be NULL); workspace icpf_dbscan_workspace_bytes(n) (a cell table of min(64 n, 8 M) int32 + 21 B per point)
+ * The reference's top-`num_clusters` selection (utils_cluster.py:40-46) is host logic on the label counts
+ * (icp_flow_b200.cluster.cluster_dbscan).
+ */
+size_t icpf_dbscan_workspace_bytes(int32_t n_points);
+int icpf_dbscan_f32(const float* points, int32_t point_stride, int32_t n_points, double eps, int32_t min_points,
+                    int32_t* out_labels, int32_t* out_num_clusters, void* workspace, size_t workspace_bytes, void* stream);
+
 /* CPU-callable test hook: the closed-form 3x3 Kabsch rotation used inside the kernels, evaluated on the host
  * for `n` row-major cross-covariance matrices H (n*9 floats) -> R (n*9 floats).  Not part of the data path. */
 void icpf_host_kabsch(const float* H, int32_t n, float* R);

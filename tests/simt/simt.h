@@ -207,6 +207,9 @@ inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 inline int __ffs(int v) { return __builtin_ffs(v); }
 inline void __threadfence() {}
 template <class T> inline T __ldcg(const T* p) { return *p; }
+template <class T> inline void __stcg(T* p, T v) { *p = v; }
+inline double __dadd_rn(double a, double b) { return a + b; }
+inline double __dmul_rn(double a, double b) { return a * b; }
 inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
 
 inline int min(int a, int b) { return a < b ? a : b; }
