@@ -426,13 +426,12 @@ def main():
     batch_bytes = 2 * P * N * 16
     pool_n = max(4, -(-int(2.2 * L2_BYTES) // batch_bytes))        # rotating pool > 2x L2 -> every step reads HBM
     src_pool, dst_pool = [], []
-    host_src = host_dst = None
+    host_packed = None
     for i in range(pool_n):
         s, d, _ = synth.make_pairs(P, N, seed=1234 + rank + 1000 * i, residual_only=True)
         if i == 0:
             # the host side of the e2e path ships the compact format: xyz of the valid rows + CSR offsets (12 B per row)
-            host_src = [t.pin_memory() for t in ops.compact_rows(torch.from_numpy(s))]
-            host_dst = [t.pin_memory() for t in ops.compact_rows(torch.from_numpy(d))]
+            host_packed = ops.pack_compact(torch.from_numpy(s), torch.from_numpy(d))      # one pinned buffer per batch
         src_pool.append(torch.from_numpy(s).to(dev))
         dst_pool.append(torch.from_numpy(d).to(dev))
     params = ops.make_params(thres=THRES, max_iterations=ICP_ITERS, relative_rmse_thr=-1.0, early_exit=False,
@@ -543,8 +542,7 @@ def main():
         # the public host-buffer call: H2D of this step's inputs, kernels, D2H of its transforms (double-buffered)
         nonlocal e2e_i
         s = e2e_i & 1
-        o = pipe.submit_compact(host_src[0], host_src[1], host_dst[0], host_dst[1], h_pose[s],
-                                ext=peer.ext(s) if peer is not None else None)
+        o = pipe.submit_packed(host_packed, h_pose[s], ext=peer.ext(s) if peer is not None else None)
         if peer is not None:
             with torch.cuda.stream(pipe.compute_stream):
                 peer.finish(s)
@@ -574,7 +572,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = pair_iters_per_step * e2e_steps / (float(t.item()) * 1e-3)
-    h2d_bytes = sum(t.numel() * t.element_size() for t in host_src + host_dst)
+    h2d_bytes = int(host_packed.buffer.numel())
 
     # ---- the gathered rows really are every rank's transforms: compare the peer-written buffer with one NCCL all_gather
     gather_verified = None
@@ -636,8 +634,8 @@ def main():
                     "gather_verified": gather_verified, "host_affinity": affinity},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": P * 64,
-                    "steps": e2e_steps, "host_format": "compact: xyz of the valid rows (12 B/row) + CSR offsets, expanded to the "
-                    "padded [P,N,4] batch by icpf_expand_rows_f32 on the device; the padded format would ship "
+                    "steps": e2e_steps, "host_format": "compact: xyz of the valid rows (12 B/row) + CSR offsets in ONE pinned buffer (one H2D copy per "
+                    "step), expanded to the padded [P,N,4] batch by icpf_expand_rows_f32 on the device; the padded format would ship "
                     f"{batch_bytes} B per step", "h2d_gbs": h2d_bytes * e2e_steps / (float(t.item()) * 1e-3) / 1e9},
             # (+ the two expand_rows kernels of the compact host format in the e2e steps)
             "gpu_launches": launches_per_step * args.steps + (launches_per_step + 2) * e2e_steps,

@@ -151,3 +151,19 @@ def test_expand_rows_rebuilds_the_padded_batch_bit_for_bit():
             rows = torch.zeros(1, 3)
         got = ops.expand_rows(put(rows), put(offsets), N).cpu().numpy()
         assert got.tobytes() == src.tobytes(), (P, N)
+
+
+def test_packed_compact_batch_views_round_trip():
+    """ops.pack_compact: both clouds' compact rows and offsets in one buffer; the views carved from a copy of the buffer
+    expand to the padded batches bit for bit."""
+    rng = np.random.default_rng(12)
+    src, dst = _batch(rng, 5, 97, "ragged")
+    if is_simt():
+        import unittest.mock as mock
+        with mock.patch.object(torch.Tensor, "pin_memory", lambda self: self):
+            pk = ops.pack_compact(torch.from_numpy(src), torch.from_numpy(dst))
+    else:
+        pk = ops.pack_compact(torch.from_numpy(src), torch.from_numpy(dst))
+    v = pk.views(put(pk.buffer.clone()))
+    assert ops.expand_rows(v[0], v[1], 97).cpu().numpy().tobytes() == src.tobytes()
+    assert ops.expand_rows(v[2], v[3], 97).cpu().numpy().tobytes() == dst.tobytes()
