@@ -33,11 +33,14 @@ __device__ __forceinline__ float mean_nn_error(const float (&m)[12], const float
                                                const unsigned short* runs) {
     float sum[1] = {0.f};
     if (GRIDNN && n_d > 0) {
-        for (int q = threadIdx.x; q < n_s; q += kThreads) {
-            const float4 raw = S[q];
+        for (int q0 = 0; q0 < n_s; q0 += kThreads) {          // (warp-uniform trip count: the far queries are scanned by the warp)
+            const int q = q0 + threadIdx.x;
+            const bool active = q < n_s;
+            const float4 raw = active ? S[q] : make_float4(0.f, 0.f, 0.f, 0.f);
             const float4 s = transform_row(m, raw);
-            const float best = nn_unbounded_grid<false>(g, sorted, runs, n_d, s.x, s.y, s.z, s.x, s.y, s.z, 0.f, 0.f, 0.f);
-            if (raw.w > 0.f) sum[0] += sqrtf(best);
+            const float best = nn_unbounded_grid_warp<false>(g, sorted, runs, n_d, active, s.x, s.y, s.z, s.x, s.y, s.z, 0.f,
+                                                             0.f, 0.f);
+            if (active && raw.w > 0.f) sum[0] += sqrtf(best);
         }
     } else {
         constexpr int QB = 4;
@@ -167,11 +170,12 @@ int launch_icp_finalize(const float* src, const float* dst, int P, int N, const 
 }
 
 // ------------------------------------------------------------------------------------------------ orchestration
-// workspace: [icp workspace][R P*9][T P*3][init pose P*16][cand idx P*5][votes P*5][histogram chunk]
+// workspace: [icp workspace][R P*9][T P*3][init pose P*16][cand idx P*5][votes P*5][need P][scoring items][histogram chunk]
 size_t path_workspace_bytes(int P, int N, int lx, int ly, int lz) {
     size_t b = icp_workspace_bytes(P) + icp_big_workspace_bytes(P, N);
     b += align_up((size_t)P * 9 * 4, 256) + align_up((size_t)P * 3 * 4, 256) + align_up((size_t)P * 16 * 4, 256);
     b += 2 * align_up((size_t)P * 5 * 4, 256) + align_up((size_t)P * 4, 256);
+    b += align_up(score_defer_words(P) * 4, 256);
     // histogram chunk [chunk, lx, ly, lz] (+ [chunk, 2, lx, ly] max planes when they do not fit shared memory)
     if (lx > 0 && ly > 0 && lz > 0)
         b += align_up((size_t)hist_chunk_pairs(P, lx, ly, lz) * ((size_t)lx * ly * lz + hist_peaks_scratch_floats(lx, ly)) * 4, 256);
@@ -196,6 +200,7 @@ struct PathWs {
     int* cand;
     float* votes;
     int* need;      // [P] pairs that take the global-memory histogram path
+    int* defer;     // candidate-scoring items (icpf_hist.cu: score_defer_words)
     float* hist;
 };
 
@@ -209,6 +214,7 @@ static PathWs carve_ws(void* workspace, int P, int N) {
     w.cand = reinterpret_cast<int*>(p); p += align_up((size_t)P * 5 * 4, 256);
     w.votes = reinterpret_cast<float*>(p); p += align_up((size_t)P * 5 * 4, 256);
     w.need = reinterpret_cast<int*>(p); p += align_up((size_t)P * 4, 256);
+    w.defer = reinterpret_cast<int*>(p); p += align_up(score_defer_words(P) * 4, 256);
     w.hist = reinterpret_cast<float*>(p);
     return w;
 }
@@ -240,7 +246,7 @@ int launch_hist_init(const float* src, const float* dst, int P, int N, const icp
     // bin width of the z axis = thres_dist (utils_hist.py:65: arange(-tau, 2 tau - eps, tau)); it only sizes NN-grid cells
     const float tau = hb.len[2] > 1 ? (hb.max[2] - hb.min[2]) / (float)(hb.len[2] - 1) : 0.1f;
     return launch_hist_score(src, dst, P, N, cand, hb.bins_x, hb.bins_y, hb.bins_z, hb.len[0], hb.len[1], hb.len[2],
-                             hb.half_bin, tau, auto_swap, out_pose, out_scores, out_which, stream);
+                             hb.half_bin, tau, auto_swap, out_pose, out_scores, out_which, w.defer, stream);
 }
 
 int launch_apply_icp(const float* src, const float* dst, const float* init_pose, int P, int N, const icpf_params& prm,

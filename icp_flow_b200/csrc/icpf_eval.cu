@@ -85,12 +85,17 @@ __device__ __forceinline__ void eval_direction_grid(const float (&m)[12], const 
                                                     const GridInfo& g, const float4* __restrict__ sorted,
                                                     const unsigned short* __restrict__ runs, int n_c, float thr,
                                                     float& err, float& inl) {
-    for (int q = threadIdx.x; q < n_q; q += kThreads) {
-        float4 r = Q[q];
+    for (int q0 = 0; q0 < n_q; q0 += kThreads) {              // (warp-uniform trip count: the far queries are scanned by the warp)
+        const int q = q0 + threadIdx.x;
+        const bool active = q < n_q;
+        float4 r = active ? Q[q] : make_float4(0.f, 0.f, 0.f, 0.f);
         if (MOVE_Q) r = transform_row(m, r);
-        const float e = sqrtf(nn_unbounded_grid<false>(g, sorted, runs, n_c, r.x, r.y, r.z, r.x, r.y, r.z, 0.f, 0.f, 0.f));
-        err += e;
-        inl += (e < thr) ? 1.f : 0.f;
+        const float e = sqrtf(nn_unbounded_grid_warp<false>(g, sorted, runs, n_c, active, r.x, r.y, r.z, r.x, r.y, r.z, 0.f,
+                                                            0.f, 0.f));
+        if (active) {
+            err += e;
+            inl += (e < thr) ? 1.f : 0.f;
+        }
     }
 }
 

@@ -262,22 +262,69 @@ struct ScoreArgs {
     float* out_pose;         // [P,16]
     float* out_scores;       // [P,6] (may be NULL)
     int* out_which;          // [P]   (may be NULL)
+    int* defer;              // deferral scratch (score_defer_words(P) words) or NULL: see hist_score_kernel
+    int P;
 };
+
+// Deferral scratch, in 32-bit words: [0] items queued, [1] items taken, [64 ..) the queue (p * 8 + k, at most 5 per
+// pair), then 16 words per pair: scores[6], best score of the first kernel, evaluated-mask, items still pending.
+constexpr int kSmCount = 148;        // B200
+constexpr int kDeferHeader = 64;
+constexpr int kDeferPairWords = 16;
+#ifndef ICPF_DEFER_BUDGET
+#define ICPF_DEFER_BUDGET 2
+#endif
+constexpr int kDeferBudget = ICPF_DEFER_BUDGET;      // chunks of kThreads rows a candidate may cost in the first kernel (power of two; 0: no deferral)
+size_t score_defer_words(int P) { return (size_t)kDeferHeader + (size_t)P * (kTopK + kDeferPairWords); }
+
+// errors.min(dim=-1) over the evaluated candidates (first minimum) -> 4x4 translation pose (utils_hist.py:104-122)
+__device__ __forceinline__ void score_select(const ScoreArgs& a, int p, const float (&score)[kCand], unsigned int evalmask,
+                                             const float (*t)[3]) {
+    const float INF = __int_as_float(0x7f800000);
+    int which = 0;
+    float best = 0.f;
+    bool have = false;
+    for (int k = 0; k < kCand; ++k) {
+        const bool ev = (evalmask >> k) & 1u;
+        const float e = ev ? score[k] : INF;        // +inf for the candidates that were excluded
+        if (a.out_scores) a.out_scores[(size_t)p * kCand + k] = e;
+        if (!ev) continue;
+        if (!have || e < best) { best = e; which = k; have = true; }      // errors.min(dim=-1): first minimum
+    }
+    if (a.out_which) a.out_which[p] = which;
+    float* o = a.out_pose + (size_t)p * 16;
+    for (int i = 0; i < 16; ++i) o[i] = (i % 5 == 0) ? 1.f : 0.f;
+    o[3] = t[which][0]; o[7] = t[which][1]; o[11] = t[which][2];
+}
 
 // GRIDNN: both clouds are counting-sorted into uniform grids in shared memory (icpf_gridnn.cuh) and the exact scores
 // come from grid searches instead of full scans -- the same minima, hence the same bits, at O(n) instead of O(n^2).
 // The rows in storage order (they fix the order of the sums) are streamed from global memory, coalesced and
 // L2-resident, so a pair costs 2 (N + 257) * 16 B of shared memory (N = 1024: 41 KB, 5 CTAs per SM).
 // !GRIDNN (clusters whose grids do not fit shared memory, N > ~7000): full scans over the rows in global memory.
-template <bool GRIDNN>
-__global__ void __launch_bounds__(kThreads) hist_score_kernel(ScoreArgs a) {
+//
+// Deferral (GRIDNN, a.defer != NULL).  A pair of unrelated clusters has no candidate that ends the others early: all six
+// are evaluated in full, about 30 times the work of a matching pair, and as ONE CTA per pair those few pairs were the
+// whole tail of the launch (C3: 5 % of the pairs, 3.4 of 3.8 ms).  So the first kernel gives every candidate after the
+// top peak a budget of kDeferBudget chunks per direction; a candidate that is neither finished nor excluded by then is
+// queued as an item (pair, candidate) and the pair's selection is left open.  The second kernel (ITEM, persistent CTAs
+// pulling from the queue) evaluates one item per CTA -- the candidates of a slow pair side by side on up to five SMs --
+// against the best score of the first kernel, and whichever CTA finishes a pair's last item selects.  A candidate is
+// either exact (same rows, same order of the sums: the same bits however it was scheduled) or provably above an exact
+// score, so the selected translation does not depend on the split; which excluded candidates read +inf does not depend
+// on timing either (the limit of an item is fixed by the first kernel).
+template <bool GRIDNN, bool ITEM>
+__device__ __forceinline__ void score_pair(const ScoreArgs& a, const int p, const int only_k) {
     __shared__ float s_t[kCand][3];
     __shared__ float s_part[kWarps][2][kCand];
     __shared__ float s_scratch[kWarps * 4];
     __shared__ float s_box[kWarps][12];
     __shared__ float s_lb[kCand];
     __shared__ float s_score[kCand];
-    const int p = blockIdx.x, tid = threadIdx.x;
+    const int tid = threadIdx.x;
+    // this pair's words of the deferral scratch
+    int* pairw = (GRIDNN && a.defer != nullptr) ? a.defer + kDeferHeader + (size_t)a.P * kTopK + (size_t)p * kDeferPairWords
+                                                : nullptr;
     const float4* S = reinterpret_cast<const float4*>(a.src) + (size_t)p * a.N;
     const float4* D = reinterpret_cast<const float4*>(a.dst) + (size_t)p * a.N;
     float cnt[2] = {0.f, 0.f};
@@ -311,6 +358,7 @@ __global__ void __launch_bounds__(kThreads) hist_score_kernel(ScoreArgs a) {
     // bbox(src))).  Candidates whose bound exceeds an exactly evaluated score can never be the arg-min and are skipped
     // (the zero-vote "filler" bins of pairs with fewer than five peaks sit metres away: result-identical, O(n) instead
     // of O(n^2) for most candidates on real frames).
+    if constexpr (!ITEM) {
     float blo[6] = {INF, INF, INF, INF, INF, INF}, bhi[6] = {-INF, -INF, -INF, -INF, -INF, -INF};
     for (int i = tid; i < n_s; i += kThreads) {
         const float4 v = S[i];
@@ -393,6 +441,7 @@ __global__ void __launch_bounds__(kThreads) hist_score_kernel(ScoreArgs a) {
         }
         __syncthreads();
     }
+    }   // !ITEM
 
     // ---- NN grids over both clouds (after the role swap), built once per pair
     GridInfo gS, gD;
@@ -439,35 +488,41 @@ __global__ void __launch_bounds__(kThreads) hist_score_kernel(ScoreArgs a) {
         };
         // mean over the rows of Q of the NN distance in the other cloud; stops (returns true in `exceeded`) once the
         // partial sum proves mean > limit.  BACK: rows of D against (S + t), else rows of (S + t) against D.
-        auto mean_nn = [&](bool back, float tx, float ty, float tz, float limit, bool can_stop, bool& exceeded) -> float {
+        // `budget` > 0: give up (`over`) when the candidate is still open after that many chunks.
+        auto mean_nn = [&](bool back, float tx, float ty, float tz, float limit, bool can_stop, int budget, bool& exceeded,
+                           bool& over) -> float {
             const int nq = back ? n_d : n_s;
             float acc = 0.f;
             exceeded = false;
+            over = false;
             int chunk = 0;
             for (int i0 = 0; i0 < nq; i0 += kThreads, ++chunk) {
                 const int i = i0 + tid;
-                if (i < nq) {
-                    float m;
-                    if (back) {
-                        const float4 v = D[i];
-                        m = nn_unbounded_grid<true>(gS, sortS, runS, n_s, v.x - tx, v.y - ty, v.z - tz, v.x, v.y, v.z,
-                                                    tx, ty, tz);
-                    } else {
-                        const float4 v = S[i];
-                        const float qx = __fadd_rn(v.x, tx), qy = __fadd_rn(v.y, ty), qz = __fadd_rn(v.z, tz);
-                        m = nn_unbounded_grid<false>(gD, sortD, runD, n_d, qx, qy, qz, qx, qy, qz, 0.f, 0.f, 0.f);
-                    }
-                    acc += sqrtf(m);
+                const bool active = i < nq;
+                float m;
+                if (back) {
+                    const float4 v = active ? D[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    m = nn_unbounded_grid_warp<true>(gS, sortS, runS, n_s, active, v.x - tx, v.y - ty, v.z - tz, v.x, v.y,
+                                                     v.z, tx, ty, tz);
+                } else {
+                    const float4 v = active ? S[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float qx = __fadd_rn(v.x, tx), qy = __fadd_rn(v.y, ty), qz = __fadd_rn(v.z, tz);
+                    m = nn_unbounded_grid_warp<false>(gD, sortD, runD, n_d, active, qx, qy, qz, qx, qy, qz, 0.f, 0.f, 0.f);
                 }
+                if (active) acc += sqrtf(m);
                 // checks after chunks 0, 1, 3, 7, ... (never after the last one)
                 if (can_stop && ((chunk + 1) & chunk) == 0 && i0 + kThreads < nq) {
                     if (block_total(acc) * 0.999f > limit * (float)nq) {
                         exceeded = true;
                         break;
                     }
+                    if (budget > 0 && chunk + 1 >= budget) {
+                        over = true;
+                        break;
+                    }
                 }
             }
-            if (exceeded) return 0.f;
+            if (exceeded || over) return 0.f;
             // the deterministic final sum of the full evaluation: lanes by butterfly, warps in order
             acc = warp_sum(acc);
             __syncthreads();
@@ -477,17 +532,54 @@ __global__ void __launch_bounds__(kThreads) hist_score_kernel(ScoreArgs a) {
             for (int w = 0; w < kWarps; ++w) t += s_chk[w];
             return __fdiv_rn(t, (float)nq);
         };
+        if constexpr (ITEM) {
+            // one queued candidate against the best score of the first kernel
+            const int k = only_k;
+            const float best = __int_as_float(__ldcg(pairw + 6));
+            const float tx = s_t[k][0], ty = s_t[k][1], tz = s_t[k][2];
+            bool fx, bx, ov;
+            const float ef = mean_nn(false, tx, ty, tz, best, true, 0, fx, ov);
+            const float eb = mean_nn(true, tx, ty, tz, fx ? best : fminf(best, ef), true, 0, bx, ov);
+            float score = INF;
+            bool exact = false;
+            if (!fx && !bx) { score = fminf(ef, eb); exact = true; }
+            else if (!fx && bx) { if (ef <= best) { score = ef; exact = true; } }
+            else if (fx && !bx) { if (eb <= best) { score = eb; exact = true; } }
+            if (tid == 0) {
+                if (exact) {
+                    pairw[k] = __float_as_int(score);
+                    atomicOr(pairw + 7, 1 << k);
+                }
+                __threadfence();
+                if (atomicSub(pairw + 8, 1) == 1) {       // the pair's last item: select
+                    __threadfence();
+                    float sc[kCand];
+                    for (int c = 0; c < kCand; ++c) sc[c] = __int_as_float(__ldcg(pairw + c));
+                    score_select(a, p, sc, (unsigned int)__ldcg(pairw + 7), s_t);
+                }
+            }
+            __syncthreads();
+            return;
+        }
         float best = INF;
         const int order[kCand] = {0, kCand - 1, 1, 2, 3, 4};
+        const int budget = (pairw != nullptr) ? kDeferBudget : 0;
+        int ndefer = 0, deferred[kCand];
         for (int o = 0; o < kCand; ++o) {
             const int k = order[o];
             const bool first = (o == 0);
             if (!first && s_lb[k] > best) continue;                 // (NaN bounds are evaluated, never skipped)
             const float tx = s_t[k][0], ty = s_t[k][1], tz = s_t[k][2];
-            bool fx, bx;
-            const float ef = mean_nn(false, tx, ty, tz, best, !first, fx);
+            bool fx, bx, ov = false;
+            const float ef = mean_nn(false, tx, ty, tz, best, !first, first ? 0 : budget, fx, ov);
             // the backward mean matters only below min(best, ef)
-            const float eb = mean_nn(true, tx, ty, tz, fx ? best : fminf(best, ef), !first, bx);
+            float eb = 0.f;
+            bx = false;
+            if (!ov) eb = mean_nn(true, tx, ty, tz, fx ? best : fminf(best, ef), !first, first ? 0 : budget, bx, ov);
+            if (ov) {                                               // still open at its budget: an item for the second kernel
+                deferred[ndefer++] = k;
+                continue;
+            }
             float score = INF;
             bool exact = false;
             if (!fx && !bx) { score = fminf(ef, eb); exact = true; }          // torch.minimum
@@ -497,6 +589,22 @@ __global__ void __launch_bounds__(kThreads) hist_score_kernel(ScoreArgs a) {
                 if (tid == 0) { s_score[k] = score; s_eval[k] = 1; }
                 best = fminf(best, score);
             }
+        }
+        __syncthreads();
+        if (ndefer > 0) {
+            if (tid == 0) {
+                unsigned int mask = 0;
+                for (int k = 0; k < kCand; ++k) {
+                    pairw[k] = __float_as_int(s_eval[k] ? s_score[k] : INF);
+                    mask |= s_eval[k] ? (1u << k) : 0u;
+                }
+                pairw[6] = __float_as_int(best);
+                pairw[7] = (int)mask;
+                pairw[8] = ndefer;
+                const int at = atomicAdd(a.defer, ndefer);
+                for (int j = 0; j < ndefer; ++j) a.defer[kDeferHeader + at + j] = p * 8 + deferred[j];
+            }
+            return;
         }
         __syncthreads();
     } else {
@@ -568,35 +676,62 @@ __global__ void __launch_bounds__(kThreads) hist_score_kernel(ScoreArgs a) {
         __syncthreads();
     }
     if (tid == 0) {
-        int which = 0;
-        float best = 0.f;
-        bool have = false;
+        float sc[kCand];
+        unsigned int mask = 0;
         for (int k = 0; k < kCand; ++k) {
-            const float e = s_eval[k] ? s_score[k] : INF;        // +inf for the candidates that were excluded
-            if (a.out_scores) a.out_scores[(size_t)p * kCand + k] = e;
-            if (!s_eval[k]) continue;
-            if (!have || e < best) { best = e; which = k; have = true; }      // errors.min(dim=-1): first minimum
+            sc[k] = s_score[k];
+            mask |= s_eval[k] ? (1u << k) : 0u;
         }
-        if (a.out_which) a.out_which[p] = which;
-        float* o = a.out_pose + (size_t)p * 16;
-        for (int i = 0; i < 16; ++i) o[i] = (i % 5 == 0) ? 1.f : 0.f;
-        o[3] = s_t[which][0]; o[7] = s_t[which][1]; o[11] = s_t[which][2];
+        score_select(a, p, sc, mask, s_t);
+    }
+}
+
+template <bool GRIDNN, bool ITEM>
+__global__ void __launch_bounds__(kThreads) hist_score_kernel(ScoreArgs a) {
+    if constexpr (ITEM) {
+        __shared__ int s_item;
+        for (;;) {
+            if (threadIdx.x == 0) s_item = atomicAdd(a.defer + 1, 1);
+            __syncthreads();
+            const int item = s_item;
+            if (item >= __ldcg(a.defer)) return;
+            const int code = a.defer[kDeferHeader + item];
+            score_pair<GRIDNN, true>(a, code >> 3, code & 7);
+            __syncthreads();
+        }
+    } else {
+        score_pair<GRIDNN, false>(a, blockIdx.x, -1);
     }
 }
 
 int launch_hist_score(const float* src, const float* dst, int P, int N, const int* cand_idx, const float* bins_x,
                       const float* bins_y, const float* bins_z, int lx, int ly, int lz, float half_bin, float tau,
-                      int auto_swap, float* out_pose, float* out_scores, int* out_which, cudaStream_t stream) {
+                      int auto_swap, float* out_pose, float* out_scores, int* out_which, int* defer, cudaStream_t stream) {
     if (P == 0) return ICPF_OK;
     const size_t with_grids = ((size_t)2 * gridnn_units(N) + up16(kRedFloats * 4)) * 16;
     const bool gridnn = with_grids <= (size_t)227 * 1024 && tau > 0.f;
     const size_t smem = gridnn ? with_grids : 0;
-    auto kernel = gridnn ? hist_score_kernel<true> : hist_score_kernel<false>;
+    if (!gridnn || kDeferBudget == 0) defer = nullptr;
+    auto kernel = gridnn ? hist_score_kernel<true, false> : hist_score_kernel<false, false>;
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
     ScoreArgs a{src, dst, N, cand_idx, bins_x, bins_y, bins_z, lx, ly, lz, half_bin, tau, auto_swap, out_pose,
-                out_scores, out_which};
+                out_scores, out_which, defer, P};
+    if (defer != nullptr) {
+        err = cudaMemsetAsync(defer, 0, 2 * sizeof(int), stream);
+        if (err != cudaSuccess) return (int)err;
+    }
     ICPF_LAUNCH(kernel, P, kThreads, smem, stream)(a);
+    err = cudaGetLastError();
+    if (err != cudaSuccess || defer == nullptr) return (int)err;
+    // the queued (pair, candidate) items: persistent CTAs, as many as the device holds at this shared-memory size
+    auto items = hist_score_kernel<true, true>;
+    err = cudaFuncSetAttribute(items, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return (int)err;
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, ((size_t)227 * 1024) / (smem + 2048)));
+    const long long want = (long long)P * kTopK;
+    const int grid = (int)std::min<long long>(want, (long long)kSmCount * per_sm);
+    ICPF_LAUNCH(items, grid, kThreads, smem, stream)(a);
     return (int)cudaGetLastError();
 }
 

@@ -67,7 +67,8 @@ int launch_hist_fused(const float* X, const float* Y, int P, int N, const float*
                       cudaStream_t stream);
 int launch_hist_score(const float* src, const float* dst, int P, int N, const int* cand_idx, const float* bins_x,
                       const float* bins_y, const float* bins_z, int lx, int ly, int lz, float half_bin, float tau,
-                      int auto_swap, float* out_pose, float* out_scores, int* out_which, cudaStream_t stream);
+                      int auto_swap, float* out_pose, float* out_scores, int* out_which, int* defer, cudaStream_t stream);
+size_t score_defer_words(int P);
 int launch_icp_finalize(const float* src, const float* dst, int P, int N, const float* init_pose, const float* icp_R,
                         const float* icp_T, int auto_swap, float tau, float* out_pose, float* out_err, int* out_flags,
                         cudaStream_t stream);

@@ -177,6 +177,7 @@ inline int __reduce_add_sync(unsigned mask, int v) { return (int)__reduce_add_sy
 // ------------------------------------------------------------------------------------------------ atomics (one host thread)
 template <class T> inline T atomicAdd(T* p, T v) { T o = *p; *p = o + v; return o; }
 inline unsigned atomicAdd(unsigned* p, int v) { unsigned o = *p; *p = o + (unsigned)v; return o; }
+template <class T> inline T atomicSub(T* p, T v) { T o = *p; *p = o - v; return o; }
 template <class T> inline T atomicAnd(T* p, T v) { T o = *p; *p = o & v; return o; }
 template <class T> inline T atomicOr(T* p, T v) { T o = *p; *p = o | v; return o; }
 template <class T> inline T atomicMax(T* p, T v) { T o = *p; *p = o > v ? o : v; return o; }
