@@ -4,12 +4,8 @@
 // every query (12 passes in estimate_init_pose, 2 in apply_icp, 2 in match_eval).  The quantity those callers consume is
 // min_j d(q, c_j) -- a minimum, so the visiting order is irrelevant and any search that provably saw the minimiser
 // returns the SAME bits as the full scan as long as each candidate distance is evaluated with the same arithmetic.
-// Search: the block of cells that just covers the gate radius first; if the best candidate found is farther than the
-// nearest un-inspected face (`box`), one more block sized to contain the ball of that candidate (which then proves it);
-// a query that found nothing within kUnbMaxR cells (far clouds: wrong candidate translations, unrelated clusters) visits
-// the grid slab by slab and column by column outwards from its own position, skipping every slab / column whose
-// lower-bound distance exceeds the best candidate (grid_pruned_min) -- the worst case is the reference's scan plus the
-// bound tests.
+// Search (nn_unbounded_grid_warp): blocks of cells around the query per lane, then a warp-wide scan of all rows for
+// the queries the blocks could not settle -- the worst case is the reference's scan, spread over the 32 lanes.
 #pragma once
 
 #include "icpf_pair.cuh"
@@ -74,113 +70,21 @@ __device__ __forceinline__ void grid_block_min(const GridInfo& g, const float4* 
     }
 }
 
-// min over ALL rows of the grid for a query the block search could not settle (nothing within kUnbMaxR cells: wrong
-// candidate translations, unrelated clusters), without visiting all of them: the sorted rows of one x-slab of cells are
-// one contiguous run and so are those of one (x, y) column, and every row of a slab / column is at least the distance
-// from the look-up position to that slab / column away (minus the grid's slack g.pad).  Slabs are visited outwards from
-// the query's own, nearer side first, and a side is closed as soon as its lower bound exceeds the best distance found --
-// lower bounds only grow outwards -- and likewise for the columns inside a slab.  Pruned rows are provably farther than
-// the minimum, visited rows are evaluated with the scan's arithmetic: the result has the bits of the full scan.  (A NaN
-// position fails every pruning test and visits everything, like the scan it replaces.)
-template <bool SHIFT>
-__device__ __forceinline__ void grid_pruned_min(const GridInfo& g, const float4* __restrict__ sorted,
-                                                const unsigned short* __restrict__ a, float lx, float ly, float lz,
-                                                float ex, float ey, float ez, float sx, float sy, float sz,
-                                                float& dmin) {
-    const float INF = __int_as_float(0x7f800000);
-    const float fx = (lx - g.ox) * g.inv_c, fy = (ly - g.oy) * g.inv_c;
-    // best distance found so far, inflated like the block search's proof (rounding of the bounds), and its square
-    float best = sqrtf(dmin) * 1.0001f + 1e-6f, best2 = best * best;
-    const int sx0 = (int)fminf(fmaxf(fx, 0.f), (float)(g.gx - 1));        // the query's own slab, clamped (NaN -> 0)
-    const int sy0 = (int)fminf(fmaxf(fy, 0.f), (float)(g.gy - 1));
-    int xlo = sx0, xhi = sx0 + 1;
-    bool xlo_open = true, xhi_open = xhi < g.gx;
-    while (xlo_open || xhi_open) {
-        // gap (cells) between the position and the next slab of either side; the nearer side goes first
-        // (distance from fx to the slab's interval [i, i + 1]; the query's own slab is clamped into the grid, so a
-        //  position outside the grid is at a positive distance from it too)
-        const float gl = xlo_open ? fmaxf(fmaxf(fx - (float)(xlo + 1), (float)xlo - fx), 0.f) : INF;
-        const float gh = xhi_open ? fmaxf(fmaxf((float)xhi - fx, fx - (float)(xhi + 1)), 0.f) : INF;
-        const bool lo_side = gl <= gh;
-        const float lbx = fmaxf((lo_side ? gl : gh) * g.c - g.pad, 0.f);
-        if (lbx >= best) {                       // every slab further out on this side is at least as far
-            if (lo_side) xlo_open = false; else xhi_open = false;
-            continue;
-        }
-        const int ix = lo_side ? xlo : xhi;
-        if (lo_side) { --xlo; xlo_open = xlo >= 0; } else { ++xhi; xhi_open = xhi < g.gx; }
-        const float lbx2 = lbx * lbx;
-        int ylo = sy0, yhi = sy0 + 1;
-        bool ylo_open = true, yhi_open = yhi < g.gy;
-        while (ylo_open || yhi_open) {
-            const float hl = ylo_open ? fmaxf(fmaxf(fy - (float)(ylo + 1), (float)ylo - fy), 0.f) : INF;
-            const float hh = yhi_open ? fmaxf(fmaxf((float)yhi - fy, fy - (float)(yhi + 1)), 0.f) : INF;
-            const bool ylo_side = hl <= hh;
-            const float lby = fmaxf((ylo_side ? hl : hh) * g.c - g.pad, 0.f);
-            if (fmaf(lby, lby, lbx2) >= best2) {
-                if (ylo_side) ylo_open = false; else yhi_open = false;
-                continue;
-            }
-            const int iy = ylo_side ? ylo : yhi;
-            if (ylo_side) { --ylo; ylo_open = ylo >= 0; } else { ++yhi; yhi_open = yhi < g.gy; }
-            const int base = (ix * g.gy + iy) * g.gz;
-            const int s = a[base], e = a[base + g.gz];
-            if (s == e) continue;
-            for (int j = s; j < e; ++j) {
-                const float4 c = sorted[j];
-                const float d = SHIFT ? sqdist(ex, ey, ez, __fadd_rn(c.x, sx), __fadd_rn(c.y, sy), __fadd_rn(c.z, sz))
-                                      : sqdist(ex, ey, ez, c.x, c.y, c.z);
-                dmin = fminf(dmin, d);
-            }
-            best = sqrtf(dmin) * 1.0001f + 1e-6f;
-            best2 = best * best;
-        }
-    }
-}
-
-// Exact  min_j sqdist(e, rows_j (+ s))  over ALL n rows of the grid -- the value of the reference's full scan.
+// Exact  min_j sqdist(e, rows_j (+ s))  over ALL n rows of the grid -- the value of the reference's full scan -- for the
+// queries of one WARP (every lane calls it; `active` says whether the lane has a query).
 //   l = where e sits relative to the un-shifted rows (e - s up to rounding; only used to pick cells, the slack g.pad
 //   absorbs its rounding);  SHIFT = candidates are evaluated as fadd(row, s), the arithmetic of the scan it replaces.
-template <bool SHIFT>
-__device__ __forceinline__ float nn_unbounded_grid(const GridInfo& g, const float4* __restrict__ sorted,
-                                                   const unsigned short* __restrict__ a, int n, float lx, float ly,
-                                                   float lz, float ex, float ey, float ez, float sx, float sy,
-                                                   float sz) {
-    const float INF = __int_as_float(0x7f800000);
-    float dmin = INF, box = 0.f;
-    float r = g.r;
-    for (int lvl = 0; lvl < 3; ++lvl) {
-        grid_block_min<SHIFT>(g, sorted, a, lx, ly, lz, ex, ey, ez, sx, sy, sz, r, dmin, box);
-        // proven when every row that was not inspected is farther than the best one that was
-        if (sqrtf(dmin) * 1.0001f + 1e-6f <= box) return dmin;
-        // next block: just large enough to contain the ball of the best candidate so far (that block proves it)
-        const float want = (dmin < INF) ? sqrtf(dmin) * g.inv_c * 1.001f + 0.02f : r + 1.0f;
-        if (!(want <= kUnbMaxR) || !(want > r)) break;
-        r = want;
-    }
-    // far query (or NaN): every slab / column that could hold a nearer row
-#ifdef ICPF_GRIDNN_FULL_SCAN
-    for (int j = 0; j < n; ++j) {
-        const float4 c = sorted[j];
-        const float d = SHIFT ? sqdist(ex, ey, ez, __fadd_rn(c.x, sx), __fadd_rn(c.y, sy), __fadd_rn(c.z, sz))
-                              : sqdist(ex, ey, ez, c.x, c.y, c.z);
-        dmin = fminf(dmin, d);
-    }
-#else
-    (void)n;
-    grid_pruned_min<SHIFT>(g, sorted, a, lx, ly, lz, ex, ey, ez, sx, sy, sz, dmin);
-#endif
-    return dmin;
-}
-
-// The same value for the queries of one WARP (every lane calls it, `active` says whether the lane has a query): the
-// block levels run per lane as above; a query they cannot settle is then scanned by the whole warp -- lane j takes the
+// The block levels run per lane: the block of cells that just covers the gate radius first; if the best candidate found
+// is farther than the nearest un-inspected face (`box`), one more block sized to contain the ball of that candidate
+// (which then proves it).  A query the levels cannot settle (nothing within kUnbMaxR cells: wrong candidate
+// translations, unrelated clusters, NaN positions) is then scanned by the whole warp -- lane j takes the
 // rows j, j + 32, ... of the sorted copy (conflict-free 16-byte loads, four independent minima in flight) and a butterfly
 // folds the 32 partial minima.  A minimum does not depend on the visiting order, every candidate is evaluated with the
 // scan's arithmetic: the bits of the full scan, at n / 32 candidates per lane instead of a divergent walk over hundreds
-// of mostly empty columns (a far query cost ~70 000 cycles in the slab / column search and ~400 here).
+// of mostly empty columns (a far query cost ~70 000 cycles in a slab / column search with lower-bound pruning, ~400 here).
+// ICPF_COOP_LEVELS=0 scans every query in full, as the reference does (the variant tests/test_simt_variants.py compares with).
 #ifndef ICPF_COOP_LEVELS
-#define ICPF_COOP_LEVELS 2          // block levels tried per lane before the warp scan
+#define ICPF_COOP_LEVELS 2          // block levels tried per lane before the warp scan (measured: 1 -> 8.66, 2 -> 8.05, 3 -> 8.41 ms on C3)
 #endif
 template <bool SHIFT>
 __device__ __forceinline__ float nn_unbounded_grid_warp(const GridInfo& g, const float4* __restrict__ sorted,

@@ -11,7 +11,9 @@
 #include "icpf_internal.h"
 #include "icpf_common.cuh"
 
+#include <math.h>
 #include <string.h>
+#include <limits>
 #include <type_traits>
 
 namespace icpf {
@@ -32,6 +34,7 @@ struct FusedHistArgs {
     float* out_votes;        // [P,5]
     int* need_global;        // [P] 1 = this pair did not fit and must take the next (wider / global) path
     int only_flagged;        // 1: second tier -- handle only the pairs the first tier flagged
+    float zt1, zt2;          // MODE 2 (three z bins): smallest differences in [min_z, max_z) that fall into bin 1 / bin 2
 };
 
 __device__ __forceinline__ int vote_bin(float v, float mn, float range, float flen, int len) {
@@ -64,8 +67,14 @@ __device__ __forceinline__ unsigned long long fused_peak_key(float v, int idx) {
 // per column at three z bins: the whole 135 x 135 window of the default translation_frame fits).  A counter that is
 // about to wrap is caught on the increment that wraps it (the atomic returns the old value) and sends the pair on to
 // the exact global-memory path.
-template <int kFusedThreads, bool FASTDIV, bool COUNT16>
+// MODE: 0 the plain IEEE division, 1 Markstein's division (FASTDIV), 2 FASTDIV and the z bin from two comparisons -- with
+// the three z bins of utils_hist.py:65 the bin is a monotone step function of the difference, so it is fixed by the two
+// differences at which the reference's formula steps (found on the host by bisection over the fp32 values, with the
+// formula itself); the run of a row only holds partners that pass the z range test, so that test goes as well.
+template <int kFusedThreads, int MODE, bool COUNT16>
 __global__ void __launch_bounds__(kFusedThreads) hist_fused_kernel(FusedHistArgs a) {
+    constexpr bool FASTDIV = MODE >= 1;
+    constexpr bool ZSTEP = MODE == 2;
     ICPF_DYN_SHARED __align__(16) float4 fsm[];
     __shared__ float s_red[kFusedThreads / 32][12];
     __shared__ int s_cnt[2];
@@ -179,7 +188,9 @@ __global__ void __launch_bounds__(kFusedThreads) hist_fused_kernel(FusedHistArgs
             __syncthreads();
             for (int j = tid; j < npow; j += kFusedThreads) {
                 float4 y = (j < n) ? yb[base + j] : make_float4(0.f, 0.f, INF, 0.f);
-                if (!(y.w > 0.f)) y.z = INF;          // unflagged rows sort to the end and never match
+                // unflagged rows sort to the end and never match; neither does a NaN height (it fails the range test of
+                // the reference, and the sort needs a total order)
+                if (!(y.w > 0.f) || !(y.z == y.z)) y.z = INF;
                 tile[j] = y;
             }
             __syncthreads();
@@ -232,14 +243,17 @@ __global__ void __launch_bounds__(kFusedThreads) hist_fused_kernel(FusedHistArgs
                         const float4 yj = tile[j];
                         const float vz = __fsub_rn(xiz, yj.z);
                         const float vx = __fsub_rn(xix, yj.x), vy = __fsub_rn(xiy, yj.y);
-                        if (vx >= a.min_x && vx < a.max_x && vy >= a.min_y && vy < a.max_y && vz >= a.min_z && vz < a.max_z) {
+                        // (the run [rs, re) was cut with the exact z predicates: min_z <= vz < max_z holds inside it)
+                        if (vx >= a.min_x && vx < a.max_x && vy >= a.min_y && vy < a.max_y &&
+                            (ZSTEP || (vz >= a.min_z && vz < a.max_z))) {
                             const int px = (FASTDIV ? vote_bin_fast(vx, a.min_x, rx, irx, flx, a.len_x)
                                                     : vote_bin(vx, a.min_x, rx, flx, a.len_x)) - bx0;
                             const int py = (FASTDIV ? vote_bin_fast(vy, a.min_y, ry, iry, fly, a.len_y)
                                                     : vote_bin(vy, a.min_y, ry, fly, a.len_y)) - by0;
-                            const int pz = FASTDIV ? vote_bin_fast(vz, a.min_z, rz, irz, flz, a.len_z)
-                                                   : vote_bin(vz, a.min_z, rz, flz, a.len_z);
-                            if (px < 0 || px >= wx || py < 0 || py >= wy) {
+                            const int pz = ZSTEP ? (vz >= a.zt1 ? 1 : 0) + (vz >= a.zt2 ? 1 : 0)
+                                                 : (FASTDIV ? vote_bin_fast(vz, a.min_z, rz, irz, flz, a.len_z)
+                                                            : vote_bin(vz, a.min_z, rz, flz, a.len_z));
+                            if ((unsigned int)px >= (unsigned int)wx || (unsigned int)py >= (unsigned int)wy) {
                                 s_bad = 1;      // cannot happen (the range is conservative); fall back if it ever does
                             } else {
                                 const int bin = (px * wy + py) * lz + pz;
@@ -348,6 +362,26 @@ __global__ void __launch_bounds__(kFusedThreads) hist_fused_kernel(FusedHistArgs
     }
 }
 
+// host restatement of vote_bin() (every step rounded to fp32) and the order-preserving map float <-> u32
+static int host_vote_bin(float v, float mn, float range, float flen, int len) {
+    volatile float x = v - mn;
+    volatile float q = x / range;
+    volatile float m = q * flen;
+    const int p = (int)floorf(m);
+    return p < len - 1 ? p : len - 1;
+}
+static uint32_t ordered_key(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+static float from_ordered_key(uint32_t k) {
+    const uint32_t u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
 int launch_hist_fused(const float* X, const float* Y, int P, int N, const float* mins, const float* maxs,
                       const int* lens, int auto_swap, int* out_idx, float* out_votes, int* need_global,
                       cudaStream_t stream) {
@@ -365,6 +399,20 @@ int launch_hist_fused(const float* X, const float* Y, int P, int N, const float*
         const int e = (int)((u >> 23) & 0xffu);
         fastdiv = fastdiv && (u & 0x7fffffu) != 0x7fffffu && e > 127 - 40 && e < 127 + 40;
     }
+    // three z bins: the differences at which the reference's bin formula steps from bin k - 1 to bin k (MODE 2)
+    float zt[2] = {0.f, 0.f};
+    const bool zstep = fastdiv && lens[2] == 3 && maxs[2] > mins[2];
+    if (zstep) {
+        const float INF = std::numeric_limits<float>::infinity();
+        for (int k = 1; k <= 2; ++k) {
+            uint32_t lo = ordered_key(mins[2]), hi = ordered_key(maxs[2]);      // first key in [lo, hi) with bin >= k
+            while (lo < hi) {
+                const uint32_t mid = lo + (hi - lo) / 2;
+                if (host_vote_bin(from_ordered_key(mid), mins[2], maxs[2] - mins[2], 3.f, 3) >= k) hi = mid; else lo = mid + 1;
+            }
+            zt[k - 1] = (lo == ordered_key(maxs[2])) ? INF : from_ordered_key(lo);
+        }
+    }
 #ifndef ICPF_FUSED_WIDE
 #define ICPF_FUSED_WIDE 1024
 #endif
@@ -378,17 +426,22 @@ int launch_hist_fused(const float* X, const float* Y, int P, int N, const float*
                             (tier == 0 ? (size_t)cap_cols * lens[2] * 4 + (size_t)(cap_cols + (cap_cols & 1)) * 8
                                        : ((size_t)(cap_cols * lens[2] + 1) / 2) * 4 + (size_t)(cap_cols + (cap_cols & 1)) * 4);
         void (*kernel)(FusedHistArgs);
+        const int mode = zstep ? 2 : (fastdiv ? 1 : 0);
         if (tier == 0)
-            kernel = wide ? (fastdiv ? hist_fused_kernel<ICPF_FUSED_WIDE, true, false> : hist_fused_kernel<ICPF_FUSED_WIDE, false, false>)
-                          : (fastdiv ? hist_fused_kernel<256, true, false> : hist_fused_kernel<256, false, false>);
+            kernel = wide ? (mode == 2 ? hist_fused_kernel<ICPF_FUSED_WIDE, 2, false>
+                                       : mode == 1 ? hist_fused_kernel<ICPF_FUSED_WIDE, 1, false> : hist_fused_kernel<ICPF_FUSED_WIDE, 0, false>)
+                          : (mode == 2 ? hist_fused_kernel<256, 2, false>
+                                       : mode == 1 ? hist_fused_kernel<256, 1, false> : hist_fused_kernel<256, 0, false>);
         else
-            kernel = wide ? (fastdiv ? hist_fused_kernel<ICPF_FUSED_WIDE, true, true> : hist_fused_kernel<ICPF_FUSED_WIDE, false, true>)
-                          : (fastdiv ? hist_fused_kernel<256, true, true> : hist_fused_kernel<256, false, true>);
+            kernel = wide ? (mode == 2 ? hist_fused_kernel<ICPF_FUSED_WIDE, 2, true>
+                                       : mode == 1 ? hist_fused_kernel<ICPF_FUSED_WIDE, 1, true> : hist_fused_kernel<ICPF_FUSED_WIDE, 0, true>)
+                          : (mode == 2 ? hist_fused_kernel<256, 2, true>
+                                       : mode == 1 ? hist_fused_kernel<256, 1, true> : hist_fused_kernel<256, 0, true>);
         cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;
         FusedHistArgs a{reinterpret_cast<const float4*>(X), reinterpret_cast<const float4*>(Y), N,
                         mins[0], mins[1], mins[2], maxs[0], maxs[1], maxs[2], lens[0], lens[1], lens[2],
-                        auto_swap, cap_cols, out_idx, out_votes, need_global, tier};
+                        auto_swap, cap_cols, out_idx, out_votes, need_global, tier, zt[0], zt[1]};
         ICPF_LAUNCH(kernel, P, wide ? ICPF_FUSED_WIDE : 256, smem, stream)(a);
         err = cudaGetLastError();
         if (err != cudaSuccess) return (int)err;

@@ -1,10 +1,10 @@
 """Kernel variants that must agree bit for bit, compared under the SIMT-on-CPU emulator (tests/simt/): the product
 build of a kernel against a build of the same sources with the simpler algorithm it replaces switched back on.
 
-  ICPF_GRIDNN_FULL_SCAN   far queries of the unbounded NN (csrc/icpf_gridnn.cuh) scan every row, as the reference does,
-                          instead of visiting the grid slab by slab with lower-bound pruning.  The NN distance is a
-                          minimum, so hist_score's scores, apply_icp's errors and match_eval's metrics must not move
-                          by a bit."""
+  ICPF_COOP_LEVELS=0      every query of the unbounded NN (csrc/icpf_gridnn.cuh) scans every row, as the reference does,
+                          instead of searching blocks of grid cells first and scanning only the far queries.  The NN
+                          distance is a minimum, so hist_score's scores, apply_icp's errors and match_eval's metrics
+                          must not move by a bit."""
 import os
 import sys
 import types
@@ -30,7 +30,7 @@ def _path_outputs(src, dst, args):
     return {k: harness.plain(v).clone() for k, v in res.items()}
 
 
-def test_pruned_far_query_search_equals_the_full_scan():
+def test_grid_search_equals_the_full_scan():
     args = types.SimpleNamespace(thres_dist=0.1, translation_frame=6.666, chunk_size=50)
     batches = []
     # unrelated clusters (every query far), large motions (most candidate translations are wrong), ragged sizes
@@ -46,7 +46,7 @@ def test_pruned_far_query_search_equals_the_full_scan():
     with harness.emulated():
         for s, d in batches:
             got.append(_path_outputs(s, d, args))
-    with harness.emulated(extra_flags=("-DICPF_GRIDNN_FULL_SCAN",), out=variant):
+    with harness.emulated(extra_flags=("-DICPF_COOP_LEVELS=0",), out=variant):
         for s, d in batches:
             want.append(_path_outputs(s, d, args))
     for g, w in zip(got, want):
