@@ -173,6 +173,10 @@ __global__ void __launch_bounds__(kFusedThreads) hist_fused_kernel(FusedHistArgs
     const int hist_words = COUNT16 ? (a.cap_cols * lz + 1) / 2 : a.cap_cols * lz;
     cnt_t* colmax = reinterpret_cast<cnt_t*>(histw + hist_words);                  // [ncol] max over z
     cnt_t* rowmax = colmax + a.cap_cols + (a.cap_cols & 1);                        // [ncol] max over the y window
+#if !defined(ICPF_SIMT_EMU)
+    unsigned int hist_s;        // (an opaque copy: a known constant base is rematerialised inside the vote loop)
+    asm volatile("mov.u32 %0, %1;" : "=r"(hist_s) : "r"((unsigned int)__cvta_generic_to_shared(histw)));
+#endif
     for (int i = tid; i < (COUNT16 ? (ncol * lz + 1) / 2 : ncol * lz); i += kFusedThreads) histw[i] = 0u;
     __syncthreads();
 
@@ -262,7 +266,13 @@ __global__ void __launch_bounds__(kFusedThreads) hist_fused_kernel(FusedHistArgs
                                     const unsigned int was = atomicAdd(&histw[bin >> 1], 1u << sh);
                                     if (((was >> sh) & 0xffffu) == 0xffffu) s_bad = 1;      // this increment wrapped it
                                 } else {
+#if defined(ICPF_SIMT_EMU) || defined(ICPF_NO_RED_PTX)
                                     atomicAdd(&histw[bin], 1u);
+#else
+                                    // (a 32-bit shared address kept in a register: the generic pointer made the compiler
+                                    //  rebuild the shared window base -- five instructions -- in every iteration)
+                                    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_s + 4u * (unsigned int)bin) : "memory");
+#endif
                                 }
                             }
                         }
