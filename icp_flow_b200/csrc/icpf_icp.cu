@@ -246,6 +246,10 @@ __global__ void __launch_bounds__(128) icp_select_batch_kernel(IcpSelectArgs a) 
     if (p < a.P) select_pair(a, p, a.batch[0]);
 }
 
+#ifndef ICPF_RESOLVE_THREADS
+#define ICPF_RESOLVE_THREADS 1024
+#endif
+constexpr int kResolveThreads = ICPF_RESOLVE_THREADS;     // one CTA: the launch is a latency chain, more threads = fewer trips
 // AND of the per-pair convergence masks -> first iteration k* where every pair passes (utils_icp_pytorch3d.py:209).
 // batch[0] = iterations the reference loop would have executed, batch[1] = converged flag.
 // `limit` = iterations the masks cover (the cap of the first pass, or max_it); `decided` (may be NULL) is set to 1 when
@@ -253,7 +257,7 @@ __global__ void __launch_bounds__(128) icp_select_batch_kernel(IcpSelectArgs a) 
 // receives the AND of the masks -- what a caller with several shards exchanges (IcpPhase, icpf_internal.h).
 // `sel.hist != NULL`: once the stop is final, the same launch hands the pairs that went beyond it their state at the stop
 // (select_pair) -- the call ends with one launch instead of two.
-__global__ void __launch_bounds__(256) icp_resolve_batch_kernel(const uint32_t* conv, int P, int max_it, int limit,
+__global__ void __launch_bounds__(kResolveThreads) icp_resolve_batch_kernel(const uint32_t* conv, int P, int max_it, int limit,
                                                                 int batch_stop, int* batch, int* decided,
                                                                 uint32_t* and_out, IcpSelectArgs sel) {
     __shared__ uint32_t s_and[4];
@@ -431,7 +435,7 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
         err = cudaGetLastError();
         if (prof_start && prof_stop) cudaEventRecord(prof_stop, stream);
         if (err != cudaSuccess) return (int)err;
-        ICPF_LAUNCH(icp_resolve_batch_kernel, 1, 256, 0, stream)(conv, P, prm.max_iterations, a.cap, prm.batch_stop, batch,
+        ICPF_LAUNCH(icp_resolve_batch_kernel, 1, kResolveThreads, 0, stream)(conv, P, prm.max_iterations, a.cap, prm.batch_stop, batch,
                                                         capped ? decided : nullptr, and_out,
                                                         (fuse_sel && !capped) ? sa : no_sel);
         err = cudaGetLastError();
@@ -447,7 +451,7 @@ int launch_icp(const float* src, const float* dst, const float* init_R, const fl
         a.decided = decided;
         ICPF_LAUNCH(kernel_full, P, kThreads, smem, stream)(a);
         a.decided = nullptr;
-        ICPF_LAUNCH(icp_resolve_batch_kernel, 1, 256, 0, stream)(conv, P, prm.max_iterations, prm.max_iterations, prm.batch_stop,
+        ICPF_LAUNCH(icp_resolve_batch_kernel, 1, kResolveThreads, 0, stream)(conv, P, prm.max_iterations, prm.max_iterations, prm.batch_stop,
                                                         batch, decided, and_out, fuse_sel ? sa : no_sel);
         err = cudaGetLastError();
         if (err != cudaSuccess) return (int)err;
