@@ -18,7 +18,8 @@ EXPORTS = (
     "icpf_icp_f32", "icpf_icp_ex_f32", "icpf_nn_f32", "icpf_transform_points_f32", "icpf_host_kabsch",
     "icpf_host_kabsch_sequence", "icpf_peer_push_f32", "icpf_expand_rows_f32", "icpf_hist_votes_f32", "icpf_hist_init_f32", "icpf_apply_icp_f32", "icpf_apply_icp_phase_f32", "icpf_hist_icp_f32",
     "icpf_match_eval_f32",
-    "icpf_cluster_index_workspace_bytes", "icpf_cluster_index_f32", "icpf_sanity_check_f32", "icpf_gather_pairs_f32",
+    "icpf_cluster_index_workspace_bytes", "icpf_cluster_index_f32", "icpf_sanity_check_f32", "icpf_sanity_check_cross_f32",
+    "icpf_match_select_workspace_bytes", "icpf_match_select_f32", "icpf_gather_pairs_f32",
     "icpf_flow_f32", "icpf_dbscan_workspace_bytes", "icpf_dbscan_f32",
 )
 
@@ -135,6 +136,14 @@ def lib() -> ctypes.CDLL:
     L.icpf_sanity_check_f32.restype = ctypes.c_int
     L.icpf_sanity_check_f32.argtypes = [vp, vp, i32, vp, vp, i32, vp, i32, i32, ctypes.c_double, ctypes.c_double, vp,
                                         vp, vp, vp]
+    L.icpf_sanity_check_cross_f32.restype = ctypes.c_int
+    L.icpf_sanity_check_cross_f32.argtypes = [vp, vp, i32, vp, vp, i32, vp, i32, i32, i32, ctypes.c_double, ctypes.c_double,
+                                              vp, vp, vp]
+    L.icpf_match_select_workspace_bytes.restype = ctypes.c_size_t
+    L.icpf_match_select_workspace_bytes.argtypes = [i32, i32]
+    L.icpf_match_select_f32.restype = ctypes.c_int
+    L.icpf_match_select_f32.argtypes = [vp, i32, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, ctypes.c_double, vp, vp, vp, vp, vp,
+                                        vp, ctypes.c_size_t, vp]
     L.icpf_gather_pairs_f32.restype = ctypes.c_int
     L.icpf_gather_pairs_f32.argtypes = [vp, i32, vp, vp, i32, vp, i32, vp, vp, i32, vp, i32, i32, vp, vp, vp, vp, vp]
     L.icpf_flow_f32.restype = ctypes.c_int

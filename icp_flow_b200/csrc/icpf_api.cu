@@ -10,7 +10,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 extern "C" {
 
-int icpf_version(void) { return 103; }   // 102: icpf_icp_ex_f32, icpf_peer_push_f32, icpf_expand_rows_f32; 103: icpf_dbscan_f32
+int icpf_version(void) { return 104; }   // 102: icpf_icp_ex_f32, icpf_peer_push_f32, icpf_expand_rows_f32; 103: icpf_dbscan_f32
 
 const char* icpf_error_string(int code) {
     switch (code) {
@@ -223,6 +223,44 @@ int icpf_sanity_check_f32(const int32_t* src_offsets, const float* src_stats, in
     return launch_sanity_check(src_offsets, src_stats, n_src_labels, dst_offsets, dst_stats, n_dst_labels, pairs, P,
                                min_cluster_size, (float)translation_frame, (float)thres_box, out_keep, out_pairs,
                                out_count, static_cast<cudaStream_t>(stream));
+}
+
+int icpf_sanity_check_cross_f32(const int32_t* src_offsets, const float* src_stats, int32_t n_src_labels,
+                                const int32_t* dst_offsets, const float* dst_stats, int32_t n_dst_labels,
+                                const int64_t* lists, int32_t n_src_list, int32_t n_dst_list, int32_t min_cluster_size,
+                                double translation_frame, double thres_box, int64_t* out_pairs, int32_t* out_count,
+                                void* stream) {
+    if (n_src_list < 0 || n_dst_list < 0 || n_src_labels < 1 || n_dst_labels < 1) return ICPF_E_SHAPE;
+    if ((long long)n_src_list * n_dst_list > 0x7fffffffLL) return ICPF_E_SHAPE;
+    if (!src_offsets || !src_stats || !dst_offsets || !dst_stats || !out_count) return ICPF_E_NULL;
+    const int P = n_src_list * n_dst_list;
+    if (P > 0 && (!lists || !out_pairs)) return ICPF_E_NULL;
+    return launch_sanity_check(src_offsets, src_stats, n_src_labels, dst_offsets, dst_stats, n_dst_labels, lists, P,
+                               min_cluster_size, (float)translation_frame, (float)thres_box, nullptr, out_pairs,
+                               out_count, static_cast<cudaStream_t>(stream), n_dst_list > 0 ? n_dst_list : 1);
+}
+
+size_t icpf_match_select_workspace_bytes(int32_t n_src, int32_t n_dst) {
+    if (n_src < 0 || n_dst < 0) return 0;
+    return match_select_workspace_bytes(n_src, n_dst);
+}
+
+int icpf_match_select_f32(const int64_t* pairs, int32_t P, const int64_t* src_labels, int32_t n_src,
+                          const int64_t* dst_labels, int32_t n_dst, const float* errors, const float* inliers,
+                          const float* ratios, const float* ious, const int32_t* accept, const float* transforms,
+                          double thres_error, float* out_rows, float* out_transforms, int64_t* out_src_left,
+                          int64_t* out_dst_left, int32_t* out_counts, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+    if (P < 0 || n_src < 0 || n_dst < 0) return ICPF_E_SHAPE;
+    if (!out_counts) return ICPF_E_NULL;
+    if (P > 0 && (!pairs || !errors || !inliers || !ratios || !ious || !accept || !transforms)) return ICPF_E_NULL;
+    if (n_src > 0 && (!src_labels || !out_rows || !out_transforms || !out_src_left)) return ICPF_E_NULL;
+    if (n_dst > 0 && (!dst_labels || !out_dst_left)) return ICPF_E_NULL;
+    if (workspace == nullptr || workspace_bytes < match_select_workspace_bytes(n_src, n_dst)) return ICPF_E_WORKSPACE;
+    if ((reinterpret_cast<uintptr_t>(workspace) & 7u) != 0) return ICPF_E_ALIGN;
+    return launch_match_select(pairs, P, src_labels, n_src, dst_labels, n_dst, errors, inliers, ratios, ious, accept,
+                               transforms, (float)thres_error, out_rows, out_transforms, out_src_left, out_dst_left,
+                               out_counts, workspace, static_cast<cudaStream_t>(stream));
 }
 
 int icpf_gather_pairs_f32(const float* src_points, int32_t src_stride, const int32_t* src_order,

@@ -98,7 +98,13 @@ int launch_cluster_index(const float* points, int stride, const float* labels, i
 int launch_sanity_check(const int* src_offsets, const float* src_stats, int n_src, const int* dst_offsets,
                         const float* dst_stats, int n_dst, const int64_t* pairs, int P, int min_cluster_size,
                         float translation_frame, float thres_box, int* out_keep, int64_t* out_pairs, int* out_count,
-                        cudaStream_t stream);
+                        cudaStream_t stream, int cross_nd = 0);
+size_t match_select_workspace_bytes(int ns, int nd);
+int launch_match_select(const int64_t* pairs, int P, const int64_t* src_unq, int ns, const int64_t* dst_unq, int nd,
+                        const float* errors, const float* inliers, const float* ratios, const float* ious,
+                        const int* accept, const float* transforms, float thres_error, float* out_rows,
+                        float* out_transforms, int64_t* out_src_left, int64_t* out_dst_left, int* out_counts,
+                        void* workspace, cudaStream_t stream);
 int launch_gather_pairs(const float* src_points, int src_stride, const int* src_order, const int* src_offsets, int n_src,
                         const float* dst_points, int dst_stride, const int* dst_order, const int* dst_offsets, int n_dst,
                         const int64_t* pairs, int P, int max_points, const int* sample_rows,

@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(1024)
 sanity_check_kernel(const int* __restrict__ src_offsets, const float* __restrict__ src_stats, int n_src,
                     const int* __restrict__ dst_offsets, const float* __restrict__ dst_stats, int n_dst,
                     const long long* __restrict__ pairs, int P, SanityGates g, int* __restrict__ out_keep,
-                    long long* __restrict__ out_pairs, int* __restrict__ out_count) {
+                    long long* __restrict__ out_pairs, int* __restrict__ out_count, int cross_nd) {
     __shared__ int wsum[32];
     __shared__ int running;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -223,8 +223,14 @@ sanity_check_kernel(const int* __restrict__ src_offsets, const float* __restrict
         bool keep = false;
         long long ls = 0, ld = 0;
         if (p < P) {
-            ls = pairs[2 * p];
-            ld = pairs[2 * p + 1];
+            if (cross_nd > 0) {
+                // all-against-all of two label lists (utils_match.py:48-50): `pairs` = [src list | dst list], src-major
+                ls = pairs[p / cross_nd];
+                ld = pairs[P / cross_nd + p % cross_nd];
+            } else {
+                ls = pairs[2 * p];
+                ld = pairs[2 * p + 1];
+            }
             const int a = pair_slot(ls, n_src), b = pair_slot(ld, n_dst);
             if (a >= 0 && b >= 0) {          // `min(pair) < 0: continue`; a label without points has length 0
                 const int na = src_offsets[a + 1] - src_offsets[a], nb = dst_offsets[b + 1] - dst_offsets[b];
@@ -241,7 +247,7 @@ sanity_check_kernel(const int* __restrict__ src_offsets, const float* __restrict
                     keep = keep && !(lo < __fmul_rn(g.thres_box, hi));
                 }
             }
-            out_keep[p] = keep ? 1 : 0;
+            if (out_keep != nullptr) out_keep[p] = keep ? 1 : 0;
         }
         const unsigned int vote = __ballot_sync(0xffffffffu, keep);
         const int rank = __popc(vote & ((1u << lane) - 1u));
@@ -405,11 +411,157 @@ int launch_cluster_index(const float* points, int stride, const float* labels, i
 int launch_sanity_check(const int* src_offsets, const float* src_stats, int n_src, const int* dst_offsets,
                         const float* dst_stats, int n_dst, const int64_t* pairs, int P, int min_cluster_size,
                         float translation_frame, float thres_box, int* out_keep, int64_t* out_pairs, int* out_count,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, int cross_nd) {
     SanityGates g{min_cluster_size, translation_frame, thres_box};
     ICPF_LAUNCH(sanity_check_kernel, 1, 1024, 0, stream)(src_offsets, src_stats, n_src, dst_offsets, dst_stats, n_dst,
                                                 reinterpret_cast<const long long*>(pairs), P, g, out_keep,
-                                                reinterpret_cast<long long*>(out_pairs), out_count);
+                                                reinterpret_cast<long long*>(out_pairs), out_count, cross_nd);
+    return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------- selection (row f1)
+// The rejection loop and selection of match_pairs (utils_match.py:70-75, 94-135) in one launch: the reference scatters
+// the accepted registrations into [n_src, n_dst] matrices pair by pair, takes per src cluster the dst cluster of least
+// min(error) (match_segments_descend: first minimum along the dst axis) and keeps it if that error is below
+// thres_error.  Here: a 64-bit atomicMin per src cluster on (ordered error bits, dst index), the winning pair recovered
+// by a second pass, an ordered compaction over the src clusters -- and the labels that stay unmatched on either side,
+// which are the dynamic stage's candidates (utils_match.py:43-47).  One CTA; the work is P + n_src + n_dst items.
+struct SelectArgs {
+    const long long* pairs;      // [P,2]
+    int P;
+    const long long* src_unq;    // [ns] sorted
+    int ns;
+    const long long* dst_unq;    // [nd] sorted
+    int nd;
+    const float* errors;         // [P,2]
+    const float* inliers;
+    const float* ratios;
+    const float* ious;
+    const int* accept;           // [P]
+    const float* transforms;     // [P,16]
+    float thres_error;
+    float* out_rows;             // [ns,10]
+    float* out_transforms;       // [ns,16]
+    long long* out_src_left;     // [ns]
+    long long* out_dst_left;     // [nd]
+    int* out_counts;             // [3] rows, src labels left, dst labels left
+    unsigned long long* best;    // [ns]  workspace
+    int* winner;                 // [ns]
+    int* dst_used;               // [nd]
+};
+
+__device__ __forceinline__ int find_label(const long long* __restrict__ sorted, int n, long long v) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (sorted[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return (lo < n && sorted[lo] == v) ? lo : -1;
+}
+
+// torch `errors.min(-1)`: NaN if either entry is NaN
+__device__ __forceinline__ float pair_min_error(const float* __restrict__ errors, int p) {
+    const float e0 = errors[2 * p], e1 = errors[2 * p + 1];
+    return (e0 != e0 || e1 != e1) ? __int_as_float(0x7fc00000) : fminf(e0, e1);
+}
+
+// order-preserving bits of a float; NaN sorts first (torch.argmin returns the position of a NaN)
+__device__ __forceinline__ unsigned int error_key(float e) {
+    if (e != e) return 0u;
+    const unsigned int u = __float_as_uint(e);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// ordered compaction step shared by the three output lists: returns the rank of this thread's item among the kept
+// items of the whole block (items before `base` counted in `running`), or -1
+__device__ __forceinline__ int block_rank(bool keep, int* wsum, int* running) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned int vote = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) wsum[warp] = __popc(vote);
+    __syncthreads();
+    int before = *running;
+    for (int w = 0; w < warp; ++w) before += wsum[w];
+    const int rank = before + __popc(vote & ((1u << lane) - 1u));
+    __syncthreads();
+    if (tid == 1023) *running = before + __popc(vote);
+    __syncthreads();
+    return keep ? rank : -1;
+}
+
+__global__ void __launch_bounds__(1024) match_select_kernel(SelectArgs a) {
+    __shared__ int wsum[32];
+    __shared__ int running;
+    const int tid = threadIdx.x;
+    for (int s = tid; s < a.ns; s += 1024) { a.best[s] = ~0ull; a.winner[s] = -1; }
+    for (int d = tid; d < a.nd; d += 1024) a.dst_used[d] = 0;
+    __syncthreads();
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int p = tid; p < a.P; p += 1024) {
+            if (a.accept[p] == 0) continue;
+            const int si = find_label(a.src_unq, a.ns, a.pairs[2 * p]), di = find_label(a.dst_unq, a.nd, a.pairs[2 * p + 1]);
+            if (si < 0 || di < 0) continue;
+            const unsigned long long key = ((unsigned long long)error_key(pair_min_error(a.errors, p)) << 32) | (unsigned int)di;
+            if (pass == 0) atomicMin(&a.best[si], key);
+            else if (key == a.best[si]) atomicMax(&a.winner[si], p);        // (a repeated pair: the last one stands)
+        }
+        __syncthreads();
+    }
+    // rows in src-cluster order
+    if (tid == 0) running = 0;
+    __syncthreads();
+    for (int base = 0; base < a.ns; base += 1024) {
+        const int s = base + tid;
+        int w = -1;
+        if (s < a.ns) {
+            w = a.winner[s];
+            if (w >= 0 && !(pair_min_error(a.errors, w) < a.thres_error)) w = -1;
+            a.winner[s] = w;
+        }
+        const int k = block_rank(w >= 0, wsum, &running);
+        if (k >= 0) {
+            const int di = (int)(a.best[s] & 0xffffffffull);
+            float* r = a.out_rows + (size_t)k * 10;
+            r[0] = (float)a.src_unq[s];
+            r[1] = (float)a.dst_unq[di];
+            r[2] = a.errors[2 * w]; r[3] = a.errors[2 * w + 1];
+            r[4] = a.inliers[2 * w]; r[5] = a.inliers[2 * w + 1];
+            r[6] = a.ratios[2 * w]; r[7] = a.ratios[2 * w + 1];
+            r[8] = a.ious[2 * w]; r[9] = a.ious[2 * w + 1];
+            for (int i = 0; i < 16; ++i) a.out_transforms[(size_t)k * 16 + i] = a.transforms[(size_t)w * 16 + i];
+            a.dst_used[di] = 1;
+        }
+    }
+    if (tid == 0) { a.out_counts[0] = running; running = 0; }
+    __syncthreads();
+    for (int base = 0; base < a.ns; base += 1024) {
+        const int s = base + tid;
+        const int k = block_rank(s < a.ns && a.winner[s] < 0, wsum, &running);
+        if (k >= 0) a.out_src_left[k] = a.src_unq[s];
+    }
+    if (tid == 0) { a.out_counts[1] = running; running = 0; }
+    __syncthreads();
+    for (int base = 0; base < a.nd; base += 1024) {
+        const int d = base + tid;
+        const int k = block_rank(d < a.nd && a.dst_used[d] == 0, wsum, &running);
+        if (k >= 0) a.out_dst_left[k] = a.dst_unq[d];
+    }
+    if (tid == 0) a.out_counts[2] = running;
+}
+
+size_t match_select_workspace_bytes(int ns, int nd) { return (size_t)ns * 12 + (size_t)nd * 4 + 64; }
+
+int launch_match_select(const int64_t* pairs, int P, const int64_t* src_unq, int ns, const int64_t* dst_unq, int nd,
+                        const float* errors, const float* inliers, const float* ratios, const float* ious,
+                        const int* accept, const float* transforms, float thres_error, float* out_rows,
+                        float* out_transforms, int64_t* out_src_left, int64_t* out_dst_left, int* out_counts,
+                        void* workspace, cudaStream_t stream) {
+    unsigned char* w = static_cast<unsigned char*>(workspace);
+    SelectArgs a{reinterpret_cast<const long long*>(pairs), P, reinterpret_cast<const long long*>(src_unq), ns,
+                 reinterpret_cast<const long long*>(dst_unq), nd, errors, inliers, ratios, ious, accept, transforms,
+                 thres_error, out_rows, out_transforms, reinterpret_cast<long long*>(out_src_left),
+                 reinterpret_cast<long long*>(out_dst_left), out_counts, reinterpret_cast<unsigned long long*>(w),
+                 reinterpret_cast<int*>(w + (size_t)ns * 8), reinterpret_cast<int*>(w + (size_t)ns * 12)};
+    ICPF_LAUNCH(match_select_kernel, 1, 1024, 0, stream)(a);
     return (int)cudaGetLastError();
 }
 

@@ -475,31 +475,38 @@ def match_eval(args, pcd1, pcd2, transformations, return_accept: bool = False):
     return errors, inliers, ratios, ious, translations, rotations
 
 
-def match_select(args, pairs, src_labels_unq, dst_labels_unq, evals, accept, transformations):
-    """The rejection loop and selection of match_pairs (utils_match.py:70-75, 94-135) without the per-pair Python loop:
-    accepted registrations are scattered into the ``[n_src, n_dst]`` matrices in one indexed store each, every src cluster
-    keeps its least-error dst cluster (``match_segments_descend``) if ``min(error) < thres_error``.  Device tensors in,
-    device tensors out; the only host sync is the data-dependent output length."""
-    errors, inliers, ratios, ious = evals[0:4]
+def match_select(args, pairs, src_labels_unq, dst_labels_unq, evals, accept, transformations, return_left: bool = False):
+    """The rejection loop and selection of match_pairs (utils_match.py:70-75, 94-135) as ONE launch
+    (``icpf_match_select_f32``): per src cluster, among its accepted registrations, the dst cluster of least min(error)
+    (``match_segments_descend`` on the reference's ``[n_src, n_dst]`` matrix), kept if that error < ``thres_error``.
+    Returns ``(rows [K,10], transformations [K,4,4])`` in src-label order; with ``return_left`` also the sorted src / dst
+    labels that stay unmatched (the candidates of match_pcds' dynamic stage).  Device tensors in, device tensors out; the
+    one host sync is the read of the three data-dependent output lengths."""
+    errors, inliers, ratios, ious = (_require_cuda_f32(x, "evals").contiguous() for x in evals[0:4])
     dev = errors.device
-    ns, nd = len(src_labels_unq), len(dst_labels_unq)
-    pairs = pairs.to(dev)
-    si = torch.searchsorted(src_labels_unq.contiguous(), pairs[:, 0].to(src_labels_unq.dtype).contiguous())
-    di = torch.searchsorted(dst_labels_unq.contiguous(), pairs[:, 1].to(dst_labels_unq.dtype).contiguous())
-    si = torch.where(accept.to(dev).bool(), si, torch.full_like(si, ns))     # rejected pairs land in a spare row
-    m_err = torch.full((ns + 1, nd, 2), 1e8, device=dev)
-    m_inl, m_rat, m_iou = (torch.zeros((ns + 1, nd, 2), device=dev) for _ in range(3))
-    m_T = torch.zeros((ns + 1, nd, 4, 4), device=dev)
-    m_err[si, di], m_inl[si, di], m_rat[si, di], m_iou[si, di] = errors, inliers, ratios, ious
-    m_T[si, di] = transformations
-    e_min = m_err[:ns].min(-1)[0]
-    rows_i = torch.arange(ns, device=dev)
-    cols_i = torch.argmin(e_min, dim=1)
-    ok = e_min[rows_i, cols_i] < args.thres_error      # an all-rejected row holds 1e8 and drops out here
-    rows_i, cols_i = rows_i[ok], cols_i[ok]
-    rows = torch.cat([src_labels_unq[rows_i][:, None].float(), dst_labels_unq[cols_i][:, None].float(),
-                      m_err[rows_i, cols_i], m_inl[rows_i, cols_i], m_rat[rows_i, cols_i], m_iou[rows_i, cols_i]], dim=1)
-    return rows, m_T[rows_i, cols_i]
+    P = int(errors.shape[0])
+    ns, nd = int(len(src_labels_unq)), int(len(dst_labels_unq))
+    p64 = pairs.to(device=dev, dtype=torch.int64).contiguous()
+    su = src_labels_unq.to(device=dev, dtype=torch.int64).contiguous()
+    du = dst_labels_unq.to(device=dev, dtype=torch.int64).contiguous()
+    acc = accept.to(device=dev, dtype=torch.int32).contiguous()
+    T = _require_cuda_f32(transformations, "transformations").contiguous()
+    rows = torch.empty(max(ns, 1), 10, device=dev, dtype=torch.float32)
+    T_out = torch.empty(max(ns, 1), 4, 4, device=dev, dtype=torch.float32)
+    src_left = torch.empty(max(ns, 1), device=dev, dtype=torch.int64)
+    dst_left = torch.empty(max(nd, 1), device=dev, dtype=torch.int64)
+    counts = torch.empty(3, device=dev, dtype=torch.int32)
+    L = _lib.lib()
+    ws = torch.empty(int(L.icpf_match_select_workspace_bytes(ns, nd)) // 8 + 1, device=dev, dtype=torch.int64)
+    with torch.cuda.device(dev):
+        code = L.icpf_match_select_f32(_ptr(p64), P, _ptr(su), ns, _ptr(du), nd, _ptr(errors), _ptr(inliers), _ptr(ratios),
+                                       _ptr(ious), _ptr(acc), _ptr(T), float(args.thres_error), _ptr(rows), _ptr(T_out),
+                                       _ptr(src_left), _ptr(dst_left), _ptr(counts), _ptr(ws), ws.numel() * 8, _stream_ptr())
+    _lib.check(code, "icpf_match_select_f32")
+    k, n_sl, n_dl = (int(v) for v in counts.cpu().tolist())        # data-dependent output lengths: the one host sync
+    if return_left:
+        return rows[:k], T_out[:k], src_left[:n_sl], dst_left[:n_dl]
+    return rows[:k], T_out[:k]
 
 
 def expand_rows(rows: torch.Tensor, offsets: torch.Tensor, max_points: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -209,11 +209,29 @@ def batch_rows(si: ScanIndex, di: ScanIndex, pairs: torch.Tensor, max_points: in
     return min(max_points, (top + PAD_QUANTUM - 1) // PAD_QUANTUM * PAD_QUANTUM)
 
 
-def _match_pairs_indexed(args, si: ScanIndex, di: ScanIndex, pairs, src_unq, dst_unq):
+def sanity_check_cross(args, si: ScanIndex, di: ScanIndex, src_list: torch.Tensor, dst_list: torch.Tensor) -> torch.Tensor:
+    """``sanity_check`` over every pair of two label lists (the dynamic stage, utils_match.py:43-51), src-major like the
+    reference's repeat_interleave / repeat enumeration, without materialising the candidates: kept pairs ``[K,2]`` int64."""
+    dev = si.points.device
+    n_s, n_d = int(len(src_list)), int(len(dst_list))
+    out = torch.empty(max(n_s * n_d, 1), 2, device=dev, dtype=torch.int64)
+    count = torch.zeros(1, device=dev, dtype=torch.int32)
+    lists = torch.cat([src_list.to(device=dev, dtype=torch.int64), dst_list.to(device=dev, dtype=torch.int64)]).contiguous()
+    with torch.cuda.device(dev):
+        code = _lib.lib().icpf_sanity_check_cross_f32(_ptr(si.offsets), _ptr(si.stats), si.n_labels, _ptr(di.offsets),
+                                                      _ptr(di.stats), di.n_labels, _ptr(lists), n_s, n_d,
+                                                      int(args.min_cluster_size), float(args.translation_frame),
+                                                      float(args.thres_box), _ptr(out), _ptr(count), _stream_ptr())
+    _lib.check(code, "icpf_sanity_check_cross_f32")
+    return out[:int(count.item())]
+
+
+def _match_pairs_indexed(args, si: ScanIndex, di: ScanIndex, pairs, src_unq, dst_unq, return_left: bool = False):
     segs_src, segs_dst = pad_pairs(si, di, pairs, batch_rows(si, di, pairs, args.max_points))
     transformations = hist_icp(args, segs_src, segs_dst)
     *evals, accept = match_eval(args, segs_src, segs_dst, transformations, return_accept=True)
-    return match_select(args, _pairs_i64(pairs, si.points.device), src_unq, dst_unq, evals, accept, transformations)
+    return match_select(args, _pairs_i64(pairs, si.points.device), src_unq, dst_unq, evals, accept, transformations,
+                        return_left=return_left)
 
 
 def match_pairs(args, src_points, dst_points, src_labels, dst_labels, pairs):
@@ -239,20 +257,22 @@ def match_pcds(args, src_points, dst_points, src_labels, dst_labels):
     empty = (torch.zeros(0, 10, device=dev), torch.zeros(0, 4, 4, device=dev))
 
     # stage 1 (utils_match.py:32-41): overlapped clusters keep their label
-    both = torch.unique(torch.cat([src_unq, dst_unq]))
+    # (torch.unique(torch.cat([src_unq, dst_unq])) through the two presence tables: no device sort)
+    n_both = max(si.n_labels, di.n_labels)
+    present = torch.zeros(n_both, device=dev, dtype=torch.bool)
+    present[:si.n_labels] |= si.counts > 0
+    present[:di.n_labels] |= di.counts > 0
+    both = torch.nonzero(present).flatten()
     pairs_true, _ = sanity_check_indexed(args, si, di, torch.stack([both, both], dim=1))
-    rows_sta, T_sta = _match_pairs_indexed(args, si, di, pairs_true, src_unq, dst_unq) if len(pairs_true) > 0 else empty
+    if len(pairs_true) > 0:
+        rows_sta, T_sta, src_left, dst_left = _match_pairs_indexed(args, si, di, pairs_true, src_unq, dst_unq, return_left=True)
+    else:
+        (rows_sta, T_sta), src_left, dst_left = empty, src_unq, dst_unq
 
     # stage 2 (utils_match.py:43-57): what is left, all against all
-    if len(rows_sta) > 0:
-        src_left = src_unq[~torch.isin(src_unq, rows_sta[:, 0].long())]
-        dst_left = dst_unq[~torch.isin(dst_unq, rows_sta[:, 1].long())]
-    else:
-        src_left, dst_left = src_unq, dst_unq
     rows_dyn, T_dyn = empty
     if len(src_left) > 0 and len(dst_left) > 0:
-        cand = torch.stack([src_left.repeat_interleave(len(dst_left)), dst_left.repeat(len(src_left))], dim=1)
-        pairs_true, _ = sanity_check_indexed(args, si, di, cand)
+        pairs_true = sanity_check_cross(args, si, di, src_left, dst_left)
         if len(pairs_true) > 0:
             rows_dyn, T_dyn = _match_pairs_indexed(args, si, di, pairs_true, src_left, dst_left)
     return torch.cat([rows_sta, rows_dyn], dim=0), torch.cat([T_sta, T_dyn], dim=0)

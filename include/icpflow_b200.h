@@ -233,6 +233,41 @@ int icpf_sanity_check_f32(const int32_t* src_offsets, const float* src_stats, in
                           double thres_box, int32_t* out_keep, int64_t* out_pairs, int32_t* out_count, void* stream);
 
 /*
+ * The same filter over ALL pairs of two label lists -- the dynamic stage of match_pcds (utils_match.py:43-51: every
+ * unmatched src cluster against every unmatched dst cluster; the reference materialises the cross product with
+ * repeat_interleave / repeat / stack) without building the candidate tensor.
+ *   lists [n_src_list + n_dst_list] int64: the src labels followed by the dst labels; candidate q is
+ *   (lists[q / n_dst_list], lists[n_src_list + q % n_dst_list]), i.e. src-major like the reference
+ *   out_pairs [n_src_list * n_dst_list, 2] int64 (kept pairs in that order), out_count [1] int32
+ */
+int icpf_sanity_check_cross_f32(const int32_t* src_offsets, const float* src_stats, int32_t n_src_labels,
+                                const int32_t* dst_offsets, const float* dst_stats, int32_t n_dst_labels,
+                                const int64_t* lists, int32_t n_src_list, int32_t n_dst_list, int32_t min_cluster_size,
+                                double translation_frame, double thres_box, int64_t* out_pairs, int32_t* out_count,
+                                void* stream);
+
+/*
+ * Selection -- replaces the rejection loop and the selection of match_pairs (utils_match.py:70-75, 94-135: a Python loop
+ * over the pairs with two torch.nonzero calls and five scattered stores each, then match_segments_descend) by one launch.
+ *   pairs [P,2] int64; src_labels [n_src] / dst_labels [n_dst] int64, SORTED (torch.unique of the scan labels)
+ *   errors, inliers, ratios, ious [P,2] fp32 and accept [P] int32 as written by icpf_match_eval_f32; transforms [P,16]
+ *   Per src label: among its accepted pairs the dst label of least min(error) (ties: lowest dst position, as argmin
+ *   over the reference's [n_src, n_dst] matrix; a NaN error wins the arg-min and then fails the threshold, as in torch),
+ *   kept if that error < thres_error.
+ *   out_rows [n_src,10] fp32: (src label, dst label, error x2, inliers x2, ratios x2, ious x2) of the kept matches in
+ *   src-label order; out_transforms [n_src,16]; out_src_left [n_src] / out_dst_left [n_dst] int64: the labels without a
+ *   kept match, sorted (the candidates of the dynamic stage); out_counts [3] int32: rows, src labels left, dst labels left.
+ *   workspace: icpf_match_select_workspace_bytes(n_src, n_dst) bytes, 8-byte aligned.
+ */
+size_t icpf_match_select_workspace_bytes(int32_t n_src, int32_t n_dst);
+int icpf_match_select_f32(const int64_t* pairs, int32_t P, const int64_t* src_labels, int32_t n_src,
+                          const int64_t* dst_labels, int32_t n_dst, const float* errors, const float* inliers,
+                          const float* ratios, const float* ious, const int32_t* accept, const float* transforms,
+                          double thres_error, float* out_rows, float* out_transforms, int64_t* out_src_left,
+                          int64_t* out_dst_left, int32_t* out_counts, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+/*
  * Padded pair batch -- replaces the gather loop of match_pairs (utils_match.py:81-91) and pad_segment
  * (utils_helper.py:185-196): out_src / out_dst [P, max_points, 4] rows (x, y, z, 1) in scan order, then
  * (1e8, 1e8, 1e8, 0).  Clusters with more than max_points rows: the reference keeps torch.randperm(len)[:max_points];

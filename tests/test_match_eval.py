@@ -154,10 +154,12 @@ def test_oracle_match_pairs_bitwise(golden, name):
     assert np.array_equal(rows.numpy(), g["mp_rows"]) and np.array_equal(T.numpy(), g["mp_T"])
 
 
+@pytest.mark.usefixtures("engine")
 @pytest.mark.parametrize("name", ["c1_demo.npz", "synth_match_dyn.npz"])
-def test_host_match_select_equals_oracle_loop(golden, name):
-    """The vectorised scatter/arg-min of icp_flow_b200.ops.match_select (host logic, runs on any device) reproduces the
-    reference's per-pair loop bit for bit when fed the same metrics."""
+def test_match_select_equals_oracle_loop(golden, name):
+    """icpf_match_select_f32 (one launch: 64-bit atomic arg-min per src cluster + ordered compaction) reproduces the
+    reference's per-pair scatter loop and match_segments_descend bit for bit when fed the same metrics, and its unmatched
+    label lists are what match_pcds derives with isin (utils_match.py:43-47)."""
     from icp_flow_b200 import ops
     g, sp, sl, dp, dl, pairs = _mp_inputs(golden, name)
     p, gates = _params(g), _gates(g)
@@ -168,11 +170,42 @@ def test_host_match_select_equals_oracle_loop(golden, name):
                           dtype=torch.int32)
     assert 0 < int(accept.sum()) < len(pairs) or name == "c1_demo.npz"
     args = types.SimpleNamespace(thres_error=gates.thres_error)
-    rows2, T2 = ops.match_select(args, tens[4], torch.unique(tens[2]), torch.unique(tens[3]), ev, accept, dbg["T"])
-    assert np.array_equal(rows2.numpy(), rows.numpy()) and np.array_equal(T2.numpy(), T.numpy())
-    # nothing accepted -> empty [0,10] / [0,4,4] like the reference's else-branch
-    rows0, T0 = ops.match_select(args, tens[4], torch.unique(tens[2]), torch.unique(tens[3]), ev, accept * 0, dbg["T"])
-    assert rows0.shape == (0, 10) and T0.shape == (0, 4, 4)
+    su, du = torch.unique(tens[2]).long(), torch.unique(tens[3]).long()
+    dev_ev = [put(x.contiguous()) for x in ev[0:4]]
+    rows2, T2, s_left, d_left = ops.match_select(args, put(tens[4]), put(su), put(du), dev_ev, put(accept), put(dbg["T"]),
+                                                 return_left=True)
+    assert np.array_equal(rows2.cpu().numpy(), rows.numpy()) and np.array_equal(T2.cpu().numpy(), T.numpy())
+    assert torch.equal(s_left.cpu(), su[~torch.isin(su, rows[:, 0].long())])
+    assert torch.equal(d_left.cpu(), du[~torch.isin(du, rows[:, 1].long())])
+    # nothing accepted -> empty [0,10] / [0,4,4] like the reference's else-branch, every label left
+    rows0, T0, s0, d0 = ops.match_select(args, put(tens[4]), put(su), put(du), dev_ev, put(accept * 0), put(dbg["T"]),
+                                         return_left=True)
+    assert rows0.shape == (0, 10) and T0.shape == (0, 4, 4) and torch.equal(s0.cpu(), su) and torch.equal(d0.cpu(), du)
+
+
+@pytest.mark.usefixtures("engine")
+def test_match_select_ties_nan_and_threshold():
+    """Arg-min semantics of the reference's matrices: equal errors -> the lowest dst position; a NaN error wins the arg-min
+    (torch) and then fails the threshold, dropping its src cluster; rejected pairs and errors at the threshold are out."""
+    from icp_flow_b200 import ops
+    su, du = torch.tensor([3, 5, 9, 12]), torch.tensor([1, 4, 7])
+    pairs = torch.tensor([[3, 7], [3, 4], [5, 1], [5, 4], [9, 1], [9, 7], [12, 4], [12, 1]])
+    err = torch.tensor([[0.05, 0.09], [0.07, 0.05], [float("nan"), 0.01], [0.02, 0.03], [0.2, 0.5], [0.01, 0.3], [0.04, 0.04],
+                        [0.03, 0.5]])
+    accept = torch.tensor([1, 1, 1, 1, 1, 0, 1, 1], dtype=torch.int32)
+    other = [torch.arange(16, dtype=torch.float32).reshape(8, 2) + k for k in (100, 200, 300)]
+    T = torch.arange(8 * 16, dtype=torch.float32).reshape(8, 4, 4)
+    args = types.SimpleNamespace(thres_error=0.2)
+    rows, Tm, s_left, d_left = ops.match_select(args, put(pairs), put(su), put(du), [put(err)] + [put(x) for x in other],
+                                                put(accept), put(T), return_left=True)
+    rows, Tm = rows.cpu(), Tm.cpu()
+    # 3: both pairs have min 0.05 -> dst 4 (position 1) before dst 7 (position 2);  5: NaN row dropped;
+    # 9: its accepted pair has min error 0.2 (not < 0.2), the better one is rejected;  12: dst 1 (0.03) beats dst 4 (0.04)
+    assert rows[:, 0].tolist() == [3.0, 12.0] and rows[:, 1].tolist() == [4.0, 1.0]
+    assert torch.equal(rows[0, 2:4], err[1]) and torch.equal(rows[1, 2:4], err[7])
+    assert torch.equal(rows[0, 4:6], other[0][1]) and torch.equal(rows[1, 8:10], other[2][7])
+    assert torch.equal(Tm[0], T[1]) and torch.equal(Tm[1], T[7])
+    assert s_left.cpu().tolist() == [5, 9] and d_left.cpu().tolist() == [7]
 
 
 @pytest.mark.usefixtures("engine")
