@@ -43,7 +43,8 @@ cluster_totals_kernel(const int* __restrict__ blockhist, int n_blocks, int n_lab
     const int l = blockIdx.x * kScanThreads + threadIdx.x;
     if (l >= n_labels) return;
     int t = 0;
-    for (int b = 0; b < n_blocks; ++b) t += blockhist[(size_t)b * n_labels + l];
+#pragma unroll 8
+    for (int b = 0; b < n_blocks; ++b) t += blockhist[(size_t)b * n_labels + l];       // (independent loads, batched by the unroll)
     offsets[l] = t;
 }
 
@@ -81,11 +82,18 @@ cluster_bases_kernel(int* __restrict__ blockhist, int n_blocks, int n_labels, co
     const int l = blockIdx.x * kScanThreads + threadIdx.x;
     if (l >= n_labels) return;
     int off = offsets[l];
-    for (int b = 0; b < n_blocks; ++b) {
-        int* p = &blockhist[(size_t)b * n_labels + l];
-        const int v = *p;
-        *p = off;
-        off += v;
+    // eight loads in flight per step: one thread walks all blocks of its label, and a load-add-store chain per block was
+    // 293 dependent L2 round trips (73 us per scan on a 150 k-point frame)
+    constexpr int kBatch = 8;
+    for (int b0 = 0; b0 < n_blocks; b0 += kBatch) {
+        int v[kBatch];
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) v[k] = (b0 + k < n_blocks) ? blockhist[(size_t)(b0 + k) * n_labels + l] : 0;
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+            if (b0 + k < n_blocks) blockhist[(size_t)(b0 + k) * n_labels + l] = off;
+            off += v[k];
+        }
     }
 }
 

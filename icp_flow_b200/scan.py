@@ -65,6 +65,8 @@ class ScanIndex:
                                             ws.numel(), _stream_ptr())
         _lib.check(code, "icpf_cluster_index_f32")
         self._counts_host = None
+        self._present_mask = None
+        self._present = None
 
     @property
     def counts(self) -> torch.Tensor:
@@ -77,9 +79,18 @@ class ScanIndex:
             self._counts_host = self.counts.cpu().numpy()
         return self._counts_host
 
+    @property
+    def present_mask(self) -> torch.Tensor:
+        """[n_labels] bool: the label owns at least one point (cached)."""
+        if self._present_mask is None:
+            self._present_mask = self.counts > 0
+        return self._present_mask
+
     def present_labels(self) -> torch.Tensor:
         """Sorted int64 labels >= 0 that own at least one point (``torch.unique(labels)`` without the negative ones)."""
-        return torch.nonzero(self.counts > 0).flatten()
+        if self._present is None:
+            self._present = torch.nonzero(self.present_mask).flatten()
+        return self._present
 
 
 # (points, labels) -> ScanIndex, so that the reference's own call sequence (sanity_check, match_pairs, again for the
@@ -260,8 +271,8 @@ def match_pcds(args, src_points, dst_points, src_labels, dst_labels):
     # (torch.unique(torch.cat([src_unq, dst_unq])) through the two presence tables: no device sort)
     n_both = max(si.n_labels, di.n_labels)
     present = torch.zeros(n_both, device=dev, dtype=torch.bool)
-    present[:si.n_labels] |= si.counts > 0
-    present[:di.n_labels] |= di.counts > 0
+    present[:si.n_labels] |= si.present_mask
+    present[:di.n_labels] |= di.present_mask
     both = torch.nonzero(present).flatten()
     pairs_true, _ = sanity_check_indexed(args, si, di, torch.stack([both, both], dim=1))
     if len(pairs_true) > 0:
