@@ -206,6 +206,18 @@ def test_match_select_ties_nan_and_threshold():
     assert torch.equal(rows[0, 4:6], other[0][1]) and torch.equal(rows[1, 8:10], other[2][7])
     assert torch.equal(Tm[0], T[1]) and torch.equal(Tm[1], T[7])
     assert s_left.cpu().tolist() == [5, 9] and d_left.cpu().tolist() == [7]
+    # no pairs at all / no labels on one side: nothing selected, every label left
+    none = [put(torch.zeros(0, 2)) for _ in range(4)]
+    r0, T0, s0, d0 = ops.match_select(args, put(torch.zeros(0, 2, dtype=torch.int64)), put(su), put(du), none,
+                                      put(torch.zeros(0, dtype=torch.int32)), put(torch.zeros(0, 4, 4)), return_left=True)
+    assert r0.shape == (0, 10) and T0.shape == (0, 4, 4) and s0.cpu().tolist() == su.tolist() and d0.cpu().tolist() == du.tolist()
+    r1, T1, s1, d1 = ops.match_select(args, put(pairs), put(su[:0]), put(du), [put(err)] + [put(x) for x in other],
+                                      put(accept), put(T), return_left=True)
+    assert r1.shape == (0, 10) and len(s1) == 0 and d1.cpu().tolist() == du.tolist()
+    # a pair whose label is not in the lists is ignored (the reference's torch.nonzero finds no row for it)
+    r2, _ = ops.match_select(args, put(torch.tensor([[3, 7], [4, 4]])), put(su), put(du), [put(err[:2])] + [put(x[:2]) for x in other],
+                             put(accept[:2]), put(T[:2]))
+    assert r2.cpu()[:, 0:2].tolist() == [[3.0, 7.0]]
 
 
 @pytest.mark.usefixtures("engine")
