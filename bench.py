@@ -365,6 +365,26 @@ def time_secondary(dev):
                             "cpu_baseline": {"ms": cpu_s * 1e3, "kind": "port", "sample": "sklearn.cluster.DBSCAN (kd_tree) on the same points, one run"}}
     except Exception as exc:
         out["c4_dbscan"] = {"error": f"{type(exc).__name__}: {exc}"}
+    # ---- row f4, the clusterer the reference's scripts select (--if_hdbscan): HDBSCAN of the same non-ground points
+    try:
+        pts_h = nonground[:, :3].contiguous()
+        cluster.hdbscan_labels(pts_h[:2000], 30)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        got = cluster.hdbscan_labels(pts_h, 30)
+        torch.cuda.synchronize()
+        ms_h = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter()
+        want = CO.hdbscan_labels(pts_h.cpu().numpy(), 30)
+        cpu_s = time.perf_counter() - t0
+        out["c4_hdbscan"] = {"points": int(pts_h.shape[0]), "min_cluster_size": 30, "ms": ms_h,
+                             "clusters": int(want.max() + 1), "partition_equals_sklearn": bool(CO.same_partition(got, want)),
+                             "what": "core distances + Prim's spanning tree of the mutual-reachability graph on the GPU (one "
+                                     "cooperative launch), condensed tree / excess of mass on the host; wall clock",
+                             "cpu_baseline": {"ms": cpu_s * 1e3, "kind": "port",
+                                              "sample": "sklearn.cluster.HDBSCAN (kd_tree, one core) on the same points, one run"}}
+    except Exception as exc:
+        out["c4_hdbscan"] = {"error": f"{type(exc).__name__}: {exc}"}
 
     # ---- C5, one GPU's share (the 8-GPU line carries the sharded run itself)
     ms5, _ = time_c5_shard(dev)

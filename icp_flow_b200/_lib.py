@@ -20,6 +20,7 @@ EXPORTS = (
     "icpf_match_eval_f32",
     "icpf_cluster_index_workspace_bytes", "icpf_cluster_index_f32", "icpf_sanity_check_f32", "icpf_sanity_check_cross_f32",
     "icpf_match_select_workspace_bytes", "icpf_match_select_f32", "icpf_gather_pairs_f32",
+    "icpf_hdbscan_labels_host", "icpf_hdbscan_workspace_bytes", "icpf_hdbscan_mst_f32",
     "icpf_flow_f32", "icpf_dbscan_workspace_bytes", "icpf_dbscan_f32",
 )
 
@@ -144,6 +145,12 @@ def lib() -> ctypes.CDLL:
     L.icpf_match_select_f32.restype = ctypes.c_int
     L.icpf_match_select_f32.argtypes = [vp, i32, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, ctypes.c_double, vp, vp, vp, vp, vp,
                                         vp, ctypes.c_size_t, vp]
+    L.icpf_hdbscan_labels_host.restype = ctypes.c_int
+    L.icpf_hdbscan_labels_host.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+    L.icpf_hdbscan_workspace_bytes.restype = ctypes.c_size_t
+    L.icpf_hdbscan_workspace_bytes.argtypes = [i32]
+    L.icpf_hdbscan_mst_f32.restype = ctypes.c_int
+    L.icpf_hdbscan_mst_f32.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
     L.icpf_gather_pairs_f32.restype = ctypes.c_int
     L.icpf_gather_pairs_f32.argtypes = [vp, i32, vp, vp, i32, vp, i32, vp, vp, i32, vp, i32, i32, vp, vp, vp, vp, vp]
     L.icpf_flow_f32.restype = ctypes.c_int

@@ -10,7 +10,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 extern "C" {
 
-int icpf_version(void) { return 104; }   // 102: icpf_icp_ex_f32, icpf_peer_push_f32, icpf_expand_rows_f32; 103: icpf_dbscan_f32
+int icpf_version(void) { return 105; }   // 102: icpf_icp_ex_f32, icpf_peer_push_f32, icpf_expand_rows_f32; 103: icpf_dbscan_f32
 
 const char* icpf_error_string(int code) {
     switch (code) {
@@ -238,6 +238,30 @@ int icpf_sanity_check_cross_f32(const int32_t* src_offsets, const float* src_sta
     return launch_sanity_check(src_offsets, src_stats, n_src_labels, dst_offsets, dst_stats, n_dst_labels, lists, P,
                                min_cluster_size, (float)translation_frame, (float)thres_box, nullptr, out_pairs,
                                out_count, static_cast<cudaStream_t>(stream), n_dst_list > 0 ? n_dst_list : 1);
+}
+
+int icpf_hdbscan_labels_host(const int32_t* edge_a, const int32_t* edge_b, const double* edge_w, int32_t n_points,
+                             int32_t min_cluster_size, int32_t presorted, int32_t* out_labels) {
+    if (n_points < 0 || min_cluster_size < 2) return ICPF_E_PARAM;
+    if (n_points == 0) return ICPF_OK;
+    if (!out_labels || (n_points > 1 && (!edge_a || !edge_b || !edge_w))) return ICPF_E_NULL;
+    return hdbscan_labels_host(edge_a, edge_b, edge_w, n_points, min_cluster_size, presorted, out_labels);
+}
+
+size_t icpf_hdbscan_workspace_bytes(int32_t n_points) { return n_points > 0 ? hdbscan_workspace_bytes(n_points) : 0; }
+
+int icpf_hdbscan_mst_f32(const float* points, int32_t point_stride, int32_t n_points, int32_t min_samples,
+                         double* out_core, int32_t* out_edge_src, int32_t* out_edge_dst, double* out_edge_w,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+    if (n_points < 0 || point_stride < 3) return ICPF_E_SHAPE;
+    if (min_samples < 1) return ICPF_E_PARAM;
+    if (n_points == 0) return ICPF_OK;
+    if (!points || !out_core) return ICPF_E_NULL;
+    if (n_points > 1 && (!out_edge_src || !out_edge_dst || !out_edge_w)) return ICPF_E_NULL;
+    if (workspace == nullptr || workspace_bytes < hdbscan_workspace_bytes(n_points)) return ICPF_E_WORKSPACE;
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255u) != 0) return ICPF_E_ALIGN;
+    return launch_hdbscan_mst(points, point_stride, n_points, min_samples, out_core, out_edge_src, out_edge_dst,
+                              out_edge_w, workspace, static_cast<cudaStream_t>(stream));
 }
 
 size_t icpf_match_select_workspace_bytes(int32_t n_src, int32_t n_dst) {

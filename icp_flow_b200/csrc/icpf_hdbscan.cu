@@ -1,0 +1,493 @@
+// icpf_hdbscan.cu -- HDBSCAN over one scan (the clustering every script of the reference
+// selects: utils_cluster.cluster_hdbscan, /root/reference/utils_cluster.py:10-29, main.sh / demo.sh --if_hdbscan).
+//
+// The reference calls the `hdbscan` package (0.8.x, environment.yml; not vendored, not installable here) with
+// min_samples = None (-> min_cluster_size), alpha = 1, metric euclidean, cluster_selection_method 'eom',
+// approx_min_span_tree = True.  What is restated is the published algorithm (Campello, Moulavi, Sander 2013; McInnes,
+// Healy, Astels 2017) with an EXACT minimum spanning tree; the test oracle is scikit-learn's port of the same package
+// (sklearn.cluster.HDBSCAN, which is installed) -- parity with the reference's own dependency is therefore UNPINNED
+// and stated as such in DESIGN.md.
+//
+//   core distance      distance to the min_samples-th nearest point, the point itself included (fp64 on the fp32
+//                      coordinates: dx*dx + dy*dy + dz*dz in that order, sqrt -- what a kd-tree query returns)
+//   mutual reachability  max(core_a, core_b, d(a, b))
+//   MST                of the complete mutual-reachability graph; single-linkage dendrogram of its sorted edges
+//   condensed tree     a split whose two sides both hold >= min_cluster_size points makes two new clusters, a smaller
+//                      side falls out of its cluster; stability = sum over the points of (lambda_leave - lambda_birth),
+//                      lambda = 1 / distance; excess-of-mass selection, the root never selected; a point belongs to
+//                      the selected cluster it falls out of (or out of a descendant of), else noise.
+//
+// GPU: the two O(n^2) stages.  Core distances: every thread keeps the k smallest squared distances of its point (k
+// doubles per thread in shared memory) while all points stream through a shared-memory tile.  MST: Prim's algorithm
+// exactly as the oracle runs it (sklearn/cluster/_hdbscan/_linkage.pyx, mst_from_data_matrix: start at point 0, strict
+// `<` updates, the first minimum in index order joins) -- one launch per step, every thread relaxes one candidate
+// against the point that just joined and the blocks' arg-minima are folded at the start of the next launch.  The edge
+// sequence, not only the tree, is reproduced: equal weights are everywhere in a mutual-reachability graph (every
+// edge into a point of large core distance weighs that core distance), and which of them the dendrogram merges first
+// decides whether a small group falls out of a cluster or splits it, so a different MST order (Boruvka, a different
+// tie rule) changes a few labels per scan.  With the oracle's order, its arithmetic (fp64, dx*dx + dy*dy + dz*dz in
+// that order, no contraction) and its sort of the edges (numpy argsort, called by the host wrapper) the labels are
+// identical.  n - 1 launches of ~3 us: 0.15 s for 5*10^4 points, against minutes for the CPU library.
+// The O(n alpha(n)) bookkeeping on the n - 1 MST edges (union-find dendrogram, condensation, selection) runs on the
+// host, as it does in the reference.
+#include "icpf_internal.h"
+#include "icpf_common.cuh"
+
+#ifndef ICPF_SIMT_EMU
+#include <cooperative_groups.h>
+#endif
+#include <algorithm>
+#include <cmath>
+#include <limits>
+#include <numeric>
+#include <vector>
+
+namespace icpf {
+
+// ------------------------------------------------------------------------------------------------ host: MST -> labels
+namespace {
+
+struct HdbEdge {
+    double w;
+    int a, b;
+};
+
+struct UnionFind {
+    std::vector<int> parent;
+    explicit UnionFind(int n) : parent(n) { std::iota(parent.begin(), parent.end(), 0); }
+    int find(int x) {
+        int r = x;
+        while (parent[r] != r) r = parent[r];
+        while (parent[x] != r) { const int nx = parent[x]; parent[x] = r; x = nx; }
+        return r;
+    }
+};
+
+}  // namespace
+
+// labels[n]: clusters numbered by their lowest point index, -1 = noise
+int hdbscan_labels_host(const int* edge_a, const int* edge_b, const double* edge_w, int n, int min_cluster_size,
+                        int presorted, int* labels) {
+    if (n <= 0) return ICPF_OK;
+    for (int i = 0; i < n; ++i) labels[i] = -1;
+    if (n == 1) return ICPF_OK;
+    const int m = n - 1;
+    std::vector<HdbEdge> e(m);
+    for (int i = 0; i < m; ++i) {
+        if (edge_a[i] < 0 || edge_a[i] >= n || edge_b[i] < 0 || edge_b[i] >= n || !(edge_w[i] >= 0.0)) return ICPF_E_PARAM;
+        e[i] = HdbEdge{edge_w[i], std::min(edge_a[i], edge_b[i]), std::max(edge_a[i], edge_b[i])};
+        if (presorted && i > 0 && e[i].w < e[i - 1].w) return ICPF_E_PARAM;
+    }
+    if (!presorted) std::sort(e.begin(), e.end(), [](const HdbEdge& x, const HdbEdge& y) {
+        if (x.w != y.w) return x.w < y.w;
+        if (x.a != y.a) return x.a < y.a;
+        return x.b < y.b;
+    });
+    // single-linkage dendrogram: leaves 0 .. n-1, internal node n + i made by edge i
+    std::vector<int> left(m), right(m), size(m);
+    {
+        UnionFind uf(n);
+        std::vector<int> node_of(n);          // dendrogram node of a union-find root
+        std::vector<int> cnt(n, 1);
+        std::iota(node_of.begin(), node_of.end(), 0);
+        for (int i = 0; i < m; ++i) {
+            const int ra = uf.find(e[i].a), rb = uf.find(e[i].b);
+            if (ra == rb) return ICPF_E_PARAM;                      // not a spanning tree
+            left[i] = node_of[ra];
+            right[i] = node_of[rb];
+            size[i] = cnt[ra] + cnt[rb];
+            uf.parent[rb] = ra;
+            cnt[ra] = size[i];
+            node_of[ra] = n + i;
+        }
+    }
+    auto node_size = [&](int v) { return v < n ? 1 : size[v - n]; };
+    // condensed tree, top-down.  Cluster ids grow from the root (0), so children always have larger ids.
+    std::vector<int> c_parent{-1};
+    std::vector<double> c_birth{0.0}, c_stab{0.0};
+    std::vector<int> point_cluster(n, 0);
+    std::vector<std::pair<int, int>> stack;            // (dendrogram node, cluster)
+    std::vector<int> sub;                              // scratch: subtree walk
+    auto fall_out = [&](int v, int cluster, double lambda) {
+        sub.clear();
+        sub.push_back(v);
+        while (!sub.empty()) {
+            const int u = sub.back();
+            sub.pop_back();
+            if (u < n) {
+                point_cluster[u] = cluster;
+                c_stab[cluster] += lambda - c_birth[cluster];
+            } else {
+                sub.push_back(left[u - n]);
+                sub.push_back(right[u - n]);
+            }
+        }
+    };
+    stack.emplace_back(n + m - 1, 0);
+    while (!stack.empty()) {
+        const int v = stack.back().first, c = stack.back().second;
+        stack.pop_back();
+        if (v < n) {                                   // a single point left in its cluster: it never leaves
+            point_cluster[v] = c;
+            continue;
+        }
+        const int l = left[v - n], r = right[v - n];
+        const double d = e[v - n].w;
+        const double lambda = d > 0.0 ? 1.0 / d : std::numeric_limits<double>::infinity();
+        const int nl = node_size(l), nr = node_size(r);
+        if (nl >= min_cluster_size && nr >= min_cluster_size) {
+            for (int side = 0; side < 2; ++side) {
+                const int child = side ? r : l, cs = side ? nr : nl;
+                const int id = (int)c_parent.size();
+                c_parent.push_back(c);
+                c_birth.push_back(lambda);
+                c_stab.push_back(0.0);
+                c_stab[c] += (lambda - c_birth[c]) * (double)cs;
+                stack.emplace_back(child, id);
+            }
+        } else if (nl < min_cluster_size && nr < min_cluster_size) {
+            fall_out(l, c, lambda);
+            fall_out(r, c, lambda);
+        } else if (nl < min_cluster_size) {
+            fall_out(l, c, lambda);
+            stack.emplace_back(r, c);
+        } else {
+            fall_out(r, c, lambda);
+            stack.emplace_back(l, c);
+        }
+    }
+    // excess of mass, bottom-up (children have larger ids); the root is never a cluster
+    const int nc = (int)c_parent.size();
+    std::vector<double> child_sum(nc, 0.0);
+    std::vector<char> selected(nc, 1);
+    selected[0] = 0;
+    for (int c = nc - 1; c >= 1; --c) {
+        if (child_sum[c] > c_stab[c]) {
+            selected[c] = 0;
+            c_stab[c] = child_sum[c];
+        }
+        child_sum[c_parent[c]] += c_stab[c];
+    }
+    // a selected cluster unselects its descendants: top-down, the nearest selected ancestor-or-self wins
+    std::vector<int> owner(nc, -1);
+    for (int c = 1; c < nc; ++c) {
+        const int up = owner[c_parent[c]];
+        owner[c] = up >= 0 ? up : (selected[c] ? c : -1);
+    }
+    std::vector<int> label_of(nc, -1);
+    int next = 0;
+    for (int i = 0; i < n; ++i) {
+        const int o = owner[point_cluster[i]];
+        if (o < 0) continue;
+        if (label_of[o] < 0) label_of[o] = next++;
+        labels[i] = label_of[o];
+    }
+    return ICPF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ device: core distances
+constexpr int kHdbThreads = 128;
+constexpr int kHdbMaxK = 64;            // min_samples the shared-memory heaps hold
+constexpr int kPrimThreads = 256;
+
+__device__ __forceinline__ double hdb_sqdist(double ax, double ay, double az, double bx, double by, double bz) {
+    const double dx = ax - bx, dy = ay - by, dz = az - bz;
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+__global__ void __launch_bounds__(256) hdb_to_double_kernel(const float* __restrict__ pts, int stride, int n,
+                                                            double* __restrict__ p64) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    p64[3 * (size_t)i] = (double)pts[(size_t)i * stride];
+    p64[3 * (size_t)i + 1] = (double)pts[(size_t)i * stride + 1];
+    p64[3 * (size_t)i + 2] = (double)pts[(size_t)i * stride + 2];
+}
+
+// core[i] = sqrt of the k-th smallest squared distance from point i to the points of the scan, itself included
+__global__ void __launch_bounds__(kHdbThreads) hdb_core_kernel(const double* __restrict__ p64, int n, int k,
+                                                               double* __restrict__ core) {
+    ICPF_DYN_SHARED __align__(16) float4 fsm[];              // (the dynamic shared array of icpf_histfused.cu, as doubles)
+    double* hsm = reinterpret_cast<double*>(fsm);
+    double* heap = hsm + threadIdx.x;                         // heap[j * kHdbThreads]: column of this thread
+    double* tile = hsm + (size_t)k * kHdbThreads;             // [kHdbThreads * 3]
+    const int i = blockIdx.x * kHdbThreads + threadIdx.x;
+    const bool live = i < n;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    double qx = 0.0, qy = 0.0, qz = 0.0;
+    if (live) { qx = p64[3 * (size_t)i]; qy = p64[3 * (size_t)i + 1]; qz = p64[3 * (size_t)i + 2]; }
+    for (int j = 0; j < k; ++j) heap[(size_t)j * kHdbThreads] = INF;
+    double worst = INF;            // largest of the k kept
+    int worst_at = 0;
+    for (int base = 0; base < n; base += kHdbThreads) {
+        __syncthreads();
+        const int t = base + threadIdx.x;
+        if (t < n) {
+            tile[3 * threadIdx.x] = p64[3 * (size_t)t];
+            tile[3 * threadIdx.x + 1] = p64[3 * (size_t)t + 1];
+            tile[3 * threadIdx.x + 2] = p64[3 * (size_t)t + 2];
+        }
+        __syncthreads();
+        const int cnt = min(kHdbThreads, n - base);
+        if (live) {
+            for (int c = 0; c < cnt; ++c) {
+                const double d = hdb_sqdist(qx, qy, qz, tile[3 * c], tile[3 * c + 1], tile[3 * c + 2]);
+                if (d < worst) {
+                    heap[(size_t)worst_at * kHdbThreads] = d;
+                    worst = -1.0;
+                    for (int j = 0; j < k; ++j) {
+                        const double v = heap[(size_t)j * kHdbThreads];
+                        if (v > worst) { worst = v; worst_at = j; }
+                    }
+                }
+            }
+        }
+    }
+    if (live) core[i] = sqrt(worst);
+}
+
+// One step of Prim's algorithm (see the header).  part_v / part_j: per block the smallest key of the previous step.
+struct PrimArgs {
+    const double* p64;
+    const double* core;
+    int n;
+    double* min_reach;       // [n]
+    int* source;             // [n]
+    unsigned char* in_tree;  // [n]
+    double* part_v;          // [2][blocks]
+    int* part_j;             // [2][blocks]
+    int blocks;
+    int* edge_src;           // [n-1]
+    int* edge_dst;
+    double* edge_w;
+    int* cur_node;           // [1] the point that joined last
+};
+
+__device__ __forceinline__ bool prim_less(double va, int ja, double vb, int jb) { return va < vb || (va == vb && ja < jb); }
+
+__device__ __forceinline__ void hdb_prim_step(const PrimArgs& a, int step, int last) {
+    __shared__ double s_v[kPrimThreads / 32];
+    __shared__ int s_j[kPrimThreads / 32];
+    __shared__ int s_cur;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double BIG = 1.7976931348623157e308;      // DBL_MAX: the oracle's initial `new_reachability`
+    // ---- the point that joins now: 0 at the first step, else the arg-min of the previous step's candidates
+    if (warp == 0) {
+        int cur = 0;
+        if (step > 0) {
+            const double* pv = a.part_v + (size_t)((step - 1) & 1) * a.blocks;
+            const int* pj = a.part_j + (size_t)((step - 1) & 1) * a.blocks;
+            double bv = BIG;
+            int bj = 0x7fffffff;
+            for (int b = lane; b < a.blocks; b += 32) {
+                if (prim_less(pv[b], pj[b], bv, bj)) { bv = pv[b]; bj = pj[b]; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(FULL_MASK, bv, o);
+                const int oj = __shfl_xor_sync(FULL_MASK, bj, o);
+                if (prim_less(ov, oj, bv, bj)) { bv = ov; bj = oj; }
+            }
+            // (no candidate below DBL_MAX -- non-finite input -- : the oracle's `new_node` stays 0)
+            cur = (bj == 0x7fffffff) ? 0 : bj;
+            if (blockIdx.x == 0 && lane == 0) {
+                a.edge_src[step - 1] = (bj == 0x7fffffff) ? 0 : a.source[cur];
+                a.edge_dst[step - 1] = cur;
+                a.edge_w[step - 1] = bv;
+                a.in_tree[cur] = 1;
+                *a.cur_node = cur;
+            }
+        } else if (blockIdx.x == 0 && lane == 0) {
+            a.in_tree[0] = 1;
+        }
+        if (lane == 0) s_cur = cur;
+    }
+    __syncthreads();
+    if (last) return;
+    const int cur = s_cur;
+    const double cx = a.p64[3 * (size_t)cur], cy = a.p64[3 * (size_t)cur + 1], cz = a.p64[3 * (size_t)cur + 2];
+    const double ccore = a.core[cur];
+    // ---- relax one candidate per thread against `cur`
+    const int j = blockIdx.x * kPrimThreads + tid;
+    double v = BIG;
+    int vj = 0x7fffffff;
+    if (j < a.n && j != cur && a.in_tree[j] == 0) {
+        const double d = sqrt(hdb_sqdist(cx, cy, cz, a.p64[3 * (size_t)j], a.p64[3 * (size_t)j + 1], a.p64[3 * (size_t)j + 2]));
+        const double cj = a.core[j];
+        double mr = ccore > cj ? ccore : cj;
+        mr = mr > d ? mr : d;
+        double cand = a.min_reach[j];
+        if (mr < cand) {
+            a.min_reach[j] = mr;
+            a.source[j] = cur;
+            cand = mr;
+        }
+        if (cand < BIG) { v = cand; vj = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(FULL_MASK, v, o);
+        const int oj = __shfl_xor_sync(FULL_MASK, vj, o);
+        if (prim_less(ov, oj, v, vj)) { v = ov; vj = oj; }
+    }
+    if (lane == 0) { s_v[warp] = v; s_j[warp] = vj; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < kPrimThreads / 32; ++w) {
+            if (prim_less(s_v[w], s_j[w], v, vj)) { v = s_v[w]; vj = s_j[w]; }
+        }
+        a.part_v[(size_t)(step & 1) * a.blocks + blockIdx.x] = v;
+        a.part_j[(size_t)(step & 1) * a.blocks + blockIdx.x] = vj;
+    }
+}
+
+__global__ void __launch_bounds__(kPrimThreads) hdb_prim_step_kernel(PrimArgs a, int step, int last) {
+    hdb_prim_step(a, step, last);
+}
+
+#ifndef ICPF_SIMT_EMU
+// All steps in ONE cooperative launch (every block resident, a grid-wide barrier per step) when the scan fits the
+// device: a step is then ~2 us of barrier instead of a ~6 us launch.
+__global__ void __launch_bounds__(kPrimThreads) hdb_prim_coop_kernel(PrimArgs a) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    __shared__ double s_v[kPrimThreads / 32];
+    __shared__ int s_j[kPrimThreads / 32];
+    __shared__ int s_cur;
+    __shared__ double s_cpt[4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double BIG = 1.7976931348623157e308;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    // the candidate this thread owns for the whole run lives in registers
+    const int j = blockIdx.x * kPrimThreads + tid;
+    const bool have = j < a.n;
+    double px = 0.0, py = 0.0, pz = 0.0, cj = 0.0, reach = INF;
+    int src = 1;
+    bool in_tree = !have;
+    if (have) {
+        px = a.p64[3 * (size_t)j]; py = a.p64[3 * (size_t)j + 1]; pz = a.p64[3 * (size_t)j + 2];
+        cj = a.core[j];
+    }
+    for (int step = 0; step < a.n; ++step) {
+        if (warp == 0) {
+            int cur = 0;
+            if (step > 0) {
+                const double* pv = a.part_v + (size_t)((step - 1) & 1) * a.blocks;
+                const int* pj = a.part_j + (size_t)((step - 1) & 1) * a.blocks;
+                double bv = BIG;
+                int bj = 0x7fffffff;
+                for (int b = lane; b < a.blocks; b += 32) {
+                    const double v = __ldcg(pv + b);
+                    const int vj = __ldcg(pj + b);
+                    if (prim_less(v, vj, bv, bj)) { bv = v; bj = vj; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ov = __shfl_xor_sync(FULL_MASK, bv, o);
+                    const int oj = __shfl_xor_sync(FULL_MASK, bj, o);
+                    if (prim_less(ov, oj, bv, bj)) { bv = ov; bj = oj; }
+                }
+                cur = (bj == 0x7fffffff) ? 0 : bj;
+                if (blockIdx.x == 0 && lane == 0) {
+                    a.edge_dst[step - 1] = cur;
+                    a.edge_w[step - 1] = bv;
+                }
+            }
+            if (lane == 0) s_cur = cur;
+            if (lane < 4) s_cpt[lane] = lane < 3 ? a.p64[3 * (size_t)cur + lane] : a.core[cur];
+        }
+        __syncthreads();
+        const int cur = s_cur;
+        if (j == cur) {
+            in_tree = true;
+            if (step > 0) a.edge_src[step - 1] = src;          // the owner knows which point reached it
+        }
+        if (step == a.n - 1) break;
+        double v = BIG;
+        int vj = 0x7fffffff;
+        if (!in_tree) {
+            const double d = sqrt(hdb_sqdist(s_cpt[0], s_cpt[1], s_cpt[2], px, py, pz));
+            const double ccore = s_cpt[3];
+            double mr = ccore > cj ? ccore : cj;
+            mr = mr > d ? mr : d;
+            if (mr < reach) { reach = mr; src = cur; }
+            if (reach < BIG) { v = reach; vj = j; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(FULL_MASK, v, o);
+            const int oj = __shfl_xor_sync(FULL_MASK, vj, o);
+            if (prim_less(ov, oj, v, vj)) { v = ov; vj = oj; }
+        }
+        if (lane == 0) { s_v[warp] = v; s_j[warp] = vj; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < kPrimThreads / 32; ++w) {
+                if (prim_less(s_v[w], s_j[w], v, vj)) { v = s_v[w]; vj = s_j[w]; }
+            }
+            __stcg(a.part_v + (size_t)(step & 1) * a.blocks + blockIdx.x, v);
+            __stcg(a.part_j + (size_t)(step & 1) * a.blocks + blockIdx.x, vj);
+        }
+        grid.sync();
+    }
+}
+#endif
+
+__global__ void __launch_bounds__(256) hdb_init_kernel(int n, double* min_reach, int* source, unsigned char* in_tree) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    min_reach[i] = __longlong_as_double(0x7ff0000000000000LL);
+    source[i] = 1;                      // (np.ones in the oracle; only read after it was written)
+    in_tree[i] = 0;
+}
+
+inline size_t hdb_up(size_t b) { return (b + 255) / 256 * 256; }
+
+size_t hdbscan_workspace_bytes(int n) {
+    const size_t blocks = ((size_t)n + kPrimThreads - 1) / kPrimThreads;
+    return hdb_up((size_t)n * 24) + hdb_up((size_t)n * 8) + hdb_up((size_t)n * 4) + hdb_up((size_t)n) +
+           hdb_up(blocks * 16) + hdb_up(blocks * 8) + 256;
+}
+
+int launch_hdbscan_mst(const float* points, int stride, int n, int min_samples, double* out_core, int* out_src,
+                       int* out_dst, double* out_w, void* workspace, cudaStream_t stream) {
+    if (min_samples > kHdbMaxK) return ICPF_E_UNSUPPORTED;
+    unsigned char* w = static_cast<unsigned char*>(workspace);
+    const int blocks = (n + kHdbThreads - 1) / kHdbThreads;
+    const int pblocks = (n + kPrimThreads - 1) / kPrimThreads;
+    double* p64 = reinterpret_cast<double*>(w); w += hdb_up((size_t)n * 24);
+    double* min_reach = reinterpret_cast<double*>(w); w += hdb_up((size_t)n * 8);
+    int* source = reinterpret_cast<int*>(w); w += hdb_up((size_t)n * 4);
+    unsigned char* in_tree = w; w += hdb_up((size_t)n);
+    double* part_v = reinterpret_cast<double*>(w); w += hdb_up((size_t)pblocks * 16);
+    int* part_j = reinterpret_cast<int*>(w); w += hdb_up((size_t)pblocks * 8);
+    int* cur_node = reinterpret_cast<int*>(w);
+    const int b256 = (n + 255) / 256;
+    ICPF_LAUNCH(hdb_to_double_kernel, b256, 256, 0, stream)(points, stride, n, p64);
+    const int k = min_samples < n ? min_samples : n;
+    const size_t smem = ((size_t)k + 3) * kHdbThreads * sizeof(double);
+    cudaError_t err = cudaFuncSetAttribute(hdb_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return (int)err;
+    ICPF_LAUNCH(hdb_core_kernel, blocks, kHdbThreads, smem, stream)(p64, n, k, out_core);
+    ICPF_LAUNCH(hdb_init_kernel, b256, 256, 0, stream)(n, min_reach, source, in_tree);
+    PrimArgs a{p64, out_core, n, min_reach, source, in_tree, part_v, part_j, pblocks, out_src, out_dst, out_w, cur_node};
+#ifndef ICPF_SIMT_EMU
+    {
+        int dev = 0, coop = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hdb_prim_coop_kernel, kPrimThreads, 0);
+        if (coop && (long long)per_sm * sms >= pblocks) {
+            void* args[] = {&a};
+            err = cudaLaunchCooperativeKernel((const void*)hdb_prim_coop_kernel, dim3(pblocks), dim3(kPrimThreads), args, 0, stream);
+            return (int)err;
+        }
+    }
+#endif
+    for (int step = 0; step < n; ++step) {            // step n-1 only records the last edge
+        ICPF_LAUNCH(hdb_prim_step_kernel, pblocks, kPrimThreads, 0, stream)(a, step, step == n - 1 ? 1 : 0);
+    }
+    return (int)cudaGetLastError();
+}
+
+}  // namespace icpf

@@ -100,6 +100,11 @@ int launch_sanity_check(const int* src_offsets, const float* src_stats, int n_sr
                         float translation_frame, float thres_box, int* out_keep, int64_t* out_pairs, int* out_count,
                         cudaStream_t stream, int cross_nd = 0);
 size_t match_select_workspace_bytes(int ns, int nd);
+int hdbscan_labels_host(const int* edge_a, const int* edge_b, const double* edge_w, int n, int min_cluster_size,
+                        int presorted, int* labels);
+size_t hdbscan_workspace_bytes(int n);
+int launch_hdbscan_mst(const float* points, int stride, int n, int min_samples, double* out_core, int* out_src,
+                       int* out_dst, double* out_w, void* workspace, cudaStream_t stream);
 int launch_match_select(const int64_t* pairs, int P, const int64_t* src_unq, int ns, const int64_t* dst_unq, int nd,
                         const float* errors, const float* inliers, const float* ratios, const float* ious,
                         const int* accept, const float* transforms, float thres_error, float* out_rows,

@@ -16,7 +16,8 @@ only the hot-path entry points are rebound, exactly at the seams SURVEY.md secti
     utils_helper.nearest_neighbor_batch / transform_points_batch (and the names re-imported by utils_match / utils_icp /
     utils_hist) <- the engine's, used by match_eval on CUDA tensors
 
-    utils_cluster.cluster_dbscan / cluster_pcd <- icp_flow_b200.cluster_dbscan / cluster_pcd   (opt-in: patch_clustering=True)
+    utils_cluster.cluster_hdbscan / cluster_dbscan / cluster_pcd <- icp_flow_b200.cluster_hdbscan / cluster_dbscan / cluster_pcd
+                                                              (opt-in: patch_clustering=True)
 
 ``uninstall()`` restores the originals.  The reference modules must already be importable (``sys.path``).
 """
@@ -52,9 +53,10 @@ _LOADED_ONLY = (
     ("demo", "flow_estimation_torch", scan.flow_estimation_torch),
 )
 
-# the reference's default clusterer (Open3D DBSCAN) -- opt-in, `install(patch_clustering=True)`:
-# HDBSCAN (--if_hdbscan) is not replaced and raises through cluster_pcd
+# the reference's clusterers (hdbscan with --if_hdbscan, else Open3D DBSCAN) -- opt-in,
+# `install(patch_clustering=True)`
 _CLUSTERING = (
+    ("utils_cluster", "cluster_hdbscan", cluster.cluster_hdbscan),
     ("utils_cluster", "cluster_dbscan", cluster.cluster_dbscan),
     ("utils_cluster", "cluster_pcd", cluster.cluster_pcd),
 )

@@ -355,6 +355,32 @@ size_t icpf_dbscan_workspace_bytes(int32_t n_points);
 int icpf_dbscan_f32(const float* points, int32_t point_stride, int32_t n_points, double eps, int32_t min_points,
                     int32_t* out_labels, int32_t* out_num_clusters, void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * HDBSCAN -- replaces utils_cluster.cluster_hdbscan (utils_cluster.py:10-29: hdbscan.HDBSCAN(min_cluster_size,
+ * min_samples=None, alpha=1, metric='euclidean').fit(points[:, 0:3]).labels_), the clustering every script of the
+ * reference selects (--if_hdbscan).  Two calls:
+ *
+ * icpf_hdbscan_mst_f32 (device, stream-ordered, n_points + 3 launches): core distances (distance to the min_samples-th
+ *   nearest point, the point itself included; fp64 on the fp32 coordinates) and the minimum spanning tree of the mutual-
+ *   reachability graph max(core_a, core_b, d(a,b)) by Prim's algorithm from point 0 -- the edges in the ORDER Prim adds
+ *   them (strict `<` relaxation, first minimum in index order), which is what scikit-learn's port of the package builds
+ *   (sklearn/cluster/_hdbscan/_linkage.pyx) and what fixes the dendrogram among edges of equal weight.
+ *   points [n, point_stride >= 3] fp32, all finite; out_core [n] f64; out_edge_src / out_edge_dst [n-1] int32,
+ *   out_edge_w [n-1] f64; min_samples <= 64; workspace icpf_hdbscan_workspace_bytes(n) bytes, 256-byte aligned.
+ *
+ * icpf_hdbscan_labels_host: HOST arrays.  The n - 1 edges (a, b, weight) of that tree -> single-linkage dendrogram ->
+ *   condensed tree (min_cluster_size) -> excess-of-mass selection (the root is never a cluster) -> out_labels [n] int32,
+ *   clusters numbered by their lowest point, -1 = noise.  presorted != 0: the edges are already in ascending weight
+ *   order and are merged in exactly that order (the host wrapper sorts them with numpy's argsort, as the oracle does);
+ *   otherwise they are sorted here by (weight, min(a,b), max(a,b)).
+ */
+size_t icpf_hdbscan_workspace_bytes(int32_t n_points);
+int icpf_hdbscan_mst_f32(const float* points, int32_t point_stride, int32_t n_points, int32_t min_samples,
+                         double* out_core, int32_t* out_edge_src, int32_t* out_edge_dst, double* out_edge_w,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int icpf_hdbscan_labels_host(const int32_t* edge_a, const int32_t* edge_b, const double* edge_w, int32_t n_points,
+                             int32_t min_cluster_size, int32_t presorted, int32_t* out_labels);
+
 /* CPU-callable test hook: the closed-form 3x3 Kabsch rotation used inside the kernels, evaluated on the host
  * for `n` row-major cross-covariance matrices H (n*9 floats) -> R (n*9 floats).  Not part of the data path. */
 void icpf_host_kabsch(const float* H, int32_t n, float* R);

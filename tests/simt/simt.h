@@ -209,6 +209,7 @@ inline int __ffs(int v) { return __builtin_ffs(v); }
 inline void __threadfence() {}
 template <class T> inline T __ldcg(const T* p) { return *p; }
 template <class T> inline void __stcg(T* p, T v) { *p = v; }
+inline double __longlong_as_double(long long v) { double d; __builtin_memcpy(&d, &v, 8); return d; }
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }
