@@ -39,3 +39,6 @@ from icp_flow_b200 import cluster
 lab = cluster.dbscan_labels(t[0][t[2] > -1e7][:, :3].contiguous(), 0.25, 20)
 torch.cuda.synchronize()
 print("dbscan ok", int(lab.max()) + 1)
+hl = cluster.hdbscan_labels(t[0][t[2] > -1e7][:1500, :3].contiguous(), 20)
+torch.cuda.synchronize()
+print("hdbscan ok", int(hl.max()) + 1, int((hl < 0).sum()))
