@@ -150,7 +150,7 @@ def lib() -> ctypes.CDLL:
     L.icpf_hdbscan_workspace_bytes.restype = ctypes.c_size_t
     L.icpf_hdbscan_workspace_bytes.argtypes = [i32]
     L.icpf_hdbscan_mst_f32.restype = ctypes.c_int
-    L.icpf_hdbscan_mst_f32.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
+    L.icpf_hdbscan_mst_f32.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, ctypes.c_size_t, vp]
     L.icpf_gather_pairs_f32.restype = ctypes.c_int
     L.icpf_gather_pairs_f32.argtypes = [vp, i32, vp, vp, i32, vp, i32, vp, vp, i32, vp, i32, i32, vp, vp, vp, vp, vp]
     L.icpf_flow_f32.restype = ctypes.c_int

@@ -251,8 +251,8 @@ int icpf_hdbscan_labels_host(const int32_t* edge_a, const int32_t* edge_b, const
 size_t icpf_hdbscan_workspace_bytes(int32_t n_points) { return n_points > 0 ? hdbscan_workspace_bytes(n_points) : 0; }
 
 int icpf_hdbscan_mst_f32(const float* points, int32_t point_stride, int32_t n_points, int32_t min_samples,
-                         double* out_core, int32_t* out_edge_src, int32_t* out_edge_dst, double* out_edge_w,
-                         void* workspace, size_t workspace_bytes, void* stream) {
+                         int32_t prim_order, double* out_core, int32_t* out_edge_src, int32_t* out_edge_dst,
+                         double* out_edge_w, void* workspace, size_t workspace_bytes, void* stream) {
     if (n_points < 0 || point_stride < 3) return ICPF_E_SHAPE;
     if (min_samples < 1) return ICPF_E_PARAM;
     if (n_points == 0) return ICPF_OK;
@@ -260,7 +260,7 @@ int icpf_hdbscan_mst_f32(const float* points, int32_t point_stride, int32_t n_po
     if (n_points > 1 && (!out_edge_src || !out_edge_dst || !out_edge_w)) return ICPF_E_NULL;
     if (workspace == nullptr || workspace_bytes < hdbscan_workspace_bytes(n_points)) return ICPF_E_WORKSPACE;
     if ((reinterpret_cast<uintptr_t>(workspace) & 255u) != 0) return ICPF_E_ALIGN;
-    return launch_hdbscan_mst(points, point_stride, n_points, min_samples, out_core, out_edge_src, out_edge_dst,
+    return launch_hdbscan_mst(points, point_stride, n_points, min_samples, prim_order, out_core, out_edge_src, out_edge_dst,
                               out_edge_w, workspace, static_cast<cudaStream_t>(stream));
 }
 

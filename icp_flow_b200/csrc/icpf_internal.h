@@ -103,8 +103,8 @@ size_t match_select_workspace_bytes(int ns, int nd);
 int hdbscan_labels_host(const int* edge_a, const int* edge_b, const double* edge_w, int n, int min_cluster_size,
                         int presorted, int* labels);
 size_t hdbscan_workspace_bytes(int n);
-int launch_hdbscan_mst(const float* points, int stride, int n, int min_samples, double* out_core, int* out_src,
-                       int* out_dst, double* out_w, void* workspace, cudaStream_t stream);
+int launch_hdbscan_mst(const float* points, int stride, int n, int min_samples, int prim_order, double* out_core,
+                       int* out_src, int* out_dst, double* out_w, void* workspace, cudaStream_t stream);
 int launch_match_select(const int64_t* pairs, int P, const int64_t* src_unq, int ns, const int64_t* dst_unq, int nd,
                         const float* errors, const float* inliers, const float* ratios, const float* ious,
                         const int* accept, const float* transforms, float thres_error, float* out_rows,

@@ -365,6 +365,11 @@ int icpf_dbscan_f32(const float* points, int32_t point_stride, int32_t n_points,
  *   reachability graph max(core_a, core_b, d(a,b)) by Prim's algorithm from point 0 -- the edges in the ORDER Prim adds
  *   them (strict `<` relaxation, first minimum in index order), which is what scikit-learn's port of the package builds
  *   (sklearn/cluster/_hdbscan/_linkage.pyx) and what fixes the dendrogram among edges of equal weight.
+ *   prim_order = 0: the tree that is unique under the strict edge order (weight, min(a,b), max(a,b)), built by Boruvka
+ *   rounds (<= log2 n rounds of n^2 candidate edges instead of n - 1 dependent steps: ~10x faster); its edges come in no
+ *   particular order, to be sorted by that order (icpf_hdbscan_labels_host with presorted = 0).  Same weights as the
+ *   oracle's tree, not its order among equal weights: a few labels per scan may differ where the oracle's own result
+ *   depends on that order.  This mode synchronises the stream once per round (the round count depends on the data).
  *   points [n, point_stride >= 3] fp32, all finite; out_core [n] f64; out_edge_src / out_edge_dst [n-1] int32,
  *   out_edge_w [n-1] f64; min_samples <= 64; workspace icpf_hdbscan_workspace_bytes(n) bytes, 256-byte aligned.
  *
@@ -376,8 +381,8 @@ int icpf_dbscan_f32(const float* points, int32_t point_stride, int32_t n_points,
  */
 size_t icpf_hdbscan_workspace_bytes(int32_t n_points);
 int icpf_hdbscan_mst_f32(const float* points, int32_t point_stride, int32_t n_points, int32_t min_samples,
-                         double* out_core, int32_t* out_edge_src, int32_t* out_edge_dst, double* out_edge_w,
-                         void* workspace, size_t workspace_bytes, void* stream);
+                         int32_t prim_order, double* out_core, int32_t* out_edge_src, int32_t* out_edge_dst,
+                         double* out_edge_w, void* workspace, size_t workspace_bytes, void* stream);
 int icpf_hdbscan_labels_host(const int32_t* edge_a, const int32_t* edge_b, const double* edge_w, int32_t n_points,
                              int32_t min_cluster_size, int32_t presorted, int32_t* out_labels);
 

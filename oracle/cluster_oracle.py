@@ -71,3 +71,38 @@ def cluster_hdbscan(points: np.ndarray, min_cluster_size: int, num_clusters: int
     clusters_labels = cluster_info[::-1][:num_clusters, 0]
     labels[np.isin(labels, clusters_labels, invert=True)] = -1
     return labels
+
+
+def mst_total_order(points: np.ndarray, min_samples: int):
+    """The minimum spanning tree of the mutual-reachability graph that is UNIQUE under the strict edge order (weight,
+    min(a,b), max(a,b)) -- Kruskal on the dense fp64 graph, for small n: (edge_a, edge_b, edge_w) in that order.  The
+    definition the engine's any-order (Boruvka) mode implements."""
+    X = np.asarray(points)[:, :3].astype(np.float64)
+    n = len(X)
+    d2 = np.zeros((n, n))
+    for c in range(3):
+        diff = X[:, None, c] - X[None, :, c]
+        d2 += diff * diff
+    D = np.sqrt(d2)
+    core = np.sort(D, axis=1)[:, min(min_samples, n) - 1]
+    M = np.maximum(np.maximum(core[:, None], core[None, :]), D)
+    iu = np.triu_indices(n, 1)
+    order = np.lexsort((iu[1], iu[0], M[iu]))
+    parent = list(range(n))
+
+    def find(x):
+        while parent[x] != x:
+            parent[x] = parent[parent[x]]
+            x = parent[x]
+        return x
+
+    ea, eb, ew = [], [], []
+    for e in order:
+        a, b = int(iu[0][e]), int(iu[1][e])
+        ra, rb = find(a), find(b)
+        if ra != rb:
+            parent[rb] = ra
+            ea.append(a), eb.append(b), ew.append(M[a, b])
+            if len(ea) == n - 1:
+                break
+    return np.array(ea, np.int32), np.array(eb, np.int32), np.array(ew, np.float64)

@@ -62,6 +62,9 @@ inline cudaError_t cudaGetLastError() { const int e = simt::last_error; simt::la
 inline const char* cudaGetErrorString(cudaError_t e) { return e == 9 ? "invalid configuration argument (simt emulator)" : "simt emulator: no CUDA runtime"; }
 template <class K> inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
 inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
+enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
 
 // ------------------------------------------------------------------------------------------------ scheduler interface
@@ -210,6 +213,7 @@ inline void __threadfence() {}
 template <class T> inline T __ldcg(const T* p) { return *p; }
 template <class T> inline void __stcg(T* p, T v) { *p = v; }
 inline double __longlong_as_double(long long v) { double d; __builtin_memcpy(&d, &v, 8); return d; }
+inline long long __double_as_longlong(double d) { long long v; __builtin_memcpy(&v, &d, 8); return v; }
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dmul_rn(double a, double b) { return a * b; }
 inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz((unsigned)v); }

@@ -106,6 +106,25 @@ def test_hdbscan_partition_equals_sklearn(seed, mcs):
         assert first == sorted(first)
 
 
+@pytest.mark.parametrize("seed,mcs", [(0, 10), (2, 10), (3, 20)])
+def test_hdbscan_any_order_tree(seed, mcs):
+    """exact_order=False: the spanning tree that is unique under the edge order (weight, min, max), by Boruvka rounds on the
+    engine.  Its labels equal those of the same tree built by Kruskal on the host (oracle) bit for bit; against sklearn
+    they may differ where sklearn's own result depends on the order of equal-weight edges -- bounded by the ARI."""
+    import ctypes
+    from sklearn.metrics import adjusted_rand_score
+    from icp_flow_b200 import _lib
+    n = 400 if is_simt() else 1200
+    pts = np.ascontiguousarray(synth.make_scene(num_clusters=8, num_points=2400, seed=seed, max_size=300)[0][:, :3][-n:], dtype=np.float32)
+    got = cluster.hdbscan_labels(put(torch.from_numpy(pts)), mcs, exact_order=False)
+    ea, eb, ew = CO.mst_total_order(pts, mcs)
+    want = np.empty(n, np.int32)
+    rc = _lib.lib().icpf_hdbscan_labels_host(ea.ctypes.data_as(ctypes.c_void_p), eb.ctypes.data_as(ctypes.c_void_p),
+                                             ew.ctypes.data_as(ctypes.c_void_p), n, mcs, 0, want.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0 and np.array_equal(got, want)
+    assert adjusted_rand_score(CO.hdbscan_labels(pts, mcs), got) > 0.95          # (a few hundred points: each flip weighs)
+
+
 def test_hdbscan_edge_cases():
     assert len(cluster.hdbscan_labels(put(torch.zeros(0, 3)), 5)) == 0
     assert cluster.hdbscan_labels(put(torch.zeros(1, 3)), 5).tolist() == [-1]
@@ -174,3 +193,6 @@ def test_hdbscan_on_a_scan_equals_sklearn():
     got = cluster.hdbscan_labels(torch.from_numpy(pts).cuda(), 30)
     want = CO.hdbscan_labels(pts, 30)
     assert want.max() >= 50 and CO.same_partition(got, want)
+    from sklearn.metrics import adjusted_rand_score
+    fast = cluster.hdbscan_labels(torch.from_numpy(pts).cuda(), 30, exact_order=False)
+    assert adjusted_rand_score(want, fast) > 0.99
