@@ -42,3 +42,6 @@ print("dbscan ok", int(lab.max()) + 1)
 hl = cluster.hdbscan_labels(t[0][t[2] > -1e7][:1500, :3].contiguous(), 20)
 torch.cuda.synchronize()
 print("hdbscan ok", int(hl.max()) + 1, int((hl < 0).sum()))
+hf = cluster.hdbscan_labels(t[0][t[2] > -1e7][:1500, :3].contiguous(), 20, exact_order=False)
+torch.cuda.synchronize()
+print("hdbscan any-order ok", int(hf.max()) + 1, int((hf < 0).sum()))
