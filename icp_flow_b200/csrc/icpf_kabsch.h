@@ -58,7 +58,7 @@ struct KabschState {
 };
 
 template <int p, int q>
-ICPF_HD ICPF_INLINE void jacobi_pair(float (&b)[9], float (&v)[9], float thr2, bool& rotated) {
+ICPF_HD ICPF_INLINE void jacobi_pair(float (&b)[9], float (&v)[9], float thr2, bool& rotated, float& max_t) {
     // columns p,q of b (3x3 row-major): b[3*i+p]
     const float bp0 = b[p], bp1 = b[3 + p], bp2 = b[6 + p];
     const float bq0 = b[q], bq1 = b[3 + q], bq2 = b[6 + q];
@@ -68,10 +68,25 @@ ICPF_HD ICPF_INLINE void jacobi_pair(float (&b)[9], float (&v)[9], float thr2, b
     // converged for this pair when the columns are orthogonal to working precision: gamma^2 <= thr^2 alpha beta
     if (!(gamma * gamma > thr2 * (alpha * beta))) return;
     rotated = true;
-    const float zeta = icpf_fast_div(beta - alpha, 2.0f * gamma);
-    const float az = fabsf(zeta);
-    const float t = copysignf(1.0f, zeta) * icpf_fast_div(1.0f, az + sqrtf(fmaf(az, az, 1.0f)));
-    const float c = icpf_rsqrt(fmaf(t, t, 1.0f));
+    float t, c;
+#ifndef ICPF_KABSCH_EXACT_ANGLE
+    // warm-started solves rotate by ~1e-3 rad: |zeta| is huge and t = 1 / (2 zeta) (1 - 1 / (4 zeta^2) + ...), c = 1 - t^2 / 2
+    // to fp32 precision; the exact formulas (two divisions, a square root, a reciprocal square root) for the rest
+    const float diff = beta - alpha;
+    if (fabsf(diff) > 64.0f * fabsf(gamma)) {
+        t = icpf_fast_div(gamma, diff);
+        t = fmaf(-t * t, t, t);                    // t (1 - t^2): the next term of the series
+        c = fmaf(-0.5f * t, t, 1.0f);
+        max_t = fmaxf(max_t, fabsf(t));
+    } else
+#endif
+    {
+        const float zeta = icpf_fast_div(beta - alpha, 2.0f * gamma);
+        const float az = fabsf(zeta);
+        t = copysignf(1.0f, zeta) * icpf_fast_div(1.0f, az + sqrtf(fmaf(az, az, 1.0f)));
+        c = icpf_rsqrt(fmaf(t, t, 1.0f));
+        max_t = 1.0f;
+    }
     const float s = c * t;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -136,12 +151,18 @@ ICPF_HD inline Rot3 kabsch_rotation(const float (&h)[9], KabschState* st = nullp
     bool any = false;
     for (int sweep = 0; sweep < 12; ++sweep) {
         bool rotated = false;
-        jacobi_pair<0, 1>(b, v, thr2, rotated);
-        jacobi_pair<0, 2>(b, v, thr2, rotated);
-        jacobi_pair<1, 2>(b, v, thr2, rotated);
+        float max_t = 0.f;
+        jacobi_pair<0, 1>(b, v, thr2, rotated, max_t);
+        jacobi_pair<0, 2>(b, v, thr2, rotated, max_t);
+        jacobi_pair<1, 2>(b, v, thr2, rotated, max_t);
         if (!rotated) break;
         any = true;
         thr2 = kThr2;
+#ifndef ICPF_KABSCH_EXACT_ANGLE
+        // cyclic Jacobi converges quadratically: after a sweep whose largest rotation was 1e-4 the columns are orthogonal to
+        // 1e-8, below the threshold the next sweep would test against
+        if (max_t < 1e-4f) break;
+#endif
     }
     // squared column norms = squared singular values; pick the two dominant columns a, b_
     float n0 = fmaf(b[6], b[6], fmaf(b[3], b[3], b[0] * b[0]));
