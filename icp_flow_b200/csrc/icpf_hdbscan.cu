@@ -731,7 +731,8 @@ int launch_hdbscan_mst(const float* points, int stride, int n, int min_samples, 
             if (err != cudaSuccess) return (int)err;
             void* args[] = {&a, &words};
             err = cudaLaunchCooperativeKernel((const void*)hdb_prim_coop_kernel, dim3(pblocks), dim3(kPrimThreads), args, 0, stream);
-            return (int)err;
+            if (err != cudaErrorCooperativeLaunchTooLarge) return (int)err;
+            (void)cudaGetLastError();              // (the device is shared right now: one launch per step instead)
         }
     }
 #endif
