@@ -46,15 +46,14 @@ def keep_largest(labels: np.ndarray, num_clusters: int) -> np.ndarray:
     """utils_cluster.py:40-46 restated on the label array: clusters outside the ``num_clusters`` largest become -1.
     (Host logic on a few hundred counts; the order among equally large clusters is numpy's argsort, as in the reference.)"""
     labels = np.array(labels)
-    lbls, counts = np.unique(labels, return_counts=True)
-    # (the reference drops the first unique label assuming it is the noise label -1, utils_cluster.py:42)
-    cluster_info = np.array(list(zip(lbls[1:], counts[1:])))
-    if len(cluster_info) == 0:          # no cluster at all: the reference would raise on the empty array; everything is noise
+    ids, counts = np.unique(labels, return_counts=True)
+    ids, counts = ids[1:], counts[1:]       # the reference drops the first unique label, taking it for the noise label -1
+    if ids.size == 0:                       # no cluster at all (the reference would raise on the empty array): all noise
         labels[:] = -1
         return labels
-    cluster_info = cluster_info[cluster_info[:, 1].argsort()]
-    clusters_labels = cluster_info[::-1][:num_clusters, 0]
-    labels[np.isin(labels, clusters_labels, invert=True)] = -1      # unclustered point
+    # ascending argsort of the sizes, read backwards: among equally large clusters the order is numpy's, as in the reference
+    keep = ids[np.argsort(counts)[::-1][:num_clusters]]
+    labels[~np.isin(labels, keep)] = -1
     return labels
 
 
