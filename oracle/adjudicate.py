@@ -11,7 +11,8 @@ to be held to the SET of outcomes the reference admits.  This module constructs 
 
   * the reference algorithm re-run in fp64 (what the reference computes when rounding is taken out of the decisions),
   * the reference algorithm re-run in fp32 on inputs whose coordinates are moved by one / a few fp32 ulps
-    (``x * (1 + k * 2^-23)``): every rounding-level decision of the run gets the chance to fall the other way,
+    (``x * (1 + k * 2^-23)``): every rounding-level decision of the run gets the chance to fall the other way
+    (three draws at 1 and 4 ulps first; for pairs still open a wider sample, twelve draws at 1, 2, 4 and 8 ulps),
   * for the ICP loop: both at the batch iteration count of the oracle and at the engine's (the batch stop itself is a
     threshold decision on a relative rmse of 1e-6),
   * for the histogram initialisation: the other orders `torch.topk` may return EQUAL vote counts in (lowest / highest
@@ -113,6 +114,20 @@ def _adjudicate(src_for_err: torch.Tensor, T_eng: torch.Tensor, T_ref: torch.Ten
     return Verdicts(err, verdict, tol)
 
 
+def _extended_jitter_labels(first_seed: int, its, seeds: int = 12, ulps=(1, 2, 4, 8)):
+    """A second, wider sample of the rounding-level outcomes, only ever evaluated for the pairs the first one left open
+    (`_adjudicate` stops as soon as nothing is left): a pair with two attractors a millimetre apart -- the reference's own
+    results on it scatter by millimetres under 2-ulp jitter -- may need more than three draws per level to show the one
+    the engine fell into (seen once in 2 720 fuzzed pairs: tools/parity_fuzz.py, seed 20138, pair 6)."""
+    out = []
+    for u in ulps:
+        for s in range(seeds):
+            if u in (1, 4) and s < first_seed:
+                continue                    # already in the first sample
+            out += [f"ulp{u}#{s}@{k}" for k in its]
+    return out
+
+
 def rank_deficient_pairs(trace: O.IcpTrace, min_inliers: int = 4, sigma_ratio: float = 1e-3) -> np.ndarray:
     """Pairs whose Kabsch system had rank <= 1 at some iteration of the oracle run (`icp_loop(..., diagnostics=True)`)."""
     assert trace.min_inliers is not None, "run icp_loop(..., diagnostics=True)"
@@ -129,6 +144,7 @@ def adjudicate_icp(src: torch.Tensor, dst: torch.Tensor, R_eng: torch.Tensor, T_
     labels = [f"fp64@{k}" for k in its]
     for u in (1, 4):
         labels += [f"ulp{u}#{s}@{k}" for s in range(seeds // 2) for k in its]
+    labels += _extended_jitter_labels(seeds // 2, its)
 
     def run(label, idx):
         kind, k = label.split("@")
@@ -158,6 +174,7 @@ def adjudicate_path(src: torch.Tensor, dst: torch.Tensor, T_eng: torch.Tensor, T
         labels += [f"topk-{t}@{k}" for t in ("low", "high") for k in its]
     for u in (1, 4):
         labels += [f"ulp{u}#{s}@{k}" for s in range(seeds // 2) for k in its]
+    labels += _extended_jitter_labels(seeds // 2, its)
 
     def run(label, idx):
         kind, k = label.split("@")
