@@ -47,11 +47,13 @@ def assert_path_parity(src, dst, T_eng, T_ref, p, its_ref, its_eng=None, stage="
     return v
 
 
-def selected_pairs_parity(stage_batches, p, ref_rows, T_eng, T_ref, max_explained=0.1, what="frame"):
+def selected_pairs_parity(stage_batches, p, ref_rows, T_eng, T_ref, max_explained=0.1, what="frame", engine_its=None):
     """Frame level: `ref_rows[:, :2]` are the selected (src label, dst label) pairs, `T_eng` / `T_ref` their transforms;
     `stage_batches` = [(segs_src [K,N,4], segs_dst, pairs [K,2]), ...] the padded candidate batches hist_icp saw (one per
     match_pairs call: the batch stop couples the pairs of a call).  Every selected pair is held to the tolerance or
-    adjudicated on its own padded clouds.  Returns the mask of the pairs that needed adjudication."""
+    adjudicated on its own padded clouds.  `engine_its(segs_src, segs_dst) -> int` (optional): the batch iterations the
+    ENGINE executes on such a candidate batch -- the batch stop is itself a threshold decision, so the admitted outcomes
+    are taken at the oracle's and at the engine's count.  Returns the mask of the pairs that needed adjudication."""
     from oracle import icp_oracle as O
     flagged = np.zeros(len(ref_rows), dtype=bool)
     seen = np.zeros(len(ref_rows), dtype=bool)
@@ -69,8 +71,10 @@ def selected_pairs_parity(stage_batches, p, ref_rows, T_eng, T_ref, max_explaine
         trace = O.icp_loop(O.transform_points_batch(a_, odbg["init"]), c_, p.thres_dist, p.max_iterations,
                            p.relative_rmse_thr, diagnostics=True)
         sub = O.IcpTrace(*[None] * 10)._replace(min_inliers=trace.min_inliers[sel], min_sigma_ratio=trace.min_sigma_ratio[sel])
+        its_eng = int(engine_its(segs_src, segs_dst)) if engine_its is not None else None
         v = assert_path_parity(segs_src[sel], segs_dst[sel], torch.as_tensor(T_eng[rows]), torch.as_tensor(T_ref[rows]), p,
-                               trace.iterations, max_explained=1.0, what=f"{what}, {len(rows)} selected pairs", trace=sub)
+                               trace.iterations, its_eng, max_explained=1.0, what=f"{what}, {len(rows)} selected pairs",
+                               trace=sub)
         flagged[rows] = v.explained
         seen[rows] = True
     assert seen.all()
