@@ -686,8 +686,11 @@ __device__ __forceinline__ void score_pair(const ScoreArgs& a, const int p, cons
     }
 }
 
+#ifndef ICPF_SCORE_MIN_CTAS
+#define ICPF_SCORE_MIN_CTAS 5      // (96 registers instead of 128 for the item kernel: 5 CTAs per SM, as many as the shared memory allows)
+#endif
 template <bool GRIDNN, bool ITEM>
-__global__ void __launch_bounds__(kThreads) hist_score_kernel(ScoreArgs a) {
+__global__ void __launch_bounds__(kThreads, ICPF_SCORE_MIN_CTAS) hist_score_kernel(ScoreArgs a) {
     if constexpr (ITEM) {
         __shared__ int s_item;
         for (;;) {
