@@ -56,6 +56,29 @@ __device__ __forceinline__ void grid_block_min(const GridInfo& g, const float4* 
     const int ix0 = max(0, (int)x0), ix1 = min(g.gx - 1, (int)x1);
     const int iy0 = max(0, (int)y0), iy1 = min(g.gy - 1, (int)y1);
     const int iz0 = max(0, (int)z0), iz1 = min(g.gz - 1, (int)z1);
+#ifndef ICPF_BLOCK_NESTED_ONLY
+    if (ix1 - ix0 <= 1 && iy1 - iy0 <= 1) {
+        // the gate block (r < 0.5 cells: at most 2 x 2 columns): its <= 4 runs walked as ONE flat candidate sequence, like
+        // grid_search of the ICP loop -- a lane's trip count is its own number of candidates, not the warp's worst column
+        const bool two_x = ix1 > ix0, two_y = iy1 > iy0;
+        const int b00 = (ix0 * g.gy + iy0) * g.gz, b01 = b00 + g.gz, b10 = b00 + g.gy * g.gz, b11 = b10 + g.gz;
+        const int s0 = a[b00 + iz0], e0 = a[b00 + iz1 + 1];
+        int s1 = 0, e1 = 0, s2 = 0, e2 = 0, s3 = 0, e3 = 0;
+        if (two_y) { s1 = a[b01 + iz0]; e1 = a[b01 + iz1 + 1]; }
+        if (two_x) { s2 = a[b10 + iz0]; e2 = a[b10 + iz1 + 1]; }
+        if (two_x && two_y) { s3 = a[b11 + iz0]; e3 = a[b11 + iz1 + 1]; }
+        const int c1 = e0 - s0, c2 = c1 + (e1 - s1), c3 = c2 + (e2 - s2), total = c3 + (e3 - s3);
+        const int o0 = s0, o1 = s1 - c1, o2 = s2 - c2, o3 = s3 - c3;
+        for (int t = 0; t < total; ++t) {
+            const int off = t < c2 ? (t < c1 ? o0 : o1) : (t < c3 ? o2 : o3);
+            const float4 c = sorted[t + off];
+            const float d = SHIFT ? sqdist(ex, ey, ez, __fadd_rn(c.x, sx), __fadd_rn(c.y, sy), __fadd_rn(c.z, sz))
+                                  : sqdist(ex, ey, ez, c.x, c.y, c.z);
+            dmin = fminf(dmin, d);
+        }
+        return;
+    }
+#endif
     for (int ix = ix0; ix <= ix1; ++ix) {
         for (int iy = iy0; iy <= iy1; ++iy) {
             const int base = (ix * g.gy + iy) * g.gz;
